@@ -1,0 +1,25 @@
+# Builds the in-tree shared library (C ABI in include/chemps2_b200.h) for sm_100a and the CPU checker in oracle/.
+NVCC ?= nvcc
+CXX ?= g++
+CUDA_HOME ?= /usr/local/cuda
+SRC := chemps2_b200/csrc
+NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
+CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -I$(CUDA_HOME)/include
+OBJS := $(SRC)/b2_core.o $(SRC)/b2_ops.o $(SRC)/b2_sigma_plan.o $(SRC)/b2_diag.o $(SRC)/b2_heff.o $(SRC)/b2_capi.o $(SRC)/b2_kernels.o
+LIB := chemps2_b200/libchemps2_b200.so
+
+all: $(LIB) oracle/libb2oracle.so
+
+$(SRC)/b2_sigma_plan.o: $(SRC)/b2_sigma_plan_f4.inc $(SRC)/b2_sigma_plan_f5.inc
+$(SRC)/%.o: $(SRC)/%.cpp $(wildcard $(SRC)/*.h) include/chemps2_b200.h
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+$(SRC)/%.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+$(LIB): $(OBJS)
+	$(NVCC) -shared -o $@ $(OBJS) -cudart static -lpthread -ldl -lrt
+oracle/libb2oracle.so: oracle/plan_exec.c
+	gcc -O2 -fPIC -shared -o $@ $<
+
+clean:
+	rm -f $(SRC)/*.o $(LIB) oracle/libb2oracle.so
+.PHONY: all clean

@@ -1,0 +1,88 @@
+"""ctypes binding of the C ABI in include/chemps2_b200.h (libchemps2_b200.so, built in-tree by `make`).
+
+The library is the product: it is loaded eagerly and a missing .so is an ImportError — there is no Python/CPU fallback.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libchemps2_b200.so")
+if not os.path.exists(LIB_PATH):
+    raise ImportError(f"{LIB_PATH} not found: run `make` (or __graft_entry__.build()) first; there is no fallback path")
+lib = C.CDLL(LIB_PATH)
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+c_lp = C.POINTER(C.c_int64)
+vp = C.c_void_p
+
+
+class FlatTerm(C.Structure):
+    _fields_ = [("dst", C.c_int32), ("src", C.c_int32), ("a_rows", C.c_int32), ("a_cols", C.c_int32), ("b_rows", C.c_int32),
+                ("b_cols", C.c_int32), ("a_space", C.c_int8), ("a_trans", C.c_int8), ("b_space", C.c_int8), ("b_trans", C.c_int8),
+                ("owner", C.c_int32), ("a_off", C.c_int64), ("b_off", C.c_int64), ("factor", C.c_double)]
+
+
+class FlatPresum(C.Structure):
+    _fields_ = [("dst_off", C.c_int64), ("src_off", C.c_int64), ("size", C.c_int64), ("space", C.c_int32), ("coef", C.c_double)]
+
+
+# every symbol include/chemps2_b200.h declares: (name, restype, argtypes)
+SIGNATURES = [
+    ("b2_last_error", C.c_char_p, []),
+    ("b2_version", C.c_char_p, []),
+    ("b2_ctx_create", C.c_int, [C.c_int, C.POINTER(vp)]),
+    ("b2_ctx_destroy", None, [vp]),
+    ("b2_ctx_device", C.c_int, [vp]),
+    ("b2_problem_set", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_dp, C.c_double]),
+    ("b2_problem_set_integrals", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_dp, c_dp, C.c_double]),
+    ("b2_bk_init", C.c_int, [vp, C.c_int]),
+    ("b2_bk_set_dim", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("b2_bk_dim", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("b2_bk_fcidim", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("b2_bk_nmin", C.c_int, [vp, C.c_int]),
+    ("b2_bk_nmax", C.c_int, [vp, C.c_int]),
+    ("b2_bk_twosmin", C.c_int, [vp, C.c_int, C.c_int]),
+    ("b2_bk_twosmax", C.c_int, [vp, C.c_int, C.c_int]),
+    ("b2_tensor_t_size", C.c_int64, [vp, C.c_int]),
+    ("b2_sobject_size", C.c_int64, [vp, C.c_int]),
+    ("b2_sobject_nkappa", C.c_int, [vp, C.c_int]),
+    ("b2_sobject_table", C.c_int, [vp, C.c_int, c_ip, c_lp]),
+    ("b2_opset_create", C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+    ("b2_opset_destroy", None, [vp]),
+    ("b2_opset_count", C.c_int, [vp]),
+    ("b2_opset_info", C.c_int, [vp, C.c_int, c_ip, c_ip, c_ip, c_lp]),
+    ("b2_opset_find", C.c_int, [vp, C.c_int, C.c_int, C.c_int]),
+    ("b2_opset_upload", C.c_int, [vp, C.c_int, c_dp]),
+    ("b2_opset_download", C.c_int, [vp, C.c_int, c_dp]),
+    ("b2_opset_clear", C.c_int, [vp]),
+    ("b2_opset_host_arena", c_dp, [vp]),
+    ("b2_opset_arena_size", C.c_int64, [vp]),
+    ("b2_heff_create", C.c_int, [vp, C.c_int, vp, vp, C.c_int, C.c_int, C.POINTER(vp)]),
+    ("b2_heff_destroy", None, [vp]),
+    ("b2_heff_veclength", C.c_int64, [vp]),
+    ("b2_heff_apply", C.c_int, [vp, c_dp, c_dp]),
+    ("b2_heff_apply_device", C.c_int, [vp, vp, vp]),
+    ("b2_heff_diag", C.c_int, [vp, c_dp]),
+    ("b2_heff_stats", C.c_int, [vp, c_dp]),
+    ("b2_heff_last_kernel_seconds", C.c_double, [vp]),
+    ("b2_heff_num_terms", C.c_int64, [vp]),
+    ("b2_heff_export_terms", C.c_int, [vp, C.POINTER(FlatTerm)]),
+    ("b2_heff_num_presum_parts", C.c_int64, [vp]),
+    ("b2_heff_presum_size", C.c_int64, [vp]),
+    ("b2_heff_export_presums", C.c_int, [vp, C.POINTER(FlatPresum)]),
+    ("b2_probe_fp64", C.c_int, [vp, C.c_int, c_dp]),
+]
+for _name, _res, _args in SIGNATURES:
+    _f = getattr(lib, _name)
+    _f.restype = _res
+    _f.argtypes = _args
+
+
+class B2Error(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise B2Error(f"chemps2_b200 error {rc}: {lib.b2_last_error().decode()}")

@@ -1,0 +1,179 @@
+"""Thin object wrappers over the C ABI; names mirror the reference classes they stand for
+(Context ~ Problem + SyBookkeeper, OpSet ~ the operator tables of DMRG.h:211-226, Heff ~ CheMPS2::Heff)."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import FlatPresum, FlatTerm, c_dp, c_ip, c_lp, check, lib, vp
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+class Context:
+    def __init__(self, device=0):
+        self.h = vp()
+        check(lib.b2_ctx_create(int(device), C.byref(self.h)))
+        self.L = 0
+
+    def close(self):
+        if self.h:
+            lib.b2_ctx_destroy(self.h)
+            self.h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_problem(self, L, group, N, twoS, irrep, orb_irrep, mx=None, tmat=None, vmat=None, econst=0.0):
+        irr = np.ascontiguousarray(orb_irrep, dtype=np.int32)
+        self.L = int(L)
+        if mx is not None:
+            mx = np.ascontiguousarray(mx, dtype=np.float64)
+            check(lib.b2_problem_set(self.h, L, group, N, twoS, irrep, irr.ctypes.data_as(c_ip), _dp(mx), float(econst)))
+        else:
+            t = np.ascontiguousarray(tmat, dtype=np.float64)
+            v = np.ascontiguousarray(vmat, dtype=np.float64)
+            check(lib.b2_problem_set_integrals(self.h, L, group, N, twoS, irrep, irr.ctypes.data_as(c_ip), _dp(t), _dp(v), float(econst)))
+
+    def bk_init(self, D):
+        check(lib.b2_bk_init(self.h, int(D)))
+
+    def bk_import(self, rows):
+        """rows: int array (n, 6) of boundary, N, twoS, irrep, curdim, fcidim as dumped by the reference"""
+        for b, n, ts, ir, cur, _ in np.asarray(rows).reshape(-1, 6):
+            check(lib.b2_bk_set_dim(self.h, int(b), int(n), int(ts), int(ir), int(cur)))
+
+    def dim(self, b, n, ts, ir):
+        return lib.b2_bk_dim(self.h, b, n, ts, ir)
+
+    def fcidim(self, b, n, ts, ir):
+        return lib.b2_bk_fcidim(self.h, b, n, ts, ir)
+
+    def sobject_table(self, site):
+        nk = lib.b2_sobject_nkappa(self.h, site)
+        labels = np.zeros((nk, 9), dtype=np.int32)
+        offs = np.zeros(nk + 1, dtype=np.int64)
+        check(lib.b2_sobject_table(self.h, site, labels.ctypes.data_as(c_ip), offs.ctypes.data_as(c_lp)))
+        return labels, offs
+
+
+class OpSet:
+    def __init__(self, ctx, boundary, moving_right):
+        self.ctx = ctx
+        self.h = vp()
+        check(lib.b2_opset_create(ctx.h, int(boundary), int(bool(moving_right)), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib.b2_opset_destroy(self.h)
+            self.h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return lib.b2_opset_count(self.h)
+
+    def info(self, idx):
+        k, i, j, s = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        check(lib.b2_opset_info(self.h, idx, C.byref(k), C.byref(i), C.byref(j), C.byref(s)))
+        return k.value, i.value, j.value, s.value
+
+    def find(self, kind, i, j):
+        return lib.b2_opset_find(self.h, kind, i, j)
+
+    def upload(self, idx, data):
+        a = np.ascontiguousarray(data, dtype=np.float64)
+        assert a.size == self.info(idx)[3], (a.size, self.info(idx))
+        check(lib.b2_opset_upload(self.h, idx, _dp(a)))
+
+    def download(self, idx):
+        a = np.zeros(self.info(idx)[3], dtype=np.float64)
+        check(lib.b2_opset_download(self.h, idx, _dp(a)))
+        return a
+
+    def upload_all(self, ops, strict=True):
+        """ops: [(kind, i, j, data)] as returned by fixtures.split_ops"""
+        for kind, i, j, data in ops:
+            idx = self.find(kind, i, j)
+            if idx < 0:
+                if strict:
+                    raise KeyError(f"operator kind={kind} ({i},{j}) not in this set")
+                continue
+            self.upload(idx, data)
+
+    def host_arena(self):
+        n = lib.b2_opset_arena_size(self.h)
+        p = lib.b2_opset_host_arena(self.h)
+        return np.ctypeslib.as_array(p, shape=(n,)) if n else np.zeros(0)
+
+
+class Heff:
+    """sigma = H_eff * S for the site pair (site, site+1); stands for CheMPS2::Heff (Heff.h:50-70)."""
+
+    def __init__(self, ctx, site, left, right, world=1, rank=0):
+        self.ctx, self.left, self.right = ctx, left, right
+        self.h = vp()
+        check(lib.b2_heff_create(ctx.h, int(site), left.h if left else None, right.h if right else None, int(world), int(rank), C.byref(self.h)))
+        self.n = lib.b2_heff_veclength(self.h)
+        self._site = int(site)
+
+    def close(self):
+        if self.h:
+            lib.b2_heff_destroy(self.h)
+            self.h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def apply(self, vec):
+        v = np.ascontiguousarray(vec, dtype=np.float64)
+        out = np.empty_like(v)
+        check(lib.b2_heff_apply(self.h, _dp(v), _dp(out)))
+        return out
+
+    def apply_device(self, dev_in_ptr, dev_out_ptr):
+        check(lib.b2_heff_apply_device(self.h, vp(dev_in_ptr), vp(dev_out_ptr)))
+
+    def kernel_seconds(self):
+        return lib.b2_heff_last_kernel_seconds(self.h)
+
+    def diag(self):
+        out = np.zeros(self.n, dtype=np.float64)
+        check(lib.b2_heff_diag(self.h, _dp(out)))
+        return out
+
+    def stats(self):
+        o = np.zeros(8)
+        check(lib.b2_heff_stats(self.h, _dp(o)))
+        keys = ["terms", "terms_zero", "presums", "flops_ref", "flops_exec", "work_doubles", "stage1", "tiles"]
+        return dict(zip(keys, o))
+
+    def export(self):
+        nt = lib.b2_heff_num_terms(self.h)
+        terms = (FlatTerm * max(nt, 1))()
+        check(lib.b2_heff_export_terms(self.h, terms))
+        npp = lib.b2_heff_num_presum_parts(self.h)
+        parts = (FlatPresum * max(npp, 1))()
+        check(lib.b2_heff_export_presums(self.h, parts))
+        return terms, nt, parts, npp, lib.b2_heff_presum_size(self.h)
+
+
+def context_from_fixture(fx, tag, device=-1):
+    """Build a Context (problem + bookkeeper dims) from a golden fixture section `tag` ('A' or 'B')."""
+    L, group, N, twoS, irrep = [int(x) for x in fx["problem/hdr"]]
+    ctx = Context(device)
+    ctx.set_problem(L, group, N, twoS, irrep, fx["problem/orb_irrep"], mx=fx["problem/mx"], econst=float(fx["problem/econst"][0]))
+    ctx.bk_init(1)
+    ctx.bk_import(fx[tag + "/bk"])
+    return ctx

@@ -1,0 +1,398 @@
+// b2_capi.cpp — the C ABI declared in include/chemps2_b200.h.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/chemps2_b200.h"
+#include "b2_core.h"
+#include "b2_device.h"
+#include "b2_heff.h"
+#include "b2_ops.h"
+#include "b2_sigma.h"
+
+using namespace b2;
+
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+   char buf[512];
+   va_list ap;
+   va_start(ap, fmt);
+   vsnprintf(buf, sizeof(buf), fmt, ap);
+   va_end(ap);
+   g_err = buf;
+   return code;
+}
+#define CUDA_TRY(call)                                                                         \
+   do {                                                                                        \
+      cudaError_t e_ = (call);                                                                 \
+      if (e_ != cudaSuccess) return fail(B2_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+   } while (0)
+
+struct b2_ctx {
+   int device = -1;
+   cudaStream_t stream = nullptr;
+   Problem prob;
+   Bookkeeper bk;
+   bool have_problem = false, have_bk = false;
+};
+
+struct b2_opset {
+   b2_ctx* ctx = nullptr;
+   OpSet set;
+   std::vector<double> host;
+   double* dev = nullptr;
+};
+
+struct b2_heff {
+   b2_ctx* ctx = nullptr;
+   b2_opset *left = nullptr, *right = nullptr;
+   SigmaPlan plan;
+   CompiledSigma comp;
+   // device copies
+   GemmItem* d_items = nullptr;
+   Tile* d_tiles1[kNumTileClasses] = {nullptr, nullptr, nullptr, nullptr};
+   Tile* d_tiles2[kNumTileClasses] = {nullptr, nullptr, nullptr, nullptr};
+   PresumJob* d_jobs = nullptr;
+   PresumPart* d_parts = nullptr;
+   double *d_presum = nullptr, *d_work = nullptr, *d_vin = nullptr, *d_vout = nullptr;
+   double *h_vin = nullptr, *h_vout = nullptr;   // pinned staging
+   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+   double last_kernel_s = 0.0;
+};
+
+template <class T> static int upload_vec(T** dptr, const std::vector<T>& v, cudaStream_t s) {
+   *dptr = nullptr;
+   if (v.empty()) return B2_OK;
+   CUDA_TRY(cudaMalloc(dptr, sizeof(T) * v.size()));
+   CUDA_TRY(cudaMemcpyAsync(*dptr, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, s));
+   return B2_OK;
+}
+
+static DevBases bases_of(const b2_heff* h, const double* vin, double* vout) {
+   DevBases b;
+   for (int i = 0; i < SP_COUNT; i++) b.p[i] = nullptr;
+   b.p[SP_LEFT] = h->left ? h->left->dev : nullptr;
+   b.p[SP_RIGHT] = h->right ? h->right->dev : nullptr;
+   b.p[SP_PRESUM] = h->d_presum;
+   b.p[SP_WORK] = h->d_work;
+   b.p[SP_VIN] = const_cast<double*>(vin);
+   b.p[SP_VOUT] = vout;
+   return b;
+}
+
+extern "C" {
+
+const char* b2_last_error(void) { return g_err.c_str(); }
+const char* b2_version(void) { return "chemps2_b200 0.1 (sm_100a)"; }
+
+int b2_ctx_create(int device, b2_ctx** out) {
+   if (!out) return fail(B2_ERR_ARG, "b2_ctx_create: out is NULL");
+   std::unique_ptr<b2_ctx> c(new b2_ctx);
+   c->device = device;
+   if (device >= 0) {
+      int n = 0;
+      cudaError_t e = cudaGetDeviceCount(&n);
+      if (e != cudaSuccess || n <= device) return fail(B2_ERR_NO_DEVICE, "b2_ctx_create: CUDA device %d not available (%s)", device, cudaGetErrorString(e));
+      CUDA_TRY(cudaSetDevice(device));
+      CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+   }
+   *out = c.release();
+   return B2_OK;
+}
+void b2_ctx_destroy(b2_ctx* ctx) {
+   if (!ctx) return;
+   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+   delete ctx;
+}
+int b2_ctx_device(const b2_ctx* ctx) { return ctx ? ctx->device : -1; }
+
+static int set_problem_common(b2_ctx* ctx, int L, int group, int N, int twoS, int irrep, const int* orb_irrep, double econst) {
+   if (!ctx || L < 2 || !orb_irrep) return fail(B2_ERR_ARG, "b2_problem_set: bad arguments");
+   const int nirr = num_irreps_of_group(group);
+   if (nirr < 0) return fail(B2_ERR_ARG, "b2_problem_set: group %d out of range", group);
+   if (irrep < 0 || irrep >= nirr) return fail(B2_ERR_ARG, "b2_problem_set: target irrep %d out of range", irrep);
+   if (N < 2) return fail(B2_ERR_ARG, "b2_problem_set: N must be >= 2 (one-body part is folded in with 1/(N-1))");
+   for (int i = 0; i < L; i++)
+      if (orb_irrep[i] < 0 || orb_irrep[i] >= nirr) return fail(B2_ERR_ARG, "b2_problem_set: orbital irrep out of range");
+   Problem& p = ctx->prob;
+   p.L = L; p.group = group; p.N = N; p.twoS = twoS; p.irrep = irrep; p.econst = econst;
+   p.orb_irrep.assign(orb_irrep, orb_irrep + L);
+   ctx->have_problem = true; ctx->have_bk = false;
+   return B2_OK;
+}
+int b2_problem_set(b2_ctx* ctx, int L, int group, int N, int twoS, int irrep, const int* orb_irrep, const double* mx_elem, double econst) {
+   if (!mx_elem) return fail(B2_ERR_ARG, "b2_problem_set: mx_elem is NULL");
+   int rc = set_problem_common(ctx, L, group, N, twoS, irrep, orb_irrep, econst);
+   if (rc) return rc;
+   ctx->prob.mx.assign(mx_elem, mx_elem + (size_t)L * L * L * L);
+   return B2_OK;
+}
+int b2_problem_set_integrals(b2_ctx* ctx, int L, int group, int N, int twoS, int irrep, const int* orb_irrep, const double* tmat,
+                             const double* vmat, double econst) {
+   if (!tmat || !vmat) return fail(B2_ERR_ARG, "b2_problem_set_integrals: NULL integrals");
+   int rc = set_problem_common(ctx, L, group, N, twoS, irrep, orb_irrep, econst);
+   if (rc) return rc;
+   ctx->prob.build(tmat, vmat);
+   return B2_OK;
+}
+
+int b2_bk_init(b2_ctx* ctx, int D) {
+   if (!ctx || !ctx->have_problem) return fail(B2_ERR_STATE, "b2_bk_init: set the problem first");
+   if (D < 1) return fail(B2_ERR_ARG, "b2_bk_init: D < 1");
+   ctx->bk.init(ctx->prob, D);
+   ctx->have_bk = true;
+   if (!ctx->bk.is_possible()) return fail(B2_ERR_ARG, "b2_bk_init: target sector not reachable (SyBookkeeper::IsPossible)");
+   return B2_OK;
+}
+int b2_bk_set_dim(b2_ctx* ctx, int boundary, int N, int twoS, int irrep, int dim) {
+   if (!ctx || !ctx->have_bk) return fail(B2_ERR_STATE, "b2_bk_set_dim: no bookkeeper");
+   ctx->bk.set_dim(boundary, N, twoS, irrep, dim);
+   return B2_OK;
+}
+int b2_bk_dim(const b2_ctx* ctx, int b, int N, int twoS, int irrep) { return (ctx && ctx->have_bk) ? ctx->bk.dim(b, N, twoS, irrep) : 0; }
+int b2_bk_fcidim(const b2_ctx* ctx, int b, int N, int twoS, int irrep) { return (ctx && ctx->have_bk) ? ctx->bk.fcidim(b, N, twoS, irrep) : 0; }
+int b2_bk_nmin(const b2_ctx* ctx, int b) { return ctx->bk.Nmin[b]; }
+int b2_bk_nmax(const b2_ctx* ctx, int b) { return ctx->bk.Nmax[b]; }
+int b2_bk_twosmin(const b2_ctx* ctx, int b, int N) { return ctx->bk.tsmin[b][N - ctx->bk.Nmin[b]]; }
+int b2_bk_twosmax(const b2_ctx* ctx, int b, int N) { return ctx->bk.tsmax[b][N - ctx->bk.Nmin[b]]; }
+
+int64_t b2_tensor_t_size(const b2_ctx* ctx, int site) { TLayout t; t.build(ctx->bk, site); return t.size; }
+int64_t b2_sobject_size(const b2_ctx* ctx, int site) { SLayout s; s.build(ctx->bk, site); return s.size; }
+int b2_sobject_nkappa(const b2_ctx* ctx, int site) { SLayout s; s.build(ctx->bk, site); return s.nkappa(); }
+int b2_sobject_table(const b2_ctx* ctx, int site, int* labels, int64_t* offsets) {
+   SLayout s; s.build(ctx->bk, site);
+   for (int k = 0; k < s.nkappa(); k++) {
+      int* l = labels + 9 * k;
+      l[0] = s.NL[k]; l[1] = s.twoSL[k]; l[2] = s.IL[k]; l[3] = s.N1[k]; l[4] = s.N2[k]; l[5] = s.twoJ[k]; l[6] = s.NR[k]; l[7] = s.twoSR[k]; l[8] = s.IR[k];
+      offsets[k] = s.blk[k].off;
+   }
+   offsets[s.nkappa()] = s.size;
+   return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ operator sets
+int b2_opset_create(b2_ctx* ctx, int boundary, int moving_right, b2_opset** out) {
+   if (!ctx || !ctx->have_bk || !out) return fail(B2_ERR_STATE, "b2_opset_create: no bookkeeper");
+   if (boundary < 1 || boundary > ctx->bk.L - 1) return fail(B2_ERR_ARG, "b2_opset_create: boundary %d out of range", boundary);
+   std::unique_ptr<b2_opset> s(new b2_opset);
+   s->ctx = ctx;
+   s->set.build_all(ctx->bk, boundary, moving_right != 0);
+   s->host.assign((size_t)s->set.size, 0.0);
+   if (ctx->device >= 0 && s->set.size > 0) {
+      CUDA_TRY(cudaSetDevice(ctx->device));
+      CUDA_TRY(cudaMalloc(&s->dev, sizeof(double) * (size_t)s->set.size));
+      CUDA_TRY(cudaMemsetAsync(s->dev, 0, sizeof(double) * (size_t)s->set.size, ctx->stream));
+   }
+   *out = s.release();
+   return B2_OK;
+}
+void b2_opset_destroy(b2_opset* set) {
+   if (!set) return;
+   if (set->dev) cudaFree(set->dev);
+   delete set;
+}
+int b2_opset_count(const b2_opset* set) { return set ? (int)set->set.ops.size() : 0; }
+int b2_opset_info(const b2_opset* set, int index, int* kind, int* si, int* sj, int64_t* size) {
+   if (!set || index < 0 || index >= (int)set->set.ops.size()) return fail(B2_ERR_ARG, "b2_opset_info: bad index");
+   const OpTensor& t = set->set.ops[index];
+   if (kind) *kind = t.kind;
+   if (si) *si = t.i;
+   if (sj) *sj = t.j;
+   if (size) *size = t.lay->size;
+   return B2_OK;
+}
+int b2_opset_find(const b2_opset* set, int kind, int si, int sj) { return set ? set->set.find(kind, si, sj) : -1; }
+int b2_opset_upload(b2_opset* set, int index, const double* packed) {
+   if (!set || index < 0 || index >= (int)set->set.ops.size() || !packed) return fail(B2_ERR_ARG, "b2_opset_upload: bad arguments");
+   const OpTensor& t = set->set.ops[index];
+   if (t.lay->size == 0) return B2_OK;
+   std::memcpy(set->host.data() + t.off, packed, sizeof(double) * (size_t)t.lay->size);
+   if (set->dev) {
+      CUDA_TRY(cudaMemcpyAsync(set->dev + t.off, set->host.data() + t.off, sizeof(double) * (size_t)t.lay->size, cudaMemcpyHostToDevice, set->ctx->stream));
+      CUDA_TRY(cudaStreamSynchronize(set->ctx->stream));
+   }
+   return B2_OK;
+}
+int b2_opset_download(b2_opset* set, int index, double* packed) {
+   if (!set || index < 0 || index >= (int)set->set.ops.size() || !packed) return fail(B2_ERR_ARG, "b2_opset_download: bad arguments");
+   const OpTensor& t = set->set.ops[index];
+   if (t.lay->size == 0) return B2_OK;
+   if (set->dev) {
+      CUDA_TRY(cudaMemcpyAsync(set->host.data() + t.off, set->dev + t.off, sizeof(double) * (size_t)t.lay->size, cudaMemcpyDeviceToHost, set->ctx->stream));
+      CUDA_TRY(cudaStreamSynchronize(set->ctx->stream));
+   }
+   std::memcpy(packed, set->host.data() + t.off, sizeof(double) * (size_t)t.lay->size);
+   return B2_OK;
+}
+int b2_opset_clear(b2_opset* set) {
+   if (!set) return fail(B2_ERR_ARG, "b2_opset_clear: NULL");
+   std::fill(set->host.begin(), set->host.end(), 0.0);
+   if (set->dev) CUDA_TRY(cudaMemsetAsync(set->dev, 0, sizeof(double) * (size_t)set->set.size, set->ctx->stream));
+   return B2_OK;
+}
+const double* b2_opset_host_arena(const b2_opset* set) { return set ? set->host.data() : nullptr; }
+int64_t b2_opset_arena_size(const b2_opset* set) { return set ? set->set.size : 0; }
+
+// ------------------------------------------------------------------------------------------------ heff
+int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int world, int rank, b2_heff** out) {
+   if (!ctx || !ctx->have_bk || !out) return fail(B2_ERR_STATE, "b2_heff_create: no bookkeeper");
+   const int L = ctx->bk.L;
+   if (site < 0 || site > L - 2) return fail(B2_ERR_ARG, "b2_heff_create: site %d out of range", site);
+   if (site > 0 && (!left || left->set.boundary != site || !left->set.moving_right)) return fail(B2_ERR_ARG, "b2_heff_create: left operator set must sit at boundary %d moving right", site);
+   if (site < L - 2 && (!right || right->set.boundary != site + 2 || right->set.moving_right)) return fail(B2_ERR_ARG, "b2_heff_create: right operator set must sit at boundary %d moving left", site + 2);
+   if (world < 1 || rank < 0 || rank >= world) return fail(B2_ERR_ARG, "b2_heff_create: bad world/rank");
+   std::unique_ptr<b2_heff> h(new b2_heff);
+   h->ctx = ctx;
+   h->left = (site > 0) ? left : nullptr;
+   h->right = (site < L - 2) ? right : nullptr;
+   build_sigma_plan(h->plan, ctx->bk, ctx->prob, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, site, world);
+   compile_sigma(h->comp, h->plan, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, rank, world);
+   if (ctx->device >= 0) {
+      CUDA_TRY(cudaSetDevice(ctx->device));
+      cudaStream_t s = ctx->stream;
+      int rc;
+      if ((rc = upload_vec(&h->d_items, h->comp.items, s))) return rc;
+      for (int c = 0; c < kNumTileClasses; c++) {
+         if ((rc = upload_vec(&h->d_tiles1[c], h->comp.tiles1[c], s))) return rc;
+         if ((rc = upload_vec(&h->d_tiles2[c], h->comp.tiles2[c], s))) return rc;
+      }
+      if ((rc = upload_vec(&h->d_jobs, h->comp.presum_jobs, s))) return rc;
+      if ((rc = upload_vec(&h->d_parts, h->comp.presum_parts, s))) return rc;
+      const size_t n = (size_t)h->plan.S.size;
+      if (h->plan.presum_size > 0) CUDA_TRY(cudaMalloc(&h->d_presum, sizeof(double) * (size_t)h->plan.presum_size));
+      if (h->comp.work_size > 0) CUDA_TRY(cudaMalloc(&h->d_work, sizeof(double) * (size_t)h->comp.work_size));
+      CUDA_TRY(cudaMalloc(&h->d_vin, sizeof(double) * (n ? n : 1)));
+      CUDA_TRY(cudaMalloc(&h->d_vout, sizeof(double) * (n ? n : 1)));
+      CUDA_TRY(cudaMallocHost(&h->h_vin, sizeof(double) * (n ? n : 1)));
+      CUDA_TRY(cudaMallocHost(&h->h_vout, sizeof(double) * (n ? n : 1)));
+      CUDA_TRY(cudaEventCreate(&h->ev0));
+      CUDA_TRY(cudaEventCreate(&h->ev1));
+      // materialise the integral-weighted operator pre-sums once (operators are fixed during the Davidson solve)
+      DevBases b = bases_of(h.get(), nullptr, nullptr);
+      if (dev_launch_presum(h->d_jobs, (int)h->comp.presum_jobs.size(), h->d_parts, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+      CUDA_TRY(cudaStreamSynchronize(s));
+   }
+   *out = h.release();
+   return B2_OK;
+}
+
+void b2_heff_destroy(b2_heff* h) {
+   if (!h) return;
+   cudaFree(h->d_items);
+   for (int c = 0; c < kNumTileClasses; c++) { cudaFree(h->d_tiles1[c]); cudaFree(h->d_tiles2[c]); }
+   cudaFree(h->d_jobs); cudaFree(h->d_parts); cudaFree(h->d_presum); cudaFree(h->d_work); cudaFree(h->d_vin); cudaFree(h->d_vout);
+   if (h->h_vin) cudaFreeHost(h->h_vin);
+   if (h->h_vout) cudaFreeHost(h->h_vout);
+   if (h->ev0) cudaEventDestroy(h->ev0);
+   if (h->ev1) cudaEventDestroy(h->ev1);
+   delete h;
+}
+
+int64_t b2_heff_veclength(const b2_heff* h) { return h ? h->plan.S.size : 0; }
+
+int b2_heff_apply_device(b2_heff* h, const double* dev_in, double* dev_out) {
+   if (!h) return fail(B2_ERR_ARG, "b2_heff_apply_device: NULL");
+   if (h->ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_heff_apply: planning-only context, no CUDA device (there is no CPU fallback)");
+   cudaStream_t s = h->ctx->stream;
+   DevBases b = bases_of(h, dev_in, dev_out);
+   CUDA_TRY(cudaEventRecord(h->ev0, s));
+   for (int c = 0; c < kNumTileClasses; c++)
+      if (dev_launch_tiles(c, h->d_tiles1[c], (int)h->comp.tiles1[c].size(), h->d_items, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+   for (int c = 0; c < kNumTileClasses; c++)
+      if (dev_launch_tiles(c, h->d_tiles2[c], (int)h->comp.tiles2[c].size(), h->d_items, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+   CUDA_TRY(cudaEventRecord(h->ev1, s));
+   return B2_OK;
+}
+
+int b2_heff_apply(b2_heff* h, const double* vec_in, double* vec_out) {
+   if (!h || !vec_in || !vec_out) return fail(B2_ERR_ARG, "b2_heff_apply: NULL argument");
+   if (h->ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_heff_apply: planning-only context, no CUDA device (there is no CPU fallback)");
+   cudaStream_t s = h->ctx->stream;
+   const size_t bytes = sizeof(double) * (size_t)h->plan.S.size;
+   std::memcpy(h->h_vin, vec_in, bytes);
+   CUDA_TRY(cudaMemcpyAsync(h->d_vin, h->h_vin, bytes, cudaMemcpyHostToDevice, s));
+   int rc = b2_heff_apply_device(h, h->d_vin, h->d_vout);
+   if (rc) return rc;
+   CUDA_TRY(cudaMemcpyAsync(h->h_vout, h->d_vout, bytes, cudaMemcpyDeviceToHost, s));
+   CUDA_TRY(cudaStreamSynchronize(s));
+   std::memcpy(vec_out, h->h_vout, bytes);
+   float ms = 0.f;
+   CUDA_TRY(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+   h->last_kernel_s = ms * 1e-3;
+   return B2_OK;
+}
+
+double b2_heff_last_kernel_seconds(const b2_heff* h) {
+   if (!h || !h->ev0) return 0.0;
+   float ms = 0.f;
+   if (cudaEventSynchronize(h->ev1) != cudaSuccess) return 0.0;
+   if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return 0.0;
+   return ms * 1e-3;
+}
+
+int b2_heff_diag(b2_heff* h, double* diag) {
+   if (!h || !diag) return fail(B2_ERR_ARG, "b2_heff_diag: NULL argument");
+   build_heff_diag(diag, h->plan.S, h->ctx->bk, h->ctx->prob, h->left ? &h->left->set : nullptr, h->left ? h->left->host.data() : nullptr,
+                   h->right ? &h->right->set : nullptr, h->right ? h->right->host.data() : nullptr, h->plan.site);
+   return B2_OK;
+}
+
+int b2_heff_stats(const b2_heff* h, double* o) {
+   if (!h || !o) return fail(B2_ERR_ARG, "b2_heff_stats: NULL");
+   o[0] = (double)h->plan.terms.size(); o[1] = (double)h->plan.skipped_zero; o[2] = (double)h->plan.presums.size();
+   o[3] = h->plan.flops_ref; o[4] = h->comp.flops_exec; o[5] = (double)h->comp.work_size; o[6] = (double)h->comp.n_stage1; o[7] = (double)h->comp.n_tiles;
+   return B2_OK;
+}
+
+// ---- flat exports for the CPU checker
+static void flat_ref(const BRef& r, const SigmaPlan& plan, const OpSet* left, const OpSet* right, int8_t* space, int8_t* trans, int64_t* off, int32_t* rows, int32_t* cols) {
+   *space = 0; *trans = 0; *off = 0; *rows = 0; *cols = 0;
+   if (r.src == SRC_NONE || r.op < 0 || r.blk < 0) return;
+   const OpLayout* lay; int64_t base;
+   if (r.src == SRC_LEFT) { lay = left->ops[r.op].lay.get(); base = left->ops[r.op].off; *space = 1; }
+   else if (r.src == SRC_RIGHT) { lay = right->ops[r.op].lay.get(); base = right->ops[r.op].off; *space = 2; }
+   else { lay = plan.presums[r.op].lay.get(); base = plan.presums[r.op].off; *space = 3; }
+   *trans = r.trans; *off = base + lay->blk[r.blk].off; *rows = lay->blk[r.blk].rows; *cols = lay->blk[r.blk].cols;
+}
+int64_t b2_heff_num_terms(const b2_heff* h) { return h ? (int64_t)h->plan.terms.size() : 0; }
+int b2_heff_export_terms(const b2_heff* h, b2_flat_term* out) {
+   if (!h || !out) return fail(B2_ERR_ARG, "b2_heff_export_terms: NULL");
+   const OpSet* l = h->left ? &h->left->set : nullptr;
+   const OpSet* r = h->right ? &h->right->set : nullptr;
+   for (size_t i = 0; i < h->plan.terms.size(); i++) {
+      const SigmaTerm& t = h->plan.terms[i];
+      b2_flat_term& f = out[i];
+      f.dst = t.dst; f.src = t.src; f.owner = t.owner; f.factor = t.factor;
+      flat_ref(t.l, h->plan, l, r, &f.a_space, &f.a_trans, &f.a_off, &f.a_rows, &f.a_cols);
+      flat_ref(t.r, h->plan, l, r, &f.b_space, &f.b_trans, &f.b_off, &f.b_rows, &f.b_cols);
+   }
+   return B2_OK;
+}
+int64_t b2_heff_num_presum_parts(const b2_heff* h) { return h ? (int64_t)h->comp.presum_parts.size() : 0; }
+int64_t b2_heff_presum_size(const b2_heff* h) { return h ? h->plan.presum_size : 0; }
+int b2_heff_export_presums(const b2_heff* h, b2_flat_presum* out) {
+   if (!h || !out) return fail(B2_ERR_ARG, "b2_heff_export_presums: NULL");
+   size_t n = 0;
+   for (const PresumJob& j : h->comp.presum_jobs)
+      for (int p = j.part_begin; p < j.part_end; p++) {
+         const PresumPart& pp = h->comp.presum_parts[p];
+         out[n].dst_off = j.dst_off; out[n].src_off = pp.src_off; out[n].size = j.size; out[n].space = pp.space; out[n].coef = pp.coef;
+         n++;
+      }
+   return B2_OK;
+}
+
+/* FP64 peak probe (roofline denominator): mode 1 = DMMA m8n8k4, mode 0 = DFMA */
+int b2_probe_fp64(b2_ctx* ctx, int use_mma, double* tflops) {
+   if (!ctx || ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_probe_fp64: no CUDA device");
+   CUDA_TRY(cudaSetDevice(ctx->device));
+   if (dev_probe_fp64(use_mma, tflops)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+   return B2_OK;
+}
+
+}   // extern "C"

@@ -1,0 +1,119 @@
+// b2_core.h — host-side symmetry bookkeeping and packed tensor layouts for the B200 DMRG sweep path.
+//
+// Everything here reproduces the *enumeration orders and block layouts* of the reference so that packed host
+// arrays are interchangeable with the reference's gStorage() arrays:
+//   Bookkeeper  <-> CheMPS2::SyBookkeeper            (SyBookkeeper.cpp:29-309)
+//   TLayout     <-> CheMPS2::TensorT sector table    (TensorT.cpp:38-104)
+//   OpLayout    <-> CheMPS2::TensorOperator table    (TensorOperator.cpp:29-102)
+//   SLayout     <-> CheMPS2::Sobject sector table    (Sobject.cpp:36-147)
+//   wigner6j/9j <-> CheMPS2::Wigner                  (Wigner.cpp:294-368)
+// The look-ups are O(1) hash look-ups instead of the reference's linear scans.
+#pragma once
+#include <cstdint>
+#include <cstdlib>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace b2 {
+
+// (-1)^{two_power/2}; same integer semantics as Special::phase (Special.h:36) / Heff::phase (Heff.h:75).
+inline int phase(int two_power) { return (((two_power / 2) % 2) != 0) ? -1 : 1; }
+inline int xorp(int a, int b) { return a ^ b; }   // abelian point-group product, Irreps.h:123
+
+double wigner6j(int two_ja, int two_jb, int two_jc, int two_jd, int two_je, int two_jf);
+double wigner9j(int two_ja, int two_jb, int two_jc, int two_jd, int two_je, int two_jf, int two_jg, int two_jh,
+                int two_ji);
+
+int num_irreps_of_group(int group);   // psi4 numbering 0..7 = c1 ci c2 cs d2 c2v c2h d2h
+
+// ---------------------------------------------------------------------------------------------------------
+// Problem: target sector + dense two-body table with the one-body part folded in (Problem.cpp:351-384).
+// Orbitals are already in DMRG order (the caller applies any reordering).
+struct Problem {
+   int L = 0, group = 0, N = 0, twoS = 0, irrep = 0;
+   double econst = 0.0;
+   std::vector<int> orb_irrep;
+   std::vector<double> mx;   // mx[a + L*(b + L*(c + L*d))]
+   double V(int a, int b, int c, int d) const { return mx[a + L * (b + L * (c + L * (size_t)d))]; }
+   // tmat[L*L] (i + L*j), vmat[L^4] physicist <ab|cd> at a + L*(b + L*(c + L*d))
+   void build(const double* tmat, const double* vmat);
+};
+
+// ---------------------------------------------------------------------------------------------------------
+struct Bookkeeper {
+   int L = 0, N = 0, twoS = 0, irrep = 0, nirr = 1;
+   std::vector<int> orb_irrep;
+   std::vector<int> Nmin, Nmax;                 // per boundary 0..L
+   std::vector<std::vector<int>> tsmin, tsmax;  // [boundary][N - Nmin]
+   std::vector<std::vector<int>> slot0;         // [boundary][N - Nmin] -> first slot of (N, tsmin, irrep 0)
+   std::vector<int> nslots;                     // per boundary
+   std::vector<std::vector<int>> fci, cur;      // [boundary][slot]
+
+   void init(const Problem& p, int D);          // FCI dims + ceil-scaled current dims (SyBookkeeper.cpp:29-49)
+   int slot(int b, int n, int two_s, int irr) const {   // -1 when outside the table (SyBookkeeper.cpp:271-280)
+      if (b < 0 || b > L) return -1;
+      if (n > Nmax[b] || n < Nmin[b]) return -1;
+      const int lo = tsmin[b][n - Nmin[b]], hi = tsmax[b][n - Nmin[b]];
+      if (((two_s - lo) & 1) || two_s < lo || two_s > hi) return -1;
+      if (irr < 0 || irr >= nirr) return -1;
+      return slot0[b][n - Nmin[b]] + ((two_s - lo) / 2) * nirr + irr;
+   }
+   int dim(int b, int n, int two_s, int irr) const { const int s = slot(b, n, two_s, irr); return s < 0 ? 0 : cur[b][s]; }
+   int fcidim(int b, int n, int two_s, int irr) const { const int s = slot(b, n, two_s, irr); return s < 0 ? 0 : fci[b][s]; }
+   void set_dim(int b, int n, int two_s, int irr, int value) {   // SyBookkeeper.cpp:163-169
+      const int s = slot(b, n, two_s, irr);
+      if (s >= 0 && fci[b][s] != 0) cur[b][s] = value;
+   }
+   int max_dim_at(int b) const;
+   int tot_dim_at(int b) const;
+   bool is_possible() const { return dim(L, N, twoS, irrep) == 1; }
+   // visit populated-or-not sectors of one boundary in the reference order N up, 2S up, irrep up
+   template <class F> void for_sectors(int b, F&& f) const {
+      for (int n = Nmin[b]; n <= Nmax[b]; n++)
+         for (int ts = tsmin[b][n - Nmin[b]]; ts <= tsmax[b][n - Nmin[b]]; ts += 2)
+            for (int ir = 0; ir < nirr; ir++) f(n, ts, ir);
+   }
+private:
+   void fill_fci();
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Packed block layouts. A block is column-major rows x cols with ld = rows, no padding, offsets in doubles.
+struct Block { int64_t off; int rows, cols; };
+
+struct TLayout {   // MPS site tensor for site `site` (left boundary site, right boundary site+1)
+   int site = 0;
+   std::vector<int> NL, twoSL, IL, NR, twoSR, IR;
+   std::vector<Block> blk;
+   int64_t size = 0;
+   std::unordered_map<uint64_t, int> index;
+   void build(const Bookkeeper& bk, int site);
+   int kappa(const Bookkeeper& bk, int nl, int tsl, int il, int nr, int tsr, int ir) const;
+   int nkappa() const { return (int)blk.size(); }
+};
+
+struct OpLayout {  // renormalized operator at `boundary` with quantum numbers (two_j, n_elec, irrep)
+   int boundary = 0, two_j = 0, n_elec = 0, irrep = 0;
+   std::vector<int> Nup, twoSup, Iup, twoSdown;
+   std::vector<Block> blk;
+   int64_t size = 0;
+   std::unordered_map<uint64_t, int> index;
+   void build(const Bookkeeper& bk, int boundary, int two_j, int n_elec, int irrep);
+   // block for up sector (n1,ts1,i1) -> down sector (n2,ts2,i2); -1 if absent (TensorOperator.cpp:119-137)
+   int kappa(const Bookkeeper& bk, int n1, int ts1, int i1, int n2, int ts2, int i2) const;
+   int nkappa() const { return (int)blk.size(); }
+};
+
+struct SLayout {   // two-site object at sites (site, site+1)
+   int site = 0;
+   std::vector<int> NL, twoSL, IL, N1, N2, twoJ, NR, twoSR, IR;
+   std::vector<Block> blk;
+   int64_t size = 0;
+   std::unordered_map<uint64_t, int> index;
+   void build(const Bookkeeper& bk, int site);
+   int kappa(const Bookkeeper& bk, int nl, int tsl, int il, int n1, int n2, int tj, int nr, int tsr, int ir) const;
+   int nkappa() const { return (int)blk.size(); }
+};
+
+}   // namespace b2

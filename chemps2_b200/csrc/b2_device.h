@@ -1,0 +1,53 @@
+// b2_device.h — device-side work lists shared between the host plan compiler (b2_heff.cpp) and the kernels
+// (b2_kernels.cu).  Plain structs, no CUDA types, so host-only translation units can include it.
+#pragma once
+#include <cstdint>
+
+namespace b2 {
+
+// address spaces an operand can live in; resolved to base pointers at launch time
+enum Space : uint8_t { SP_NONE = 0, SP_LEFT = 1, SP_RIGHT = 2, SP_PRESUM = 3, SP_WORK = 4, SP_VIN = 5, SP_VOUT = 6, SP_COUNT = 7 };
+
+struct DevBases { double* p[SP_COUNT]; };
+
+enum ItemKind : uint8_t { IT_GEMM = 0, IT_AXPY = 1 };
+
+// C_tile += alpha * opX(X)[M x K] * opY(Y)[K x N]     (IT_GEMM)
+// C_tile += alpha * X[M x N]                          (IT_AXPY)
+// X, Y are column-major with leading dimensions ldx, ldy; tx/ty = 1 means the stored matrix enters transposed.
+struct GemmItem {
+   int64_t xoff, yoff;
+   int32_t ldx, ldy;
+   int32_t k;
+   uint8_t xs, ys, tx, ty;
+   double alpha;
+   uint8_t kind, pad[7];
+};
+
+// One output tile: rows [m0, m0+mrem) x cols [n0, n0+nrem) of the column-major matrix at (cspace, coff, ldc).
+// The tile is written exactly once (no atomics, deterministic): C = sum over items[item_begin, item_end).
+struct Tile {
+   int64_t coff;
+   int32_t ldc, m0, n0, mrem, nrem;
+   int32_t item_begin, item_end;
+   uint8_t cspace, pad[3];
+};
+
+// out[dst_off + e] = sum_{parts} coef * src[e]   for e < size
+struct PresumPart { int64_t src_off; double coef; uint8_t space, pad[7]; };
+struct PresumJob { int64_t dst_off, size; int32_t part_begin, part_end; };
+
+// tile classes: CTA tile edge and threads per CTA
+constexpr int kNumTileClasses = 4;
+constexpr int kTileEdge[kNumTileClasses] = {64, 32, 16, 8};
+constexpr int kTileThreads[kNumTileClasses] = {128, 128, 32, 32};
+
+// ---- launchers implemented in b2_kernels.cu (all asynchronous on `stream`, a cudaStream_t passed as void*)
+int dev_launch_tiles(int tile_class, const Tile* d_tiles, int ntiles, const GemmItem* d_items, const DevBases& bases, void* stream);
+int dev_launch_presum(const PresumJob* d_jobs, int njobs, const PresumPart* d_parts, const DevBases& bases, void* stream);
+int dev_fill_zero(double* d_ptr, int64_t n, void* stream);
+// FP64 peak probes: returns achieved TFLOP/s of a register-resident DMMA (m8n8k4) / DFMA loop
+int dev_probe_fp64(int use_mma, double* tflops_out);
+const char* dev_last_error();
+
+}   // namespace b2

@@ -1,0 +1,143 @@
+/* chemps2_b200.h — C ABI of the B200-native two-site DMRG sweep hot path.
+ *
+ * The reference (SebWouters/CheMPS2) has no FFI seam for this path: the boundary is its C++ classes
+ * (SURVEY.md 8(b)).  Every entry point below names the reference interface it replaces; INTEGRATION.md shows
+ * the C++ shim a CheMPS2 maintainer would put behind the unchanged public headers.
+ *
+ * Conventions
+ *   - plain C types only, opaque handles, caller-owned host buffers, library-owned device buffers;
+ *   - every function returns 0 on success and a negative code on error; b2_last_error() gives the message
+ *     (the reference asserts/aborts on impossible input: the C++ shim turns a non-zero code into abort());
+ *   - packed tensor layouts are exactly the reference's gStorage() layouts (column-major blocks, enumeration
+ *     orders of TensorT.cpp:38-104, TensorOperator.cpp:29-102, Sobject.cpp:36-147), so host arrays can be
+ *     handed over unchanged;
+ *   - all compute runs on the GPU; there is NO CPU fallback.  A context created with device = -1 is a
+ *     planning-only context (sector tables, plans, exports); compute calls on it fail with B2_ERR_NO_DEVICE.
+ */
+#ifndef CHEMPS2_B200_H
+#define CHEMPS2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_OK 0
+#define B2_ERR_ARG (-1)
+#define B2_ERR_NO_DEVICE (-2)
+#define B2_ERR_CUDA (-3)
+#define B2_ERR_STATE (-4)
+
+/* operator kinds; (two_j, n_elec): L(1,1) S0(0,2) S1(2,2) F0(0,0) F1(2,0) A(0,2) B(2,2) C(0,0) D(2,0) Q(1,1) X(0,0) */
+enum { B2_L = 0, B2_S0, B2_S1, B2_F0, B2_F1, B2_A, B2_B, B2_C, B2_D, B2_Q, B2_X };
+
+typedef struct b2_ctx b2_ctx;
+typedef struct b2_opset b2_opset;
+typedef struct b2_heff b2_heff;
+typedef struct b2_mps b2_mps;
+
+const char* b2_last_error(void);
+const char* b2_version(void);
+
+/* ------------------------------------------------------------------------------------------------ context
+ * device >= 0: CUDA ordinal (one process per GPU).  device = -1: planning-only (no GPU touched). */
+int b2_ctx_create(int device, b2_ctx** out);
+void b2_ctx_destroy(b2_ctx* ctx);
+int b2_ctx_device(const b2_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------ problem
+ * Replaces CheMPS2::Problem (Problem.h:44-128) as seen by the hot path: target sector, orbital irreps in DMRG
+ * order and the dense table gMxElement(a,b,c,d) = mx[a + L*(b + L*(c + L*d))] (Problem.cpp:351-384).
+ * b2_problem_set takes the folded table as the reference holds it; b2_problem_set_integrals builds it from
+ * T (i + L*j) and physicist V <ab|cd> exactly like Problem::construct_mxelem. */
+int b2_problem_set(b2_ctx* ctx, int L, int group, int N, int twoS, int irrep, const int* orb_irrep, const double* mx_elem,
+                   double econst);
+int b2_problem_set_integrals(b2_ctx* ctx, int L, int group, int N, int twoS, int irrep, const int* orb_irrep,
+                             const double* tmat, const double* vmat, double econst);
+
+/* ------------------------------------------------------------------------------------------------ bookkeeper
+ * Replaces CheMPS2::SyBookkeeper (SyBookkeeper.h:41-143).  b2_bk_init = constructor (FCI dims, ceil-scaled to D);
+ * b2_bk_set_dim = SetDim; the getters mirror gCurrentDim / gFCIdim / gNmin / gNmax / gTwoSmin / gTwoSmax. */
+int b2_bk_init(b2_ctx* ctx, int D);
+int b2_bk_set_dim(b2_ctx* ctx, int boundary, int N, int twoS, int irrep, int dim);
+int b2_bk_dim(const b2_ctx* ctx, int boundary, int N, int twoS, int irrep);
+int b2_bk_fcidim(const b2_ctx* ctx, int boundary, int N, int twoS, int irrep);
+int b2_bk_nmin(const b2_ctx* ctx, int boundary);
+int b2_bk_nmax(const b2_ctx* ctx, int boundary);
+int b2_bk_twosmin(const b2_ctx* ctx, int boundary, int N);
+int b2_bk_twosmax(const b2_ctx* ctx, int boundary, int N);
+
+/* packed sizes / block tables (for host code that needs the reference's kappa2index) */
+int64_t b2_tensor_t_size(const b2_ctx* ctx, int site);                       /* TensorT::gKappa2index(gNKappa()) */
+int64_t b2_sobject_size(const b2_ctx* ctx, int site);                        /* Sobject::gKappa2index(gNKappa()) */
+int b2_sobject_nkappa(const b2_ctx* ctx, int site);
+/* labels[9*k..]: NL,2SL,IL,N1,N2,2J,NR,2SR,IR ; offsets[k], k < nkappa+1 */
+int b2_sobject_table(const b2_ctx* ctx, int site, int* labels, int64_t* offsets);
+
+/* ------------------------------------------------------------------------------------------------ operator sets
+ * One arena (device + host mirror) holding every renormalized operator of one boundary and one direction; replaces
+ * the pointer tables Ltensors/F0tensors/.../Xtensors[boundary-1] of DMRG.h:211-226 allocated by
+ * DMRG::allocateTensors (DMRGoperators.cpp:909-1145).  moving_right != 0: operators of the block left of `boundary`. */
+int b2_opset_create(b2_ctx* ctx, int boundary, int moving_right, b2_opset** out);
+void b2_opset_destroy(b2_opset* set);
+int b2_opset_count(const b2_opset* set);
+int b2_opset_info(const b2_opset* set, int index, int* kind, int* site_i, int* site_j, int64_t* size);
+int b2_opset_find(const b2_opset* set, int kind, int site_i, int site_j);   /* index or -1 */
+/* packed data in the reference's TensorOperator storage order <-> gStorage() */
+int b2_opset_upload(b2_opset* set, int index, const double* packed);
+int b2_opset_download(b2_opset* set, int index, double* packed);
+int b2_opset_clear(b2_opset* set);
+
+/* ------------------------------------------------------------------------------------------------ effective Hamiltonian
+ * b2_heff_create builds the SigmaPlan for the site pair (site, site+1) from the operator sets at boundaries
+ * `site` (left, may be NULL at the left edge) and `site+2` (right, may be NULL at the right edge).
+ * world/rank: GPU sharding by the reference's ownership maps (MPIchemps2.h:158-231); world = 1 keeps every term.
+ *
+ * b2_heff_apply        = Heff::makeHeff (Heff.cpp:43-248): vec_out = H_eff * vec_in, both HOST buffers of
+ *                        b2_heff_veclength doubles in the symmetric convention (Sobject.cpp:624-636).
+ * b2_heff_apply_device = same on device-resident vectors (what the device Davidson uses).
+ * b2_heff_diag         = Heff::fillHeffDiag (Heff.cpp:250-315). */
+int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int world, int rank, b2_heff** out);
+void b2_heff_destroy(b2_heff* h);
+int64_t b2_heff_veclength(const b2_heff* h);
+int b2_heff_apply(b2_heff* h, const double* vec_in, double* vec_out);
+int b2_heff_apply_device(b2_heff* h, const double* dev_in, double* dev_out);
+int b2_heff_diag(b2_heff* h, double* diag);
+/* statistics: [0] #terms, [1] #terms dropped (zero prefactor), [2] #presummed operators, [3] reference FLOPs per apply
+ * (2mnk per reference dgemm_), [4] executed FLOPs per apply, [5] workspace doubles, [6] #stage-1 GEMMs, [7] #tiles */
+int b2_heff_stats(const b2_heff* h, double* out8);
+/* seconds spent in the kernels of the last b2_heff_apply* call, measured with CUDA events on the launch stream */
+double b2_heff_last_kernel_seconds(const b2_heff* h);
+
+/* flat export of the plan (tests / the CPU checker in oracle/ only) */
+typedef struct {
+   int32_t dst, src;          /* Sobject block ids */
+   int32_t a_rows, a_cols;    /* stored shape of the left operator block (0 when absent) */
+   int32_t b_rows, b_cols;    /* stored shape of the right operator block */
+   int8_t a_space, a_trans;   /* 0 none, 1 left arena, 2 right arena, 3 presum arena */
+   int8_t b_space, b_trans;
+   int32_t owner;
+   int64_t a_off, b_off;      /* offsets (doubles) inside the arena named by *_space */
+   double factor;
+} b2_flat_term;
+typedef struct {
+   int64_t dst_off;           /* in the presum arena */
+   int64_t src_off;           /* in the arena of `space` */
+   int64_t size;
+   int32_t space;             /* 1 left arena, 2 right arena */
+   double coef;
+} b2_flat_presum;
+int64_t b2_heff_num_terms(const b2_heff* h);
+int b2_heff_export_terms(const b2_heff* h, b2_flat_term* out);
+int64_t b2_heff_num_presum_parts(const b2_heff* h);
+int64_t b2_heff_presum_size(const b2_heff* h);
+int b2_heff_export_presums(const b2_heff* h, b2_flat_presum* out);
+/* host mirrors of the operator arenas (valid until the set is destroyed) */
+const double* b2_opset_host_arena(const b2_opset* set);
+int64_t b2_opset_arena_size(const b2_opset* set);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,342 @@
+/* TEST INFRASTRUCTURE ONLY — never linked into or called by the product.
+ *
+ * Drives the UNMODIFIED CheMPS2 reference (oracle/_ref/libchemps2.so) through its own classes to
+ *   (1) dump golden fixtures of the two-site sweep hot path: bookkeeper dims, MPS tensors, every renormalized
+ *       operator at the two boundaries of a site pair, the vector going into and coming out of Heff::makeHeff,
+ *       the Heff diagonal, and operator sets before/after updateMovingLeft/Right;
+ *   (2) print per-sweep energies / discarded weights of a full DMRG::Solve() for end-to-end parity;
+ *   (3) time Heff::makeHeff (the CPU baseline of bench.py).
+ *
+ * Private members of the reference classes are reached with the `#define private public` trick; this file
+ * contains no reference source code.
+ *
+ * Fixture container (".b2fx"): records of { int32 name_len, name, int32 dtype (0=int32,1=float64), int64 count, data }.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <iostream>
+#include <sstream>
+#include <sys/time.h>
+#include <omp.h>
+
+#define private public
+#define protected public
+#include "Initialize.h"
+#include "Hamiltonian.h"
+#include "Problem.h"
+#include "ConvergenceScheme.h"
+#include "SyBookkeeper.h"
+#include "TensorT.h"
+#include "TensorOperator.h"
+#include "TensorL.h"
+#include "TensorX.h"
+#include "TensorQ.h"
+#include "TensorS0.h"
+#include "TensorS1.h"
+#include "TensorF0.h"
+#include "TensorF1.h"
+#include "Sobject.h"
+#include "Heff.h"
+#include "DMRG.h"
+#include "Wigner.h"
+#undef private
+#undef protected
+
+using namespace CheMPS2;
+
+struct Writer {
+   FILE * f;
+   explicit Writer(const std::string & path){ f = fopen(path.c_str(), "wb"); if (!f){ perror(path.c_str()); exit(2); } }
+   ~Writer(){ fclose(f); }
+   void rec(const std::string & name, int dtype, long long n, const void * data){
+      int len = (int) name.size();
+      fwrite(&len, 4, 1, f); fwrite(name.data(), 1, len, f); fwrite(&dtype, 4, 1, f); fwrite(&n, 8, 1, f);
+      fwrite(data, dtype == 0 ? 4 : 8, n, f);
+   }
+   void ints(const std::string & name, const std::vector<int> & v){ rec(name, 0, v.size(), v.data()); }
+   void dbls(const std::string & name, const std::vector<double> & v){ rec(name, 1, v.size(), v.data()); }
+   void dbls(const std::string & name, const double * p, long long n){ rec(name, 1, n, p); }
+};
+
+enum { K_L = 0, K_S0, K_S1, K_F0, K_F1, K_A, K_B, K_C, K_D, K_Q, K_X };
+
+static void push_op(std::vector<int> & meta, std::vector<double> & data, int kind, int i, int j, Tensor * t){
+   if (t == NULL) return;
+   const int size = t->gKappa2index(t->gNKappa());
+   meta.push_back(kind); meta.push_back(i); meta.push_back(j); meta.push_back(size);
+   data.insert(data.end(), t->gStorage(), t->gStorage() + size);
+}
+
+/* All operators in table slot t (boundary t+1). Index conventions: DMRGoperators.cpp:909-1140. */
+static void dump_ops(Writer & w, const std::string & prefix, DMRG & d, int t, bool moving_right){
+   std::vector<int> meta; std::vector<double> data;
+   const int L = d.L;
+   if (moving_right){
+      for (int k = 0; k <= t; k++) push_op(meta, data, K_L, t - k, t - k, d.Ltensors[t][k]);
+      for (int c2 = 0; c2 <= t; c2++) for (int c3 = 0; c3 <= t - c2; c3++){
+         const int j = t - c3, i = j - c2;
+         push_op(meta, data, K_S0, i, j, d.S0tensors[t][c2][c3]);
+         if (c2 > 0) push_op(meta, data, K_S1, i, j, d.S1tensors[t][c2][c3]);
+         push_op(meta, data, K_F0, i, j, d.F0tensors[t][c2][c3]);
+         push_op(meta, data, K_F1, i, j, d.F1tensors[t][c2][c3]);
+      }
+      for (int c2 = 0; c2 < L - 1 - t; c2++) for (int c3 = 0; c3 < L - 1 - t - c2; c3++){
+         const int i = t + 1 + c3, j = i + c2;
+         push_op(meta, data, K_A, i, j, d.Atensors[t][c2][c3]);
+         if (c2 > 0) push_op(meta, data, K_B, i, j, d.Btensors[t][c2][c3]);
+         push_op(meta, data, K_C, i, j, d.Ctensors[t][c2][c3]);
+         push_op(meta, data, K_D, i, j, d.Dtensors[t][c2][c3]);
+      }
+      for (int c2 = 0; c2 < L - 1 - t; c2++) push_op(meta, data, K_Q, t + 1 + c2, t + 1 + c2, d.Qtensors[t][c2]);
+      push_op(meta, data, K_X, -1, -1, d.Xtensors[t]);
+   } else {
+      for (int k = 0; k < L - 1 - t; k++) push_op(meta, data, K_L, t + 1 + k, t + 1 + k, d.Ltensors[t][k]);
+      for (int c2 = 0; c2 < L - 1 - t; c2++) for (int c3 = 0; c3 < L - 1 - t - c2; c3++){
+         const int i = t + 1 + c3, j = i + c2;
+         push_op(meta, data, K_S0, i, j, d.S0tensors[t][c2][c3]);
+         if (c2 > 0) push_op(meta, data, K_S1, i, j, d.S1tensors[t][c2][c3]);
+         push_op(meta, data, K_F0, i, j, d.F0tensors[t][c2][c3]);
+         push_op(meta, data, K_F1, i, j, d.F1tensors[t][c2][c3]);
+      }
+      for (int c2 = 0; c2 <= t; c2++) for (int c3 = 0; c3 <= t - c2; c3++){
+         const int j = t - c3, i = j - c2;
+         push_op(meta, data, K_A, i, j, d.Atensors[t][c2][c3]);
+         if (c2 > 0) push_op(meta, data, K_B, i, j, d.Btensors[t][c2][c3]);
+         push_op(meta, data, K_C, i, j, d.Ctensors[t][c2][c3]);
+         push_op(meta, data, K_D, i, j, d.Dtensors[t][c2][c3]);
+      }
+      for (int c2 = 0; c2 <= t; c2++) push_op(meta, data, K_Q, t - c2, t - c2, d.Qtensors[t][c2]);
+      push_op(meta, data, K_X, -1, -1, d.Xtensors[t]);
+   }
+   std::vector<int> hdr; hdr.push_back(t + 1); hdr.push_back(moving_right ? 1 : 0);
+   w.ints(prefix + "/hdr", hdr);   /* boundary, moving_right */
+   w.ints(prefix + "/meta", meta);
+   w.dbls(prefix + "/data", data);
+}
+
+static void dump_bk(Writer & w, const std::string & prefix, const SyBookkeeper * bk){
+   std::vector<int> rows;   /* boundary, N, twoS, irrep, curdim, fcidim */
+   for (int b = 0; b <= bk->gL(); b++)
+      for (int N = bk->gNmin(b); N <= bk->gNmax(b); N++)
+         for (int ts = bk->gTwoSmin(b, N); ts <= bk->gTwoSmax(b, N); ts += 2)
+            for (int ir = 0; ir < bk->getNumberOfIrreps(); ir++){
+               rows.push_back(b); rows.push_back(N); rows.push_back(ts); rows.push_back(ir);
+               rows.push_back(bk->gCurrentDim(b, N, ts, ir)); rows.push_back(bk->gFCIdim(b, N, ts, ir));
+            }
+   w.ints(prefix, rows);
+}
+
+static void dump_mps(Writer & w, const std::string & prefix, DMRG & d){
+   for (int s = 0; s < d.L; s++){
+      std::ostringstream nm; nm << prefix << "/" << s;
+      w.dbls(nm.str(), d.MPS[s]->gStorage(), d.MPS[s]->gKappa2index(d.MPS[s]->gNKappa()));
+   }
+}
+
+static void dump_problem(Writer & w, Problem * prob, Hamiltonian * ham, int group){
+   const int L = prob->gL();
+   std::vector<int> hdr; hdr.push_back(L); hdr.push_back(group); hdr.push_back(prob->gN()); hdr.push_back(prob->gTwoS()); hdr.push_back(prob->gIrrep());
+   w.ints("problem/hdr", hdr);
+   std::vector<int> irr; for (int i = 0; i < L; i++) irr.push_back(prob->gIrrep(i));
+   w.ints("problem/orb_irrep", irr);
+   std::vector<double> mx((size_t) L * L * L * L), tm((size_t) L * L), vm((size_t) L * L * L * L);
+   for (int a = 0; a < L; a++) for (int b = 0; b < L; b++){
+      tm[a + L * b] = ham->getTmat(prob->bReorder ? prob->f2[a] : a, prob->bReorder ? prob->f2[b] : b);
+      for (int c = 0; c < L; c++) for (int e = 0; e < L; e++){
+         mx[a + L * (b + L * (c + (size_t) L * e))] = prob->gMxElement(a, b, c, e);
+         vm[a + L * (b + L * (c + (size_t) L * e))] = ham->getVmat(prob->bReorder ? prob->f2[a] : a, prob->bReorder ? prob->f2[b] : b,
+                                                                    prob->bReorder ? prob->f2[c] : c, prob->bReorder ? prob->f2[e] : e);
+      }
+   }
+   w.dbls("problem/mx", mx); w.dbls("problem/tmat", tm); w.dbls("problem/vmat", vm);
+   std::vector<double> ec; ec.push_back(prob->gEconst()); w.dbls("problem/econst", ec);
+}
+
+/* sigma case at site `index`: S (symmetric convention), H*S, diag(H) straight from Heff::makeHeff / fillHeffDiag */
+static void dump_sigma(Writer & w, const std::string & prefix, DMRG & d, int index){
+   Sobject S(index, d.denBK);
+   S.Join(d.MPS[index], d.MPS[index + 1]);
+   const int n = S.gKappa2index(S.gNKappa());
+   w.dbls(prefix + "/joined", S.gStorage(), n);   /* program convention, output of Join */
+   S.prog2symm();
+   std::vector<double> out(n), diag(n);
+   Heff solver(d.denBK, d.Prob, 1e-5);
+   solver.makeHeff(S.gStorage(), out.data(), &S, d.Ltensors, d.Atensors, d.Btensors, d.Ctensors, d.Dtensors, d.S0tensors, d.S1tensors,
+                   d.F0tensors, d.F1tensors, d.Qtensors, d.Xtensors, 0, NULL);
+   solver.fillHeffDiag(diag.data(), &S, d.Ctensors, d.Dtensors, d.F0tensors, d.F1tensors, d.Xtensors, 0, NULL);
+   std::vector<int> hdr; hdr.push_back(index); hdr.push_back(n); hdr.push_back(S.gNKappa());
+   w.ints(prefix + "/hdr", hdr);
+   w.dbls(prefix + "/vec_in", S.gStorage(), n);
+   w.dbls(prefix + "/vec_out", out);
+   w.dbls(prefix + "/diag", diag);
+   /* a second, random input so that parity does not hinge on the structure of the joined state */
+   std::vector<double> rin(n), rout(n);
+   unsigned int st = 12345u + index;
+   for (int i = 0; i < n; i++){ st = st * 1664525u + 1013904223u; rin[i] = ((st >> 8) & 0xFFFF) / 65536.0 - 0.5; }
+   solver.makeHeff(rin.data(), rout.data(), &S, d.Ltensors, d.Atensors, d.Btensors, d.Ctensors, d.Dtensors, d.S0tensors, d.S1tensors,
+                   d.F0tensors, d.F1tensors, d.Qtensors, d.Xtensors, 0, NULL);
+   w.dbls(prefix + "/rnd_in", rin);
+   w.dbls(prefix + "/rnd_out", rout);
+   if (index > 0) dump_ops(w, prefix + "/left", d, index - 1, true);
+   if (index < d.L - 2) dump_ops(w, prefix + "/right", d, index + 1, false);
+}
+
+struct Setup {
+   Hamiltonian * ham; Problem * prob; int group;
+   Setup() : ham(NULL), prob(NULL), group(0) {}
+};
+
+static Setup make_setup(int argc, char ** argv){
+   Setup s; std::string fcidump; int twoS = 0, N = 0, irrep = 0, hubL = 0; double hubU = 0.0; bool reorder = false;
+   for (int i = 2; i < argc; i++){
+      std::string a = argv[i];
+      if (a == "--fcidump") fcidump = argv[++i];
+      else if (a == "--group") s.group = atoi(argv[++i]);
+      else if (a == "--twoS") twoS = atoi(argv[++i]);
+      else if (a == "--N") N = atoi(argv[++i]);
+      else if (a == "--irrep") irrep = atoi(argv[++i]);
+      else if (a == "--hubbard"){ hubL = atoi(argv[++i]); hubU = atof(argv[++i]); }
+      else if (a == "--reorder") reorder = true;
+   }
+   if (hubL > 0){   /* 1-D Hubbard chain, open ends, C1 (pattern of the reference's tests/test4) */
+      std::vector<int> irr(hubL, 0);
+      s.group = 0;
+      s.ham = new Hamiltonian(hubL, 0, irr.data());
+      for (int i = 0; i < hubL; i++) for (int j = 0; j < hubL; j++){
+         s.ham->setTmat(i, j, 0.0);
+         for (int k = 0; k < hubL; k++) for (int l = 0; l < hubL; l++) s.ham->setVmat(i, j, k, l, 0.0);
+      }
+      s.ham->setEconst(0.0);
+      for (int i = 0; i < hubL - 1; i++) s.ham->setTmat(i, i + 1, -1.0);
+      for (int i = 0; i < hubL; i++) s.ham->setVmat(i, i, i, i, hubU);
+   } else {
+      s.ham = new Hamiltonian(fcidump, s.group);
+   }
+   s.prob = new Problem(s.ham, twoS, N, irrep);
+   if (reorder && s.group == 7) s.prob->SetupReorderD2h();
+   return s;
+}
+
+static int argi(int argc, char ** argv, const char * key, int def){ for (int i = 2; i < argc - 1; i++) if (!strcmp(argv[i], key)) return atoi(argv[i + 1]); return def; }
+static double argd(int argc, char ** argv, const char * key, double def){ for (int i = 2; i < argc - 1; i++) if (!strcmp(argv[i], key)) return atof(argv[i + 1]); return def; }
+static const char * args(int argc, char ** argv, const char * key, const char * def){ for (int i = 2; i < argc - 1; i++) if (!strcmp(argv[i], key)) return argv[i + 1]; return def; }
+
+static double now(){ struct timeval t; gettimeofday(&t, NULL); return t.tv_sec + 1e-6 * t.tv_usec; }
+
+int main(int argc, char ** argv){
+   if (argc < 2){ fprintf(stderr, "usage: ref_driver dump|energies|time|wigner ...\n"); return 1; }
+   const std::string mode = argv[1];
+   std::cout.precision(15);
+
+   if (mode == "wigner"){   /* table of 6j / 9j values for the parity test of b2::wigner6j/9j */
+      Writer w(args(argc, argv, "--out", "wigner.b2fx"));
+      std::vector<int> a6; std::vector<double> v6; std::vector<int> a9; std::vector<double> v9;
+      unsigned int st = 777u;
+      for (int n = 0; n < 4000; n++){
+         int j[9]; for (int k = 0; k < 9; k++){ st = st * 1664525u + 1013904223u; j[k] = (st >> 10) % (n < 2000 ? 7 : 40); }
+         a6.insert(a6.end(), j, j + 6); v6.push_back(Wigner::wigner6j(j[0], j[1], j[2], j[3], j[4], j[5]));
+         for (int k = 0; k < 9; k++) j[k] = j[k] % 9;
+         a9.insert(a9.end(), j, j + 9); v9.push_back(Wigner::wigner9j(j[0], j[1], j[2], j[3], j[4], j[5], j[6], j[7], j[8]));
+      }
+      w.ints("w6j/args", a6); w.dbls("w6j/vals", v6); w.ints("w9j/args", a9); w.dbls("w9j/vals", v9);
+      return 0;
+   }
+
+   Setup s = make_setup(argc, argv);
+   const int D = argi(argc, argv, "--D", 20);
+   const int seed = argi(argc, argv, "--seed", 1234);
+   const double rtol = argd(argc, argv, "--rtol", 1e-8);
+   const double noise = argd(argc, argv, "--noise", 0.0);
+   const int L = s.prob->gL();
+
+   if (mode == "energies"){   /* schedule "D:econv:maxsweeps:noise:rtol,..." */
+      std::string sched = args(argc, argv, "--schedule", "");
+      std::vector<std::vector<double> > ins;
+      { std::stringstream ss(sched); std::string item;
+        while (std::getline(ss, item, ',')){ std::vector<double> v; std::stringstream s2(item); std::string x; while (std::getline(s2, x, ':')) v.push_back(atof(x.c_str())); ins.push_back(v); } }
+      ConvergenceScheme scheme(ins.size());
+      for (size_t i = 0; i < ins.size(); i++) scheme.set_instruction(i, (int) ins[i][0], ins[i][1], (int) ins[i][2], ins[i][3], ins[i][4]);
+      srand(seed);
+      const double t0 = now();
+      DMRG d(s.prob, &scheme, false, "/tmp");
+      const double e = d.Solve();
+      printf("B2REF final_energy %.15f wall %.3f threads %d\n", e, now() - t0, omp_get_max_threads());
+      return 0;
+   }
+
+   ConvergenceScheme scheme(1);
+   scheme.set_instruction(0, D, 1e-10, 2, noise, rtol);
+   srand(seed);
+   DMRG d(s.prob, &scheme, false, "/tmp");   /* random MPS + PreSolve (all right-moving operators) */
+
+   if (mode == "dump"){
+      Writer w(args(argc, argv, "--out", "case.b2fx"));
+      const int siteA = argi(argc, argv, "--siteA", L / 2);       /* sigma case met during the left sweep  */
+      const int siteB = argi(argc, argv, "--siteB", L / 2 - 1);   /* sigma case met during the right sweep */
+      const int presweeps = argi(argc, argv, "--presweeps", 0);   /* full left+right sweeps before the dumps */
+      dump_problem(w, s.prob, s.ham, s.group);
+      std::vector<double> energies;
+      bool change = false;
+      for (int sw = 0; sw < presweeps; sw++){
+         energies.push_back(d.sweepleft(change, 0, true)); change = true;
+         energies.push_back(d.sweepright(change, 0, true));
+      }
+      /* left sweep by hand (DMRG.cpp:357-386) */
+      for (int index = L - 2; index > 0; index--){
+         if (index == siteA){
+            dump_bk(w, "A/bk", d.denBK); dump_mps(w, "A/mps", d); dump_sigma(w, "A", d, index);
+         }
+         const double e = d.solve_site(index, rtol, 0.0, D, true, false, change);
+         energies.push_back(e);
+         if (index == siteA){   /* operator update moving left: inputs = A/right ops + new MPS[index+1]; outputs = table `index` */
+            dump_bk(w, "UL/bk", d.denBK); dump_mps(w, "UL/mps", d);
+         }
+         d.updateMovingLeftSafe(index);
+         if (index == siteA) dump_ops(w, "UL/new", d, index, false);
+      }
+      change = true;
+      for (int index = 0; index < L - 2; index++){
+         if (index == siteB){
+            dump_bk(w, "B/bk", d.denBK); dump_mps(w, "B/mps", d); dump_sigma(w, "B", d, index);
+         }
+         const double e = d.solve_site(index, rtol, 0.0, D, true, true, change);
+         energies.push_back(e);
+         if (index == siteB){ dump_bk(w, "UR/bk", d.denBK); dump_mps(w, "UR/mps", d); }
+         d.updateMovingRightSafe(index);
+         if (index == siteB) dump_ops(w, "UR/new", d, index, true);
+      }
+      w.dbls("energies", energies);
+      printf("B2REF dumped; last energy %.12f\n", energies.back());
+      return 0;
+   }
+
+   if (mode == "time"){   /* time Heff::makeHeff at one site; operators are whatever the un-optimised random MPS gives */
+      const int site = argi(argc, argv, "--site", L / 2);
+      const int reps = argi(argc, argv, "--reps", 3);
+      for (int index = L - 2; index > site; index--) d.updateMovingLeftSafe(index);   /* no solve: only build right operators */
+      Sobject S(site, d.denBK);
+      S.Join(d.MPS[site], d.MPS[site + 1]);
+      S.prog2symm();
+      const int n = S.gKappa2index(S.gNKappa());
+      std::vector<double> out(n);
+      Heff solver(d.denBK, d.Prob, 1e-5);
+      double best = 1e99, tot = 0.0;
+      for (int r = 0; r < reps + 1; r++){
+         const double t0 = now();
+         solver.makeHeff(S.gStorage(), out.data(), &S, d.Ltensors, d.Atensors, d.Btensors, d.Ctensors, d.Dtensors, d.S0tensors, d.S1tensors,
+                         d.F0tensors, d.F1tensors, d.Qtensors, d.Xtensors, 0, NULL);
+         const double dt = now() - t0;
+         if (r > 0){ tot += dt; if (dt < best) best = dt; }
+      }
+      double nrm = 0.0; for (int i = 0; i < n; i++) nrm += out[i] * out[i];
+      printf("B2REF time site %d veclength %d nkappa %d reps %d mean_s %.6f best_s %.6f threads %d norm2 %.12e\n",
+             site, n, S.gNKappa(), reps, tot / reps, best, omp_get_max_threads(), nrm);
+      return 0;
+   }
+   fprintf(stderr, "unknown mode\n");
+   return 1;
+}

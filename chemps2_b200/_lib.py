@@ -34,8 +34,15 @@ SIGNATURES = [
     ("b2_ctx_create", C.c_int, [C.c_int, C.POINTER(vp)]),
     ("b2_ctx_destroy", None, [vp]),
     ("b2_ctx_device", C.c_int, [vp]),
+    ("b2_ctx_set_stream", C.c_int, [vp, vp]),
+    ("b2_ctx_stream", vp, [vp]),
+    ("b2_opset_fill_hash", C.c_int, [vp, C.c_uint64, C.c_double]),
+    ("b2_hash_fill", C.c_int, [c_dp, C.c_int64, C.c_uint64, C.c_uint64, C.c_double]),
     ("b2_problem_set", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_dp, C.c_double]),
     ("b2_problem_set_integrals", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_dp, c_dp, C.c_double]),
+    ("b2_problem_mx", C.c_int, [vp, c_dp]),
+    ("b2_wigner6j", C.c_double, [C.c_int] * 6),
+    ("b2_wigner9j", C.c_double, [C.c_int] * 9),
     ("b2_bk_init", C.c_int, [vp, C.c_int]),
     ("b2_bk_set_dim", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("b2_bk_dim", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),

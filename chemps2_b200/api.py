@@ -4,7 +4,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import FlatPresum, FlatTerm, c_dp, c_ip, c_lp, check, lib, vp
+from ._lib import B2Error, FlatPresum, FlatTerm, c_dp, c_ip, c_lp, check, lib, vp  # noqa: F401
 
 
 def _dp(a):
@@ -38,6 +38,14 @@ class Context:
             t = np.ascontiguousarray(tmat, dtype=np.float64)
             v = np.ascontiguousarray(vmat, dtype=np.float64)
             check(lib.b2_problem_set_integrals(self.h, L, group, N, twoS, irrep, irr.ctypes.data_as(c_ip), _dp(t), _dp(v), float(econst)))
+
+    def set_stream(self, cuda_stream):
+        check(lib.b2_ctx_set_stream(self.h, vp(int(cuda_stream))))
+
+    def mx_elem(self):
+        out = np.zeros(self.L ** 4, dtype=np.float64)
+        check(lib.b2_problem_mx(self.h, _dp(out)))
+        return out
 
     def bk_init(self, D):
         check(lib.b2_bk_init(self.h, int(D)))
@@ -109,6 +117,9 @@ class OpSet:
                 continue
             self.upload(idx, data)
 
+    def fill_hash(self, seed, amp=1.0):
+        check(lib.b2_opset_fill_hash(self.h, int(seed), float(amp)))
+
     def host_arena(self):
         n = lib.b2_opset_arena_size(self.h)
         p = lib.b2_opset_host_arena(self.h)
@@ -177,3 +188,12 @@ def context_from_fixture(fx, tag, device=-1):
     ctx.bk_init(1)
     ctx.bk_import(fx[tag + "/bk"])
     return ctx
+
+
+S_KEY = (3 << 60)   # key of the synthetic two-site vector, same as op_key(3, 0, -1, -1) in oracle/ref_driver.cpp
+
+
+def hash_fill(n, seed, key=S_KEY, amp=1.0):
+    out = np.zeros(int(n), dtype=np.float64)
+    check(lib.b2_hash_fill(_dp(out), int(n), int(seed), int(key), float(amp)))
+    return out

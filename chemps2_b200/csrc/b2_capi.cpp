@@ -36,6 +36,7 @@ static int fail(int code, const char* fmt, ...) {
 struct b2_ctx {
    int device = -1;
    cudaStream_t stream = nullptr;
+   bool own_stream = true;
    Problem prob;
    Bookkeeper bk;
    bool have_problem = false, have_bk = false;
@@ -44,8 +45,9 @@ struct b2_ctx {
 struct b2_opset {
    b2_ctx* ctx = nullptr;
    OpSet set;
-   std::vector<double> host;
+   std::vector<double> host;   // host mirror, allocated on first use (upload / download / planning-only contexts)
    double* dev = nullptr;
+   void ensure_host() { if (host.size() != (size_t)set.size) host.assign((size_t)set.size, 0.0); }
 };
 
 struct b2_heff {
@@ -106,10 +108,17 @@ int b2_ctx_create(int device, b2_ctx** out) {
 }
 void b2_ctx_destroy(b2_ctx* ctx) {
    if (!ctx) return;
-   if (ctx->stream) cudaStreamDestroy(ctx->stream);
+   if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
    delete ctx;
 }
 int b2_ctx_device(const b2_ctx* ctx) { return ctx ? ctx->device : -1; }
+int b2_ctx_set_stream(b2_ctx* ctx, void* cuda_stream) {
+   if (!ctx || ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_ctx_set_stream: no CUDA device");
+   if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
+   ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false;
+   return B2_OK;
+}
+void* b2_ctx_stream(const b2_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 static int set_problem_common(b2_ctx* ctx, int L, int group, int N, int twoS, int irrep, const int* orb_irrep, double econst) {
    if (!ctx || L < 2 || !orb_irrep) return fail(B2_ERR_ARG, "b2_problem_set: bad arguments");
@@ -140,6 +149,14 @@ int b2_problem_set_integrals(b2_ctx* ctx, int L, int group, int N, int twoS, int
    ctx->prob.build(tmat, vmat);
    return B2_OK;
 }
+
+int b2_problem_mx(const b2_ctx* ctx, double* mx_out) {
+   if (!ctx || !ctx->have_problem || !mx_out) return fail(B2_ERR_STATE, "b2_problem_mx: no problem set");
+   std::memcpy(mx_out, ctx->prob.mx.data(), sizeof(double) * ctx->prob.mx.size());
+   return B2_OK;
+}
+double b2_wigner6j(int a, int b, int c, int d, int e, int f) { return wigner6j(a, b, c, d, e, f); }
+double b2_wigner9j(int a, int b, int c, int d, int e, int f, int g, int h, int i) { return wigner9j(a, b, c, d, e, f, g, h, i); }
 
 int b2_bk_init(b2_ctx* ctx, int D) {
    if (!ctx || !ctx->have_problem) return fail(B2_ERR_STATE, "b2_bk_init: set the problem first");
@@ -182,7 +199,7 @@ int b2_opset_create(b2_ctx* ctx, int boundary, int moving_right, b2_opset** out)
    std::unique_ptr<b2_opset> s(new b2_opset);
    s->ctx = ctx;
    s->set.build_all(ctx->bk, boundary, moving_right != 0);
-   s->host.assign((size_t)s->set.size, 0.0);
+   if (ctx->device < 0) s->ensure_host();
    if (ctx->device >= 0 && s->set.size > 0) {
       CUDA_TRY(cudaSetDevice(ctx->device));
       CUDA_TRY(cudaMalloc(&s->dev, sizeof(double) * (size_t)s->set.size));
@@ -211,6 +228,7 @@ int b2_opset_upload(b2_opset* set, int index, const double* packed) {
    if (!set || index < 0 || index >= (int)set->set.ops.size() || !packed) return fail(B2_ERR_ARG, "b2_opset_upload: bad arguments");
    const OpTensor& t = set->set.ops[index];
    if (t.lay->size == 0) return B2_OK;
+   set->ensure_host();
    std::memcpy(set->host.data() + t.off, packed, sizeof(double) * (size_t)t.lay->size);
    if (set->dev) {
       CUDA_TRY(cudaMemcpyAsync(set->dev + t.off, set->host.data() + t.off, sizeof(double) * (size_t)t.lay->size, cudaMemcpyHostToDevice, set->ctx->stream));
@@ -222,6 +240,7 @@ int b2_opset_download(b2_opset* set, int index, double* packed) {
    if (!set || index < 0 || index >= (int)set->set.ops.size() || !packed) return fail(B2_ERR_ARG, "b2_opset_download: bad arguments");
    const OpTensor& t = set->set.ops[index];
    if (t.lay->size == 0) return B2_OK;
+   set->ensure_host();
    if (set->dev) {
       CUDA_TRY(cudaMemcpyAsync(set->host.data() + t.off, set->dev + t.off, sizeof(double) * (size_t)t.lay->size, cudaMemcpyDeviceToHost, set->ctx->stream));
       CUDA_TRY(cudaStreamSynchronize(set->ctx->stream));
@@ -231,11 +250,36 @@ int b2_opset_download(b2_opset* set, int index, double* packed) {
 }
 int b2_opset_clear(b2_opset* set) {
    if (!set) return fail(B2_ERR_ARG, "b2_opset_clear: NULL");
-   std::fill(set->host.begin(), set->host.end(), 0.0);
+   if (!set->host.empty()) std::fill(set->host.begin(), set->host.end(), 0.0);
    if (set->dev) CUDA_TRY(cudaMemsetAsync(set->dev, 0, sizeof(double) * (size_t)set->set.size, set->ctx->stream));
    return B2_OK;
 }
-const double* b2_opset_host_arena(const b2_opset* set) { return set ? set->host.data() : nullptr; }
+const double* b2_opset_host_arena(const b2_opset* set) {
+   if (!set) return nullptr;
+   const_cast<b2_opset*>(set)->ensure_host();
+   return set->host.data();
+}
+int b2_opset_fill_hash(b2_opset* set, uint64_t seed, double amp) {
+   if (!set) return fail(B2_ERR_ARG, "b2_opset_fill_hash: NULL");
+   const uint64_t side = set->set.moving_right ? 1 : 2;
+   for (const OpTensor& t : set->set.ops) {
+      const uint64_t key = (side << 60) | ((uint64_t)t.kind << 40) | ((uint64_t)(t.i + 1) << 20) | (uint64_t)(t.j + 1);
+      if (set->dev) {
+         if (dev_fill_hash(set->dev + t.off, t.lay->size, seed, key, amp, set->ctx->stream)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+      } else {
+         set->ensure_host();
+         double* p = set->host.data() + t.off;
+         for (int64_t e = 0; e < t.lay->size; e++) p[e] = amp * hash_value(seed, key, (uint64_t)e);
+      }
+   }
+   if (set->dev) CUDA_TRY(cudaStreamSynchronize(set->ctx->stream));
+   return B2_OK;
+}
+int b2_hash_fill(double* out, int64_t n, uint64_t seed, uint64_t key, double amp) {
+   if (!out) return fail(B2_ERR_ARG, "b2_hash_fill: NULL");
+   for (int64_t e = 0; e < n; e++) out[e] = amp * hash_value(seed, key, (uint64_t)e);
+   return B2_OK;
+}
 int64_t b2_opset_arena_size(const b2_opset* set) { return set ? set->set.size : 0; }
 
 // ------------------------------------------------------------------------------------------------ heff

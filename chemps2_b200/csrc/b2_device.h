@@ -46,6 +46,15 @@ constexpr int kTileThreads[kNumTileClasses] = {128, 128, 32, 32};
 int dev_launch_tiles(int tile_class, const Tile* d_tiles, int ntiles, const GemmItem* d_items, const DevBases& bases, void* stream);
 int dev_launch_presum(const PresumJob* d_jobs, int njobs, const PresumPart* d_parts, const DevBases& bases, void* stream);
 int dev_fill_zero(double* d_ptr, int64_t n, void* stream);
+// p[e] = amp * hash(seed, key, e): deterministic synthetic operator contents (bench / full-size parity vs oracle/ref_driver synth)
+int dev_fill_hash(double* d_ptr, int64_t n, uint64_t seed, uint64_t key, double amp, void* stream);
+inline double hash_value(uint64_t seed, uint64_t key, uint64_t e) {
+   uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (key + 1) + 0xD1B54A32D192ED03ULL * (e + 1);
+   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+   z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+   z = z ^ (z >> 31);
+   return (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+}
 // FP64 peak probes: returns achieved TFLOP/s of a register-resident DMMA (m8n8k4) / DFMA loop
 int dev_probe_fp64(int use_mma, double* tflops_out);
 const char* dev_last_error();

@@ -180,6 +180,24 @@ int dev_fill_zero(double* d_ptr, int64_t n, void* stream) {
    return 0;
 }
 
+__global__ void k_fill_hash(double* p, int64_t n, uint64_t seed, uint64_t key, double amp) {
+   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+      uint64_t z = seed + 0x9E3779B97F4A7C15ULL * (key + 1) + 0xD1B54A32D192ED03ULL * ((uint64_t)e + 1);
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+      z = z ^ (z >> 31);
+      p[e] = amp * ((double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5);
+   }
+}
+int dev_fill_hash(double* d_ptr, int64_t n, uint64_t seed, uint64_t key, double amp, void* stream) {
+   if (n <= 0) return 0;
+   const int blocks = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+   k_fill_hash<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_ptr, n, seed, key, amp);
+   cudaError_t e = cudaGetLastError();
+   if (e != cudaSuccess) return cuda_fail(e, "k_fill_hash launch");
+   return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // FP64 peak probes (register resident, no memory traffic): the measured roofline denominator for the DMMA kernels.
 __global__ void k_probe_mma(double* out, int iters) {

@@ -1,0 +1,124 @@
+"""Synthetic workloads of bench.py and the full-size tests (host side, numpy only; nothing here computes sigma).
+
+The generators follow SURVEY.md 8(d): the BASELINE configs whose real integrals cannot travel (no network, no psi4) are
+replaced by seeded synthetic integrals of the same shape and symmetry:  chemist (ik|jl) = sum_P B^P_ik B^P_jl  with every
+B^P symmetric and belonging to one irrep, so the table has the 8-fold permutational symmetry and the point-group
+selection rules the reference's Hamiltonian class asserts (Hamiltonian.cpp:108-127).
+"""
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DRIVER = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+
+# N2 cc-pVDZ (reference tests/matrixelements/N2.CCPVDZ.FCIDUMP header: 28 orbitals, 14 electrons, D2h): orbital irreps in
+# psi4 numbering AFTER Problem::SetupReorderD2h (Problem.cpp:57-95): Ag x7, B1u x7, B3u x3, B2g x3, B2u x3, B3g x3, B1g, Au
+N2_CCPVDZ_IRREPS = [0] * 7 + [5] * 7 + [7] * 3 + [2] * 3 + [6] * 3 + [3] * 3 + [1] + [4]
+
+
+def synthetic_integrals(L, irreps, seed, naux, width, amp, local=False):
+    """-> (tmat[L,L], vmat[L,L,L,L] physicist <ab|cd> = (ac|bd)) ; seeded, symmetric, irrep-adapted"""
+    rng = np.random.default_rng(seed)
+    irr = np.asarray(irreps)
+    nirr_prod = irr[:, None] ^ irr[None, :]
+    idx = np.arange(L)
+    B = np.zeros((naux, L, L))
+    groups = sorted(set(nirr_prod.ravel().tolist()))
+    for P in range(naux):
+        c = rng.uniform(0, L)
+        g = groups[P % len(groups)] if len(groups) > 1 else 0
+        xi = rng.standard_normal((L, L))
+        xi = 0.5 * (xi + xi.T)
+        m = amp * np.exp(-(np.abs(idx[:, None] - c) + np.abs(idx[None, :] - c)) / width) * (1.0 + 0.1 * xi)
+        if local:
+            m = m * np.exp(-np.abs(idx[:, None] - idx[None, :]) / 1.5)
+        B[P] = np.where(nirr_prod == g, m, 0.0)
+    chem = np.einsum("pik,pjl->ikjl", B, B, optimize=True)          # (ik|jl)
+    vmat = np.ascontiguousarray(chem.transpose(0, 2, 1, 3))         # <ij|kl> = (ik|jl)
+    xi = rng.standard_normal((L, L))
+    xi = 0.5 * (xi + xi.T)
+    t = -0.5 * np.exp(-np.abs(idx[:, None] - idx[None, :]) / 1.5) * (1.0 + 0.1 * xi)
+    t[idx, idx] = -1.0 + 0.05 * rng.standard_normal(L)
+    tmat = np.where(nirr_prod == 0, t, 0.0)
+    return tmat, vmat
+
+
+class Workload:
+    def __init__(self, name, L, group, N, twoS, irrep, irreps, D, site, seed, **gen):
+        self.name, self.L, self.group, self.N, self.twoS, self.irrep = name, L, group, N, twoS, irrep
+        self.irreps, self.D, self.site, self.seed, self.gen = list(irreps), D, site, seed, gen
+        self._ints = None
+
+    def integrals(self):
+        if self._ints is None:
+            self._ints = synthetic_integrals(self.L, self.irreps, self.seed, **self.gen)
+        return self._ints
+
+    def context(self, device):
+        from . import api
+        t, v = self.integrals()
+        ctx = api.Context(device)
+        # column-major (first index fastest) flat tables, as b2_problem_set_integrals expects
+        ctx.set_problem(self.L, self.group, self.N, self.twoS, self.irrep, self.irreps, tmat=t.ravel(order="F"), vmat=v.ravel(order="F"))
+        ctx.bk_init(self.D)
+        return ctx
+
+    def write_problem_file(self, path):
+        """binary problem file read by `ref_driver synth`"""
+        t, v = self.integrals()
+        with open(path, "wb") as f:
+            np.array([self.L, self.group, self.N, self.twoS, self.irrep], dtype="<i4").tofile(f)
+            np.array(self.irreps, dtype="<i4").tofile(f)
+            np.array([0.0], dtype="<f8").tofile(f)
+            t.ravel(order="F").astype("<f8").tofile(f)
+            v.ravel(order="F").astype("<f8").tofile(f)
+
+    def describe(self):
+        return f"{self.name}: {self.N}e/{self.L}o group {self.group} D={self.D} site pair ({self.site},{self.site + 1})"
+
+
+def get(name, D=None, site=None):
+    """named workloads = the BASELINE.json configs (shape + symmetry), synthetic integrals"""
+    if name == "synth40":      # config 5: 40e/40o C1, no locality
+        w = Workload(name, 40, 0, 40, 0, 0, [0] * 40, 4000, 19, 40404000, naux=80, width=6.0, amp=0.25)
+    elif name == "synth60":    # config 4: 60e/60o 1-D chain
+        w = Workload(name, 60, 0, 60, 0, 0, [0] * 60, 4000, 29, 60604000, naux=120, width=2.0, amp=0.6, local=True)
+    elif name == "n2":         # config 2: N2/cc-pVDZ shape (14e/28o, D2h, reordered)
+        w = Workload(name, 28, 7, 14, 0, 0, N2_CCPVDZ_IRREPS, 2000, 13, 14282000, naux=96, width=6.0, amp=0.3)
+    elif name == "tetracene":  # config 3: 18e/18o C1
+        w = Workload(name, 18, 0, 18, 0, 0, [0] * 18, 3000, 8, 18183000, naux=36, width=3.0, amp=0.4, local=True)
+    elif name == "tiny":       # CPU-checkable stand-in used by smoke() and the fast tests
+        w = Workload(name, 8, 5, 8, 0, 0, [0, 0, 2, 3, 0, 0, 2, 3], 40, 3, 8080, naux=16, width=3.0, amp=0.4)
+    else:
+        raise KeyError(name)
+    if D is not None:
+        w.D = int(D)
+    if site is not None:
+        w.site = int(site)
+    return w
+
+
+def run_reference_synth(w, seed, reps=1, amp=1.0, threads=None, out_path=None, workdir="/tmp"):
+    """Runs the UNMODIFIED reference's Heff::makeHeff (oracle/_ref/ref_driver synth) on workload `w` with hash-filled
+    operators.  Test / bench-baseline infrastructure only.  -> dict(mean_s, best_s, threads, veclength, vec_out, diag)"""
+    if not os.path.exists(REF_DRIVER):
+        raise FileNotFoundError(REF_DRIVER + " missing (oracle/build_ref.sh builds it where /root/reference exists)")
+    pfile = os.path.join(workdir, f"b2_problem_{w.name}_{os.getpid()}.bin")
+    ofile = out_path or os.path.join(workdir, f"b2_refout_{w.name}_{os.getpid()}.bin")
+    w.write_problem_file(pfile)
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1")
+    env["OMP_NUM_THREADS"] = str(threads or os.cpu_count())
+    cmd = [REF_DRIVER, "synth", "--problem", pfile, "--D", str(w.D), "--site", str(w.site), "--reps", str(reps), "--seed", str(seed),
+           "--amp", repr(amp), "--out", ofile]
+    res = subprocess.run(cmd, env=env, check=True, capture_output=True, text=True)
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("B2REF synth")][-1].split()
+    kv = {line[i]: line[i + 1] for i in range(2, len(line) - 1, 2)}
+    raw = np.fromfile(ofile, dtype="<f8")
+    n = int(kv["veclength"])
+    os.remove(pfile)
+    if out_path is None:
+        os.remove(ofile)
+    return dict(mean_s=float(kv["mean_s"]), best_s=float(kv["best_s"]), diag_s=float(kv["diag_s"]), setup_s=float(kv["setup_s"]),
+                threads=int(kv["threads"]), veclength=n, vec_out=raw[:n], diag=raw[n:2 * n])

@@ -45,6 +45,9 @@ const char* b2_version(void);
 int b2_ctx_create(int device, b2_ctx** out);
 void b2_ctx_destroy(b2_ctx* ctx);
 int b2_ctx_device(const b2_ctx* ctx);
+/* run every kernel / copy of this context on the caller's CUDA stream (a cudaStream_t, e.g. torch's current stream) */
+int b2_ctx_set_stream(b2_ctx* ctx, void* cuda_stream);
+void* b2_ctx_stream(const b2_ctx* ctx);
 
 /* ------------------------------------------------------------------------------------------------ problem
  * Replaces CheMPS2::Problem (Problem.h:44-128) as seen by the hot path: target sector, orbital irreps in DMRG
@@ -55,6 +58,12 @@ int b2_problem_set(b2_ctx* ctx, int L, int group, int N, int twoS, int irrep, co
                    double econst);
 int b2_problem_set_integrals(b2_ctx* ctx, int L, int group, int N, int twoS, int irrep, const int* orb_irrep,
                              const double* tmat, const double* vmat, double econst);
+
+/* copy of the folded table gMxElement (L^4 doubles) as the library holds it */
+int b2_problem_mx(const b2_ctx* ctx, double* mx_out);
+/* Wigner 6j / 9j symbols with doubled arguments, as Wigner::wigner6j / wigner9j (Wigner.cpp:294-368) */
+double b2_wigner6j(int two_ja, int two_jb, int two_jc, int two_jd, int two_je, int two_jf);
+double b2_wigner9j(int two_ja, int two_jb, int two_jc, int two_jd, int two_je, int two_jf, int two_jg, int two_jh, int two_ji);
 
 /* ------------------------------------------------------------------------------------------------ bookkeeper
  * Replaces CheMPS2::SyBookkeeper (SyBookkeeper.h:41-143).  b2_bk_init = constructor (FCI dims, ceil-scaled to D);
@@ -88,6 +97,10 @@ int b2_opset_find(const b2_opset* set, int kind, int site_i, int site_j);   /* i
 int b2_opset_upload(b2_opset* set, int index, const double* packed);
 int b2_opset_download(b2_opset* set, int index, double* packed);
 int b2_opset_clear(b2_opset* set);
+/* synthetic contents: element e of operator (kind,i,j) = amp * hash(seed, side, kind, i, j, e) in [-amp/2, amp/2); the
+ * identical fill is produced by oracle/ref_driver.cpp `synth`, which lets bench.py compare with the reference at full size */
+int b2_opset_fill_hash(b2_opset* set, uint64_t seed, double amp);
+int b2_hash_fill(double* out, int64_t n, uint64_t seed, uint64_t key, double amp);
 
 /* ------------------------------------------------------------------------------------------------ effective Hamiltonian
  * b2_heff_create builds the SigmaPlan for the site pair (site, site+1) from the operator sets at boundaries
@@ -133,6 +146,8 @@ int b2_heff_export_terms(const b2_heff* h, b2_flat_term* out);
 int64_t b2_heff_num_presum_parts(const b2_heff* h);
 int64_t b2_heff_presum_size(const b2_heff* h);
 int b2_heff_export_presums(const b2_heff* h, b2_flat_presum* out);
+/* FP64 peak probe, register resident: use_mma = 1 times DMMA (mma.sync m8n8k4 f64), 0 times DFMA; result in TFLOP/s */
+int b2_probe_fp64(b2_ctx* ctx, int use_mma, double* tflops);
 /* host mirrors of the operator arenas (valid until the set is destroyed) */
 const double* b2_opset_host_arena(const b2_opset* set);
 int64_t b2_opset_arena_size(const b2_opset* set);

@@ -227,6 +227,140 @@ static const char * args(int argc, char ** argv, const char * key, const char * 
 
 static double now(){ struct timeval t; gettimeofday(&t, NULL); return t.tv_sec + 1e-6 * t.tv_usec; }
 
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * "synth" mode: the reference's Heff::makeHeff on a synthetic workload WITHOUT running a DMRG calculation first.
+ * The operator tables of the two boundaries next to the site pair are allocated with the reference's own constructors
+ * (same index conventions as DMRG::allocateTensors, DMRGoperators.cpp:909-1145) and filled with a deterministic hash
+ * of (seed, kind, site_i, site_j, element) — the same fill chemps2_b200's b2_opset_fill_hash produces — so the GPU
+ * result can be compared with the reference's at the full benchmark size, and the reference can be timed on it. */
+static inline double hash_value(unsigned long long seed, unsigned long long key, unsigned long long e){
+   unsigned long long z = seed + 0x9E3779B97F4A7C15ULL * (key + 1) + 0xD1B54A32D192ED03ULL * (e + 1);
+   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+   z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+   z = z ^ (z >> 31);
+   return (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+}
+static inline unsigned long long op_key(int side, int kind, int i, int j){
+   return ((unsigned long long) side << 60) | ((unsigned long long) kind << 40) | ((unsigned long long)(i + 1) << 20) | (unsigned long long)(j + 1);
+}
+static void fill_tensor(Tensor * t, unsigned long long seed, unsigned long long key, double amp){
+   const long long n = t->gKappa2index(t->gNKappa());
+   double * p = t->gStorage();
+   #pragma omp parallel for schedule(static)
+   for (long long e = 0; e < n; e++) p[e] = amp * hash_value(seed, key, e);
+}
+
+struct Tables {
+   TensorL *** Lt; TensorF0 **** F0; TensorF1 **** F1; TensorS0 **** S0; TensorS1 **** S1;
+   TensorOperator **** A; TensorOperator **** B; TensorOperator **** C; TensorOperator **** Dd; TensorQ *** Q; TensorX ** X;
+   explicit Tables(int L){
+      Lt = new TensorL ** [L]; F0 = new TensorF0 *** [L]; F1 = new TensorF1 *** [L]; S0 = new TensorS0 *** [L]; S1 = new TensorS1 *** [L];
+      A = new TensorOperator *** [L]; B = new TensorOperator *** [L]; C = new TensorOperator *** [L]; Dd = new TensorOperator *** [L];
+      Q = new TensorQ ** [L]; X = new TensorX * [L];
+      for (int i = 0; i < L; i++){ Lt[i] = NULL; F0[i] = NULL; F1[i] = NULL; S0[i] = NULL; S1[i] = NULL; A[i] = NULL; B[i] = NULL; C[i] = NULL; Dd[i] = NULL; Q[i] = NULL; X[i] = NULL; }
+   }
+};
+
+/* table slot t = boundary t+1; side = 1 (moving right, left of the site pair) or 2 (moving left, right of the pair) */
+static void alloc_fill_side(Tables & T, SyBookkeeper * bk, Problem * prob, int t, bool mr, unsigned long long seed, double amp){
+   const int L = bk->gL(); const int side = mr ? 1 : 2; const int b = t + 1;
+   const int n_in  = mr ? t + 1 : L - 1 - t;   /* sites inside the renormalized block  */
+   const int n_out = mr ? L - 1 - t : t + 1;   /* sites outside (complementary operators) */
+   T.Lt[t] = new TensorL * [n_in];
+   for (int k = 0; k < n_in; k++){
+      const int s = mr ? t - k : t + 1 + k;
+      T.Lt[t][k] = new TensorL(b, bk->gIrrep(s), mr, bk, bk); fill_tensor(T.Lt[t][k], seed, op_key(side, K_L, s, s), amp);
+   }
+   T.F0[t] = new TensorF0 ** [n_in]; T.F1[t] = new TensorF1 ** [n_in]; T.S0[t] = new TensorS0 ** [n_in]; T.S1[t] = new TensorS1 ** [n_in];
+   for (int c2 = 0; c2 < n_in; c2++){
+      T.F0[t][c2] = new TensorF0 * [n_in - c2]; T.F1[t][c2] = new TensorF1 * [n_in - c2]; T.S0[t][c2] = new TensorS0 * [n_in - c2];
+      T.S1[t][c2] = (c2 > 0) ? new TensorS1 * [n_in - c2] : NULL;
+      for (int c3 = 0; c3 < n_in - c2; c3++){
+         int i, j; if (mr){ j = t - c3; i = j - c2; } else { i = t + 1 + c3; j = i + c2; }
+         const int I = Irreps::directProd(bk->gIrrep(i), bk->gIrrep(j));
+         T.F0[t][c2][c3] = new TensorF0(b, I, mr, bk); fill_tensor(T.F0[t][c2][c3], seed, op_key(side, K_F0, i, j), amp);
+         T.F1[t][c2][c3] = new TensorF1(b, I, mr, bk); fill_tensor(T.F1[t][c2][c3], seed, op_key(side, K_F1, i, j), amp);
+         T.S0[t][c2][c3] = new TensorS0(b, I, mr, bk); fill_tensor(T.S0[t][c2][c3], seed, op_key(side, K_S0, i, j), amp);
+         if (c2 > 0){ T.S1[t][c2][c3] = new TensorS1(b, I, mr, bk); fill_tensor(T.S1[t][c2][c3], seed, op_key(side, K_S1, i, j), amp); }
+      }
+   }
+   T.A[t] = new TensorOperator ** [n_out]; T.B[t] = new TensorOperator ** [n_out]; T.C[t] = new TensorOperator ** [n_out]; T.Dd[t] = new TensorOperator ** [n_out];
+   for (int c2 = 0; c2 < n_out; c2++){
+      T.A[t][c2] = new TensorOperator * [n_out - c2]; T.B[t][c2] = (c2 > 0) ? new TensorOperator * [n_out - c2] : NULL;
+      T.C[t][c2] = new TensorOperator * [n_out - c2]; T.Dd[t][c2] = new TensorOperator * [n_out - c2];
+      for (int c3 = 0; c3 < n_out - c2; c3++){
+         int i, j; if (mr){ i = t + 1 + c3; j = i + c2; } else { j = t - c3; i = j - c2; }
+         const int I = Irreps::directProd(bk->gIrrep(i), bk->gIrrep(j));
+         T.A[t][c2][c3] = new TensorOperator(b, 0, 2, I, mr, true, false, bk, bk); fill_tensor(T.A[t][c2][c3], seed, op_key(side, K_A, i, j), amp);
+         if (c2 > 0){ T.B[t][c2][c3] = new TensorOperator(b, 2, 2, I, mr, true, false, bk, bk); fill_tensor(T.B[t][c2][c3], seed, op_key(side, K_B, i, j), amp); }
+         T.C[t][c2][c3] = new TensorOperator(b, 0, 0, I, mr, true, false, bk, bk); fill_tensor(T.C[t][c2][c3], seed, op_key(side, K_C, i, j), amp);
+         T.Dd[t][c2][c3] = new TensorOperator(b, 2, 0, I, mr, mr, false, bk, bk); fill_tensor(T.Dd[t][c2][c3], seed, op_key(side, K_D, i, j), amp);
+      }
+   }
+   T.Q[t] = new TensorQ * [n_out];
+   for (int c2 = 0; c2 < n_out; c2++){
+      const int s = mr ? t + 1 + c2 : t - c2;
+      T.Q[t][c2] = new TensorQ(b, bk->gIrrep(s), mr, bk, prob, s); fill_tensor(T.Q[t][c2], seed, op_key(side, K_Q, s, s), amp);
+   }
+   T.X[t] = new TensorX(b, mr, bk, prob); fill_tensor(T.X[t], seed, op_key(side, K_X, -1, -1), amp);
+}
+
+static int run_synth(int argc, char ** argv){
+   const char * pfile = args(argc, argv, "--problem", NULL);
+   if (!pfile){ fprintf(stderr, "synth: --problem file needed\n"); return 1; }
+   FILE * f = fopen(pfile, "rb"); if (!f){ perror(pfile); return 2; }
+   int hdr[5]; if (fread(hdr, 4, 5, f) != 5) return 2;
+   const int L = hdr[0], group = hdr[1], N = hdr[2], twoS = hdr[3], irrep = hdr[4];
+   std::vector<int> irr(L); std::vector<double> tm((size_t) L * L), vm((size_t) L * L * L * L); double econst = 0.0;
+   if (fread(irr.data(), 4, L, f) != (size_t) L || fread(&econst, 8, 1, f) != 1 || fread(tm.data(), 8, tm.size(), f) != tm.size() || fread(vm.data(), 8, vm.size(), f) != vm.size()) return 2;
+   fclose(f);
+   Hamiltonian ham(L, group, irr.data());
+   ham.setEconst(econst);
+   for (int a = 0; a < L; a++) for (int b = a; b < L; b++) if (irr[a] == irr[b]) ham.setTmat(a, b, tm[a + L * b]);
+   for (int a = 0; a < L; a++) for (int b = 0; b < L; b++) for (int c = 0; c < L; c++) for (int e = 0; e < L; e++)
+      if (Irreps::directProd(Irreps::directProd(irr[a], irr[b]), Irreps::directProd(irr[c], irr[e])) == 0) ham.setVmat(a, b, c, e, vm[a + L * (b + L * (c + (size_t) L * e))]);
+   Problem prob(&ham, twoS, N, irrep);
+   prob.construct_mxelem();
+   const int D = argi(argc, argv, "--D", 100);
+   const int site = argi(argc, argv, "--site", L / 2 - 1);
+   const int reps = argi(argc, argv, "--reps", 1);
+   const unsigned long long seed = (unsigned long long) argi(argc, argv, "--seed", 1);
+   const double amp = argd(argc, argv, "--amp", 1.0);
+   SyBookkeeper bk(&prob, D);
+   const char * dfile = args(argc, argv, "--dims", NULL);
+   if (dfile){   /* rows of int32: boundary N twoS irrep dim */
+      FILE * g = fopen(dfile, "rb"); if (!g){ perror(dfile); return 2; }
+      int row[5]; while (fread(row, 4, 5, g) == 5) bk.SetDim(row[0], row[1], row[2], row[3], row[4]);
+      fclose(g);
+   }
+   const double t_alloc = now();
+   Tables T(L);
+   if (site > 0) alloc_fill_side(T, &bk, &prob, site - 1, true, seed, amp);
+   if (site < L - 2) alloc_fill_side(T, &bk, &prob, site + 1, false, seed, amp);
+   Sobject S(site, &bk);
+   const long long n = S.gKappa2index(S.gNKappa());
+   for (long long e = 0; e < n; e++) S.gStorage()[e] = hash_value(seed, op_key(3, 0, -1, -1), e);
+   std::vector<double> out(n), diag(n);
+   Heff solver(&bk, &prob, 1e-5);
+   const double t_setup = now() - t_alloc;
+   double best = 1e99, tot = 0.0;
+   for (int r = 0; r < reps; r++){
+      const double t0 = now();
+      solver.makeHeff(S.gStorage(), out.data(), &S, T.Lt, T.A, T.B, T.C, T.Dd, T.S0, T.S1, T.F0, T.F1, T.Q, T.X, 0, NULL);
+      const double dt = now() - t0; tot += dt; if (dt < best) best = dt;
+   }
+   const double t1 = now();
+   solver.fillHeffDiag(diag.data(), &S, T.C, T.Dd, T.F0, T.F1, T.X, 0, NULL);
+   const double t_diag = now() - t1;
+   const char * ofile = args(argc, argv, "--out", NULL);
+   if (ofile){ FILE * g = fopen(ofile, "wb"); fwrite(out.data(), 8, n, g); fwrite(diag.data(), 8, n, g); fclose(g); }
+   double nrm = 0.0; for (long long i = 0; i < n; i++) nrm += out[i] * out[i];
+   printf("B2REF synth site %d veclength %lld nkappa %d reps %d mean_s %.6f best_s %.6f diag_s %.6f setup_s %.3f threads %d norm2 %.12e\n",
+          site, n, S.gNKappa(), reps, tot / reps, best, t_diag, t_setup, omp_get_max_threads(), nrm);
+   return 0;
+}
+
 int main(int argc, char ** argv){
    if (argc < 2){ fprintf(stderr, "usage: ref_driver dump|energies|time|wigner ...\n"); return 1; }
    const std::string mode = argv[1];
@@ -245,6 +379,8 @@ int main(int argc, char ** argv){
       w.ints("w6j/args", a6); w.dbls("w6j/vals", v6); w.ints("w9j/args", a9); w.dbls("w9j/vals", v9);
       return 0;
    }
+
+   if (mode == "synth") return run_synth(argc, argv);
 
    Setup s = make_setup(argc, argv);
    const int D = argi(argc, argv, "--D", 20);

@@ -1,0 +1,34 @@
+import glob
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # the product library and the CPU checker are built in-tree; build them if this checkout has not been built yet
+    if not (os.path.exists(os.path.join(ROOT, "chemps2_b200", "libchemps2_b200.so")) and os.path.exists(os.path.join(ROOT, "oracle", "libb2oracle.so"))):
+        subprocess.run(["make", "-j8"], cwd=ROOT, check=True, stdout=subprocess.DEVNULL)
+
+
+GOLDEN = sorted(p for p in glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")) if not p.endswith("wigner.npz"))
+
+
+@pytest.fixture(scope="session", params=GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def golden(request):
+    from chemps2_b200 import fixtures
+    return fixtures.load(request.param)
+
+
+def has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False

@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Generates the golden fixtures in this directory by running the UNMODIFIED reference (oracle/_ref, built by
+oracle/build_ref.sh from /root/reference) through oracle/ref_driver.cpp.  Runs only where /root/reference exists
+(the build container); the committed .npz files are what travels.
+
+Each sigma case holds: the problem (integral table), bookkeeper dims, every renormalized operator at both boundaries
+of a site pair, vec_in / vec_out / diag straight from Heff::makeHeff / Heff::fillHeffDiag (Heff.cpp:43-315), plus the
+operator sets before/after DMRG::updateMovingLeft/Right (DMRGoperators.cpp:243-907) for the update parity tests.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from chemps2_b200.fixtures import read_b2fx  # noqa: E402
+
+ME = "/root/reference/tests/matrixelements"
+DRV = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+
+# name -> ref_driver arguments.  Systems are the reference's own test systems:
+# test1 (N2/STO-3G, D2h, several spin/irrep sectors), test2 (H2O/6-31G, C2v), test3 (CH4/STO-3G), test4 (Hubbard sextet).
+CASES = {
+    "n2_sto3g_singlet": f"--fcidump {ME}/N2.STO3G.FCIDUMP --group 7 --twoS 0 --N 14 --irrep 0 --D 24 --presweeps 1",
+    "n2_sto3g_quintet_b1u": f"--fcidump {ME}/N2.STO3G.FCIDUMP --group 7 --twoS 4 --N 14 --irrep 5 --D 32 --presweeps 0 --reorder",
+    "h2o_631g": f"--fcidump {ME}/H2O.631G.FCIDUMP --group 5 --twoS 0 --N 10 --irrep 0 --D 20 --presweeps 1",
+    "hubbard10_sextet": "--hubbard 10 4.0 --twoS 5 --N 9 --irrep 0 --D 16 --presweeps 1",
+    "ch4_sto3g_triplet_edges": f"--fcidump {ME}/CH4.STO3G.FCIDUMP --group 5 --twoS 2 --N 10 --irrep 1 --D 24 --presweeps 0 --siteA 7 --siteB 0",
+    "ch4_sto3g_near_edges": f"--fcidump {ME}/CH4.STO3G.FCIDUMP --group 5 --twoS 0 --N 10 --irrep 0 --D 24 --presweeps 0 --siteA 6 --siteB 1",
+}
+
+
+def main():
+    env = dict(os.environ, OMP_NUM_THREADS="4", OPENBLAS_NUM_THREADS="1")
+    for name, args in CASES.items():
+        tmp = f"/tmp/{name}.b2fx"
+        subprocess.run([DRV, "dump", *args.split(), "--seed", "1234", "--out", tmp], check=True, env=env, stdout=subprocess.DEVNULL)
+        fx = read_b2fx(tmp)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
+        print(name, os.path.getsize(os.path.join(HERE, name + ".npz")) // 1024, "KiB")
+    tmp = "/tmp/wigner.b2fx"
+    subprocess.run([DRV, "wigner", "--out", tmp], check=True, env=env)
+    np.savez_compressed(os.path.join(HERE, "wigner.npz"), **read_b2fx(tmp))
+
+
+if __name__ == "__main__":
+    main()

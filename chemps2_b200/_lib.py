@@ -79,11 +79,23 @@ SIGNATURES = [
     ("b2_heff_presum_size", C.c_int64, [vp]),
     ("b2_heff_export_presums", C.c_int, [vp, C.POINTER(FlatPresum)]),
     ("b2_probe_fp64", C.c_int, [vp, C.c_int, c_dp]),
+    ("b2_heff_worklists", C.c_int, [vp, vp]),
+    ("b2_ctx_set_option", C.c_int, [vp, C.c_char_p, C.c_double]),
 ]
 for _name, _res, _args in SIGNATURES:
     _f = getattr(lib, _name)
     _f.restype = _res
     _f.argtypes = _args
+
+
+class Worklists(C.Structure):
+    _fields_ = [("items1", vp), ("items2", vp), ("tiles1", vp * 4), ("tiles2", vp * 4), ("reduces", vp), ("waves", vp),
+                ("n_items1", C.c_int64), ("n_items2", C.c_int64), ("n_tiles1", C.c_int64 * 4), ("n_tiles2", C.c_int64 * 4),
+                ("n_reduces", C.c_int64), ("n_waves", C.c_int64), ("work_size", C.c_int64), ("part_size", C.c_int64)]
+
+
+lib.b2_heff_worklists.restype = C.c_int
+lib.b2_heff_worklists.argtypes = [vp, C.POINTER(Worklists)]
 
 
 class B2Error(RuntimeError):

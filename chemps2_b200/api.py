@@ -39,6 +39,9 @@ class Context:
             v = np.ascontiguousarray(vmat, dtype=np.float64)
             check(lib.b2_problem_set_integrals(self.h, L, group, N, twoS, irrep, irr.ctypes.data_as(c_ip), _dp(t), _dp(v), float(econst)))
 
+    def set_option(self, name, value):
+        check(lib.b2_ctx_set_option(self.h, name.encode(), float(value)))
+
     def set_stream(self, cuda_stream):
         check(lib.b2_ctx_set_stream(self.h, vp(int(cuda_stream))))
 
@@ -165,10 +168,11 @@ class Heff:
         return out
 
     def stats(self):
-        o = np.zeros(8)
+        o = np.zeros(12)
         check(lib.b2_heff_stats(self.h, _dp(o)))
-        keys = ["terms", "terms_zero", "presums", "flops_ref", "flops_exec", "work_doubles", "stage1", "tiles"]
-        return dict(zip(keys, o))
+        keys = ["terms", "terms_zero", "presums", "flops_ref", "flops_exec", "work_doubles", "stage1", "tiles", "waves", "launches",
+                "part_doubles", "worklist_bytes"]
+        return {k: float(v) for k, v in zip(keys, o)}
 
     def export(self):
         nt = lib.b2_heff_num_terms(self.h)

@@ -40,6 +40,7 @@ struct b2_ctx {
    Problem prob;
    Bookkeeper bk;
    bool have_problem = false, have_bk = false;
+   CompileOptions copt;
 };
 
 struct b2_opset {
@@ -56,7 +57,9 @@ struct b2_heff {
    SigmaPlan plan;
    CompiledSigma comp;
    // device copies
-   GemmItem* d_items = nullptr;
+   GemmItem *d_items1 = nullptr, *d_items2 = nullptr;
+   ReduceJob* d_reduces = nullptr;
+   double* d_part = nullptr;
    Tile* d_tiles1[kNumTileClasses] = {nullptr, nullptr, nullptr, nullptr};
    Tile* d_tiles2[kNumTileClasses] = {nullptr, nullptr, nullptr, nullptr};
    PresumJob* d_jobs = nullptr;
@@ -65,6 +68,7 @@ struct b2_heff {
    double *h_vin = nullptr, *h_vout = nullptr;   // pinned staging
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
    double last_kernel_s = 0.0;
+   long long launches = 0;
 };
 
 template <class T> static int upload_vec(T** dptr, const std::vector<T>& v, cudaStream_t s) {
@@ -82,6 +86,7 @@ static DevBases bases_of(const b2_heff* h, const double* vin, double* vout) {
    b.p[SP_RIGHT] = h->right ? h->right->dev : nullptr;
    b.p[SP_PRESUM] = h->d_presum;
    b.p[SP_WORK] = h->d_work;
+   b.p[SP_PART] = h->d_part;
    b.p[SP_VIN] = const_cast<double*>(vin);
    b.p[SP_VOUT] = vout;
    return b;
@@ -295,12 +300,15 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
    h->left = (site > 0) ? left : nullptr;
    h->right = (site < L - 2) ? right : nullptr;
    build_sigma_plan(h->plan, ctx->bk, ctx->prob, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, site, world);
-   compile_sigma(h->comp, h->plan, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, rank, world);
+   compile_sigma(h->comp, h->plan, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, rank, world, ctx->copt);
    if (ctx->device >= 0) {
       CUDA_TRY(cudaSetDevice(ctx->device));
       cudaStream_t s = ctx->stream;
       int rc;
-      if ((rc = upload_vec(&h->d_items, h->comp.items, s))) return rc;
+      if ((rc = upload_vec(&h->d_items1, h->comp.items1, s))) return rc;
+      if ((rc = upload_vec(&h->d_items2, h->comp.items2, s))) return rc;
+      if ((rc = upload_vec(&h->d_reduces, h->comp.reduces, s))) return rc;
+      if (h->comp.part_size > 0) CUDA_TRY(cudaMalloc(&h->d_part, sizeof(double) * (size_t)h->comp.part_size));
       for (int c = 0; c < kNumTileClasses; c++) {
          if ((rc = upload_vec(&h->d_tiles1[c], h->comp.tiles1[c], s))) return rc;
          if ((rc = upload_vec(&h->d_tiles2[c], h->comp.tiles2[c], s))) return rc;
@@ -327,7 +335,7 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
 
 void b2_heff_destroy(b2_heff* h) {
    if (!h) return;
-   cudaFree(h->d_items);
+   cudaFree(h->d_items1); cudaFree(h->d_items2); cudaFree(h->d_reduces); cudaFree(h->d_part);
    for (int c = 0; c < kNumTileClasses; c++) { cudaFree(h->d_tiles1[c]); cudaFree(h->d_tiles2[c]); }
    cudaFree(h->d_jobs); cudaFree(h->d_parts); cudaFree(h->d_presum); cudaFree(h->d_work); cudaFree(h->d_vin); cudaFree(h->d_vout);
    if (h->h_vin) cudaFreeHost(h->h_vin);
@@ -345,10 +353,15 @@ int b2_heff_apply_device(b2_heff* h, const double* dev_in, double* dev_out) {
    cudaStream_t s = h->ctx->stream;
    DevBases b = bases_of(h, dev_in, dev_out);
    CUDA_TRY(cudaEventRecord(h->ev0, s));
-   for (int c = 0; c < kNumTileClasses; c++)
-      if (dev_launch_tiles(c, h->d_tiles1[c], (int)h->comp.tiles1[c].size(), h->d_items, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
-   for (int c = 0; c < kNumTileClasses; c++)
-      if (dev_launch_tiles(c, h->d_tiles2[c], (int)h->comp.tiles2[c].size(), h->d_items, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+   if (dev_fill_zero(dev_out, h->plan.S.size, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+   for (const Wave& w : h->comp.waves) {
+      for (int c = 0; c < kNumTileClasses; c++)
+         if (dev_launch_tiles(c, h->d_tiles1[c] + w.t1_begin[c], w.t1_end[c] - w.t1_begin[c], h->d_items1, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+      for (int c = 0; c < kNumTileClasses; c++)
+         if (dev_launch_tiles(c, h->d_tiles2[c] + w.t2_begin[c], w.t2_end[c] - w.t2_begin[c], h->d_items2, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+      if (dev_launch_reduce(h->d_reduces + w.red_begin, w.red_end - w.red_begin, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+      h->launches += 1;
+   }
    CUDA_TRY(cudaEventRecord(h->ev1, s));
    return B2_OK;
 }
@@ -390,6 +403,16 @@ int b2_heff_stats(const b2_heff* h, double* o) {
    if (!h || !o) return fail(B2_ERR_ARG, "b2_heff_stats: NULL");
    o[0] = (double)h->plan.terms.size(); o[1] = (double)h->plan.skipped_zero; o[2] = (double)h->plan.presums.size();
    o[3] = h->plan.flops_ref; o[4] = h->comp.flops_exec; o[5] = (double)h->comp.work_size; o[6] = (double)h->comp.n_stage1; o[7] = (double)h->comp.n_tiles;
+   o[8] = (double)h->comp.waves.size();
+   double launches = 1.0, bytes = 0.0;
+   for (const Wave& w : h->comp.waves) {
+      for (int c = 0; c < kNumTileClasses; c++) launches += (w.t1_end[c] > w.t1_begin[c]) + (w.t2_end[c] > w.t2_begin[c]);
+      launches += (w.red_end > w.red_begin);
+   }
+   o[9] = launches; o[10] = (double)h->comp.part_size;
+   bytes += sizeof(GemmItem) * (double)(h->comp.items1.size() + h->comp.items2.size()) + sizeof(ReduceJob) * (double)h->comp.reduces.size();
+   for (int c = 0; c < kNumTileClasses; c++) bytes += sizeof(Tile) * (double)(h->comp.tiles1[c].size() + h->comp.tiles2[c].size());
+   o[11] = bytes;
    return B2_OK;
 }
 
@@ -428,6 +451,28 @@ int b2_heff_export_presums(const b2_heff* h, b2_flat_presum* out) {
          out[n].dst_off = j.dst_off; out[n].src_off = pp.src_off; out[n].size = j.size; out[n].space = pp.space; out[n].coef = pp.coef;
          n++;
       }
+   return B2_OK;
+}
+
+int b2_heff_worklists(const b2_heff* h, b2_worklists* o) {
+   if (!h || !o) return fail(B2_ERR_ARG, "b2_heff_worklists: NULL");
+   const CompiledSigma& c = h->comp;
+   o->items1 = c.items1.data(); o->n_items1 = (int64_t)c.items1.size();
+   o->items2 = c.items2.data(); o->n_items2 = (int64_t)c.items2.size();
+   for (int k = 0; k < kNumTileClasses; k++) {
+      o->tiles1[k] = c.tiles1[k].data(); o->n_tiles1[k] = (int64_t)c.tiles1[k].size();
+      o->tiles2[k] = c.tiles2[k].data(); o->n_tiles2[k] = (int64_t)c.tiles2[k].size();
+   }
+   o->reduces = c.reduces.data(); o->n_reduces = (int64_t)c.reduces.size();
+   o->waves = c.waves.data(); o->n_waves = (int64_t)c.waves.size();
+   o->work_size = c.work_size; o->part_size = c.part_size;
+   return B2_OK;
+}
+int b2_ctx_set_option(b2_ctx* ctx, const char* name, double value) {
+   if (!ctx || !name) return fail(B2_ERR_ARG, "b2_ctx_set_option: NULL");
+   if (!std::strcmp(name, "work_budget")) { if (value < 1024) return fail(B2_ERR_ARG, "work_budget too small"); ctx->copt.work_budget = (int64_t)value; }
+   else if (!std::strcmp(name, "chunk_k")) { if (value < 8) return fail(B2_ERR_ARG, "chunk_k too small"); ctx->copt.chunk_k = (int64_t)value; }
+   else return fail(B2_ERR_ARG, "b2_ctx_set_option: unknown option %s", name);
    return B2_OK;
 }
 

@@ -6,31 +6,41 @@
 namespace b2 {
 
 // address spaces an operand can live in; resolved to base pointers at launch time
-enum Space : uint8_t { SP_NONE = 0, SP_LEFT = 1, SP_RIGHT = 2, SP_PRESUM = 3, SP_WORK = 4, SP_VIN = 5, SP_VOUT = 6, SP_COUNT = 7 };
+enum Space : uint8_t { SP_NONE = 0, SP_LEFT = 1, SP_RIGHT = 2, SP_PRESUM = 3, SP_WORK = 4, SP_VIN = 5, SP_VOUT = 6, SP_PART = 7, SP_COUNT = 8 };
 
 struct DevBases { double* p[SP_COUNT]; };
 
 enum ItemKind : uint8_t { IT_GEMM = 0, IT_AXPY = 1 };
+enum ItemFlags : uint8_t { IF_TX = 1, IF_TY = 2, IF_AXPY = 4 };
 
-// C_tile += alpha * opX(X)[M x K] * opY(Y)[K x N]     (IT_GEMM)
-// C_tile += alpha * X[M x N]                          (IT_AXPY)
-// X, Y are column-major with leading dimensions ldx, ldy; tx/ty = 1 means the stored matrix enters transposed.
+// C_tile += alpha * opX(X)[M x K] * opY(Y)[K x N]     (GEMM)
+// C_tile += alpha * X[M x N]                          (IF_AXPY)
+// X, Y are column-major with leading dimensions ldx, ldy; IF_TX / IF_TY: the stored matrix enters transposed.
 struct GemmItem {
    int64_t xoff, yoff;
-   int32_t ldx, ldy;
-   int32_t k;
-   uint8_t xs, ys, tx, ty;
    double alpha;
-   uint8_t kind, pad[7];
+   int32_t ldx, ldy, k;
+   uint8_t xs, ys, flags, pad;
 };
+static_assert(sizeof(GemmItem) == 40, "GemmItem layout");
 
-// One output tile: rows [m0, m0+mrem) x cols [n0, n0+nrem) of the column-major matrix at (cspace, coff, ldc).
-// The tile is written exactly once (no atomics, deterministic): C = sum over items[item_begin, item_end).
+// One unit of CTA work: the partial sum over items[item_begin, item_end) for rows [m0, m0+mrem) x cols [n0, n0+nrem)
+// of a target matrix.  The result goes to the column-major matrix at (cspace, coff, ldc), rows from cm0, cols from cn0:
+//   accumulate = 0:  C  = acc   (stage-1 intermediates in the workspace; split-K partial slots)
+//   accumulate = 1:  C += acc   (sigma; at most one CTA per launch touches a given sigma tile => deterministic, no atomics)
 struct Tile {
    int64_t coff;
-   int32_t ldc, m0, n0, mrem, nrem;
+   int32_t ldc, m0, n0, mrem, nrem, cm0, cn0;
    int32_t item_begin, item_end;
-   uint8_t cspace, pad[3];
+   uint8_t cspace, accumulate, pad[2];
+};
+static_assert(sizeof(Tile) == 48, "Tile layout");
+
+// sigma tile += sum_{p < nparts} partial slot p   (fixed order => deterministic)
+struct ReduceJob {
+   int64_t dst_off, part_off;
+   int32_t ldc, m0, n0, mrem, nrem, nparts;
+   int64_t part_stride;
 };
 
 // out[dst_off + e] = sum_{parts} coef * src[e]   for e < size
@@ -44,6 +54,7 @@ constexpr int kTileThreads[kNumTileClasses] = {128, 128, 32, 32};
 
 // ---- launchers implemented in b2_kernels.cu (all asynchronous on `stream`, a cudaStream_t passed as void*)
 int dev_launch_tiles(int tile_class, const Tile* d_tiles, int ntiles, const GemmItem* d_items, const DevBases& bases, void* stream);
+int dev_launch_reduce(const ReduceJob* d_jobs, int njobs, const DevBases& bases, void* stream);
 int dev_launch_presum(const PresumJob* d_jobs, int njobs, const PresumPart* d_parts, const DevBases& bases, void* stream);
 int dev_fill_zero(double* d_ptr, int64_t n, void* stream);
 // p[e] = amp * hash(seed, key, e): deterministic synthetic operator contents (bench / full-size parity vs oracle/ref_driver synth)

@@ -42,6 +42,9 @@ __global__ void __launch_bounds__(WM * WN * 32) k_tiles(const Tile* __restrict__
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
    const int wm = warp % WM, wn = warp / WM;
    const int g = lane >> 2, q = lane & 3;        // fragment coordinates
+   // 8x8 sub-tiles of this warp that lie (partly) inside the tile; the rest is skipped (warp-uniform)
+   const int mi_n = min(MI, max(0, (t.mrem - wm * WTM + 7) >> 3));
+   const int ni_n = min(NI, max(0, (t.nrem - wn * WTN + 7) >> 3));
 
    double acc[MI][NI][2];
 #pragma unroll
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(WM * WN * 32) k_tiles(const Tile* __restrict__
    for (int it = t.item_begin; it < t.item_end; it++) {
       const GemmItem I = items[it];
       const double* __restrict__ X = bases.p[I.xs] + I.xoff;
-      if (I.kind == IT_AXPY) {
+      if (I.flags & IF_AXPY) {
 #pragma unroll
          for (int i = 0; i < MI; i++)
 #pragma unroll
@@ -67,9 +70,10 @@ __global__ void __launch_bounds__(WM * WN * 32) k_tiles(const Tile* __restrict__
       }
       const double* __restrict__ Y = bases.p[I.ys] + I.yoff;
       const int K = I.k;
+      const bool tx = I.flags & IF_TX, ty = I.flags & IF_TY;
       for (int k0 = 0; k0 < K; k0 += KC) {
          // ---- stage the X panel: Xs[k][m] = alpha * opX(X)[m0+m][k0+k]
-         if (I.tx == 0) {
+         if (!tx) {
             for (int idx = tid; idx < TM * KC; idx += NT) {
                const int m = idx % TM, k = idx / TM;
                double v = 0.0;
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(WM * WN * 32) k_tiles(const Tile* __restrict__
             }
          }
          // ---- stage the Y panel: Ys[k][n] = opY(Y)[k0+k][n0+n]
-         if (I.ty == 0) {
+         if (!ty) {
             for (int idx = tid; idx < TN * KC; idx += NT) {
                const int k = idx % KC, n = idx / KC;
                double v = 0.0;
@@ -111,7 +115,8 @@ __global__ void __launch_bounds__(WM * WN * 32) k_tiles(const Tile* __restrict__
 #pragma unroll
             for (int i = 0; i < MI; i++)
 #pragma unroll
-               for (int j = 0; j < NI; j++) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+               for (int j = 0; j < NI; j++)
+                  if (i < mi_n && j < ni_n) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
          }
          __syncthreads();
       }
@@ -124,8 +129,14 @@ __global__ void __launch_bounds__(WM * WN * 32) k_tiles(const Tile* __restrict__
       for (int j = 0; j < NI; j++) {
          const int r = wm * WTM + i * 8 + g, c = wn * WTN + j * 8 + 2 * q;
          if (r < t.mrem) {
-            if (c < t.nrem) C[(size_t)(t.m0 + r) + (size_t)(t.n0 + c) * t.ldc] = acc[i][j][0];
-            if (c + 1 < t.nrem) C[(size_t)(t.m0 + r) + (size_t)(t.n0 + c + 1) * t.ldc] = acc[i][j][1];
+            double* p0 = C + (size_t)(t.cm0 + r) + (size_t)(t.cn0 + c) * t.ldc;
+            if (t.accumulate) {
+               if (c < t.nrem) p0[0] += acc[i][j][0];
+               if (c + 1 < t.nrem) p0[t.ldc] += acc[i][j][1];
+            } else {
+               if (c < t.nrem) p0[0] = acc[i][j][0];
+               if (c + 1 < t.nrem) p0[t.ldc] = acc[i][j][1];
+            }
          }
       }
 }
@@ -142,6 +153,28 @@ int dev_launch_tiles(int tile_class, const Tile* d_tiles, int ntiles, const Gemm
    }
    cudaError_t e = cudaGetLastError();
    if (e != cudaSuccess) return cuda_fail(e, "k_tiles launch");
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// split-K epilogue: sigma tile += partial slots, summed in slot order (deterministic)
+__global__ void k_reduce(const ReduceJob* __restrict__ jobs, DevBases bases) {
+   const ReduceJob j = jobs[blockIdx.x];
+   const double* __restrict__ part = bases.p[SP_PART] + j.part_off;
+   double* __restrict__ C = bases.p[SP_VOUT] + j.dst_off;
+   const int n = j.mrem * j.nrem;
+   for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      double v = 0.0;
+      for (int p = 0; p < j.nparts; p++) v += part[(size_t)p * j.part_stride + e];
+      const int r = e % j.mrem, c = e / j.mrem;
+      C[(size_t)(j.m0 + r) + (size_t)(j.n0 + c) * j.ldc] += v;
+   }
+}
+int dev_launch_reduce(const ReduceJob* d_jobs, int njobs, const DevBases& bases, void* stream) {
+   if (njobs <= 0) return 0;
+   k_reduce<<<njobs, 256, 0, (cudaStream_t)stream>>>(d_jobs, bases);
+   cudaError_t e = cudaGetLastError();
+   if (e != cudaSuccess) return cuda_fail(e, "k_reduce launch");
    return 0;
 }
 

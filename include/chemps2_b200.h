@@ -118,8 +118,9 @@ int b2_heff_apply(b2_heff* h, const double* vec_in, double* vec_out);
 int b2_heff_apply_device(b2_heff* h, const double* dev_in, double* dev_out);
 int b2_heff_diag(b2_heff* h, double* diag);
 /* statistics: [0] #terms, [1] #terms dropped (zero prefactor), [2] #presummed operators, [3] reference FLOPs per apply
- * (2mnk per reference dgemm_), [4] executed FLOPs per apply, [5] workspace doubles, [6] #stage-1 GEMMs, [7] #tiles */
-int b2_heff_stats(const b2_heff* h, double* out8);
+ * (2mnk per reference dgemm_), [4] executed FLOPs per apply, [5] workspace doubles, [6] #stage-1 GEMMs, [7] #CTAs,
+ * [8] #waves, [9] kernel launches per apply, [10] split-K partial doubles, [11] bytes of device work lists */
+int b2_heff_stats(const b2_heff* h, double* out12);
 /* seconds spent in the kernels of the last b2_heff_apply* call, measured with CUDA events on the launch stream */
 double b2_heff_last_kernel_seconds(const b2_heff* h);
 
@@ -148,6 +149,15 @@ int64_t b2_heff_presum_size(const b2_heff* h);
 int b2_heff_export_presums(const b2_heff* h, b2_flat_presum* out);
 /* FP64 peak probe, register resident: use_mma = 1 times DMMA (mma.sync m8n8k4 f64), 0 times DFMA; result in TFLOP/s */
 int b2_probe_fp64(b2_ctx* ctx, int use_mma, double* tflops);
+/* raw view of the compiled device work lists (structs of chemps2_b200/csrc/b2_device.h / b2_heff.h); used by the
+ * work-list emulator in oracle/ that checks the scheduling (waves, split-K, reduces) on the CPU */
+typedef struct {
+   const void *items1, *items2, *tiles1[4], *tiles2[4], *reduces, *waves;
+   int64_t n_items1, n_items2, n_tiles1[4], n_tiles2[4], n_reduces, n_waves, work_size, part_size;
+} b2_worklists;
+int b2_heff_worklists(const b2_heff* h, b2_worklists* out);
+/* scheduling knobs of plans created afterwards: "work_budget" (doubles of stage-1 workspace per wave), "chunk_k" */
+int b2_ctx_set_option(b2_ctx* ctx, const char* name, double value);
 /* host mirrors of the operator arenas (valid until the set is destroyed) */
 const double* b2_opset_host_arena(const b2_opset* set);
 int64_t b2_opset_arena_size(const b2_opset* set);

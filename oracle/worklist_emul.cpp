@@ -1,0 +1,71 @@
+/* TEST INFRASTRUCTURE ONLY — never called by the product path (there is no CPU fallback).
+ *
+ * Executes the compiled device work lists (stage-1 tiles, stage-2 tiles, split-K reduce jobs, wave by wave) with plain
+ * loops, following exactly the semantics documented in chemps2_b200/csrc/b2_device.h.  It lets the CPU test-suite check
+ * the scheduler of b2_heff.cpp (waves, workspace reuse, split-K, deduplicated intermediates) against the reference's
+ * golden sigma vectors without a GPU.  The arithmetic being scheduled is Heff::makeHeff's (Heff.cpp:43-248).
+ */
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../chemps2_b200/csrc/b2_heff.h"
+#include "../include/chemps2_b200.h"
+
+using namespace b2;
+
+static void run_tile(const Tile& t, const GemmItem* items, double* const* base) {
+   std::vector<double> acc((size_t)t.mrem * t.nrem, 0.0);
+   for (int it = t.item_begin; it < t.item_end; it++) {
+      const GemmItem& I = items[it];
+      const double* X = base[I.xs] + I.xoff;
+      if (I.flags & IF_AXPY) {
+         for (int c = 0; c < t.nrem; c++)
+            for (int r = 0; r < t.mrem; r++) acc[r + (size_t)t.mrem * c] += I.alpha * X[(size_t)(t.m0 + r) + (size_t)(t.n0 + c) * I.ldx];
+         continue;
+      }
+      const double* Y = base[I.ys] + I.yoff;
+      for (int c = 0; c < t.nrem; c++)
+         for (int r = 0; r < t.mrem; r++) {
+            double s = 0.0;
+            for (int k = 0; k < I.k; k++) {
+               const double x = (I.flags & IF_TX) ? X[(size_t)k + (size_t)(t.m0 + r) * I.ldx] : X[(size_t)(t.m0 + r) + (size_t)k * I.ldx];
+               const double y = (I.flags & IF_TY) ? Y[(size_t)(t.n0 + c) + (size_t)k * I.ldy] : Y[(size_t)k + (size_t)(t.n0 + c) * I.ldy];
+               s += x * y;
+            }
+            acc[r + (size_t)t.mrem * c] += I.alpha * s;
+         }
+   }
+   double* C = base[t.cspace] + t.coff;
+   for (int c = 0; c < t.nrem; c++)
+      for (int r = 0; r < t.mrem; r++) {
+         double* p = C + (size_t)(t.cm0 + r) + (size_t)(t.cn0 + c) * t.ldc;
+         if (t.accumulate) *p += acc[r + (size_t)t.mrem * c]; else *p = acc[r + (size_t)t.mrem * c];
+      }
+}
+
+extern "C" void b2o_run_worklists(const b2_worklists* wl, const double* left, const double* right, const double* presum, const double* vin,
+                                  double* vout, int64_t veclength) {
+   std::vector<double> work((size_t)wl->work_size + 1, 0.0), part((size_t)wl->part_size + 1, 0.0);
+   double* base[SP_COUNT] = {nullptr, const_cast<double*>(left), const_cast<double*>(right), const_cast<double*>(presum), work.data(),
+                             const_cast<double*>(vin), vout, part.data()};
+   std::memset(vout, 0, sizeof(double) * (size_t)veclength);
+   const Wave* waves = (const Wave*)wl->waves;
+   for (int64_t w = 0; w < wl->n_waves; w++) {
+      const Wave& W = waves[w];
+      std::fill(work.begin(), work.end(), 1e300);   // poison: a wave must not read intermediates of an earlier wave
+      std::fill(part.begin(), part.end(), 1e300);
+      for (int c = 0; c < kNumTileClasses; c++)
+         for (int i = W.t1_begin[c]; i < W.t1_end[c]; i++) run_tile(((const Tile*)wl->tiles1[c])[i], (const GemmItem*)wl->items1, base);
+      for (int c = 0; c < kNumTileClasses; c++)
+         for (int i = W.t2_begin[c]; i < W.t2_end[c]; i++) run_tile(((const Tile*)wl->tiles2[c])[i], (const GemmItem*)wl->items2, base);
+      for (int i = W.red_begin; i < W.red_end; i++) {
+         const ReduceJob& j = ((const ReduceJob*)wl->reduces)[i];
+         for (int e = 0; e < j.mrem * j.nrem; e++) {
+            double v = 0.0;
+            for (int p = 0; p < j.nparts; p++) v += part[(size_t)j.part_off + (size_t)p * j.part_stride + e];
+            vout[(size_t)j.dst_off + (size_t)(j.m0 + e % j.mrem) + (size_t)(j.n0 + e / j.mrem) * j.ldc] += v;
+         }
+      }
+   }
+}

@@ -26,9 +26,11 @@ def _dp(a):
     return a.ctypes.data_as(c_dp)
 
 
-def build_case(fx, tag, device=-1, world=1, rank=0):
+def build_case(fx, tag, device=-1, world=1, rank=0, options=None):
     """-> (ctx, left, right, heff) for fixture section `tag`"""
     ctx = api.context_from_fixture(fx, tag, device)
+    for name, value in (options or {}).items():
+        ctx.set_option(name, value)
     site = int(fx[tag + "/hdr"][0])
     L = ctx.L
     left = right = None
@@ -71,3 +73,21 @@ def cpu_apply(ctx, left, right, heff, vec, world=1, rank=0):
 
 def _site_of(heff):
     return heff._site
+
+
+def emulate_worklists(ctx, left, right, heff, vec):
+    """sigma via the work-list emulator (oracle/worklist_emul.cpp): executes the compiled device lists on the CPU"""
+    from chemps2_b200._lib import Worklists, check, lib
+    o = oracle_lib()
+    o.b2o_run_worklists.argtypes = [C.POINTER(Worklists), c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int64]
+    wl = Worklists()
+    check(lib.b2_heff_worklists(heff.h, C.byref(wl)))
+    terms, nt, parts, npp, psize = heff.export()
+    la = left.host_arena() if left else np.zeros(1)
+    ra = right.host_arena() if right else np.zeros(1)
+    presum = np.zeros(max(psize, 1))
+    o.b2o_presum(parts, npp, _dp(la), _dp(ra), _dp(presum), psize)
+    vin = np.ascontiguousarray(vec, dtype=np.float64)
+    vout = np.zeros_like(vin)
+    o.b2o_run_worklists(C.byref(wl), _dp(la), _dp(ra), _dp(presum), _dp(vin), _dp(vout), vin.size)
+    return vout

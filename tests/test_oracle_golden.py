@@ -101,6 +101,21 @@ def test_sigma_plan_owner_sharding(golden, world):
     assert np.abs(tot - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("options", [{}, {"work_budget": 2048, "chunk_k": 64}, {"work_budget": 50000, "chunk_k": 16}],
+                         ids=["default", "tiny-waves", "tiny-chunks"])
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_compiled_worklists_vs_reference(golden, tag, options):
+    """the device work lists (waves, split-K chunks, reduces, shared intermediates) executed by the CPU emulator
+    reproduce Heff::makeHeff — checks the scheduler of b2_heff.cpp without a GPU"""
+    ctx, left, right, heff = cpu_check.build_case(golden, tag, options=options)
+    vin, ref = golden[f"{tag}/rnd_in"], golden[f"{tag}/rnd_out"]
+    out = cpu_check.emulate_worklists(ctx, left, right, heff, vin)
+    assert np.abs(out - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+    st = heff.stats()
+    if options.get("work_budget", 1e9) < 10000 and st["terms"] > 500:
+        assert st["waves"] > 1
+
+
 def test_no_device_is_loud(golden):
     """planning-only context: compute entry points fail with B2_ERR_NO_DEVICE instead of falling back to the CPU"""
     ctx, left, right, heff = cpu_check.build_case(golden, "A")

@@ -204,7 +204,6 @@ int b2_opset_create(b2_ctx* ctx, int boundary, int moving_right, b2_opset** out)
    std::unique_ptr<b2_opset> s(new b2_opset);
    s->ctx = ctx;
    s->set.build_all(ctx->bk, boundary, moving_right != 0);
-   if (ctx->device < 0) s->ensure_host();
    if (ctx->device >= 0 && s->set.size > 0) {
       CUDA_TRY(cudaSetDevice(ctx->device));
       CUDA_TRY(cudaMalloc(&s->dev, sizeof(double) * (size_t)s->set.size));

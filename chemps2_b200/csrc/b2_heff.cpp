@@ -215,6 +215,11 @@ void compile_sigma(CompiledSigma& out, const SigmaPlan& plan, const OpSet* left,
          }
    };
 
+   // block-axpy terms first inside every target block: the kernel consumes them before it starts its GEMM pipeline
+   for (int k = 0; k < nk; k++)
+      std::stable_partition(order.begin() + cnt[k], order.begin() + cnt[k + 1],
+                            [&](int ti) { return plan.terms[ti].l.src == SRC_NONE && plan.terms[ti].r.src == SRC_NONE; });
+
    open_wave();
    for (int k = 0; k < nk; k++) {
       const Block& db = S.blk[k];

@@ -27,16 +27,57 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-constexpr int KC = 8;   // k-chunk staged per shared-memory panel
+constexpr int KC = 16;       // k-chunk staged per pipeline stage
+constexpr int STAGES = 3;    // cp.async pipeline depth
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
+   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+   const int bytes = valid ? 8 : 0;   // src-size 0 => the 8 destination bytes are zero-filled
+   asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// Shared-memory operand panels keep the operand's own contiguous direction (so global reads stay coalesced whatever
+// the transposition flag) and are padded so that the 64-bit DMMA fragment loads of a half-warp hit 16 distinct bank pairs:
+//   "m-major"  P[k][m], stride T+4   (T = 64/32/16/8: stride == 4 mod 8 doubles)
+//   "k-major"  P[m][k], stride KC+4  (20 doubles)
+template <int T> struct Panel {
+   static constexpr int SM = T + 4, SK = KC + 4;
+   static constexpr int SIZE = (KC * SM > T * SK) ? KC * SM : T * SK;
+};
+
+// Stage one k-chunk of op(M)[r0 + r][k0 + k], r < T, k < KC, of a column-major matrix with leading dimension ld.
+//   contig_r = true : the stored matrix is R x K (rows contiguous)   -> m-major panel
+//   contig_r = false: the stored matrix is K x R (k contiguous)      -> k-major panel
+template <int T, int NT>
+__device__ __forceinline__ void stage_panel(double* P, const double* __restrict__ G, int ld, bool contig_r, int r0, int rrem, int k0, int K, int tid) {
+   if (contig_r) {
+#pragma unroll
+      for (int idx = tid; idx < T * KC; idx += NT) {
+         const int r = idx % T, k = idx / T;
+         const bool ok = (r < rrem) && (k0 + k < K);
+         cp_async8(P + k * Panel<T>::SM + r, ok ? G + (size_t)(r0 + r) + (size_t)(k0 + k) * ld : G, ok);
+      }
+   } else {
+#pragma unroll
+      for (int idx = tid; idx < T * KC; idx += NT) {
+         const int k = idx % KC, r = idx / KC;
+         const bool ok = (r < rrem) && (k0 + k < K);
+         cp_async8(P + r * Panel<T>::SK + k, ok ? G + (size_t)(k0 + k) + (size_t)(r0 + r) * ld : G, ok);
+      }
+   }
+}
 
 template <int TM, int TN, int WM, int WN>
 __global__ void __launch_bounds__(WM * WN * 32) k_tiles(const Tile* __restrict__ tiles, const GemmItem* __restrict__ items, DevBases bases) {
    constexpr int NT = WM * WN * 32;
    constexpr int WTM = TM / WM, WTN = TN / WN;   // warp tile
    constexpr int MI = WTM / 8, NI = WTN / 8;     // 8x8 MMA tiles per warp
-   constexpr int SX = TM + 4, SY = TN + 4;       // strides == 4 (mod 16) doubles: conflict-free half-warp fragment loads
-   __shared__ double Xs[KC * SX];
-   __shared__ double Ys[KC * SY];
+   constexpr int XSZ = Panel<TM>::SIZE, YSZ = Panel<TN>::SIZE;
+   extern __shared__ double smem[];
+   double* Xs = smem;                    // STAGES panels
+   double* Ys = smem + STAGES * XSZ;
 
    const Tile t = tiles[blockIdx.x];
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -52,75 +93,84 @@ __global__ void __launch_bounds__(WM * WN * 32) k_tiles(const Tile* __restrict__
 #pragma unroll
       for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-   for (int it = t.item_begin; it < t.item_end; it++) {
-      const GemmItem I = items[it];
+   // ---- block-axpy items come first in every item range (b2_heff.cpp sorts them there)
+   int it0 = t.item_begin;
+   for (; it0 < t.item_end; it0++) {
+      const GemmItem I = items[it0];
+      if (!(I.flags & IF_AXPY)) break;
       const double* __restrict__ X = bases.p[I.xs] + I.xoff;
-      if (I.flags & IF_AXPY) {
 #pragma unroll
-         for (int i = 0; i < MI; i++)
+      for (int i = 0; i < MI; i++)
 #pragma unroll
-            for (int j = 0; j < NI; j++) {
-               const int r = wm * WTM + i * 8 + g, c = wn * WTN + j * 8 + 2 * q;
-               if (r < t.mrem) {
-                  if (c < t.nrem) acc[i][j][0] += I.alpha * X[(size_t)(t.m0 + r) + (size_t)(t.n0 + c) * I.ldx];
-                  if (c + 1 < t.nrem) acc[i][j][1] += I.alpha * X[(size_t)(t.m0 + r) + (size_t)(t.n0 + c + 1) * I.ldx];
-               }
+         for (int j = 0; j < NI; j++) {
+            const int r = wm * WTM + i * 8 + g, c = wn * WTN + j * 8 + 2 * q;
+            if (r < t.mrem) {
+               if (c < t.nrem) acc[i][j][0] += I.alpha * X[(size_t)(t.m0 + r) + (size_t)(t.n0 + c) * I.ldx];
+               if (c + 1 < t.nrem) acc[i][j][1] += I.alpha * X[(size_t)(t.m0 + r) + (size_t)(t.n0 + c + 1) * I.ldx];
             }
-         continue;
+         }
+   }
+
+   // ---- GEMM items: one flattened stream of k-chunks over all items, software-pipelined with cp.async
+   int p_it = it0, p_k0 = 0;            // producer cursor
+   GemmItem P;
+   if (p_it < t.item_end) P = items[p_it];
+   auto issue = [&](int stage) {
+      if (p_it < t.item_end) {
+         stage_panel<TM, NT>(Xs + stage * XSZ, bases.p[P.xs] + P.xoff, P.ldx, !(P.flags & IF_TX), t.m0, t.mrem, p_k0, P.k, tid);
+         stage_panel<TN, NT>(Ys + stage * YSZ, bases.p[P.ys] + P.yoff, P.ldy, (P.flags & IF_TY) != 0, t.n0, t.nrem, p_k0, P.k, tid);
+         p_k0 += KC;
+         if (p_k0 >= P.k) {
+            p_k0 = 0;
+            if (++p_it < t.item_end) P = items[p_it];
+         }
       }
-      const double* __restrict__ Y = bases.p[I.ys] + I.yoff;
-      const int K = I.k;
-      const bool tx = I.flags & IF_TX, ty = I.flags & IF_TY;
-      for (int k0 = 0; k0 < K; k0 += KC) {
-         // ---- stage the X panel: Xs[k][m] = alpha * opX(X)[m0+m][k0+k]
-         if (!tx) {
-            for (int idx = tid; idx < TM * KC; idx += NT) {
-               const int m = idx % TM, k = idx / TM;
-               double v = 0.0;
-               if (m < t.mrem && k0 + k < K) v = I.alpha * X[(size_t)(t.m0 + m) + (size_t)(k0 + k) * I.ldx];
-               Xs[k * SX + m] = v;
-            }
-         } else {
-            for (int idx = tid; idx < TM * KC; idx += NT) {
-               const int k = idx % KC, m = idx / KC;
-               double v = 0.0;
-               if (m < t.mrem && k0 + k < K) v = I.alpha * X[(size_t)(k0 + k) + (size_t)(t.m0 + m) * I.ldx];
-               Xs[k * SX + m] = v;
-            }
-         }
-         // ---- stage the Y panel: Ys[k][n] = opY(Y)[k0+k][n0+n]
-         if (!ty) {
-            for (int idx = tid; idx < TN * KC; idx += NT) {
-               const int k = idx % KC, n = idx / KC;
-               double v = 0.0;
-               if (n < t.nrem && k0 + k < K) v = Y[(size_t)(k0 + k) + (size_t)(t.n0 + n) * I.ldy];
-               Ys[k * SY + n] = v;
-            }
-         } else {
-            for (int idx = tid; idx < TN * KC; idx += NT) {
-               const int n = idx % TN, k = idx / TN;
-               double v = 0.0;
-               if (n < t.nrem && k0 + k < K) v = Y[(size_t)(t.n0 + n) + (size_t)(k0 + k) * I.ldy];
-               Ys[k * SY + n] = v;
-            }
-         }
-         __syncthreads();
+      cp_async_commit();
+   };
 #pragma unroll
-         for (int kk = 0; kk < KC; kk += 4) {
+   for (int s = 0; s < STAGES - 1; s++) issue(s);
+
+   int c_it = it0, c_k0 = 0, stage = 0;
+   GemmItem Cn;
+   if (c_it < t.item_end) Cn = items[c_it];
+   while (c_it < t.item_end) {
+      cp_async_wait<STAGES - 2>();
+      __syncthreads();
+      issue((stage + STAGES - 1) % STAGES);   // refills the stage consumed in the previous iteration
+      const double* xs = Xs + stage * XSZ;
+      const double* ys = Ys + stage * YSZ;
+      const bool xm = !(Cn.flags & IF_TX), ym = (Cn.flags & IF_TY) != 0;   // m-major panels?
+      const int kvalid = min(KC, Cn.k - c_k0);
+      const double alpha = Cn.alpha;
+#pragma unroll
+      for (int kk = 0; kk < KC; kk += 4) {
+         if (kk < kvalid) {
             double a[MI], b[NI];
 #pragma unroll
-            for (int i = 0; i < MI; i++) a[i] = Xs[(kk + q) * SX + wm * WTM + i * 8 + g];
+            for (int i = 0; i < MI; i++) {
+               const int r = wm * WTM + i * 8 + g;
+               a[i] = alpha * (xm ? xs[(kk + q) * Panel<TM>::SM + r] : xs[r * Panel<TM>::SK + kk + q]);
+            }
 #pragma unroll
-            for (int j = 0; j < NI; j++) b[j] = Ys[(kk + q) * SY + wn * WTN + j * 8 + g];
+            for (int j = 0; j < NI; j++) {
+               const int c = wn * WTN + j * 8 + g;
+               b[j] = ym ? ys[(kk + q) * Panel<TN>::SM + c] : ys[c * Panel<TN>::SK + kk + q];
+            }
 #pragma unroll
             for (int i = 0; i < MI; i++)
 #pragma unroll
                for (int j = 0; j < NI; j++)
                   if (i < mi_n && j < ni_n) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
          }
-         __syncthreads();
       }
+      c_k0 += KC;
+      if (c_k0 >= Cn.k) {
+         c_k0 = 0;
+         if (++c_it < t.item_end) Cn = items[c_it];
+      }
+      stage = (stage + 1) % STAGES;
    }
+   cp_async_wait<0>();
 
    double* __restrict__ C = bases.p[t.cspace] + t.coff;
 #pragma unroll
@@ -141,17 +191,30 @@ __global__ void __launch_bounds__(WM * WN * 32) k_tiles(const Tile* __restrict__
       }
 }
 
+template <int TM, int TN, int WM, int WN>
+static cudaError_t launch_tiles_t(const Tile* d_tiles, int ntiles, const GemmItem* d_items, const DevBases& bases, cudaStream_t s) {
+   constexpr size_t smem = sizeof(double) * STAGES * (Panel<TM>::SIZE + Panel<TN>::SIZE);
+   static bool configured = false;
+   if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(k_tiles<TM, TN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      configured = true;
+   }
+   k_tiles<TM, TN, WM, WN><<<ntiles, WM * WN * 32, smem, s>>>(d_tiles, d_items, bases);
+   return cudaGetLastError();
+}
+
 int dev_launch_tiles(int tile_class, const Tile* d_tiles, int ntiles, const GemmItem* d_items, const DevBases& bases, void* stream) {
    if (ntiles <= 0) return 0;
    cudaStream_t s = (cudaStream_t)stream;
+   cudaError_t e;
    switch (tile_class) {
-      case 0: k_tiles<64, 64, 2, 2><<<ntiles, 128, 0, s>>>(d_tiles, d_items, bases); break;
-      case 1: k_tiles<32, 32, 2, 2><<<ntiles, 128, 0, s>>>(d_tiles, d_items, bases); break;
-      case 2: k_tiles<16, 16, 1, 1><<<ntiles, 32, 0, s>>>(d_tiles, d_items, bases); break;
-      case 3: k_tiles<8, 8, 1, 1><<<ntiles, 32, 0, s>>>(d_tiles, d_items, bases); break;
+      case 0: e = launch_tiles_t<64, 64, 2, 2>(d_tiles, ntiles, d_items, bases, s); break;
+      case 1: e = launch_tiles_t<32, 32, 2, 2>(d_tiles, ntiles, d_items, bases, s); break;
+      case 2: e = launch_tiles_t<16, 16, 1, 1>(d_tiles, ntiles, d_items, bases, s); break;
+      case 3: e = launch_tiles_t<8, 8, 1, 1>(d_tiles, ntiles, d_items, bases, s); break;
       default: snprintf(g_dev_err, sizeof(g_dev_err), "bad tile class %d", tile_class); return -1;
    }
-   cudaError_t e = cudaGetLastError();
    if (e != cudaSuccess) return cuda_fail(e, "k_tiles launch");
    return 0;
 }

@@ -65,6 +65,51 @@ class Workload:
         ctx.bk_init(self.D)
         return ctx
 
+    def sector_rows(self, ctx):
+        """[(boundary, N, twoS, irrep, fcidim)] for every sector of the bookkeeper"""
+        from ._lib import lib
+        rows = []
+        nirr = {0: 1, 1: 2, 2: 2, 3: 2, 4: 4, 5: 4, 6: 4, 7: 8}[self.group]
+        for b in range(self.L + 1):
+            for n in range(lib.b2_bk_nmin(ctx.h, b), lib.b2_bk_nmax(ctx.h, b) + 1):
+                for ts in range(lib.b2_bk_twosmin(ctx.h, b, n), lib.b2_bk_twosmax(ctx.h, b, n) + 1, 2):
+                    for ir in range(nirr):
+                        rows.append((b, n, ts, ir, ctx.fcidim(b, n, ts, ir)))
+        return rows
+
+    def apply_distribution(self, ctx, dist="flat", sigma_n=1.6, sigma_s=1.3):
+        """Virtual-dimension distribution over the symmetry sectors of every boundary.
+        'flat'  = SyBookkeeper's initial FCI-scaled distribution (what the reference starts its first sweep with);
+        'gauss' = model of a converged state: dims ~ D * exp(-(N-Nbar)^2/2sn^2 - S^2/2ss^2), capped by the FCI dims
+                  (O(50) populated sectors with leading dims of 0.05-0.1 D).
+        -> int32 array (n,5) of (boundary, N, twoS, irrep, dim) actually set"""
+        rows = self.sector_rows(ctx)
+        out = []
+        if dist == "flat":
+            for b, n, ts, ir, fci in rows:
+                out.append((b, n, ts, ir, ctx.dim(b, n, ts, ir)))
+            return np.array(out, dtype=np.int32)
+        assert dist == "gauss", dist
+        by_b = {}
+        for r in rows:
+            by_b.setdefault(r[0], []).append(r)
+        for b, lst in by_b.items():
+            nbar = self.N * b / self.L
+            fsum = {}
+            for _, n, ts, ir, fci in lst:
+                fsum[(n, ts)] = fsum.get((n, ts), 0) + fci
+            raw = np.array([np.exp(-(n - nbar) ** 2 / (2 * sigma_n ** 2) - (ts / 2.0) ** 2 / (2 * sigma_s ** 2)) * (fci / fsum[(n, ts)] if fci else 0.0)
+                            for _, n, ts, ir, fci in lst])
+            tot = raw.sum()
+            for (bb, n, ts, ir, fci), w in zip(lst, raw):
+                d = int(min(fci, np.floor(self.D * w / tot + 0.5))) if tot > 0 else 0
+                if b == 0 or b == self.L:
+                    d = min(fci, 1)
+                out.append((bb, n, ts, ir, d))
+        arr = np.array(out, dtype=np.int32)
+        ctx.bk_import(np.concatenate([arr, np.zeros((len(arr), 1), dtype=np.int32)], axis=1))
+        return arr
+
     def write_problem_file(self, path):
         """binary problem file read by `ref_driver synth`"""
         t, v = self.integrals()
@@ -100,7 +145,7 @@ def get(name, D=None, site=None):
     return w
 
 
-def run_reference_synth(w, seed, reps=1, amp=1.0, threads=None, out_path=None, workdir="/tmp"):
+def run_reference_synth(w, seed, reps=1, amp=1.0, threads=None, out_path=None, workdir="/tmp", dims=None):
     """Runs the UNMODIFIED reference's Heff::makeHeff (oracle/_ref/ref_driver synth) on workload `w` with hash-filled
     operators.  Test / bench-baseline infrastructure only.  -> dict(mean_s, best_s, threads, veclength, vec_out, diag)"""
     if not os.path.exists(REF_DRIVER):
@@ -112,12 +157,19 @@ def run_reference_synth(w, seed, reps=1, amp=1.0, threads=None, out_path=None, w
     env["OMP_NUM_THREADS"] = str(threads or os.cpu_count())
     cmd = [REF_DRIVER, "synth", "--problem", pfile, "--D", str(w.D), "--site", str(w.site), "--reps", str(reps), "--seed", str(seed),
            "--amp", repr(amp), "--out", ofile]
+    dfile = None
+    if dims is not None:
+        dfile = os.path.join(workdir, f"b2_dims_{w.name}_{os.getpid()}.bin")
+        np.ascontiguousarray(dims, dtype="<i4").tofile(dfile)
+        cmd += ["--dims", dfile]
     res = subprocess.run(cmd, env=env, check=True, capture_output=True, text=True)
     line = [ln for ln in res.stdout.splitlines() if ln.startswith("B2REF synth")][-1].split()
     kv = {line[i]: line[i + 1] for i in range(2, len(line) - 1, 2)}
     raw = np.fromfile(ofile, dtype="<f8")
     n = int(kv["veclength"])
     os.remove(pfile)
+    if dfile:
+        os.remove(dfile)
     if out_path is None:
         os.remove(ofile)
     return dict(mean_s=float(kv["mean_s"]), best_s=float(kv["best_s"]), diag_s=float(kv["diag_s"]), setup_s=float(kv["setup_s"]),

@@ -43,6 +43,7 @@ SIGNATURES = [
     ("b2_problem_mx", C.c_int, [vp, c_dp]),
     ("b2_wigner6j", C.c_double, [C.c_int] * 6),
     ("b2_wigner9j", C.c_double, [C.c_int] * 9),
+    ("b2_small_symmetric_eig", C.c_int, [C.c_int, c_dp, c_dp, c_dp]),
     ("b2_bk_init", C.c_int, [vp, C.c_int]),
     ("b2_bk_set_dim", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("b2_bk_dim", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -72,6 +73,10 @@ SIGNATURES = [
     ("b2_heff_apply_device", C.c_int, [vp, vp, vp]),
     ("b2_heff_diag", C.c_int, [vp, c_dp]),
     ("b2_heff_stats", C.c_int, [vp, c_dp]),
+    ("b2_heff_diag_device", C.c_int, [vp, vp]),
+    ("b2_heff_solve", C.c_int, [vp, c_dp, C.c_double, c_dp, c_ip]),
+    ("b2_heff_solve_device", C.c_int, [vp, vp, C.c_double, c_dp, c_ip]),
+    ("b2_heff_set_allreduce", C.c_int, [vp, vp, vp]),
     ("b2_heff_last_kernel_seconds", C.c_double, [vp]),
     ("b2_heff_num_terms", C.c_int64, [vp]),
     ("b2_heff_export_terms", C.c_int, [vp, C.POINTER(FlatTerm)]),

@@ -167,6 +167,13 @@ class Heff:
         check(lib.b2_heff_diag(self.h, _dp(out)))
         return out
 
+    def solve(self, s_prog, rtol=1e-5):
+        """Heff::SolveDAVIDSON: s_prog = Sobject storage (program convention) -> (eigenvalue, solution, n_matvec)"""
+        v = np.array(s_prog, dtype=np.float64, copy=True)
+        e, nm = C.c_double(), C.c_int()
+        check(lib.b2_heff_solve(self.h, _dp(v), float(rtol), C.byref(e), C.byref(nm)))
+        return e.value, v, nm.value
+
     def stats(self):
         o = np.zeros(12)
         check(lib.b2_heff_stats(self.h, _dp(o)))

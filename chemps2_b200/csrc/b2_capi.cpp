@@ -3,6 +3,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -10,6 +11,7 @@
 
 #include "../../include/chemps2_b200.h"
 #include "b2_core.h"
+#include "b2_davidson.h"
 #include "b2_device.h"
 #include "b2_heff.h"
 #include "b2_ops.h"
@@ -59,6 +61,10 @@ struct b2_heff {
    // device copies
    GemmItem *d_items1 = nullptr, *d_items2 = nullptr;
    ReduceJob* d_reduces = nullptr;
+   DiagItem* d_diag_items = nullptr;
+   DiagTile* d_diag_tiles = nullptr;
+   int64_t* d_blk_off = nullptr;                 // Sobject block offsets (nkappa + 1)
+   double *d_p2s = nullptr, *d_s2p = nullptr;    // sqrt(2SR+1) and its inverse per block (Sobject.cpp:624-650)
    double* d_part = nullptr;
    Tile* d_tiles1[kNumTileClasses] = {nullptr, nullptr, nullptr, nullptr};
    Tile* d_tiles2[kNumTileClasses] = {nullptr, nullptr, nullptr, nullptr};
@@ -67,6 +73,8 @@ struct b2_heff {
    double *d_presum = nullptr, *d_work = nullptr, *d_vin = nullptr, *d_vout = nullptr;
    double *h_vin = nullptr, *h_vout = nullptr;   // pinned staging
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+   b2_allreduce_fn allreduce = nullptr;          // sums partial sigma / diag vectors over the GPUs (NCCL in the caller)
+   void* allreduce_user = nullptr;
    double last_kernel_s = 0.0;
    long long launches = 0;
 };
@@ -162,6 +170,12 @@ int b2_problem_mx(const b2_ctx* ctx, double* mx_out) {
 }
 double b2_wigner6j(int a, int b, int c, int d, int e, int f) { return wigner6j(a, b, c, d, e, f); }
 double b2_wigner9j(int a, int b, int c, int d, int e, int f, int g, int h, int i) { return wigner9j(a, b, c, d, e, f, g, h, i); }
+
+int b2_small_symmetric_eig(int n, const double* a, double* eval, double* evec) {
+   if (n < 1 || n > 32 || !a || !eval || !evec) return fail(B2_ERR_ARG, "b2_small_symmetric_eig: bad arguments");
+   small_symmetric_eig(n, a, n, eval, evec);
+   return B2_OK;
+}
 
 int b2_bk_init(b2_ctx* ctx, int D) {
    if (!ctx || !ctx->have_problem) return fail(B2_ERR_STATE, "b2_bk_init: set the problem first");
@@ -307,6 +321,19 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
       if ((rc = upload_vec(&h->d_items1, h->comp.items1, s))) return rc;
       if ((rc = upload_vec(&h->d_items2, h->comp.items2, s))) return rc;
       if ((rc = upload_vec(&h->d_reduces, h->comp.reduces, s))) return rc;
+      if ((rc = upload_vec(&h->d_diag_items, h->comp.diag_items, s))) return rc;
+      if ((rc = upload_vec(&h->d_diag_tiles, h->comp.diag_tiles, s))) return rc;
+      {
+         const SLayout& S = h->plan.S;
+         std::vector<int64_t> off(S.nkappa() + 1);
+         std::vector<double> p2s(S.nkappa()), s2p(S.nkappa());
+         for (int k = 0; k < S.nkappa(); k++) { off[k] = S.blk[k].off; p2s[k] = std::sqrt(S.twoSR[k] + 1.0); s2p[k] = 1.0 / p2s[k]; }
+         off[S.nkappa()] = S.size;
+         if ((rc = upload_vec(&h->d_blk_off, off, s))) return rc;
+         if ((rc = upload_vec(&h->d_p2s, p2s, s))) return rc;
+         if ((rc = upload_vec(&h->d_s2p, s2p, s))) return rc;
+         CUDA_TRY(cudaStreamSynchronize(s));   // the staging vectors above go out of scope
+      }
       if (h->comp.part_size > 0) CUDA_TRY(cudaMalloc(&h->d_part, sizeof(double) * (size_t)h->comp.part_size));
       for (int c = 0; c < kNumTileClasses; c++) {
          if ((rc = upload_vec(&h->d_tiles1[c], h->comp.tiles1[c], s))) return rc;
@@ -334,6 +361,7 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
 
 void b2_heff_destroy(b2_heff* h) {
    if (!h) return;
+   cudaFree(h->d_diag_items); cudaFree(h->d_diag_tiles); cudaFree(h->d_blk_off); cudaFree(h->d_p2s); cudaFree(h->d_s2p);
    cudaFree(h->d_items1); cudaFree(h->d_items2); cudaFree(h->d_reduces); cudaFree(h->d_part);
    for (int c = 0; c < kNumTileClasses; c++) { cudaFree(h->d_tiles1[c]); cudaFree(h->d_tiles2[c]); }
    cudaFree(h->d_jobs); cudaFree(h->d_parts); cudaFree(h->d_presum); cudaFree(h->d_work); cudaFree(h->d_vin); cudaFree(h->d_vout);
@@ -391,10 +419,83 @@ double b2_heff_last_kernel_seconds(const b2_heff* h) {
    return ms * 1e-3;
 }
 
+int b2_heff_diag_device(b2_heff* h, double* dev_diag) {
+   if (!h || !dev_diag) return fail(B2_ERR_ARG, "b2_heff_diag_device: NULL argument");
+   if (h->ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_heff_diag: planning-only context, no CUDA device (there is no CPU fallback)");
+   cudaStream_t s = h->ctx->stream;
+   DevBases b = bases_of(h, nullptr, nullptr);
+   if (dev_fill_zero(dev_diag, h->plan.S.size, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+   if (dev_launch_diag(h->d_diag_tiles, (int)h->comp.diag_tiles.size(), h->d_diag_items, b, dev_diag, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+   return B2_OK;
+}
+
 int b2_heff_diag(b2_heff* h, double* diag) {
    if (!h || !diag) return fail(B2_ERR_ARG, "b2_heff_diag: NULL argument");
-   build_heff_diag(diag, h->plan.S, h->ctx->bk, h->ctx->prob, h->left ? &h->left->set : nullptr, h->left ? h->left->host.data() : nullptr,
-                   h->right ? &h->right->set : nullptr, h->right ? h->right->host.data() : nullptr, h->plan.site);
+   if (h->ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_heff_diag: planning-only context, no CUDA device (there is no CPU fallback)");
+   int rc = b2_heff_diag_device(h, h->d_vout);
+   if (rc) return rc;
+   const size_t bytes = sizeof(double) * (size_t)h->plan.S.size;
+   CUDA_TRY(cudaMemcpyAsync(h->h_vout, h->d_vout, bytes, cudaMemcpyDeviceToHost, h->ctx->stream));
+   CUDA_TRY(cudaStreamSynchronize(h->ctx->stream));
+   std::memcpy(diag, h->h_vout, bytes);
+   return B2_OK;
+}
+
+int b2_heff_solve_device(b2_heff* h, double* dev_s, double rtol, double* eigenvalue, int* n_matvec) {
+   if (!h || !dev_s || !eigenvalue) return fail(B2_ERR_ARG, "b2_heff_solve: NULL argument");
+   if (h->ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_heff_solve: planning-only context, no CUDA device (there is no CPU fallback)");
+   cudaStream_t s = h->ctx->stream;
+   const int64_t n = h->plan.S.size;
+   const int nk = h->plan.S.nkappa();
+   double* d_diag = nullptr;
+   CUDA_TRY(cudaMalloc(&d_diag, sizeof(double) * (size_t)(n ? n : 1)));
+   int rc = B2_OK, nm = 0;
+   char err[256] = "";
+   do {
+      if (dev_scale_blocks(dev_s, h->d_blk_off, h->d_p2s, nk, s)) { rc = fail(B2_ERR_CUDA, "prog2symm launch failed"); break; }   // Heff.cpp:345
+      if ((rc = b2_heff_diag_device(h, d_diag))) break;                                                                            // Heff.cpp:352
+      if (h->allreduce && (rc = h->allreduce(h->allreduce_user, d_diag, n, (void*)s))) { rc = fail(B2_ERR_STATE, "all-reduce callback failed"); break; }
+      DavidsonParams prm;
+      prm.rtol = rtol;
+      MatVec mv = [h](const double* in, double* out) -> int {
+         int r = b2_heff_apply_device(h, in, out);
+         if (r) return r;
+         if (h->allreduce) return h->allreduce(h->allreduce_user, out, h->plan.S.size, (void*)h->ctx->stream);
+         return 0;
+      };
+      if (davidson_solve((void*)s, n, mv, dev_s, d_diag, prm, eigenvalue, &nm, err, sizeof(err))) { rc = fail(B2_ERR_CUDA, "%s", err); break; }
+      if (dev_scale_blocks(dev_s, h->d_blk_off, h->d_s2p, nk, s)) { rc = fail(B2_ERR_CUDA, "symm2prog launch failed"); break; }   // Heff.cpp:374
+      cudaError_t e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) { rc = fail(B2_ERR_CUDA, "b2_heff_solve: %s", cudaGetErrorString(e)); break; }
+   } while (0);
+   cudaFree(d_diag);
+   if (n_matvec) *n_matvec = nm;
+   return rc;
+}
+
+int b2_heff_solve(b2_heff* h, double* s_host, double rtol, double* eigenvalue, int* n_matvec) {
+   if (!h || !s_host || !eigenvalue) return fail(B2_ERR_ARG, "b2_heff_solve: NULL argument");
+   if (h->ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_heff_solve: planning-only context, no CUDA device (there is no CPU fallback)");
+   cudaStream_t s = h->ctx->stream;
+   const size_t bytes = sizeof(double) * (size_t)h->plan.S.size;
+   double* d_s = nullptr;
+   CUDA_TRY(cudaMalloc(&d_s, bytes ? bytes : 8));
+   std::memcpy(h->h_vin, s_host, bytes);
+   cudaError_t e = cudaMemcpyAsync(d_s, h->h_vin, bytes, cudaMemcpyHostToDevice, s);
+   int rc = (e == cudaSuccess) ? b2_heff_solve_device(h, d_s, rtol, eigenvalue, n_matvec) : fail(B2_ERR_CUDA, "H2D: %s", cudaGetErrorString(e));
+   if (!rc) {
+      e = cudaMemcpyAsync(h->h_vin, d_s, bytes, cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) rc = fail(B2_ERR_CUDA, "D2H: %s", cudaGetErrorString(e));
+      else std::memcpy(s_host, h->h_vin, bytes);
+   }
+   cudaFree(d_s);
+   return rc;
+}
+
+int b2_heff_set_allreduce(b2_heff* h, b2_allreduce_fn fn, void* user) {
+   if (!h) return fail(B2_ERR_ARG, "b2_heff_set_allreduce: NULL");
+   h->allreduce = fn; h->allreduce_user = user;
    return B2_OK;
 }
 

@@ -47,6 +47,10 @@ struct ReduceJob {
 struct PresumPart { int64_t src_off; double coef; uint8_t space, pad[7]; };
 struct PresumJob { int64_t dst_off, size; int32_t part_begin, part_end; };
 
+// Diagonal of H_eff: diag[dst tile](i, j) = sum_items f * a(i) * b(j) with a(i) = A[i*(lda+1)] (or 1), b(j) likewise
+struct DiagItem { int64_t aoff, boff; double f; int32_t lda, ldb; uint8_t as, bs, pad[6]; };
+struct DiagTile { int64_t coff; int32_t ldc, m0, n0, mrem, nrem, item_begin, item_end, pad; };
+
 // tile classes: CTA tile edge and threads per CTA
 constexpr int kNumTileClasses = 4;
 constexpr int kTileEdge[kNumTileClasses] = {64, 32, 16, 8};
@@ -55,6 +59,7 @@ constexpr int kTileThreads[kNumTileClasses] = {128, 128, 32, 32};
 // ---- launchers implemented in b2_kernels.cu (all asynchronous on `stream`, a cudaStream_t passed as void*)
 int dev_launch_tiles(int tile_class, const Tile* d_tiles, int ntiles, const GemmItem* d_items, const DevBases& bases, void* stream);
 int dev_launch_reduce(const ReduceJob* d_jobs, int njobs, const DevBases& bases, void* stream);
+int dev_launch_diag(const DiagTile* d_tiles, int ntiles, const DiagItem* d_items, const DevBases& bases, double* d_out, void* stream);
 int dev_launch_presum(const PresumJob* d_jobs, int njobs, const PresumPart* d_parts, const DevBases& bases, void* stream);
 int dev_fill_zero(double* d_ptr, int64_t n, void* stream);
 // p[e] = amp * hash(seed, key, e): deterministic synthetic operator contents (bench / full-size parity vs oracle/ref_driver synth)
@@ -66,6 +71,31 @@ inline double hash_value(uint64_t seed, uint64_t key, uint64_t e) {
    z = z ^ (z >> 31);
    return (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
 }
+// ---- Davidson vector algebra (b2_blas1.cu).  All scalars stay on the device unless stated otherwise; every reduction is a
+// fixed-order two-level tree (deterministic).  `scratch` holds >= kRedScratch doubles + one counter per call site.
+constexpr int kRedBlocks = 592;                 // 4 x 148 SMs
+constexpr int kMaxVec = 32;                     // Davidson MAX_NUM_VEC (Options.h:70)
+constexpr int kRedScratch = kRedBlocks * (kMaxVec + 2) + 64;
+struct Coefs { double c[kMaxVec]; };
+// out[j] = <x, Y_j>, Y_j = ybase + j*ystride, j < m
+int dev_multi_dot(const double* x, const double* ybase, int64_t ystride, int m, int64_t n, double* out, double* scratch, void* stream);
+// y += sign * coef[0] * x   (coef on device)
+int dev_axpy_dev(double* y, const double* x, const double* coef, double sign, int64_t n, void* stream);
+// x *= 1/sqrt(ss[0])
+int dev_scale_rsqrt(double* x, const double* ss, int64_t n, void* stream);
+// u = sum_j a.c[j] V_j ; t = sum_j a.c[j] HV_j - theta*u ; out[0] = ||t||^2
+int dev_ritz_residual(double* u, double* t, const double* V, const double* HV, int64_t stride, int m, Coefs a, double theta, int64_t n,
+                      double* out, double* scratch, void* stream);
+// work = u / clamp(diag - theta) ; out[0] = <work,t>, out[1] = <work,u>     (Davidson.cpp:328-338)
+int dev_precond_dots(double* work, const double* u, const double* t, const double* diag, double theta, double cutoff, int64_t n, double* out,
+                     double* scratch, void* stream);
+// t = -(t - (out[0]/out[1]) u) / clamp(diag - theta)                          (Davidson.cpp:339-348)
+int dev_precond_apply(double* t, const double* u, const double* diag, const double* dots, double theta, double cutoff, int64_t n, void* stream);
+// out = sum_j a.c[j] V_j
+int dev_lincomb(double* out, const double* V, int64_t stride, int m, Coefs a, int64_t n, void* stream);
+// x[off_k .. off_k+len_k) *= scale_k for every block k (prog2symm / symm2prog, Sobject.cpp:624-650)
+int dev_scale_blocks(double* x, const int64_t* d_off, const double* d_scale, int nblocks, void* stream);
+
 // FP64 peak probes: returns achieved TFLOP/s of a register-resident DMMA (m8n8k4) / DFMA loop
 int dev_probe_fp64(int use_mma, double* tflops_out);
 const char* dev_last_error();

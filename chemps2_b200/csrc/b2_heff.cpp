@@ -266,6 +266,31 @@ void compile_sigma(CompiledSigma& out, const SigmaPlan& plan, const OpSet* left,
       emit_block(k, ib, (int)out.items2.size());
    }
    close_wave();
+
+   // ---- diagonal of H_eff (Heff::fillHeffDiag, Heff.cpp:250-315 + HeffDiagonal.cpp): exactly the terms that map a block
+   // onto itself — families 1A-1D, 2d3, 2b3/2c3/2e3/2f3 and 2a3 — restricted to the operator-block diagonals:
+   //    diag[k](i,j) = sum_t f_t * op(A_t)(i,i) * op(B_t)(j,j)
+   for (int k = 0; k < nk; k++) {
+      const int ib = (int)out.diag_items.size();
+      for (int oi = cnt[k]; oi < cnt[k + 1]; oi++) {
+         const SigmaTerm& t = plan.terms[order[oi]];
+         if (t.src != t.dst) continue;
+         const BlockAddr A = resolve(t.l, plan, left, right), B = resolve(t.r, plan, left, right);
+         DiagItem d{};
+         d.f = t.factor; d.as = A.space; d.aoff = A.off; d.lda = A.rows; d.bs = B.space; d.boff = B.off; d.ldb = B.rows;
+         out.diag_items.push_back(d);
+      }
+      const int ie = (int)out.diag_items.size();
+      if (ie == ib) continue;
+      const Block& db = S.blk[k];
+      for (int n0 = 0; n0 < db.cols; n0 += 32)
+         for (int m0 = 0; m0 < db.rows; m0 += 32) {
+            DiagTile t{};
+            t.coff = db.off; t.ldc = db.rows; t.m0 = m0; t.n0 = n0; t.mrem = std::min(32, db.rows - m0); t.nrem = std::min(32, db.cols - n0);
+            t.item_begin = ib; t.item_end = ie;
+            out.diag_tiles.push_back(t);
+         }
+   }
    for (int c = 0; c < kNumTileClasses; c++) out.n_tiles += (long long)out.tiles1[c].size() + (long long)out.tiles2[c].size();
 }
 

@@ -26,6 +26,8 @@ struct CompiledSigma {
    std::vector<Tile> tiles2[kNumTileClasses];   // stage 2: sigma tiles / partial slots
    std::vector<ReduceJob> reduces;
    std::vector<Wave> waves;
+   std::vector<DiagItem> diag_items;            // terms with dst == src: they are the diagonal of H_eff
+   std::vector<DiagTile> diag_tiles;
    std::vector<PresumJob> presum_jobs;
    std::vector<PresumPart> presum_parts;
    int64_t work_size = 0;                       // doubles (max over waves)

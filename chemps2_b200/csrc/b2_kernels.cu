@@ -220,24 +220,78 @@ int dev_launch_tiles(int tile_class, const Tile* d_tiles, int ntiles, const Gemm
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// split-K epilogue: sigma tile += partial slots, summed in slot order (deterministic)
-__global__ void k_reduce(const ReduceJob* __restrict__ jobs, DevBases bases) {
+// split-K epilogue: sigma tile += partial slots, summed in slot order (deterministic); one thread per tile element
+__global__ void __launch_bounds__(256) k_reduce(const ReduceJob* __restrict__ jobs, DevBases bases) {
    const ReduceJob j = jobs[blockIdx.x];
-   const double* __restrict__ part = bases.p[SP_PART] + j.part_off;
-   double* __restrict__ C = bases.p[SP_VOUT] + j.dst_off;
    const int n = j.mrem * j.nrem;
-   for (int e = threadIdx.x; e < n; e += blockDim.x) {
-      double v = 0.0;
-      for (int p = 0; p < j.nparts; p++) v += part[(size_t)p * j.part_stride + e];
-      const int r = e % j.mrem, c = e / j.mrem;
-      C[(size_t)(j.m0 + r) + (size_t)(j.n0 + c) * j.ldc] += v;
+   const int e = blockIdx.y * 256 + threadIdx.x;
+   if (e >= n) return;
+   const double* __restrict__ part = bases.p[SP_PART] + j.part_off + e;
+   double v = 0.0;
+   int p = 0;
+   for (; p + 4 <= j.nparts; p += 4) {   // four independent loads in flight, summed in slot order
+      const double a0 = part[(size_t)p * j.part_stride], a1 = part[(size_t)(p + 1) * j.part_stride];
+      const double a2 = part[(size_t)(p + 2) * j.part_stride], a3 = part[(size_t)(p + 3) * j.part_stride];
+      v += a0; v += a1; v += a2; v += a3;
    }
+   for (; p < j.nparts; p++) v += part[(size_t)p * j.part_stride];
+   double* __restrict__ C = bases.p[SP_VOUT] + j.dst_off;
+   const int r = e % j.mrem, c = e / j.mrem;
+   C[(size_t)(j.m0 + r) + (size_t)(j.n0 + c) * j.ldc] += v;
 }
 int dev_launch_reduce(const ReduceJob* d_jobs, int njobs, const DevBases& bases, void* stream) {
    if (njobs <= 0) return 0;
-   k_reduce<<<njobs, 256, 0, (cudaStream_t)stream>>>(d_jobs, bases);
+   for (int j0 = 0; j0 < njobs; j0 += 32768) {
+      const int nj = (njobs - j0 < 32768) ? njobs - j0 : 32768;
+      dim3 grid(nj, 16);   // 16 x 256 threads cover the largest (64 x 64) tile
+      k_reduce<<<grid, 256, 0, (cudaStream_t)stream>>>(d_jobs + j0, bases);
+   }
    cudaError_t e = cudaGetLastError();
    if (e != cudaSuccess) return cuda_fail(e, "k_reduce launch");
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Heff diagonal: 32x32 output tile per CTA, rank-1 updates from gathered operator-block diagonals (HBM/L2 gather bound)
+__global__ void __launch_bounds__(256) k_diag(const DiagTile* __restrict__ tiles, const DiagItem* __restrict__ items, DevBases bases, double* __restrict__ out) {
+   constexpr int T = 32, CH = 16;
+   __shared__ double as[CH][T + 1], bs[CH][T + 1];
+   const DiagTile t = tiles[blockIdx.x];
+   const int tid = threadIdx.x, i = tid % T, j0 = tid / T;   // thread owns rows i, cols j0, j0+8, j0+16, j0+24
+   double acc[4] = {0.0, 0.0, 0.0, 0.0};
+   for (int c0 = t.item_begin; c0 < t.item_end; c0 += CH) {
+      for (int idx = tid; idx < 2 * CH * T; idx += 256) {
+         const int which = idx / (CH * T), rem = idx % (CH * T), c = rem / T, e = rem % T;
+         double v = 0.0;
+         if (c0 + c < t.item_end) {
+            const DiagItem I = items[c0 + c];
+            if (which == 0) {
+               if (e < t.mrem) v = I.f * (I.as ? bases.p[I.as][I.aoff + (size_t)(t.m0 + e) * (I.lda + 1)] : 1.0);
+            } else {
+               if (e < t.nrem) v = I.bs ? bases.p[I.bs][I.boff + (size_t)(t.n0 + e) * (I.ldb + 1)] : 1.0;
+            }
+         }
+         if (which == 0) as[c][e] = v; else bs[c][e] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int c = 0; c < CH; c++) {
+         const double a = as[c][i];
+#pragma unroll
+         for (int r = 0; r < 4; r++) acc[r] += a * bs[c][j0 + 8 * r];
+      }
+      __syncthreads();
+   }
+   if (i < t.mrem)
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+         if (j0 + 8 * r < t.nrem) out[t.coff + (size_t)(t.m0 + i) + (size_t)(t.n0 + j0 + 8 * r) * t.ldc] = acc[r];
+}
+int dev_launch_diag(const DiagTile* d_tiles, int ntiles, const DiagItem* d_items, const DevBases& bases, double* d_out, void* stream) {
+   if (ntiles <= 0) return 0;
+   k_diag<<<ntiles, 256, 0, (cudaStream_t)stream>>>(d_tiles, d_items, bases, d_out);
+   cudaError_t e = cudaGetLastError();
+   if (e != cudaSuccess) return cuda_fail(e, "k_diag launch");
    return 0;
 }
 

@@ -65,6 +65,10 @@ int b2_problem_mx(const b2_ctx* ctx, double* mx_out);
 double b2_wigner6j(int two_ja, int two_jb, int two_jc, int two_jd, int two_je, int two_jf);
 double b2_wigner9j(int two_ja, int two_jb, int two_jc, int two_jd, int two_je, int two_jf, int two_jg, int two_jh, int two_ji);
 
+/* eigen-decomposition of a small symmetric matrix (n <= 32, column-major, ld = n), eigenvalues ascending: the host-side
+ * Rayleigh-Ritz step of the device Davidson (stands in for dsyev_ at Davidson.cpp:276) */
+int b2_small_symmetric_eig(int n, const double* a, double* eval, double* evec);
+
 /* ------------------------------------------------------------------------------------------------ bookkeeper
  * Replaces CheMPS2::SyBookkeeper (SyBookkeeper.h:41-143).  b2_bk_init = constructor (FCI dims, ceil-scaled to D);
  * b2_bk_set_dim = SetDim; the getters mirror gCurrentDim / gFCIdim / gNmin / gNmax / gTwoSmin / gTwoSmax. */
@@ -117,6 +121,18 @@ int64_t b2_heff_veclength(const b2_heff* h);
 int b2_heff_apply(b2_heff* h, const double* vec_in, double* vec_out);
 int b2_heff_apply_device(b2_heff* h, const double* dev_in, double* dev_out);
 int b2_heff_diag(b2_heff* h, double* diag);
+int b2_heff_diag_device(b2_heff* h, double* dev_diag);
+/* b2_heff_solve = Heff::SolveDAVIDSON (Heff.cpp:317-386) with CheMPS2::Davidson (Davidson.cpp) running on the device:
+ * s (HOST, Sobject storage in the reference's "program" convention) holds the initial guess on entry and the lowest
+ * eigenvector on exit; *eigenvalue excludes Econst exactly like the reference's return value; rtol = the sweep
+ * instruction's Davidson tolerance (ConvergenceScheme); constants 32 / 3 / 1e-12 are Options.h:70-72.
+ * b2_heff_solve_device = same with s resident on the device. */
+int b2_heff_solve(b2_heff* h, double* s, double rtol, double* eigenvalue, int* n_matvec);
+int b2_heff_solve_device(b2_heff* h, double* dev_s, double rtol, double* eigenvalue, int* n_matvec);
+/* multi-GPU: callback that sums a device vector over all ranks in place on the given stream (the caller owns the NCCL
+ * communicator); replaces MPI_Reduce/MPI_Bcast of Heff.cpp:350-365.  Return 0 on success. */
+typedef int (*b2_allreduce_fn)(void* user, double* dev_ptr, int64_t n, void* cuda_stream);
+int b2_heff_set_allreduce(b2_heff* h, b2_allreduce_fn fn, void* user);
 /* statistics: [0] #terms, [1] #terms dropped (zero prefactor), [2] #presummed operators, [3] reference FLOPs per apply
  * (2mnk per reference dgemm_), [4] executed FLOPs per apply, [5] workspace doubles, [6] #stage-1 GEMMs, [7] #CTAs,
  * [8] #waves, [9] kernel launches per apply, [10] split-K partial doubles, [11] bytes of device work lists */

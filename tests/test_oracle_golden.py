@@ -121,3 +121,20 @@ def test_no_device_is_loud(golden):
     ctx, left, right, heff = cpu_check.build_case(golden, "A")
     with pytest.raises(api.B2Error):
         heff.apply(golden["A/vec_in"])
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 32])
+def test_small_symmetric_eig(n):
+    """host Rayleigh-Ritz step of the device Davidson (stand-in for dsyev_, Davidson.cpp:276)"""
+    from chemps2_b200._lib import c_dp, check
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal((n, n))
+    a = a + a.T
+    if n == 7:
+        a[3, :] = a[2, :]; a[:, 3] = a[:, 2]; a[3, 3] = a[2, 2]   # degenerate pair
+    ev, vec = np.zeros(n), np.zeros(n * n)
+    check(lib.b2_small_symmetric_eig(n, a.ravel(order="F").ctypes.data_as(c_dp), ev.ctypes.data_as(c_dp), vec.ctypes.data_as(c_dp)))
+    v = vec.reshape(n, n, order="F")
+    assert np.abs(ev - np.linalg.eigvalsh(a)).max() < 1e-12 * max(1.0, np.abs(a).max())
+    assert np.abs(v.T @ v - np.eye(n)).max() < 1e-12
+    assert np.abs(a @ v - v * ev).max() < 1e-11 * max(1.0, np.abs(a).max())

@@ -67,3 +67,32 @@ def test_sigma_synthetic_vs_cpu_checker(name, D):
     out = heff.apply(vin)
     ref = cpu_check.cpu_apply(hctx, hsets[0], hsets[1], hheff, vin)
     assert _close(out, ref)
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_heff_diagonal_vs_reference(golden, tag):
+    """b2_heff_diag (device gather kernel) == Heff::fillHeffDiag of the reference"""
+    ctx, left, right, heff = cpu_check.build_case(golden, tag, device=0)
+    assert _close(heff.diag(), golden[f"{tag}/diag"])
+
+
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_davidson_solve_vs_reference(golden, tag):
+    """b2_heff_solve (device Davidson) reproduces the site energy DMRG::solve_site printed for the same Sobject, operators
+    and rtol (1e-8): the reference's energy list `energies` is indexed presweeps, left sweep (L-2 .. 1), right sweep (0 .. L-3)."""
+    ctx, left, right, heff = cpu_check.build_case(golden, tag, device=0)
+    L = ctx.L
+    site = int(golden[tag + "/hdr"][0])
+    en = golden["energies"]
+    npre = len(en) - 2 * (L - 2)
+    idx = npre + ((L - 2 - site) if tag == "A" else (L - 2) + site)
+    e, sol, nm = heff.solve(golden[tag + "/joined"], rtol=1e-8)
+    assert abs(e + float(golden["problem/econst"][0]) - en[idx]) < 1e-9      # north_star: energies within 1e-9 Eh
+    assert 1 <= nm < 200
+    # the solution is a normalised eigenvector: residual small in the symmetric convention
+    labels, offs = ctx.sobject_table(site)
+    scale = np.concatenate([np.full(offs[k + 1] - offs[k], np.sqrt(labels[k][7] + 1.0)) for k in range(len(labels))])
+    x = sol * scale
+    assert abs(np.linalg.norm(x) - 1.0) < 1e-10
+    r = heff.apply(x) - e * x
+    assert np.linalg.norm(r) < 5e-8

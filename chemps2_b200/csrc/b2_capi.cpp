@@ -504,14 +504,8 @@ int b2_heff_stats(const b2_heff* h, double* o) {
    o[0] = (double)h->plan.terms.size(); o[1] = (double)h->plan.skipped_zero; o[2] = (double)h->plan.presums.size();
    o[3] = h->plan.flops_ref; o[4] = h->comp.flops_exec; o[5] = (double)h->comp.work_size; o[6] = (double)h->comp.n_stage1; o[7] = (double)h->comp.n_tiles;
    o[8] = (double)h->comp.waves.size();
-   double launches = 1.0, bytes = 0.0;
-   for (const Wave& w : h->comp.waves) {
-      for (int c = 0; c < kNumTileClasses; c++) launches += (w.t1_end[c] > w.t1_begin[c]) + (w.t2_end[c] > w.t2_begin[c]);
-      launches += (w.red_end > w.red_begin);
-   }
-   o[9] = launches; o[10] = (double)h->comp.part_size;
-   bytes += sizeof(GemmItem) * (double)(h->comp.items1.size() + h->comp.items2.size()) + sizeof(ReduceJob) * (double)h->comp.reduces.size();
-   for (int c = 0; c < kNumTileClasses; c++) bytes += sizeof(Tile) * (double)(h->comp.tiles1[c].size() + h->comp.tiles2[c].size());
+   o[9] = 1.0 + h->comp.launches(); o[10] = (double)h->comp.part_size;
+   const double bytes = h->comp.bytes();
    o[11] = bytes;
    return B2_OK;
 }

@@ -1,0 +1,226 @@
+// b2_compile.cpp — see b2_compile.h.  Host only; everything it emits is deterministic (no atomics on the device).
+//
+// Scheduling:
+//   * a three-factor term is split into a stage-1 product W (order chosen per term to minimise FLOPs) kept in a workspace,
+//     and a stage-2 product accumulated into the destination tile; identical stage-1 products inside a wave are shared;
+//   * the term list is cut into WAVES so that the stage-1 workspace stays below CompileOptions::work_budget;
+//   * inside a wave the terms of one destination tile are cut into split-K CHUNKS of ~chunk_k accumulated inner dimension,
+//     one CTA each; a tile with one chunk adds straight into the destination, otherwise the chunks write partial slots
+//     and a reduce job sums them in a fixed order.
+#include "b2_compile.h"
+
+#include <algorithm>
+#include <unordered_map>
+
+namespace b2 {
+
+namespace {
+
+int tile_class_for(int m, int n) {
+   const int d = std::min(m, n);
+   if (d > 32) return 0;
+   if (d > 16) return 1;
+   if (d > 8) return 2;
+   return 3;
+}
+
+// balanced tiling: ceil(M / edge) tiles of equal size (rounded up to the 8-row MMA granule) instead of full tiles + a sliver
+inline int balanced_step(int M, int edge) {
+   const int nt = (M + edge - 1) / edge;
+   const int s = ((M + nt - 1) / nt + 7) / 8 * 8;
+   return std::min(s, edge);
+}
+
+struct WKey {
+   int64_t off1, off2; int32_t rows1, rows2; uint8_t s1, s2, t1, t2;
+   bool operator==(const WKey& o) const {
+      return off1 == o.off1 && off2 == o.off2 && rows1 == o.rows1 && rows2 == o.rows2 && s1 == o.s1 && s2 == o.s2 && t1 == o.t1 && t2 == o.t2;
+   }
+};
+struct WKeyHash {
+   size_t operator()(const WKey& k) const {
+      uint64_t h = (uint64_t)k.off1 * 0x9E3779B97F4A7C15ULL ^ (uint64_t)k.off2 * 0xC2B2AE3D27D4EB4FULL ^ ((uint64_t)k.s1 << 8) ^ ((uint64_t)k.s2 << 16) ^
+                   ((uint64_t)k.t1 << 4) ^ ((uint64_t)k.t2 << 5);
+      return (size_t)(h ^ (h >> 29));
+   }
+};
+struct WInfo { int64_t off; int rows, cols; };
+
+inline void set_x(GemmItem& g, const MatRef& m) { g.xs = m.space; g.xoff = m.off; g.ldx = m.rows; if (m.trans) g.flags |= IF_TX; }
+inline void set_y(GemmItem& g, const MatRef& m) { g.ys = m.space; g.yoff = m.off; g.ldy = m.rows; if (m.trans) g.flags |= IF_TY; }
+
+}   // namespace
+
+double CompiledWork::launches() const {
+   double n = 0.0;
+   for (const Wave& w : waves) {
+      for (int c = 0; c < kNumTileClasses; c++) n += (w.t1_end[c] > w.t1_begin[c]) + (w.t2_end[c] > w.t2_begin[c]);
+      n += (w.red_end > w.red_begin);
+   }
+   return n;
+}
+double CompiledWork::bytes() const {
+   double b = sizeof(GemmItem) * (double)(items1.size() + items2.size()) + sizeof(ReduceJob) * (double)reduces.size();
+   for (int c = 0; c < kNumTileClasses; c++) b += sizeof(Tile) * (double)(tiles1[c].size() + tiles2[c].size());
+   return b;
+}
+
+void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vector<DstBlock>& dst, uint8_t dst_space, const CompileOptions& opt) {
+   out = CompiledWork();
+   std::unordered_map<WKey, WInfo, WKeyHash> wmap;
+   int64_t wave_work = 0, wave_part = 0;
+   Wave wave{};
+   auto open_wave = [&]() {
+      for (int c = 0; c < kNumTileClasses; c++) {
+         wave.t1_begin[c] = (int)out.tiles1[c].size();
+         wave.t2_begin[c] = (int)out.tiles2[c].size();
+      }
+      wave.red_begin = (int)out.reduces.size();
+      wave_work = 0; wave_part = 0;
+      wmap.clear();
+   };
+   auto weight_sort = [&](std::vector<Tile>& v, int b, int e, const std::vector<GemmItem>& items) {
+      // heaviest CTAs first (static load balance across the SMs)
+      std::vector<std::pair<long long, int>> ord(e - b);
+      for (int i = b; i < e; i++) {
+         long long w = 0;
+         for (int it = v[i].item_begin; it < v[i].item_end; it++) w += items[it].k + 4;
+         ord[i - b] = {-w * ((v[i].mrem + 7) / 8) * ((v[i].nrem + 7) / 8), i};
+      }
+      std::sort(ord.begin(), ord.end());
+      std::vector<Tile> sorted(e - b);
+      for (int i = 0; i < e - b; i++) sorted[i] = v[ord[i].second];
+      std::copy(sorted.begin(), sorted.end(), v.begin() + b);
+   };
+   auto close_wave = [&]() {
+      bool any = (int)out.reduces.size() > wave.red_begin;
+      for (int c = 0; c < kNumTileClasses; c++) {
+         wave.t1_end[c] = (int)out.tiles1[c].size();
+         wave.t2_end[c] = (int)out.tiles2[c].size();
+         any = any || wave.t1_end[c] > wave.t1_begin[c] || wave.t2_end[c] > wave.t2_begin[c];
+         weight_sort(out.tiles1[c], wave.t1_begin[c], wave.t1_end[c], out.items1);
+         weight_sort(out.tiles2[c], wave.t2_begin[c], wave.t2_end[c], out.items2);
+      }
+      wave.red_end = (int)out.reduces.size();
+      out.work_size = std::max(out.work_size, wave_work);
+      out.part_size = std::max(out.part_size, wave_part);
+      if (any) out.waves.push_back(wave);
+   };
+
+   // W = op(a) * op(b), shared inside the wave
+   auto get_w = [&](const MatRef& a, const MatRef& b) -> WInfo {
+      WKey key{a.off, b.off, a.rows, b.rows, a.space, b.space, a.trans, b.trans};
+      auto it = wmap.find(key);
+      if (it != wmap.end()) return it->second;
+      WInfo w{};
+      w.rows = a.op_rows(); w.cols = b.op_cols();
+      GemmItem g{};
+      g.alpha = 1.0; g.k = a.op_cols();
+      set_x(g, a); set_y(g, b);
+      w.off = wave_work;
+      wave_work += ((int64_t)w.rows * w.cols + 15) / 16 * 16;
+      const int ib = (int)out.items1.size();
+      out.items1.push_back(g);
+      const int cls = tile_class_for(w.rows, w.cols), e = kTileEdge[cls];
+      const int sm = balanced_step(w.rows, e), sn = balanced_step(w.cols, e);
+      for (int n0 = 0; n0 < w.cols; n0 += sn)
+         for (int m0 = 0; m0 < w.rows; m0 += sm) {
+            Tile t{};
+            t.coff = w.off; t.ldc = w.rows; t.m0 = t.cm0 = m0; t.n0 = t.cn0 = n0;
+            t.mrem = std::min(sm, w.rows - m0); t.nrem = std::min(sn, w.cols - n0);
+            t.item_begin = ib; t.item_end = ib + 1; t.cspace = SP_WORK; t.accumulate = 0;
+            out.tiles1[cls].push_back(t);
+         }
+      out.flops_exec += 2.0 * w.rows * w.cols * g.k;
+      out.n_stage1++;
+      wmap.emplace(key, w);
+      return w;
+   };
+
+   // emit the stage-2 CTAs of items2[ib, ie) for destination block d (all inside the current wave)
+   auto emit_block = [&](const DstBlock& db, int ib, int ie) {
+      if (ie <= ib) return;
+      const int M = db.rows, N = db.cols;
+      std::vector<int> cuts{ib};
+      int64_t acc = 0;
+      for (int i = ib; i < ie; i++) {
+         acc += out.items2[i].k + 4;
+         if (acc >= opt.chunk_k && i + 1 < ie) { cuts.push_back(i + 1); acc = 0; }
+      }
+      cuts.push_back(ie);
+      const int nchunks = (int)cuts.size() - 1;
+      const int cls = tile_class_for(M, N), e = kTileEdge[cls];
+      const int sm = balanced_step(M, e), sn = balanced_step(N, e);
+      for (int n0 = 0; n0 < N; n0 += sn)
+         for (int m0 = 0; m0 < M; m0 += sm) {
+            const int mrem = std::min(sm, M - m0), nrem = std::min(sn, N - n0);
+            if (nchunks == 1) {
+               Tile t{};
+               t.coff = db.off; t.ldc = M; t.m0 = t.cm0 = m0; t.n0 = t.cn0 = n0; t.mrem = mrem; t.nrem = nrem;
+               t.item_begin = ib; t.item_end = ie; t.cspace = dst_space; t.accumulate = 1;
+               out.tiles2[cls].push_back(t);
+            } else {
+               const int64_t stride = ((int64_t)mrem * nrem + 15) / 16 * 16;
+               ReduceJob r{};
+               r.dst_off = db.off; r.ldc = M; r.m0 = m0; r.n0 = n0; r.mrem = mrem; r.nrem = nrem;
+               r.part_off = wave_part; r.nparts = nchunks; r.part_stride = stride; r.dst_space = dst_space;
+               out.reduces.push_back(r);
+               for (int c = 0; c < nchunks; c++) {
+                  Tile t{};
+                  t.coff = wave_part + c * stride; t.ldc = mrem; t.m0 = m0; t.n0 = n0; t.cm0 = 0; t.cn0 = 0; t.mrem = mrem; t.nrem = nrem;
+                  t.item_begin = cuts[c]; t.item_end = cuts[c + 1]; t.cspace = SP_PART; t.accumulate = 0;
+                  out.tiles2[cls].push_back(t);
+               }
+               wave_part += stride * nchunks;
+            }
+         }
+   };
+
+   open_wave();
+   size_t i0 = 0;
+   while (i0 < terms.size()) {
+      size_t i1 = i0;
+      while (i1 < terms.size() && terms[i1].dst == terms[i0].dst) i1++;
+      // block-axpy terms first inside every destination block: the kernel consumes them before it starts its GEMM pipeline
+      std::stable_partition(terms.begin() + i0, terms.begin() + i1, [](const Term3& t) { return !t.p.present() && !t.r.present(); });
+      const DstBlock& db = dst[terms[i0].dst];
+      const int M = db.rows, N = db.cols;
+      int ib = (int)out.items2.size();
+      for (size_t i = i0; i < i1; i++) {
+         const Term3& t = terms[i];
+         GemmItem g{};
+         g.alpha = t.f;
+         const bool hp = t.p.present(), hq = t.q.present(), hr = t.r.present();
+         if (hp && hq && hr) {
+            const double kq1 = t.q.op_rows(), kq2 = t.q.op_cols();
+            const double f_left = (double)M * kq1 * kq2 + (double)M * kq2 * N;     // (P*Q)*R
+            const double f_right = kq1 * kq2 * N + (double)M * kq1 * N;            // P*(Q*R)
+            if (f_left <= f_right) {
+               const WInfo w = get_w(t.p, t.q);
+               g.xs = SP_WORK; g.xoff = w.off; g.ldx = w.rows; set_y(g, t.r); g.k = w.cols;
+            } else {
+               const WInfo w = get_w(t.q, t.r);
+               set_x(g, t.p); g.ys = SP_WORK; g.yoff = w.off; g.ldy = w.rows; g.k = w.rows;
+            }
+         } else if (hp && hq) { set_x(g, t.p); set_y(g, t.q); g.k = t.p.op_cols(); }
+         else if (hq && hr) { set_x(g, t.q); set_y(g, t.r); g.k = t.q.op_cols(); }
+         else if (hp && hr) { set_x(g, t.p); set_y(g, t.r); g.k = t.p.op_cols(); }
+         else if (hq) { set_x(g, t.q); g.flags |= IF_AXPY; g.k = 0; }     // f * op(Q)
+         else continue;                                                   // nothing to add
+         out.flops_exec += (g.flags & IF_AXPY) ? 2.0 * M * N : 2.0 * M * N * g.k;
+         out.items2.push_back(g);
+         if (wave_work >= opt.work_budget) {   // workspace full: flush what this block has so far and start a new wave
+            emit_block(db, ib, (int)out.items2.size());
+            close_wave();
+            open_wave();
+            ib = (int)out.items2.size();
+         }
+      }
+      emit_block(db, ib, (int)out.items2.size());
+      i0 = i1;
+   }
+   close_wave();
+   for (int c = 0; c < kNumTileClasses; c++) out.n_tiles += (long long)out.tiles1[c].size() + (long long)out.tiles2[c].size();
+}
+
+}   // namespace b2

@@ -6,6 +6,8 @@
 namespace b2 {
 
 // address spaces an operand can live in; resolved to base pointers at launch time
+// sigma build: LEFT/RIGHT = operator arenas of the two boundaries, VIN/VOUT = S and sigma.
+// operator update: LEFT = old operator arena, RIGHT = MPS site tensor, VOUT = new operator arena.
 enum Space : uint8_t { SP_NONE = 0, SP_LEFT = 1, SP_RIGHT = 2, SP_PRESUM = 3, SP_WORK = 4, SP_VIN = 5, SP_VOUT = 6, SP_PART = 7, SP_COUNT = 8 };
 
 struct DevBases { double* p[SP_COUNT]; };
@@ -14,7 +16,7 @@ enum ItemKind : uint8_t { IT_GEMM = 0, IT_AXPY = 1 };
 enum ItemFlags : uint8_t { IF_TX = 1, IF_TY = 2, IF_AXPY = 4 };
 
 // C_tile += alpha * opX(X)[M x K] * opY(Y)[K x N]     (GEMM)
-// C_tile += alpha * X[M x N]                          (IF_AXPY)
+// C_tile += alpha * opX(X)[M x N]                     (IF_AXPY)
 // X, Y are column-major with leading dimensions ldx, ldy; IF_TX / IF_TY: the stored matrix enters transposed.
 struct GemmItem {
    int64_t xoff, yoff;
@@ -41,6 +43,7 @@ struct ReduceJob {
    int64_t dst_off, part_off;
    int32_t ldc, m0, n0, mrem, nrem, nparts;
    int64_t part_stride;
+   uint8_t dst_space, pad[7];
 };
 
 // out[dst_off + e] = sum_{parts} coef * src[e]   for e < size

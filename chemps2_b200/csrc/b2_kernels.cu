@@ -105,8 +105,13 @@ __global__ void __launch_bounds__(WM * WN * 32) k_tiles(const Tile* __restrict__
          for (int j = 0; j < NI; j++) {
             const int r = wm * WTM + i * 8 + g, c = wn * WTN + j * 8 + 2 * q;
             if (r < t.mrem) {
-               if (c < t.nrem) acc[i][j][0] += I.alpha * X[(size_t)(t.m0 + r) + (size_t)(t.n0 + c) * I.ldx];
-               if (c + 1 < t.nrem) acc[i][j][1] += I.alpha * X[(size_t)(t.m0 + r) + (size_t)(t.n0 + c + 1) * I.ldx];
+               if (I.flags & IF_TX) {
+                  if (c < t.nrem) acc[i][j][0] += I.alpha * X[(size_t)(t.n0 + c) + (size_t)(t.m0 + r) * I.ldx];
+                  if (c + 1 < t.nrem) acc[i][j][1] += I.alpha * X[(size_t)(t.n0 + c + 1) + (size_t)(t.m0 + r) * I.ldx];
+               } else {
+                  if (c < t.nrem) acc[i][j][0] += I.alpha * X[(size_t)(t.m0 + r) + (size_t)(t.n0 + c) * I.ldx];
+                  if (c + 1 < t.nrem) acc[i][j][1] += I.alpha * X[(size_t)(t.m0 + r) + (size_t)(t.n0 + c + 1) * I.ldx];
+               }
             }
          }
    }
@@ -235,7 +240,7 @@ __global__ void __launch_bounds__(256) k_reduce(const ReduceJob* __restrict__ jo
       v += a0; v += a1; v += a2; v += a3;
    }
    for (; p < j.nparts; p++) v += part[(size_t)p * j.part_stride];
-   double* __restrict__ C = bases.p[SP_VOUT] + j.dst_off;
+   double* __restrict__ C = bases.p[j.dst_space] + j.dst_off;
    const int r = e % j.mrem, c = e / j.mrem;
    C[(size_t)(j.m0 + r) + (size_t)(j.n0 + c) * j.ldc] += v;
 }

@@ -21,7 +21,8 @@ static void run_tile(const Tile& t, const GemmItem* items, double* const* base) 
       const double* X = base[I.xs] + I.xoff;
       if (I.flags & IF_AXPY) {
          for (int c = 0; c < t.nrem; c++)
-            for (int r = 0; r < t.mrem; r++) acc[r + (size_t)t.mrem * c] += I.alpha * X[(size_t)(t.m0 + r) + (size_t)(t.n0 + c) * I.ldx];
+            for (int r = 0; r < t.mrem; r++)
+               acc[r + (size_t)t.mrem * c] += I.alpha * ((I.flags & IF_TX) ? X[(size_t)(t.n0 + c) + (size_t)(t.m0 + r) * I.ldx] : X[(size_t)(t.m0 + r) + (size_t)(t.n0 + c) * I.ldx]);
          continue;
       }
       const double* Y = base[I.ys] + I.yoff;
@@ -64,7 +65,7 @@ extern "C" void b2o_run_worklists(const b2_worklists* wl, const double* left, co
          for (int e = 0; e < j.mrem * j.nrem; e++) {
             double v = 0.0;
             for (int p = 0; p < j.nparts; p++) v += part[(size_t)j.part_off + (size_t)p * j.part_stride + e];
-            vout[(size_t)j.dst_off + (size_t)(j.m0 + e % j.mrem) + (size_t)(j.n0 + e / j.mrem) * j.ldc] += v;
+            base[j.dst_space][(size_t)j.dst_off +  (size_t)(j.m0 + e % j.mrem) + (size_t)(j.n0 + e / j.mrem) * j.ldc] += v;
          }
       }
    }

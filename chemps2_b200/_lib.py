@@ -86,6 +86,15 @@ SIGNATURES = [
     ("b2_probe_fp64", C.c_int, [vp, C.c_int, c_dp]),
     ("b2_heff_worklists", C.c_int, [vp, vp]),
     ("b2_ctx_set_option", C.c_int, [vp, C.c_char_p, C.c_double]),
+    ("b2_update_create", C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.POINTER(vp)]),
+    ("b2_update_destroy", None, [vp]),
+    ("b2_update_run", C.c_int, [vp, c_dp]),
+    ("b2_update_run_device", C.c_int, [vp, vp]),
+    ("b2_update_stats", C.c_int, [vp, c_dp]),
+    ("b2_update_worklists", C.c_int, [vp, C.c_int, vp]),
+    ("b2_update_num_presum_parts", C.c_int64, [vp]),
+    ("b2_update_presum_size", C.c_int64, [vp]),
+    ("b2_update_export_presums", C.c_int, [vp, C.POINTER(FlatPresum)]),
 ]
 for _name, _res, _args in SIGNATURES:
     _f = getattr(lib, _name)

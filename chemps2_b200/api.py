@@ -191,6 +191,36 @@ class Heff:
         return terms, nt, parts, npp, lib.b2_heff_presum_size(self.h)
 
 
+class Update:
+    """operator renormalisation of one sweep step; stands for DMRG::updateMovingRight/Left (DMRGoperators.cpp:243-907)"""
+
+    def __init__(self, ctx, index, moving_right, old_set, new_set):
+        self.ctx, self.old_set, self.new_set = ctx, old_set, new_set
+        self.h = vp()
+        check(lib.b2_update_create(ctx.h, int(index), int(bool(moving_right)), old_set.h if old_set else None, new_set.h, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib.b2_update_destroy(self.h)
+            self.h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, t_storage):
+        t = np.ascontiguousarray(t_storage, dtype=np.float64)
+        check(lib.b2_update_run(self.h, _dp(t)))
+
+    def stats(self):
+        o = np.zeros(8)
+        check(lib.b2_update_stats(self.h, _dp(o)))
+        keys = ["terms", "mix_terms", "presums", "flops_ref", "flops_exec", "work_doubles", "waves", "launches"]
+        return {k: float(v) for k, v in zip(keys, o)}
+
+
 def context_from_fixture(fx, tag, device=-1):
     """Build a Context (problem + bookkeeper dims) from a golden fixture section `tag` ('A' or 'B')."""
     L, group, N, twoS, irrep = [int(x) for x in fx["problem/hdr"]]
@@ -199,6 +229,9 @@ def context_from_fixture(fx, tag, device=-1):
     ctx.bk_init(1)
     ctx.bk_import(fx[tag + "/bk"])
     return ctx
+
+
+KIND_NAMES = ["L", "S0", "S1", "F0", "F1", "A", "B", "C", "D", "Q", "X"]
 
 
 S_KEY = (3 << 60)   # key of the synthetic two-site vector, same as op_key(3, 0, -1, -1) in oracle/ref_driver.cpp

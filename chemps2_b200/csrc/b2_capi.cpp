@@ -3,6 +3,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -16,6 +17,7 @@
 #include "b2_heff.h"
 #include "b2_ops.h"
 #include "b2_sigma.h"
+#include "b2_update.h"
 
 using namespace b2;
 
@@ -567,6 +569,157 @@ int b2_ctx_set_option(b2_ctx* ctx, const char* name, double value) {
    if (!std::strcmp(name, "work_budget")) { if (value < 1024) return fail(B2_ERR_ARG, "work_budget too small"); ctx->copt.work_budget = (int64_t)value; }
    else if (!std::strcmp(name, "chunk_k")) { if (value < 8) return fail(B2_ERR_ARG, "chunk_k too small"); ctx->copt.chunk_k = (int64_t)value; }
    else return fail(B2_ERR_ARG, "b2_ctx_set_option: unknown option %s", name);
+   return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ operator update
+struct b2_update {
+   b2_ctx* ctx = nullptr;
+   b2_opset *old_set = nullptr, *new_set = nullptr;
+   UpdatePlan plan;
+   CompiledWork pass[2];
+   std::vector<PresumJob> presum_jobs;
+   std::vector<PresumPart> presum_parts;
+   GemmItem *d_items1[2] = {nullptr, nullptr}, *d_items2[2] = {nullptr, nullptr};
+   ReduceJob* d_reduces[2] = {nullptr, nullptr};
+   Tile* d_tiles1[2][kNumTileClasses] = {};
+   Tile* d_tiles2[2][kNumTileClasses] = {};
+   PresumJob* d_jobs = nullptr;
+   PresumPart* d_parts = nullptr;
+   double *d_presum = nullptr, *d_work = nullptr, *d_part = nullptr, *d_t = nullptr, *h_t = nullptr;
+};
+
+static void fill_worklists(const CompiledWork& c, b2_worklists* o) {
+   o->items1 = c.items1.data(); o->n_items1 = (int64_t)c.items1.size();
+   o->items2 = c.items2.data(); o->n_items2 = (int64_t)c.items2.size();
+   for (int k = 0; k < kNumTileClasses; k++) {
+      o->tiles1[k] = c.tiles1[k].data(); o->n_tiles1[k] = (int64_t)c.tiles1[k].size();
+      o->tiles2[k] = c.tiles2[k].data(); o->n_tiles2[k] = (int64_t)c.tiles2[k].size();
+   }
+   o->reduces = c.reduces.data(); o->n_reduces = (int64_t)c.reduces.size();
+   o->waves = c.waves.data(); o->n_waves = (int64_t)c.waves.size();
+   o->work_size = c.work_size; o->part_size = c.part_size;
+}
+
+int b2_update_create(b2_ctx* ctx, int index, int moving_right, b2_opset* old_set, b2_opset* new_set, b2_update** out) {
+   if (!ctx || !ctx->have_bk || !new_set || !out) return fail(B2_ERR_STATE, "b2_update_create: bad arguments");
+   const int L = ctx->bk.L;
+   if (index < 0 || index > L - 1) return fail(B2_ERR_ARG, "b2_update_create: site %d out of range", index);
+   const bool mr = moving_right != 0;
+   const int b_old = mr ? index : index + 1, b_new = mr ? index + 1 : index;
+   if (new_set->set.boundary != b_new || new_set->set.moving_right != mr) return fail(B2_ERR_ARG, "b2_update_create: new_set must sit at boundary %d", b_new);
+   const bool need_old = mr ? (index > 0) : (index < L - 1);
+   if (need_old && (!old_set || old_set->set.boundary != b_old || old_set->set.moving_right != mr)) return fail(B2_ERR_ARG, "b2_update_create: old_set must sit at boundary %d", b_old);
+   std::unique_ptr<b2_update> u(new b2_update);
+   u->ctx = ctx; u->old_set = need_old ? old_set : nullptr; u->new_set = new_set;
+   build_update_plan(u->plan, ctx->bk, ctx->prob, u->old_set ? &u->old_set->set : nullptr, new_set->set, index, mr);
+   compile_terms(u->pass[0], u->plan.terms, u->plan.dst, SP_VOUT, ctx->copt);
+   compile_terms(u->pass[1], u->plan.mix_terms, u->plan.dst, SP_VOUT, ctx->copt);
+   for (const Presum& p : u->plan.presums) {
+      PresumJob j{};
+      j.dst_off = p.off; j.size = p.lay->size; j.part_begin = (int)u->presum_parts.size();
+      for (auto& pr : p.parts) {
+         PresumPart pp{};
+         pp.src_off = u->old_set->set.ops[pr.second].off; pp.coef = pr.first; pp.space = SP_LEFT;
+         u->presum_parts.push_back(pp);
+      }
+      j.part_end = (int)u->presum_parts.size();
+      u->presum_jobs.push_back(j);
+   }
+   if (ctx->device >= 0) {
+      CUDA_TRY(cudaSetDevice(ctx->device));
+      cudaStream_t s = ctx->stream;
+      int rc;
+      int64_t work = 0, part = 0;
+      for (int p = 0; p < 2; p++) {
+         if ((rc = upload_vec(&u->d_items1[p], u->pass[p].items1, s))) return rc;
+         if ((rc = upload_vec(&u->d_items2[p], u->pass[p].items2, s))) return rc;
+         if ((rc = upload_vec(&u->d_reduces[p], u->pass[p].reduces, s))) return rc;
+         for (int c = 0; c < kNumTileClasses; c++) {
+            if ((rc = upload_vec(&u->d_tiles1[p][c], u->pass[p].tiles1[c], s))) return rc;
+            if ((rc = upload_vec(&u->d_tiles2[p][c], u->pass[p].tiles2[c], s))) return rc;
+         }
+         work = std::max(work, u->pass[p].work_size); part = std::max(part, u->pass[p].part_size);
+      }
+      if ((rc = upload_vec(&u->d_jobs, u->presum_jobs, s))) return rc;
+      if ((rc = upload_vec(&u->d_parts, u->presum_parts, s))) return rc;
+      if (u->plan.presum_size > 0) CUDA_TRY(cudaMalloc(&u->d_presum, sizeof(double) * (size_t)u->plan.presum_size));
+      if (work > 0) CUDA_TRY(cudaMalloc(&u->d_work, sizeof(double) * (size_t)work));
+      if (part > 0) CUDA_TRY(cudaMalloc(&u->d_part, sizeof(double) * (size_t)part));
+      const size_t nt = (size_t)(u->plan.T.size ? u->plan.T.size : 1);
+      CUDA_TRY(cudaMalloc(&u->d_t, sizeof(double) * nt));
+      CUDA_TRY(cudaMallocHost(&u->h_t, sizeof(double) * nt));
+      CUDA_TRY(cudaStreamSynchronize(s));
+   }
+   *out = u.release();
+   return B2_OK;
+}
+void b2_update_destroy(b2_update* u) {
+   if (!u) return;
+   for (int p = 0; p < 2; p++) {
+      cudaFree(u->d_items1[p]); cudaFree(u->d_items2[p]); cudaFree(u->d_reduces[p]);
+      for (int c = 0; c < kNumTileClasses; c++) { cudaFree(u->d_tiles1[p][c]); cudaFree(u->d_tiles2[p][c]); }
+   }
+   cudaFree(u->d_jobs); cudaFree(u->d_parts); cudaFree(u->d_presum); cudaFree(u->d_work); cudaFree(u->d_part); cudaFree(u->d_t);
+   if (u->h_t) cudaFreeHost(u->h_t);
+   delete u;
+}
+int b2_update_run_device(b2_update* u, const double* t_dev) {
+   if (!u || !t_dev) return fail(B2_ERR_ARG, "b2_update_run_device: NULL");
+   if (u->ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_update_run: planning-only context, no CUDA device (there is no CPU fallback)");
+   cudaStream_t s = u->ctx->stream;
+   DevBases b;
+   for (int i = 0; i < SP_COUNT; i++) b.p[i] = nullptr;
+   b.p[SP_LEFT] = u->old_set ? u->old_set->dev : nullptr;
+   b.p[SP_RIGHT] = const_cast<double*>(t_dev);
+   b.p[SP_PRESUM] = u->d_presum; b.p[SP_WORK] = u->d_work; b.p[SP_PART] = u->d_part;
+   b.p[SP_VOUT] = u->new_set->dev;
+   if (dev_launch_presum(u->d_jobs, (int)u->presum_jobs.size(), u->d_parts, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+   if (dev_fill_zero(u->new_set->dev, u->new_set->set.size, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+   for (int p = 0; p < 2; p++)
+      for (const Wave& w : u->pass[p].waves) {
+         for (int c = 0; c < kNumTileClasses; c++)
+            if (dev_launch_tiles(c, u->d_tiles1[p][c] + w.t1_begin[c], w.t1_end[c] - w.t1_begin[c], u->d_items1[p], b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+         for (int c = 0; c < kNumTileClasses; c++)
+            if (dev_launch_tiles(c, u->d_tiles2[p][c] + w.t2_begin[c], w.t2_end[c] - w.t2_begin[c], u->d_items2[p], b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+         if (dev_launch_reduce(u->d_reduces[p] + w.red_begin, w.red_end - w.red_begin, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+      }
+   return B2_OK;
+}
+int b2_update_run(b2_update* u, const double* t_host) {
+   if (!u || !t_host) return fail(B2_ERR_ARG, "b2_update_run: NULL");
+   if (u->ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_update_run: planning-only context, no CUDA device (there is no CPU fallback)");
+   const size_t bytes = sizeof(double) * (size_t)u->plan.T.size;
+   std::memcpy(u->h_t, t_host, bytes);
+   CUDA_TRY(cudaMemcpyAsync(u->d_t, u->h_t, bytes, cudaMemcpyHostToDevice, u->ctx->stream));
+   int rc = b2_update_run_device(u, u->d_t);
+   if (rc) return rc;
+   CUDA_TRY(cudaStreamSynchronize(u->ctx->stream));
+   return B2_OK;
+}
+int b2_update_stats(const b2_update* u, double* o) {
+   if (!u || !o) return fail(B2_ERR_ARG, "b2_update_stats: NULL");
+   o[0] = (double)u->plan.terms.size(); o[1] = (double)u->plan.mix_terms.size(); o[2] = (double)u->plan.presums.size(); o[3] = u->plan.flops_ref;
+   o[4] = u->pass[0].flops_exec + u->pass[1].flops_exec; o[5] = (double)std::max(u->pass[0].work_size, u->pass[1].work_size);
+   o[6] = (double)(u->pass[0].waves.size() + u->pass[1].waves.size()); o[7] = 2.0 + u->pass[0].launches() + u->pass[1].launches();
+   return B2_OK;
+}
+int b2_update_worklists(const b2_update* u, int pass, b2_worklists* o) {
+   if (!u || !o || pass < 0 || pass > 1) return fail(B2_ERR_ARG, "b2_update_worklists: bad arguments");
+   fill_worklists(u->pass[pass], o);
+   return B2_OK;
+}
+int64_t b2_update_num_presum_parts(const b2_update* u) { return u ? (int64_t)u->presum_parts.size() : 0; }
+int64_t b2_update_presum_size(const b2_update* u) { return u ? u->plan.presum_size : 0; }
+int b2_update_export_presums(const b2_update* u, b2_flat_presum* out) {
+   if (!u || !out) return fail(B2_ERR_ARG, "b2_update_export_presums: NULL");
+   size_t n = 0;
+   for (const PresumJob& j : u->presum_jobs)
+      for (int p = j.part_begin; p < j.part_end; p++) {
+         const PresumPart& pp = u->presum_parts[p];
+         out[n].dst_off = j.dst_off; out[n].src_off = pp.src_off; out[n].size = j.size; out[n].space = pp.space; out[n].coef = pp.coef;
+         n++;
+      }
    return B2_OK;
 }
 

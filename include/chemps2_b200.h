@@ -172,6 +172,28 @@ typedef struct {
    int64_t n_items1, n_items2, n_tiles1[4], n_tiles2[4], n_reduces, n_waves, work_size, part_size;
 } b2_worklists;
 int b2_heff_worklists(const b2_heff* h, b2_worklists* out);
+
+/* ------------------------------------------------------------------------------------------------ operator update
+ * Replaces DMRG::updateMovingRight / updateMovingLeft (DMRGoperators.cpp:243-907) together with the tensor algebra they
+ * call: TensorOperator::update (TensorOperator.cpp:163-405), TensorL::create (TensorL.cpp:41-206), TensorS0/S1/F0/F1::makenew,
+ * the A/B/C/D daxpy mixing (DMRGoperators.cpp:367-405), TensorQ::AddTerm* and TensorX::update.
+ * index = site of the MPS tensor T that was just optimised.  moving_right != 0: old_set sits at boundary `index` (NULL when
+ * index == 0), new_set at boundary index+1.  moving_right == 0: old_set at boundary index+1 (NULL when index == L-1), new_set
+ * at boundary `index`.  b2_update_run takes T as the reference's TensorT::gStorage() (HOST); every operator of new_set is
+ * overwritten on the device (b2_opset_download brings one back). */
+typedef struct b2_update b2_update;
+int b2_update_create(b2_ctx* ctx, int index, int moving_right, b2_opset* old_set, b2_opset* new_set, b2_update** out);
+void b2_update_destroy(b2_update* u);
+int b2_update_run(b2_update* u, const double* t_host);
+int b2_update_run_device(b2_update* u, const double* t_dev);
+/* [0] #terms, [1] #mix terms, [2] #presums, [3] reference FLOPs, [4] executed FLOPs, [5] workspace doubles, [6] #waves, [7] launches */
+int b2_update_stats(const b2_update* u, double* out8);
+/* work lists of pass 0 (contractions) / pass 1 (A,B,C,D mixing) and the pre-sum jobs, for the CPU emulator in oracle/ */
+int b2_update_worklists(const b2_update* u, int pass, b2_worklists* out);
+int64_t b2_update_num_presum_parts(const b2_update* u);
+int64_t b2_update_presum_size(const b2_update* u);
+int b2_update_export_presums(const b2_update* u, b2_flat_presum* out);
+
 /* scheduling knobs of plans created afterwards: "work_budget" (doubles of stage-1 workspace per wave), "chunk_k" */
 int b2_ctx_set_option(b2_ctx* ctx, const char* name, double value);
 /* host mirrors of the operator arenas (valid until the set is destroyed) */

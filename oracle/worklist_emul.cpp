@@ -45,12 +45,26 @@ static void run_tile(const Tile& t, const GemmItem* items, double* const* base) 
       }
 }
 
+static void run_lists(const b2_worklists* wl, double** base);
+
 extern "C" void b2o_run_worklists(const b2_worklists* wl, const double* left, const double* right, const double* presum, const double* vin,
                                   double* vout, int64_t veclength) {
-   std::vector<double> work((size_t)wl->work_size + 1, 0.0), part((size_t)wl->part_size + 1, 0.0);
-   double* base[SP_COUNT] = {nullptr, const_cast<double*>(left), const_cast<double*>(right), const_cast<double*>(presum), work.data(),
-                             const_cast<double*>(vin), vout, part.data()};
+   double* base[SP_COUNT] = {nullptr, const_cast<double*>(left), const_cast<double*>(right), const_cast<double*>(presum), nullptr,
+                             const_cast<double*>(vin), vout, nullptr};
    std::memset(vout, 0, sizeof(double) * (size_t)veclength);
+   run_lists(wl, base);
+}
+
+/* operator update: spaces LEFT = old operator arena, RIGHT = MPS tensor, PRESUM, VOUT = new operator arena (zeroed by the caller
+ * before pass 0, kept between the passes) */
+extern "C" void b2o_run_update_pass(const b2_worklists* wl, const double* old_arena, const double* t, const double* presum, double* new_arena) {
+   double* base[SP_COUNT] = {nullptr, const_cast<double*>(old_arena), const_cast<double*>(t), const_cast<double*>(presum), nullptr, nullptr, new_arena, nullptr};
+   run_lists(wl, base);
+}
+
+static void run_lists(const b2_worklists* wl, double** base) {
+   std::vector<double> work((size_t)wl->work_size + 1, 0.0), part((size_t)wl->part_size + 1, 0.0);
+   base[SP_WORK] = work.data(); base[SP_PART] = part.data();
    const Wave* waves = (const Wave*)wl->waves;
    for (int64_t w = 0; w < wl->n_waves; w++) {
       const Wave& W = waves[w];

@@ -91,3 +91,62 @@ def emulate_worklists(ctx, left, right, heff, vec):
     vout = np.zeros_like(vin)
     o.b2o_run_worklists(C.byref(wl), _dp(la), _dp(ra), _dp(presum), _dp(vin), _dp(vout), vin.size)
     return vout
+
+
+def build_update_case(fx, which, device=-1, options=None):
+    """which = 'UR' (moving right after the solve at siteB) or 'UL' (moving left after the solve at siteA).
+    -> (ctx, old_set, new_set, update, t_storage, expected [(kind, i, j, data)])"""
+    tag = "B" if which == "UR" else "A"
+    site = int(fx[tag + "/hdr"][0])
+    mr = which == "UR"
+    ctx = api.context_from_fixture(fx, which, device)
+    for name, value in (options or {}).items():
+        ctx.set_option(name, value)
+    L = ctx.L
+    index = site if mr else site + 1
+    old = None
+    key = tag + ("/left" if mr else "/right")
+    if key + "/hdr" in fx:
+        b, omr, ops = split_ops(fx, key)
+        assert omr == mr and b == (index if mr else index + 1)
+        old = api.OpSet(ctx, b, mr)
+        old.upload_all(ops)
+    nb, nmr, expected = split_ops(fx, which + "/new")
+    assert nmr == mr and nb == (index + 1 if mr else index)
+    new = api.OpSet(ctx, nb, mr)
+    upd = api.Update(ctx, index, mr, old, new)
+    return ctx, old, new, upd, fx[f"{which}/mps/{index}"], expected
+
+
+def emulate_update(old, new, upd, t_storage):
+    """runs both passes of the compiled update work lists on the CPU (oracle/worklist_emul.cpp) -> new arena (numpy)"""
+    from chemps2_b200._lib import Worklists, check, lib
+    o = oracle_lib()
+    o.b2o_run_update_pass.argtypes = [C.POINTER(Worklists), c_dp, c_dp, c_dp, c_dp]
+    npp = lib.b2_update_num_presum_parts(upd.h)
+    parts = (FlatPresum * max(npp, 1))()
+    check(lib.b2_update_export_presums(upd.h, parts))
+    psize = lib.b2_update_presum_size(upd.h)
+    oa = old.host_arena() if old else np.zeros(1)
+    presum = np.zeros(max(psize, 1))
+    o.b2o_presum(parts, npp, _dp(oa), _dp(oa), _dp(presum), psize)
+    arena = np.zeros(max(lib.b2_opset_arena_size(new.h), 1))
+    t = np.ascontiguousarray(t_storage, dtype=np.float64)
+    for p in (0, 1):
+        wl = Worklists()
+        check(lib.b2_update_worklists(upd.h, p, C.byref(wl)))
+        o.b2o_run_update_pass(C.byref(wl), _dp(oa), _dp(t), _dp(presum), _dp(arena))
+    return arena
+
+
+def op_slices(new):
+    """[(kind, i, j, offset, size)] of an OpSet arena"""
+    from chemps2_b200._lib import lib
+    out = []
+    # offsets follow the 16-double alignment of OpSet::add
+    off = 0
+    for idx in range(len(new)):
+        k, i, j, size = new.info(idx)
+        out.append((k, i, j, off, size))
+        off += (size + 15) // 16 * 16
+    return out

@@ -47,24 +47,82 @@ template <int T> struct Panel {
    static constexpr int SIZE = (KC * SM > T * SK) ? KC * SM : T * SK;
 };
 
-// Stage one k-chunk of op(M)[r0 + r][k0 + k], r < T, k < KC, of a column-major matrix with leading dimension ld.
-//   contig_r = true : the stored matrix is R x K (rows contiguous)   -> m-major panel
-//   contig_r = false: the stored matrix is K x R (k contiguous)      -> k-major panel
-template <int T, int NT>
-__device__ __forceinline__ void stage_panel(double* P, const double* __restrict__ G, int ld, bool contig_r, int r0, int rrem, int k0, int K, int tid) {
-   if (contig_r) {
-#pragma unroll
-      for (int idx = tid; idx < T * KC; idx += NT) {
-         const int r = idx % T, k = idx / T;
-         const bool ok = (r < rrem) && (k0 + k < K);
-         cp_async8(P + k * Panel<T>::SM + r, ok ? G + (size_t)(r0 + r) + (size_t)(k0 + k) * ld : G, ok);
+// Per-item staging cursor of one operand panel.  For a T x KC panel and NT threads every thread copies E = T*KC/NT
+// elements per chunk; with the thread -> element map below all E elements of a thread share one coordinate, so the
+// global pointer, the validity of that coordinate and the shared-memory slot are computed once per item and a chunk
+// costs one predicate + one pointer bump + one cp.async per element (the index arithmetic used to dominate issue slots).
+//   contig_r  (stored R x K, rows contiguous)  -> "m-major" panel P[k][r]:  r = tid % T fixed,   k = tid / T + e * (NT / T)
+//   !contig_r (stored K x R, k contiguous)     -> "k-major" panel P[r][k]:  k = tid % KC fixed,  r = tid / KC + e * (NT / KC)
+template <int T, int NT> struct Stager {
+   static constexpr int E = (T * KC) / NT;
+   static_assert((T * KC) % NT == 0 && E >= 1, "panel must split evenly over the CTA");
+   const double* g;      // global pointer of element e = 0 of the current chunk
+   long long estep;      // global stride between consecutive e
+   long long cstep;      // global stride between consecutive chunks
+   int soff, sstep;      // shared-memory slot of e = 0 and stride between consecutive e
+   int fix_ok;           // the fixed coordinate is inside the matrix (contig_r: r < rrem; else evaluated per chunk: k0 + k < K)
+   int var0, varstep;    // the varying coordinate of e = 0 and its step
+   int kfix;             // !contig_r: k of this thread
+   bool contig;
+
+   __device__ __forceinline__ void init(const double* G, int ld, bool contig_r, int r0, int rrem, int tid) {
+      contig = contig_r;
+      if (contig_r) {
+         const int r = tid % T, kb = tid / T;
+         g = G + (size_t)(r0 + r) + (size_t)kb * ld;
+         estep = (long long)(NT / T) * ld; cstep = (long long)KC * ld;
+         soff = kb * Panel<T>::SM + r; sstep = (NT / T) * Panel<T>::SM;
+         fix_ok = r < rrem; var0 = kb; varstep = NT / T; kfix = 0;
+      } else {
+         const int k = tid % KC, rb = tid / KC;
+         g = G + (size_t)k + (size_t)(r0 + rb) * ld;
+         estep = (long long)(NT / KC) * ld; cstep = KC;
+         soff = rb * Panel<T>::SK + k; sstep = (NT / KC) * Panel<T>::SK;
+         fix_ok = 1; var0 = rb; varstep = NT / KC; kfix = k;
       }
-   } else {
+   }
+   // copies the chunk that starts at k0 (kleft = K - k0 > 0 columns left); rrem = rows of the tile
+   __device__ __forceinline__ void chunk(double* P, int kleft, int rrem) {
+      const double* p = g;
+      if (contig) {
 #pragma unroll
-      for (int idx = tid; idx < T * KC; idx += NT) {
-         const int k = idx % KC, r = idx / KC;
-         const bool ok = (r < rrem) && (k0 + k < K);
-         cp_async8(P + r * Panel<T>::SK + k, ok ? G + (size_t)(k0 + k) + (size_t)(r0 + r) * ld : G, ok);
+         for (int e = 0; e < E; e++) {
+            const bool ok = fix_ok && (var0 + e * varstep < kleft);
+            cp_async8(P + soff + e * sstep, ok ? p : g, ok);
+            p += estep;
+         }
+      } else {
+         const bool kok = kfix < kleft;
+#pragma unroll
+         for (int e = 0; e < E; e++) {
+            const bool ok = kok && (var0 + e * varstep < rrem);
+            cp_async8(P + soff + e * sstep, ok ? p : g, ok);
+            p += estep;
+         }
+      }
+      g += cstep;
+   }
+};
+
+// one k-chunk of MMAs; XM / YM: the X / Y panel is m-major (compile-time so that the fragment addresses fold to immediates)
+template <int TM, int TN, int MI, int NI, bool XM, bool YM>
+__device__ __forceinline__ void mma_chunk(double (&acc)[MI][NI][2], const double* __restrict__ xs, const double* __restrict__ ys, int rbase, int cbase,
+                                          int q, int kvalid, double alpha, int mi_n, int ni_n) {
+   const double* xa = XM ? xs + q * Panel<TM>::SM + rbase : xs + rbase * Panel<TM>::SK + q;
+   const double* yb = YM ? ys + q * Panel<TN>::SM + cbase : ys + cbase * Panel<TN>::SK + q;
+#pragma unroll
+   for (int kk = 0; kk < KC; kk += 4) {
+      if (kk < kvalid) {
+         double a[MI], b[NI];
+#pragma unroll
+         for (int i = 0; i < MI; i++) a[i] = alpha * (XM ? xa[kk * Panel<TM>::SM + i * 8] : xa[i * 8 * Panel<TM>::SK + kk]);
+#pragma unroll
+         for (int j = 0; j < NI; j++) b[j] = YM ? yb[kk * Panel<TN>::SM + j * 8] : yb[j * 8 * Panel<TN>::SK + kk];
+#pragma unroll
+         for (int i = 0; i < MI; i++)
+#pragma unroll
+            for (int j = 0; j < NI; j++)
+               if (i < mi_n && j < ni_n) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
       }
    }
 }
@@ -93,7 +151,7 @@ __global__ void __launch_bounds__(WM * WN * 32) k_tiles(const Tile* __restrict__
 #pragma unroll
       for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-   // ---- block-axpy items come first in every item range (b2_heff.cpp sorts them there)
+   // ---- block-axpy items come first in every item range (b2_compile.cpp sorts them there)
    int it0 = t.item_begin;
    for (; it0 < t.item_end; it0++) {
       const GemmItem I = items[it0];
@@ -117,62 +175,48 @@ __global__ void __launch_bounds__(WM * WN * 32) k_tiles(const Tile* __restrict__
    }
 
    // ---- GEMM items: one flattened stream of k-chunks over all items, software-pipelined with cp.async
-   int p_it = it0, p_k0 = 0;            // producer cursor
-   GemmItem P;
-   if (p_it < t.item_end) P = items[p_it];
+   int p_it = it0, p_left = 0;          // producer cursor: item, columns of K still to stage
+   Stager<TM, NT> sx;
+   Stager<TN, NT> sy;
+   auto producer_load_item = [&]() {
+      const GemmItem P = items[p_it];
+      sx.init(bases.p[P.xs] + P.xoff, P.ldx, !(P.flags & IF_TX), t.m0, t.mrem, tid);
+      sy.init(bases.p[P.ys] + P.yoff, P.ldy, (P.flags & IF_TY) != 0, t.n0, t.nrem, tid);
+      p_left = P.k;
+   };
+   if (p_it < t.item_end) producer_load_item();
    auto issue = [&](int stage) {
       if (p_it < t.item_end) {
-         stage_panel<TM, NT>(Xs + stage * XSZ, bases.p[P.xs] + P.xoff, P.ldx, !(P.flags & IF_TX), t.m0, t.mrem, p_k0, P.k, tid);
-         stage_panel<TN, NT>(Ys + stage * YSZ, bases.p[P.ys] + P.yoff, P.ldy, (P.flags & IF_TY) != 0, t.n0, t.nrem, p_k0, P.k, tid);
-         p_k0 += KC;
-         if (p_k0 >= P.k) {
-            p_k0 = 0;
-            if (++p_it < t.item_end) P = items[p_it];
-         }
+         sx.chunk(Xs + stage * XSZ, p_left, t.mrem);
+         sy.chunk(Ys + stage * YSZ, p_left, t.nrem);
+         p_left -= KC;
+         if (p_left <= 0 && ++p_it < t.item_end) producer_load_item();
       }
       cp_async_commit();
    };
 #pragma unroll
    for (int s = 0; s < STAGES - 1; s++) issue(s);
 
-   int c_it = it0, c_k0 = 0, stage = 0;
-   GemmItem Cn;
-   if (c_it < t.item_end) Cn = items[c_it];
+   int c_it = it0, c_left = 0, stage = 0, cflags = 0;
+   double alpha = 0.0;
+   if (c_it < t.item_end) { const GemmItem Cn = items[c_it]; c_left = Cn.k; cflags = Cn.flags; alpha = Cn.alpha; }
+   const int rbase = wm * WTM + g, cbase = wn * WTN + g;
    while (c_it < t.item_end) {
       cp_async_wait<STAGES - 2>();
       __syncthreads();
       issue((stage + STAGES - 1) % STAGES);   // refills the stage consumed in the previous iteration
       const double* xs = Xs + stage * XSZ;
       const double* ys = Ys + stage * YSZ;
-      const bool xm = !(Cn.flags & IF_TX), ym = (Cn.flags & IF_TY) != 0;   // m-major panels?
-      const int kvalid = min(KC, Cn.k - c_k0);
-      const double alpha = Cn.alpha;
-#pragma unroll
-      for (int kk = 0; kk < KC; kk += 4) {
-         if (kk < kvalid) {
-            double a[MI], b[NI];
-#pragma unroll
-            for (int i = 0; i < MI; i++) {
-               const int r = wm * WTM + i * 8 + g;
-               a[i] = alpha * (xm ? xs[(kk + q) * Panel<TM>::SM + r] : xs[r * Panel<TM>::SK + kk + q]);
-            }
-#pragma unroll
-            for (int j = 0; j < NI; j++) {
-               const int c = wn * WTN + j * 8 + g;
-               b[j] = ym ? ys[(kk + q) * Panel<TN>::SM + c] : ys[c * Panel<TN>::SK + kk + q];
-            }
-#pragma unroll
-            for (int i = 0; i < MI; i++)
-#pragma unroll
-               for (int j = 0; j < NI; j++)
-                  if (i < mi_n && j < ni_n) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-         }
+      const int kvalid = min(KC, c_left);
+      if (!(cflags & IF_TX)) {
+         if (cflags & IF_TY) mma_chunk<TM, TN, MI, NI, true, true>(acc, xs, ys, rbase, cbase, q, kvalid, alpha, mi_n, ni_n);
+         else mma_chunk<TM, TN, MI, NI, true, false>(acc, xs, ys, rbase, cbase, q, kvalid, alpha, mi_n, ni_n);
+      } else {
+         if (cflags & IF_TY) mma_chunk<TM, TN, MI, NI, false, true>(acc, xs, ys, rbase, cbase, q, kvalid, alpha, mi_n, ni_n);
+         else mma_chunk<TM, TN, MI, NI, false, false>(acc, xs, ys, rbase, cbase, q, kvalid, alpha, mi_n, ni_n);
       }
-      c_k0 += KC;
-      if (c_k0 >= Cn.k) {
-         c_k0 = 0;
-         if (++c_it < t.item_end) Cn = items[c_it];
-      }
+      c_left -= KC;
+      if (c_left <= 0 && ++c_it < t.item_end) { const GemmItem Cn = items[c_it]; c_left = Cn.k; cflags = Cn.flags; alpha = Cn.alpha; }
       stage = (stage + 1) % STAGES;
    }
    cp_async_wait<0>();

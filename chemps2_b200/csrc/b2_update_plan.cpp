@@ -78,7 +78,7 @@ struct UGen {
    }
 
    // ---- emit  new[op][k] += f * op(T[ux<->U]) * mid * op(T[dx<->Dn]);  mid_kind: 0 identity (ux == dx), 1 given MatRef
-   void emit(int new_op, int k, const Sec& U, const Sec& Dn, const Sec& ux, const Sec& dx, const MatRef* mid, double f) {
+   void emit(int new_op, int k, const Sec& U, const Sec& Dn, const Sec& ux, const Sec& dx, const MatRef* mid, double f, bool count = true) {
       if (f == 0.0) return;
       if (dim_old(ux) <= 0 || dim_old(dx) <= 0) return;
       MatRef tu = tref(ux, U, true), td = tref(dx, Dn, false);
@@ -90,7 +90,7 @@ struct UGen {
       if (mid) t.q = *mid;
       plan.terms.push_back(t);
       const double m = plan.dst[t.dst].rows, n = plan.dst[t.dst].cols, du = dim_old(ux), dd = dim_old(dx);
-      plan.flops_ref += mid ? 2.0 * (m * dd * du + m * n * dd) : 2.0 * m * n * du;
+      if (count) plan.flops_ref += mid ? 2.0 * (m * dd * du + m * n * dd) : 2.0 * m * n * du;
    }
 
    // sectors of block k of new operator `op`

@@ -86,6 +86,17 @@ SIGNATURES = [
     ("b2_probe_fp64", C.c_int, [vp, C.c_int, c_dp]),
     ("b2_heff_worklists", C.c_int, [vp, vp]),
     ("b2_ctx_set_option", C.c_int, [vp, C.c_char_p, C.c_double]),
+    ("b2_dmrg_create", C.c_int, [vp, C.POINTER(vp)]),
+    ("b2_dmrg_destroy", None, [vp]),
+    ("b2_dmrg_mps_size", C.c_int64, [vp, C.c_int]),
+    ("b2_dmrg_set_mps", C.c_int, [vp, C.c_int, c_dp]),
+    ("b2_dmrg_get_mps", C.c_int, [vp, C.c_int, c_dp]),
+    ("b2_dmrg_random_mps", C.c_int, [vp, C.c_uint64]),
+    ("b2_dmrg_opset", vp, [vp, C.c_int, C.c_int]),
+    ("b2_dmrg_set_opset", C.c_int, [vp, C.c_int, C.c_int, vp]),
+    ("b2_dmrg_update", C.c_int, [vp, C.c_int, C.c_int]),
+    ("b2_dmrg_solve_site", C.c_int, [vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_ip]),
+    ("b2_dmrg_sweep", C.c_int, [vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, c_dp, c_dp]),
     ("b2_update_create", C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.POINTER(vp)]),
     ("b2_update_destroy", None, [vp]),
     ("b2_update_run", C.c_int, [vp, c_dp]),

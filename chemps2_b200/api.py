@@ -221,6 +221,66 @@ class Update:
         return {k: float(v) for k, v in zip(keys, o)}
 
 
+class DMRG:
+    """sweep driver; stands for the hot-path part of CheMPS2::DMRG (DMRG.cpp:357-452)"""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.h = vp()
+        check(lib.b2_dmrg_create(ctx.h, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib.b2_dmrg_destroy(self.h)
+            self.h = vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_mps(self, site, data):
+        a = np.ascontiguousarray(data, dtype=np.float64)
+        check(lib.b2_dmrg_set_mps(self.h, int(site), _dp(a)))
+
+    def get_mps(self, site):
+        a = np.zeros(lib.b2_dmrg_mps_size(self.h, int(site)), dtype=np.float64)
+        check(lib.b2_dmrg_get_mps(self.h, int(site), _dp(a)))
+        return a
+
+    def random_mps(self, seed):
+        check(lib.b2_dmrg_random_mps(self.h, int(seed)))
+
+    def update(self, index, moving_right):
+        check(lib.b2_dmrg_update(self.h, int(index), int(bool(moving_right))))
+
+    def opset_download(self, boundary, moving_right, kind, i, j):
+        """one operator of the driver's set at (boundary, direction) -> numpy, or None"""
+        h = lib.b2_dmrg_opset(self.h, int(boundary), int(bool(moving_right)))
+        if not h:
+            return None
+        idx = lib.b2_opset_find(h, kind, i, j)
+        if idx < 0:
+            return None
+        size = C.c_int64()
+        check(lib.b2_opset_info(h, idx, None, None, None, C.byref(size)))
+        a = np.zeros(size.value, dtype=np.float64)
+        check(lib.b2_opset_download(h, idx, _dp(a)))
+        return a
+
+    def solve_site(self, index, rtol, noise, D, moving_right, change):
+        e, dw, nm = C.c_double(), C.c_double(), C.c_int()
+        check(lib.b2_dmrg_solve_site(self.h, int(index), float(rtol), float(noise), int(D), int(bool(moving_right)), int(bool(change)),
+                                     C.byref(e), C.byref(dw), C.byref(nm)))
+        return e.value, dw.value, nm.value
+
+    def sweep(self, to_right, rtol, noise, D, change):
+        e, dw = C.c_double(), C.c_double()
+        check(lib.b2_dmrg_sweep(self.h, int(bool(to_right)), float(rtol), float(noise), int(D), int(bool(change)), C.byref(e), C.byref(dw)))
+        return e.value, dw.value
+
+
 def context_from_fixture(fx, tag, device=-1):
     """Build a Context (problem + bookkeeper dims) from a golden fixture section `tag` ('A' or 'B')."""
     L, group, N, twoS, irrep = [int(x) for x in fx["problem/hdr"]]

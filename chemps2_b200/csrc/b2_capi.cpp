@@ -17,6 +17,7 @@
 #include "b2_heff.h"
 #include "b2_ops.h"
 #include "b2_sigma.h"
+#include "b2_sobject.h"
 #include "b2_update.h"
 
 using namespace b2;
@@ -720,6 +721,208 @@ int b2_update_export_presums(const b2_update* u, b2_flat_presum* out) {
          out[n].dst_off = j.dst_off; out[n].src_off = pp.src_off; out[n].size = j.size; out[n].space = pp.space; out[n].coef = pp.coef;
          n++;
       }
+   return B2_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ sweep driver
+// upload a compiled work list, run it once on the context stream, free it (used for small one-shot contractions: Join)
+static int run_compiled_once(b2_ctx* ctx, const CompiledWork& w, DevBases b) {
+   cudaStream_t s = ctx->stream;
+   GemmItem *i1 = nullptr, *i2 = nullptr;
+   ReduceJob* red = nullptr;
+   Tile *t1[kNumTileClasses] = {}, *t2[kNumTileClasses] = {};
+   double *work = nullptr, *part = nullptr;
+   int rc = B2_OK;
+   auto cleanup = [&]() {
+      cudaFree(i1); cudaFree(i2); cudaFree(red); cudaFree(work); cudaFree(part);
+      for (int c = 0; c < kNumTileClasses; c++) { cudaFree(t1[c]); cudaFree(t2[c]); }
+   };
+   do {
+      if ((rc = upload_vec(&i1, w.items1, s))) break;
+      if ((rc = upload_vec(&i2, w.items2, s))) break;
+      if ((rc = upload_vec(&red, w.reduces, s))) break;
+      for (int c = 0; c < kNumTileClasses && !rc; c++) { rc = upload_vec(&t1[c], w.tiles1[c], s); if (!rc) rc = upload_vec(&t2[c], w.tiles2[c], s); }
+      if (rc) break;
+      if (w.work_size > 0 && cudaMalloc(&work, sizeof(double) * (size_t)w.work_size) != cudaSuccess) { rc = fail(B2_ERR_CUDA, "workspace allocation failed"); break; }
+      if (w.part_size > 0 && cudaMalloc(&part, sizeof(double) * (size_t)w.part_size) != cudaSuccess) { rc = fail(B2_ERR_CUDA, "workspace allocation failed"); break; }
+      b.p[SP_WORK] = work; b.p[SP_PART] = part;
+      for (const Wave& wv : w.waves) {
+         for (int c = 0; c < kNumTileClasses && !rc; c++)
+            if (dev_launch_tiles(c, t1[c] + wv.t1_begin[c], wv.t1_end[c] - wv.t1_begin[c], i1, b, s)) rc = fail(B2_ERR_CUDA, "%s", dev_last_error());
+         for (int c = 0; c < kNumTileClasses && !rc; c++)
+            if (dev_launch_tiles(c, t2[c] + wv.t2_begin[c], wv.t2_end[c] - wv.t2_begin[c], i2, b, s)) rc = fail(B2_ERR_CUDA, "%s", dev_last_error());
+         if (!rc && dev_launch_reduce(red + wv.red_begin, wv.red_end - wv.red_begin, b, s)) rc = fail(B2_ERR_CUDA, "%s", dev_last_error());
+         if (rc) break;
+      }
+      cudaError_t e = cudaStreamSynchronize(s);
+      if (!rc && e != cudaSuccess) rc = fail(B2_ERR_CUDA, "run_compiled_once: %s", cudaGetErrorString(e));
+   } while (0);
+   cleanup();
+   return rc;
+}
+
+struct b2_dmrg {
+   b2_ctx* ctx = nullptr;
+   int L = 0;
+   std::vector<std::vector<double>> mps;   // TensorT storage per site in the layouts of the current bookkeeper
+   std::vector<b2_opset*> left, right;     // operator sets per boundary: moving right (sites < b) / moving left (sites >= b)
+   unsigned long long rng = 0x9E3779B97F4A7C15ULL;
+   double next_uniform() {                 // xorshift64*: our own stream (the reference uses rand(), Sobject.cpp:652-659)
+      rng ^= rng >> 12; rng ^= rng << 25; rng ^= rng >> 27;
+      return (double)((rng * 0x2545F4914F6CDD1DULL) >> 11) * (1.0 / 9007199254740992.0);
+   }
+};
+
+int b2_dmrg_create(b2_ctx* ctx, b2_dmrg** out) {
+   if (!ctx || !ctx->have_bk || !out) return fail(B2_ERR_STATE, "b2_dmrg_create: no bookkeeper");
+   if (ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_dmrg_create: planning-only context, no CUDA device (there is no CPU fallback)");
+   std::unique_ptr<b2_dmrg> d(new b2_dmrg);
+   d->ctx = ctx; d->L = ctx->bk.L;
+   d->mps.resize(d->L);
+   for (int s = 0; s < d->L; s++) { TLayout t; t.build(ctx->bk, s); d->mps[s].assign((size_t)t.size, 0.0); }
+   d->left.assign(d->L + 1, nullptr); d->right.assign(d->L + 1, nullptr);
+   *out = d.release();
+   return B2_OK;
+}
+void b2_dmrg_destroy(b2_dmrg* d) {
+   if (!d) return;
+   for (b2_opset* s : d->left) b2_opset_destroy(s);
+   for (b2_opset* s : d->right) b2_opset_destroy(s);
+   delete d;
+}
+int64_t b2_dmrg_mps_size(const b2_dmrg* d, int site) { return (d && site >= 0 && site < d->L) ? (int64_t)d->mps[site].size() : -1; }
+int b2_dmrg_set_mps(b2_dmrg* d, int site, const double* t) {
+   if (!d || site < 0 || site >= d->L || !t) return fail(B2_ERR_ARG, "b2_dmrg_set_mps: bad arguments");
+   TLayout lay; lay.build(d->ctx->bk, site);
+   d->mps[site].assign(t, t + lay.size);
+   return B2_OK;
+}
+int b2_dmrg_get_mps(const b2_dmrg* d, int site, double* t) {
+   if (!d || site < 0 || site >= d->L || !t) return fail(B2_ERR_ARG, "b2_dmrg_get_mps: bad arguments");
+   std::memcpy(t, d->mps[site].data(), sizeof(double) * d->mps[site].size());
+   return B2_OK;
+}
+int b2_dmrg_random_mps(b2_dmrg* d, uint64_t seed) {
+   if (!d) return fail(B2_ERR_ARG, "b2_dmrg_random_mps: NULL");
+   d->rng = seed * 0x9E3779B97F4A7C15ULL + 0xD1B54A32D192ED03ULL;
+   for (int s = 0; s < d->L; s++) {   // DMRG::setupBookkeeperAndMPS (DMRG.cpp:149-169): random() then left_normalize with R discarded
+      TLayout lay; lay.build(d->ctx->bk, s);
+      d->mps[s].resize((size_t)lay.size);
+      for (double& x : d->mps[s]) x = d->next_uniform();
+      left_normalize_host(d->ctx->bk, lay, d->mps[s].data());
+   }
+   return B2_OK;
+}
+b2_opset* b2_dmrg_opset(b2_dmrg* d, int boundary, int moving_right) {
+   if (!d || boundary < 0 || boundary > d->L) return nullptr;
+   return moving_right ? d->left[boundary] : d->right[boundary];
+}
+int b2_dmrg_set_opset(b2_dmrg* d, int boundary, int moving_right, b2_opset* set) {
+   if (!d || boundary < 1 || boundary > d->L - 1) return fail(B2_ERR_ARG, "b2_dmrg_set_opset: bad arguments");
+   auto& slot = moving_right ? d->left[boundary] : d->right[boundary];
+   if (slot && slot != set) b2_opset_destroy(slot);
+   slot = set;
+   return B2_OK;
+}
+
+// DMRG::updateMovingRight(index) / updateMovingLeft(index-1): operators of the boundary next to site `index` from T = MPS[index]
+int b2_dmrg_update(b2_dmrg* d, int index, int moving_right) {
+   if (!d || index < 0 || index >= d->L) return fail(B2_ERR_ARG, "b2_dmrg_update: bad arguments");
+   b2_ctx* ctx = d->ctx;
+   const bool mr = moving_right != 0;
+   const int b_old = mr ? index : index + 1, b_new = mr ? index + 1 : index;
+   if (b_new < 1 || b_new > d->L - 1) return fail(B2_ERR_ARG, "b2_dmrg_update: no operators live at boundary %d", b_new);
+   b2_opset* old_set = mr ? d->left[b_old] : d->right[b_old];
+   const bool need_old = mr ? (index > 0) : (index < d->L - 1);
+   if (need_old && !old_set) return fail(B2_ERR_STATE, "b2_dmrg_update: operators of boundary %d are missing", b_old);
+   b2_opset* fresh = nullptr;
+   int rc = b2_opset_create(ctx, b_new, mr, &fresh);
+   if (rc) return rc;
+   b2_update* u = nullptr;
+   rc = b2_update_create(ctx, index, mr, need_old ? old_set : nullptr, fresh, &u);
+   if (!rc) rc = b2_update_run(u, d->mps[index].data());
+   b2_update_destroy(u);
+   if (rc) { b2_opset_destroy(fresh); return rc; }
+   return b2_dmrg_set_opset(d, b_new, mr, fresh);
+}
+
+// DMRG::solve_site (DMRG.cpp:419-452): Join -> Heff::SolveDAVIDSON -> (noise) -> Split.  *energy includes Econst.
+int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, int moving_right, int change, double* energy,
+                       double* discarded_weight, int* n_matvec) {
+   if (!d || index < 0 || index > d->L - 2 || !energy) return fail(B2_ERR_ARG, "b2_dmrg_solve_site: bad arguments");
+   b2_ctx* ctx = d->ctx;
+   const int L = d->L;
+   cudaStream_t s = ctx->stream;
+   b2_opset* lset = index > 0 ? d->left[index] : nullptr;
+   b2_opset* rset = index < L - 2 ? d->right[index + 2] : nullptr;
+   if ((index > 0 && !lset) || (index < L - 2 && !rset)) return fail(B2_ERR_STATE, "b2_dmrg_solve_site: boundary operators for site %d are missing", index);
+   b2_heff* h = nullptr;
+   int rc = b2_heff_create(ctx, index, lset, rset, 1, 0, &h);
+   if (rc) return rc;
+   const SLayout& S = h->plan.S;
+   TLayout TL, TR;
+   TL.build(ctx->bk, index); TR.build(ctx->bk, index + 1);
+   double *d_tl = nullptr, *d_tr = nullptr, *d_s = nullptr;
+   std::vector<double> s_host((size_t)S.size);
+   do {
+      if (cudaMalloc(&d_tl, sizeof(double) * (size_t)std::max<int64_t>(TL.size, 1)) != cudaSuccess || cudaMalloc(&d_tr, sizeof(double) * (size_t)std::max<int64_t>(TR.size, 1)) != cudaSuccess ||
+          cudaMalloc(&d_s, sizeof(double) * (size_t)std::max<int64_t>(S.size, 1)) != cudaSuccess) { rc = fail(B2_ERR_CUDA, "b2_dmrg_solve_site: allocation failed"); break; }
+      cudaMemcpyAsync(d_tl, d->mps[index].data(), sizeof(double) * (size_t)TL.size, cudaMemcpyHostToDevice, s);
+      cudaMemcpyAsync(d_tr, d->mps[index + 1].data(), sizeof(double) * (size_t)TR.size, cudaMemcpyHostToDevice, s);
+      // ---- Join (Sobject.cpp:212-258) on the device
+      std::vector<Term3> jt; std::vector<DstBlock> jd;
+      join_terms(jt, jd, ctx->bk, S, TL, TR);
+      CompiledWork jw;
+      compile_terms(jw, jt, jd, SP_VOUT, ctx->copt);
+      DevBases b;
+      for (int i = 0; i < SP_COUNT; i++) b.p[i] = nullptr;
+      b.p[SP_LEFT] = d_tl; b.p[SP_RIGHT] = d_tr; b.p[SP_VOUT] = d_s;
+      if (dev_fill_zero(d_s, S.size, s)) { rc = fail(B2_ERR_CUDA, "%s", dev_last_error()); break; }
+      if ((rc = run_compiled_once(ctx, jw, b))) break;
+      // ---- Heff::SolveDAVIDSON on the device
+      double ev = 0.0; int nm = 0;
+      if ((rc = b2_heff_solve_device(h, d_s, rtol, &ev, &nm))) break;
+      *energy = ev + ctx->prob.econst;
+      if (n_matvec) *n_matvec = nm;
+      if (cudaMemcpyAsync(s_host.data(), d_s, sizeof(double) * (size_t)S.size, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) { rc = fail(B2_ERR_CUDA, "b2_dmrg_solve_site: D2H failed"); break; }
+      if (noise > 0.0) for (double& x : s_host) x += (d->next_uniform() - 0.5) * noise;   // Sobject::addNoise
+      // ---- Split (host SVD + truncation); the bookkeeper dims of boundary index+1 change here
+      SLayout Scopy = S;
+      const double dw = split_host(ctx->bk, index, Scopy, s_host.data(), D, moving_right != 0, change != 0, d->mps[index], d->mps[index + 1]);
+      if (discarded_weight) *discarded_weight = dw;
+   } while (0);
+   cudaFree(d_tl); cudaFree(d_tr); cudaFree(d_s);
+   b2_heff_destroy(h);
+   if (!rc) {   // operator sets living at the re-dimensioned boundary are stale now
+      b2_dmrg_set_opset(d, index + 1, 1, nullptr);
+      b2_dmrg_set_opset(d, index + 1, 0, nullptr);
+   }
+   return rc;
+}
+
+// DMRG::sweepleft / sweepright (DMRG.cpp:357-417): returns the lowest site energy of the half sweep
+int b2_dmrg_sweep(b2_dmrg* d, int to_right, double rtol, double noise, int D, int change, double* min_energy, double* max_discarded) {
+   if (!d || !min_energy) return fail(B2_ERR_ARG, "b2_dmrg_sweep: bad arguments");
+   const int L = d->L;
+   double emin = 1e300, dmax = 0.0;
+   int rc;
+   if (!to_right) {
+      for (int index = L - 2; index > 0; index--) {
+         double e, dw;
+         if ((rc = b2_dmrg_solve_site(d, index, rtol, noise, D, 0, change, &e, &dw, nullptr))) return rc;
+         emin = std::min(emin, e); dmax = std::max(dmax, dw);
+         if ((rc = b2_dmrg_update(d, index + 1, 0))) return rc;
+      }
+   } else {
+      for (int index = 0; index < L - 2; index++) {
+         double e, dw;
+         if ((rc = b2_dmrg_solve_site(d, index, rtol, noise, D, 1, change, &e, &dw, nullptr))) return rc;
+         emin = std::min(emin, e); dmax = std::max(dmax, dw);
+         if ((rc = b2_dmrg_update(d, index, 1))) return rc;
+      }
+   }
+   *min_energy = emin;
+   if (max_discarded) *max_discarded = dmax;
    return B2_OK;
 }
 

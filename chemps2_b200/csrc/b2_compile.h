@@ -39,8 +39,8 @@ struct Wave {
 };
 
 struct CompileOptions {
-   int64_t work_budget = (int64_t)1 << 27;   // doubles of stage-1 workspace per wave (1 GiB): measured best on B200 (profiles/)
-   int64_t chunk_k = 1024;                   // split-K: accumulated inner dimension per CTA
+   int64_t work_budget = (int64_t)3 << 27;   // doubles of stage-1 workspace per wave (3 GiB): measured best on B200 (profiles/r1_tuning.md)
+   int64_t chunk_k = 2048;                   // split-K: accumulated inner dimension per CTA
 };
 
 struct CompiledWork {

@@ -1,0 +1,277 @@
+// b2_sobject.cpp — two-site object algebra: Join as contraction terms for the device kernels, Split on the host.
+//
+//   join_terms : Sobject::Join (Sobject.cpp:212-258)  S[kappa] = sum_jM f6j * T_i[L -> M] * T_{i+1}[M -> R]   -> Term3 list
+//   split_host : Sobject::Split (Sobject.cpp:260-622) per-centre-sector SVD, global truncation to D, discarded weight,
+//                new virtual dimensions written into the bookkeeper, new site tensors (lambda on the side the sweep moves to).
+//                The SVD is a one-sided Jacobi written here (the reference calls LAPACK dgesdd_, :412-419); this step is
+//                host-side in the reference too and is listed as "next" for the device in SURVEY.md 8(f).
+#include "b2_sobject.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace b2 {
+
+void join_terms(std::vector<Term3>& terms, std::vector<DstBlock>& dst, const Bookkeeper& bk, const SLayout& S, const TLayout& TL, const TLayout& TR) {
+   terms.clear();
+   dst.resize(S.nkappa());
+   const int ix = S.site;
+   for (int k = 0; k < S.nkappa(); k++) {
+      dst[k] = DstBlock{S.blk[k].off, S.blk[k].rows, S.blk[k].cols};
+      const int NL = S.NL[k], TwoSL = S.twoSL[k], IL = S.IL[k], NR = S.NR[k], TwoSR = S.twoSR[k], IR = S.IR[k];
+      const int TwoJ = S.twoJ[k], N1 = S.N1[k], N2 = S.N2[k];
+      const int TwoS1 = (N1 == 1) ? 1 : 0, TwoS2 = (N2 == 1) ? 1 : 0;
+      const int fase = phase(TwoSL + TwoSR + TwoS1 + TwoS2);
+      const int NM = NL + N1;
+      const int IM = (TwoS1 == 1) ? xorp(IL, bk.orb_irrep[ix]) : IL;
+      const int lo = std::max(std::abs(TwoSL - TwoS1), std::abs(TwoSR - TwoS2)), hi = std::min(TwoSL + TwoS1, TwoSR + TwoS2);
+      for (int TwoJM = lo; TwoJM <= hi; TwoJM += 2) {
+         if (bk.dim(ix + 1, NM, TwoJM, IM) <= 0) continue;
+         const int kl = TL.kappa(bk, NL, TwoSL, IL, NM, TwoJM, IM), kr = TR.kappa(bk, NM, TwoJM, IM, NR, TwoSR, IR);
+         if (kl < 0 || kr < 0) continue;
+         Term3 t;
+         t.dst = k;
+         t.f = fase * std::sqrt(1.0 * (TwoJ + 1) * (TwoJM + 1)) * wigner6j(TwoSL, TwoSR, TwoJ, TwoS2, TwoS1, TwoJM);
+         t.p.space = SP_LEFT; t.p.off = TL.blk[kl].off; t.p.rows = TL.blk[kl].rows; t.p.cols = TL.blk[kl].cols;
+         t.r.space = SP_RIGHT; t.r.off = TR.blk[kr].off; t.r.rows = TR.blk[kr].rows; t.r.cols = TR.blk[kr].cols;
+         if (t.f != 0.0) terms.push_back(t);
+      }
+   }
+}
+
+// thin SVD of the column-major m x n matrix a (ld = m): a = U diag(s) V^T with k = min(m, n); u is m x k (ld m), vt is k x n (ld k).
+// One-sided Jacobi (Hestenes) on the columns of the taller orientation; singular values sorted in decreasing order.
+void jacobi_svd(int m, int n, const double* a, double* s, double* u, double* vt) {
+   const bool flip = m < n;                 // work on the transpose so that rows >= cols
+   const int R = flip ? n : m, C = flip ? m : n;
+   std::vector<double> W((size_t)R * C), V((size_t)C * C, 0.0);
+   for (int j = 0; j < C; j++)
+      for (int i = 0; i < R; i++) W[i + (size_t)R * j] = flip ? a[j + (size_t)m * i] : a[i + (size_t)m * j];
+   for (int j = 0; j < C; j++) V[j + (size_t)C * j] = 1.0;
+   double scale = 0.0;
+   for (double x : W) scale = std::max(scale, std::fabs(x));
+   const double tiny = scale * scale * 1e-300;
+   for (int sweep = 0; sweep < 60; sweep++) {
+      bool rotated = false;
+      for (int p = 0; p < C - 1; p++)
+         for (int q = p + 1; q < C; q++) {
+            double* wp = &W[(size_t)R * p];
+            double* wq = &W[(size_t)R * q];
+            double alpha = 0.0, beta = 0.0, gamma = 0.0;
+            for (int i = 0; i < R; i++) { alpha += wp[i] * wp[i]; beta += wq[i] * wq[i]; gamma += wp[i] * wq[i]; }
+            if (std::fabs(gamma) <= 1e-15 * std::sqrt(alpha * beta) || std::fabs(gamma) <= tiny) continue;
+            rotated = true;
+            const double zeta = (beta - alpha) / (2.0 * gamma);
+            const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+            const double c = 1.0 / std::sqrt(1.0 + t * t), sn = c * t;
+            for (int i = 0; i < R; i++) { const double x = wp[i], y = wq[i]; wp[i] = c * x - sn * y; wq[i] = sn * x + c * y; }
+            double* vp = &V[(size_t)C * p];
+            double* vq = &V[(size_t)C * q];
+            for (int i = 0; i < C; i++) { const double x = vp[i], y = vq[i]; vp[i] = c * x - sn * y; vq[i] = sn * x + c * y; }
+         }
+      if (!rotated) break;
+   }
+   std::vector<double> nrm(C);
+   std::vector<int> idx(C);
+   for (int j = 0; j < C; j++) {
+      double x = 0.0;
+      for (int i = 0; i < R; i++) x += W[i + (size_t)R * j] * W[i + (size_t)R * j];
+      nrm[j] = std::sqrt(x); idx[j] = j;
+   }
+   std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return nrm[x] > nrm[y]; });
+   const int k = C;   // = min(m, n)
+   for (int jj = 0; jj < k; jj++) {
+      const int j = idx[jj];
+      s[jj] = nrm[j];
+      const double inv = nrm[j] > 0.0 ? 1.0 / nrm[j] : 0.0;
+      // W(:,j)/s = left vectors of the worked-on matrix; V(:,j) = right vectors
+      if (!flip) {
+         for (int i = 0; i < m; i++) u[i + (size_t)m * jj] = W[i + (size_t)R * j] * inv;
+         for (int i = 0; i < n; i++) vt[jj + (size_t)k * i] = V[i + (size_t)C * j];
+      } else {   // a^T = W V^T  =>  a = V W^T : U = V, V^T rows = normalised W columns
+         for (int i = 0; i < m; i++) u[i + (size_t)m * jj] = V[i + (size_t)C * j];
+         for (int i = 0; i < n; i++) vt[jj + (size_t)k * i] = W[i + (size_t)R * j] * inv;
+      }
+   }
+}
+
+namespace {
+struct Center { int NM, TwoJM, IM; };
+struct Piece { int n, ts, ir, dim, start; };
+
+std::vector<Piece> left_pieces(const Bookkeeper& bk, int ix, const Center& c) {   // Sobject.cpp:321-334
+   std::vector<Piece> v;
+   int tot = 0;
+   for (int NL = c.NM - 2; NL <= c.NM; NL++) {
+      const int TwoS1 = (NL + 1 == c.NM) ? 1 : 0;
+      for (int TwoSL = c.TwoJM - TwoS1; TwoSL <= c.TwoJM + TwoS1; TwoSL += 2) {
+         if (TwoSL < 0) continue;
+         const int IL = TwoS1 ? xorp(bk.orb_irrep[ix], c.IM) : c.IM;
+         const int d = bk.dim(ix, NL, TwoSL, IL);
+         if (d > 0) { v.push_back({NL, TwoSL, IL, d, tot}); tot += d; }
+      }
+   }
+   return v;
+}
+std::vector<Piece> right_pieces(const Bookkeeper& bk, int ix, const Center& c) {   // Sobject.cpp:335-348
+   std::vector<Piece> v;
+   int tot = 0;
+   for (int NR = c.NM; NR <= c.NM + 2; NR++) {
+      const int TwoS2 = (NR == c.NM + 1) ? 1 : 0;
+      for (int TwoSR = c.TwoJM - TwoS2; TwoSR <= c.TwoJM + TwoS2; TwoSR += 2) {
+         if (TwoSR < 0) continue;
+         const int IR = TwoS2 ? xorp(bk.orb_irrep[ix + 1], c.IM) : c.IM;
+         const int d = bk.dim(ix + 2, NR, TwoSR, IR);
+         if (d > 0) { v.push_back({NR, TwoSR, IR, d, tot}); tot += d; }
+      }
+   }
+   return v;
+}
+}   // namespace
+
+double split_host(Bookkeeper& bk, int ix, const SLayout& S, const double* s_storage, int D, bool moving_right, bool change,
+                  std::vector<double>& t_left, std::vector<double>& t_right) {
+   std::vector<Center> centers;
+   bk.for_sectors(ix + 1, [&](int n, int ts, int ir) { if (bk.fcidim(ix + 1, n, ts, ir) > 0) centers.push_back({n, ts, ir}); });
+   const int nc = (int)centers.size();
+   std::vector<std::vector<double>> Lam(nc), Us(nc), VTs(nc);
+   std::vector<int> cdim(nc, 0), dimLtot(nc, 0), dimRtot(nc, 0);
+   std::vector<std::vector<Piece>> LP(nc), RP(nc);
+   for (int ic = 0; ic < nc; ic++) {
+      const Center& c = centers[ic];
+      LP[ic] = left_pieces(bk, ix, c);
+      RP[ic] = right_pieces(bk, ix, c);
+      for (auto& p : LP[ic]) dimLtot[ic] += p.dim;
+      for (auto& p : RP[ic]) dimRtot[ic] += p.dim;
+      cdim[ic] = std::min(dimLtot[ic], dimRtot[ic]);
+      if (cdim[ic] <= 0) continue;
+      const int M = dimLtot[ic], N = dimRtot[ic];
+      std::vector<double> mem((size_t)M * N, 0.0);
+      for (auto& pl : LP[ic]) {
+         const int TwoS1 = (pl.n + 1 == c.NM) ? 1 : 0;
+         for (auto& pr : RP[ic]) {
+            const int TwoS2 = (pr.n == c.NM + 1) ? 1 : 0;
+            const int fase = phase(pl.ts + pr.ts + TwoS1 + TwoS2);
+            const int jmin = std::max(std::abs(pr.ts - pl.ts), std::abs(TwoS2 - TwoS1)), jmax = std::min(TwoS1 + TwoS2, pl.ts + pr.ts);
+            for (int TwoJ = jmin; TwoJ <= jmax; TwoJ += 2) {
+               const int k = S.kappa(bk, pl.n, pl.ts, pl.ir, c.NM - pl.n, pr.n - c.NM, TwoJ, pr.n, pr.ts, pr.ir);
+               if (k < 0) continue;
+               const double pref = fase * std::sqrt(1.0 * (TwoJ + 1) * (pr.ts + 1)) * wigner6j(pl.ts, pr.ts, TwoJ, TwoS2, TwoS1, c.TwoJM);   // :378-381
+               const double* blk = s_storage + S.blk[k].off;
+               for (int r = 0; r < pr.dim; r++)
+                  for (int l = 0; l < pl.dim; l++) mem[pl.start + l + (size_t)M * (pr.start + r)] += pref * blk[l + (size_t)pl.dim * r];
+            }
+         }
+      }
+      Lam[ic].resize(cdim[ic]); Us[ic].resize((size_t)cdim[ic] * M); VTs[ic].resize((size_t)cdim[ic] * N);
+      jacobi_svd(M, N, mem.data(), Lam[ic].data(), Us[ic].data(), VTs[ic].data());
+   }
+
+   double discarded = 0.0;
+   if (change) {   // Sobject.cpp:437-499
+      std::vector<int> newdim(cdim);
+      long total = 0;
+      for (int ic = 0; ic < nc; ic++) total += newdim[ic];
+      if (total > D) {
+         std::vector<double> values;
+         for (int ic = 0; ic < nc; ic++) values.insert(values.end(), Lam[ic].begin(), Lam[ic].begin() + newdim[ic]);
+         std::sort(values.begin(), values.end(), [](double a, double b) { return a > b; });
+         const double lower = values[D];
+         for (int ic = 0; ic < nc; ic++)
+            for (int cnt = 0; cnt < newdim[ic]; cnt++)
+               if (Lam[ic][cnt] <= lower) newdim[ic] = cnt;
+         double tot = 0.0, dis = 0.0;
+         for (int ic = 0; ic < nc; ic++)
+            for (int il = 0; il < cdim[ic]; il++) {
+               const double w = (centers[ic].TwoJM + 1) * Lam[ic][il] * Lam[ic][il];
+               tot += w;
+               if (Lam[ic][il] <= lower) dis += w;
+            }
+         discarded = dis / tot;
+      }
+      bool differs = false;
+      for (int ic = 0; ic < nc; ic++)
+         if (newdim[ic] != bk.dim(ix + 1, centers[ic].NM, centers[ic].TwoJM, centers[ic].IM)) differs = true;
+      if (differs)
+         for (int ic = 0; ic < nc; ic++) bk.set_dim(ix + 1, centers[ic].NM, centers[ic].TwoJM, centers[ic].IM, newdim[ic]);
+   }
+
+   // new site tensors in the (possibly changed) layouts  (Sobject.cpp:519-589)
+   TLayout TL, TR;
+   TL.build(bk, ix);
+   TR.build(bk, ix + 1);
+   t_left.assign((size_t)TL.size, 0.0);
+   t_right.assign((size_t)TR.size, 0.0);
+   for (int ic = 0; ic < nc; ic++) {
+      const Center& c = centers[ic];
+      const int dimM = bk.dim(ix + 1, c.NM, c.TwoJM, c.IM);
+      if (dimM <= 0) continue;
+      const int lim = std::min(dimM, cdim[ic]);
+      for (auto& pl : LP[ic]) {
+         const int k = TL.kappa(bk, pl.n, pl.ts, pl.ir, c.NM, c.TwoJM, c.IM);
+         if (k < 0) continue;
+         double* blk = t_left.data() + TL.blk[k].off;
+         for (int r = 0; r < lim; r++) {
+            const double f = moving_right ? 1.0 : Lam[ic][r];
+            for (int l = 0; l < pl.dim; l++) blk[l + (size_t)pl.dim * r] = f * Us[ic][pl.start + l + (size_t)dimLtot[ic] * r];
+         }
+      }
+      for (auto& pr : RP[ic]) {
+         const int k = TR.kappa(bk, c.NM, c.TwoJM, c.IM, pr.n, pr.ts, pr.ir);
+         if (k < 0) continue;
+         double* blk = t_right.data() + TR.blk[k].off;
+         const double fb = std::sqrt((c.TwoJM + 1.0) / (pr.ts + 1));
+         for (int l = 0; l < lim; l++) {
+            const double f = fb * (moving_right ? Lam[ic][l] : 1.0);
+            for (int r = 0; r < pr.dim; r++) blk[l + (size_t)dimM * r] = f * VTs[ic][l + (size_t)cdim[ic] * (pr.start + r)];
+         }
+      }
+   }
+   return discarded;
+}
+
+// Left-normalise a site tensor in place (what TensorT::QR does with the R factor discarded, TensorT.cpp:188-289): for every right
+// sector the stacked left blocks get orthonormal columns (modified Gram-Schmidt, twice).
+void left_normalize_host(const Bookkeeper& bk, const TLayout& T, double* t) {
+   const int ix = T.site;
+   bk.for_sectors(ix + 1, [&](int NR, int TwoSR, int IR) {
+      const int dR = bk.dim(ix + 1, NR, TwoSR, IR);
+      if (dR <= 0) return;
+      std::vector<int> ks;
+      int rows = 0;
+      for (int k = 0; k < T.nkappa(); k++)
+         if (T.NR[k] == NR && T.twoSR[k] == TwoSR && T.IR[k] == IR) { ks.push_back(k); rows += T.blk[k].rows; }
+      if (rows == 0) return;
+      std::vector<double> A((size_t)rows * dR);
+      int r0 = 0;
+      for (int k : ks) {
+         for (int c = 0; c < dR; c++)
+            for (int r = 0; r < T.blk[k].rows; r++) A[r0 + r + (size_t)rows * c] = t[T.blk[k].off + r + (size_t)T.blk[k].rows * c];
+         r0 += T.blk[k].rows;
+      }
+      for (int c = 0; c < dR; c++) {
+         double* col = &A[(size_t)rows * c];
+         for (int pass = 0; pass < 2; pass++)
+            for (int p = 0; p < c; p++) {
+               const double* q = &A[(size_t)rows * p];
+               double d = 0.0;
+               for (int r = 0; r < rows; r++) d += q[r] * col[r];
+               for (int r = 0; r < rows; r++) col[r] -= d * q[r];
+            }
+         double n = 0.0;
+         for (int r = 0; r < rows; r++) n += col[r] * col[r];
+         n = std::sqrt(n);
+         const double inv = (n > 1e-14) ? 1.0 / n : 0.0;
+         for (int r = 0; r < rows; r++) col[r] *= inv;
+      }
+      r0 = 0;
+      for (int k : ks) {
+         for (int c = 0; c < dR; c++)
+            for (int r = 0; r < T.blk[k].rows; r++) t[T.blk[k].off + r + (size_t)T.blk[k].rows * c] = A[r0 + r + (size_t)rows * c];
+         r0 += T.blk[k].rows;
+      }
+   });
+}
+
+}   // namespace b2

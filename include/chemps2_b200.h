@@ -194,6 +194,28 @@ int64_t b2_update_num_presum_parts(const b2_update* u);
 int64_t b2_update_presum_size(const b2_update* u);
 int b2_update_export_presums(const b2_update* u, b2_flat_presum* out);
 
+/* ------------------------------------------------------------------------------------------------ sweep driver
+ * The part of CheMPS2::DMRG the hot path lives in (DMRG.cpp:357-452): it owns the MPS site tensors (host, TensorT::gStorage()
+ * layouts) and one operator set per boundary and direction (device), and strings the pieces together:
+ *   b2_dmrg_update      = DMRG::updateMovingRight(index) (moving_right != 0: operators of boundary index+1 from MPS[index])
+ *                         / updateMovingLeft (moving_right == 0: operators of boundary index from MPS[index])
+ *   b2_dmrg_solve_site  = DMRG::solve_site: Sobject::Join (device) -> Heff::SolveDAVIDSON (device) -> addNoise -> Sobject::Split
+ *                         (host SVD; virtual dimensions of boundary index+1 are rewritten when change != 0); *energy includes Econst
+ *   b2_dmrg_sweep       = DMRG::sweepleft (to_right == 0: index L-2 .. 1) / sweepright (index 0 .. L-3) incl. the operator updates */
+typedef struct b2_dmrg b2_dmrg;
+int b2_dmrg_create(b2_ctx* ctx, b2_dmrg** out);
+void b2_dmrg_destroy(b2_dmrg* d);
+int64_t b2_dmrg_mps_size(const b2_dmrg* d, int site);
+int b2_dmrg_set_mps(b2_dmrg* d, int site, const double* t_storage);
+int b2_dmrg_get_mps(const b2_dmrg* d, int site, double* t_storage);
+int b2_dmrg_random_mps(b2_dmrg* d, uint64_t seed);           /* random + left-normalised, DMRG.cpp:149-169 (own RNG stream) */
+b2_opset* b2_dmrg_opset(b2_dmrg* d, int boundary, int moving_right);
+int b2_dmrg_set_opset(b2_dmrg* d, int boundary, int moving_right, b2_opset* set);   /* the driver takes ownership */
+int b2_dmrg_update(b2_dmrg* d, int index, int moving_right);
+int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, int moving_right, int change, double* energy,
+                       double* discarded_weight, int* n_matvec);
+int b2_dmrg_sweep(b2_dmrg* d, int to_right, double rtol, double noise, int D, int change, double* min_energy, double* max_discarded);
+
 /* scheduling knobs of plans created afterwards: "work_budget" (doubles of stage-1 workspace per wave), "chunk_k" */
 int b2_ctx_set_option(b2_ctx* ctx, const char* name, double value);
 /* host mirrors of the operator arenas (valid until the set is destroyed) */

@@ -1,0 +1,97 @@
+"""End-to-end parity of the sweep (Join -> device Davidson -> Split -> operator updates) against the reference's own sweep.
+
+The golden fixtures hold the reference's MPS, virtual dimensions and boundary operators at the moment DMRG::solve_site is
+about to be called at site A during a left sweep, and the energy of every later micro-iteration of that left sweep and of
+the following right sweep.  Starting from that state, our sweep must reproduce those energies (north_star: 1e-9 Eh)."""
+import numpy as np
+import pytest
+
+import cpu_check
+from chemps2_b200 import api, fixtures
+
+pytestmark = pytest.mark.gpu
+
+
+def _start_from_fixture(golden, tag):
+    ctx = api.context_from_fixture(golden, tag, device=0)
+    d = api.DMRG(ctx)
+    for s in range(ctx.L):
+        d.set_mps(s, golden[f"{tag}/mps/{s}"])
+    return ctx, d
+
+
+def test_rebuilt_operators_match_reference(golden):
+    """operators rebuilt from the reference's MPS by our own updates (moving right over sites 0..A-1 and moving left over sites
+    L-1..A+2) equal the reference's operator sets at the two boundaries of the site pair"""
+    ctx, d = _start_from_fixture(golden, "A")
+    L, site = ctx.L, int(golden["A/hdr"][0])
+    for i in range(site):
+        d.update(i, True)
+    for i in range(L - 1, site + 1, -1):
+        d.update(i, False)
+    for side, b, mr in (("left", site, True), ("right", site + 2, False)):
+        if f"A/{side}/hdr" not in golden:
+            continue
+        _, _, ops = fixtures.split_ops(golden, f"A/{side}")
+        for kind, i, j, data in ops:
+            if data.size == 0:
+                continue
+            got = d.opset_download(b, mr, kind, i, j)
+            assert np.abs(got - data).max() <= 1e-10 * max(1.0, np.abs(data).max()), (side, api.KIND_NAMES[kind], i, j)
+
+
+def test_sweep_energies_match_reference(golden):
+    ctx, d = _start_from_fixture(golden, "A")
+    L, site = ctx.L, int(golden["A/hdr"][0])
+    D = _fixture_D(golden)
+    en = golden["energies"]
+    npre = len(en) - 2 * (L - 2)
+    for i in range(site):
+        d.update(i, True)
+    for i in range(L - 1, site + 1, -1):
+        d.update(i, False)
+    change = npre > 0   # the first-ever left sweep of the reference runs with fixed dimensions (DMRG.cpp:270,311)
+    got, ref = [], []
+    for index in range(site, 0, -1):                       # rest of the left sweep
+        e, dw, nm = d.solve_site(index, 1e-8, 0.0, D, False, change)
+        d.update(index + 1, False)
+        got.append(e); ref.append(en[npre + (L - 2 - index)])
+    for index in range(0, L - 2):                          # the following right sweep
+        e, dw, nm = d.solve_site(index, 1e-8, 0.0, D, True, True)
+        d.update(index, True)
+        got.append(e); ref.append(en[npre + (L - 2) + index])
+    got, ref = np.array(got), np.array(ref)
+    assert np.abs(got - ref).max() < 1e-9, np.abs(got - ref).max()
+
+
+def _fixture_D(golden):
+    """bond dimension the fixture was generated with (tests/golden/make_golden.py): keyed by (L, N, twoS)"""
+    L, _, N, twoS, _ = [int(x) for x in golden["problem/hdr"]]
+    return {(10, 14, 0): 24, (10, 14, 4): 32, (13, 10, 0): 20, (10, 9, 5): 16, (9, 10, 2): 24, (9, 10, 0): 24}[(L, N, twoS)]
+
+
+def test_full_dmrg_n2_sto3g_known_answer():
+    """own start (random MPS), own sweeps: N2/STO-3G 1Ag ground state.  Known answer of the reference's test5
+    (tests/test5.cpp.in:83): -107.648250974014, pinned there to 1e-8."""
+    import os
+    fx = fixtures.load(os.path.join(os.path.dirname(__file__), "golden", "n2_sto3g_singlet.npz"))
+    L, group, N, twoS, irrep = [int(x) for x in fx["problem/hdr"]]
+    ctx = api.Context(0)
+    ctx.set_problem(L, group, N, twoS, irrep, fx["problem/orb_irrep"], mx=fx["problem/mx"], econst=float(fx["problem/econst"][0]))
+    D = 200
+    ctx.bk_init(D)
+    d = api.DMRG(ctx)
+    d.random_mps(1234)
+    for i in range(L - 2):
+        d.update(i, True)                                   # DMRG::PreSolve (DMRG.cpp:257-266)
+    e_prev, change = 0.0, False
+    for it in range(8):
+        noise = 0.05 * 1e-3 if it < 3 else 0.0
+        el, _ = d.sweep(False, 1e-8, noise, D, change)
+        change = True
+        er, _ = d.sweep(True, 1e-8, noise, D, change)
+        e = min(el, er)
+        if it >= 3 and abs(e - e_prev) < 1e-10:
+            break
+        e_prev = e
+    assert abs(e - (-107.648250974014)) < 1e-8, e

@@ -67,6 +67,17 @@ double CompiledWork::bytes() const {
 
 void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vector<DstBlock>& dst, uint8_t dst_space, const CompileOptions& opt) {
    out = CompiledWork();
+   {  // every destination block must form ONE contiguous group: two groups would become two CTAs that read-modify-write the same
+      // tile in one launch.  Generators that visit a block twice (e.g. TensorQ/TensorX: update + AddTerms) are regrouped here.
+      std::vector<char> seen(dst.size(), 0);
+      bool grouped = true;
+      for (size_t i = 0; i < terms.size() && grouped; i++) {
+         if (i > 0 && terms[i].dst == terms[i - 1].dst) continue;
+         if (seen[terms[i].dst]) grouped = false;
+         seen[terms[i].dst] = 1;
+      }
+      if (!grouped) std::stable_sort(terms.begin(), terms.end(), [](const Term3& a, const Term3& b) { return a.dst < b.dst; });
+   }
    std::unordered_map<WKey, WInfo, WKeyHash> wmap;
    int64_t wave_work = 0, wave_part = 0;
    Wave wave{};

@@ -148,6 +148,11 @@ int davidson_solve(void* stream_v, int64_t n, const MatVec& matvec, double* x_de
       DV_CUDA(fetch(1));
       const double rnorm = std::sqrt(h_scal[0]);
       if (!(rnorm > prm.rtol)) break;   // converged (Davidson.cpp:141,160)
+      if (nmult > prm.max_matvec) {
+         snprintf(errbuf, errlen, "davidson: no convergence after %d matrix-vector products (residual %.3e, rtol %.3e)", nmult, rnorm, prm.rtol);
+         cleanup();
+         return -4;
+      }
       // ---- CalculateNewVec (Davidson.cpp:322-350)
       DV_DEV(dev_precond_dots(work, u, t, diag_dev, theta, prm.cutoff, n, scal, scratch, s));
       DV_DEV(dev_precond_apply(t, u, diag_dev, scal, theta, prm.cutoff, n, s));

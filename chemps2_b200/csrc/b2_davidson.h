@@ -13,6 +13,7 @@ struct DavidsonParams {
    int keep_vec = 3;          // DAVIDSON_NUM_VEC_KEEP  (Options.h:71)
    double rtol = 1e-5;        // per-instruction residual tolerance
    double cutoff = 1e-12;     // DAVIDSON_PRECOND_CUTOFF (Options.h:72)
+   int max_matvec = 5000;     // safety net (the reference loops until convergence)
 };
 
 // out_dev = H * in_dev, asynchronous on `stream`; returns 0 on success

@@ -3,14 +3,15 @@
 // k_tiles<TM,TN,WM,WN>: grouped FP64 contraction.  One CTA owns one output tile of one symmetry block and
 //   accumulates EVERY term that lands on it in registers (deterministic, no atomics):
 //       C_tile = sum_items alpha * opX(X) * opY(Y)
-//   Operand panels are staged through shared memory (k-major, padded so that the DMMA fragment loads are
-//   bank-conflict free for 64-bit accesses) and multiplied with FP64 tensor-core MMA
+//   Operand panels are staged through shared memory (one odd-stride layout, conflict free for the staging writes of both
+//   operand orientations and for the DMMA fragment loads) and multiplied with FP64 tensor-core MMA
 //   (mma.sync.aligned.m8n8k4.f64 -> SASS DMMA).  tcgen05/UMMA has no FP64 path, so warp-level DMMA is the
 //   tensor pipe this workload can use on sm_100a.
 // k_presum: integral-weighted operator pre-sums (HBM-bound, vectorised, coalesced).
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <type_traits>
 
 #include "b2_device.h"
 
@@ -24,111 +25,145 @@ static int cuda_fail(cudaError_t e, const char* what) {
 }
 
 __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
-   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
 constexpr int KC = 16;       // k-chunk staged per pipeline stage
 constexpr int STAGES = 3;    // cp.async pipeline depth
 
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-   const int bytes = valid ? 8 : 0;   // src-size 0 => the 8 destination bytes are zero-filled
+   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async8_zfill(double* smem_dst, const double* gsrc, bool valid) {
+   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+   const int bytes = valid ? 8 : 0;   // src-size 0 => nothing is read, the 8 destination bytes are zero-filled
    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(bytes));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// Shared-memory operand panels keep the operand's own contiguous direction (so global reads stay coalesced whatever
-// the transposition flag) and are padded so that the 64-bit DMMA fragment loads of a half-warp hit 16 distinct bank pairs:
-//   "m-major"  P[k][m], stride T+4   (T = 64/32/16/8: stride == 4 mod 8 doubles)
-//   "k-major"  P[m][k], stride KC+4  (20 doubles)
+// Shared-memory operand panels: ONE layout whatever the transposition flag of the operand, P[k][r] with an ODD row
+// stride RS = T + 1 doubles.  Together with the k-interleaved MMA steps (step s multiplies k = s, s+4, s+8, s+12, i.e.
+// fragment lane q holds k = s + 4q) every access pattern of a half-warp hits 16 distinct 8-byte bank pairs:
+//   fragment loads     (4 q) x (4 rows):  (4q*RS + g) mod 16  -> 4*(q*RS mod 4) + g        distinct because RS is odd
+//   row-contiguous staging: 16 consecutive r at one k                                       consecutive addresses
+//   k-contiguous staging:   16 consecutive k at one r:  k*RS mod 16                         distinct because RS is odd
+// and every address is (lane part) + (compile-time part): no swizzle arithmetic in the inner loop.
 template <int T> struct Panel {
-   static constexpr int SM = T + 4, SK = KC + 4;
-   static constexpr int SIZE = (KC * SM > T * SK) ? KC * SM : T * SK;
+   static constexpr int RS = T + 1;
+   static constexpr int SIZE = KC * RS;
 };
 
-// Per-item staging cursor of one operand panel.  For a T x KC panel and NT threads every thread copies E = T*KC/NT
-// elements per chunk; with the thread -> element map below all E elements of a thread share one coordinate, so the
-// global pointer, the validity of that coordinate and the shared-memory slot are computed once per item and a chunk
-// costs one predicate + one pointer bump + one cp.async per element (the index arithmetic used to dominate issue slots).
-//   contig_r  (stored R x K, rows contiguous)  -> "m-major" panel P[k][r]:  r = tid % T fixed,   k = tid / T + e * (NT / T)
-//   !contig_r (stored K x R, k contiguous)     -> "k-major" panel P[r][k]:  k = tid % KC fixed,  r = tid / KC + e * (NT / KC)
+// Per-item staging cursor of one T x KC operand panel copied by NT threads, E = T*KC/NT elements per thread and chunk,
+// one 8-byte cp.async each.  The thread -> element map keeps the GLOBAL reads in as few 128-byte lines as possible (the
+// LSU spends one shared-memory wavefront per line a cp.async touches):
+//   rows contiguous (stored R x K):  r = tid % T, k = tid / T + e*(NT/T)     a warp reads 32 consecutive rows of one column
+//   k contiguous    (stored K x R):  k = tid % 16, r = tid / 16 + e*(NT/16)  a half-warp reads the 16 k of one row
+// Element e sits at a compile-time shared-memory offset from element 0 and one constant pointer bump further in global
+// memory.  Rows past the tile edge: the row-contiguous map clamps its (single) row, the k-contiguous map zero-fills them
+// (rowmask); k past the end of the item is zero-filled in the tail chunk.
 template <int T, int NT> struct Stager {
    static constexpr int E = (T * KC) / NT;
-   static_assert((T * KC) % NT == 0 && E >= 1, "panel must split evenly over the CTA");
-   const double* g;      // global pointer of element e = 0 of the current chunk
-   long long estep;      // global stride between consecutive e
-   long long cstep;      // global stride between consecutive chunks
-   int soff, sstep;      // shared-memory slot of e = 0 and stride between consecutive e
-   int fix_ok;           // the fixed coordinate is inside the matrix (contig_r: r < rrem; else evaluated per chunk: k0 + k < K)
-   int var0, varstep;    // the varying coordinate of e = 0 and its step
-   int kfix;             // !contig_r: k of this thread
-   bool contig;
+   static_assert((T * KC) % NT == 0 && E >= 2 && E <= 16 && NT % 16 == 0 && NT % T == 0, "panel must split evenly over the CTA");
+   static constexpr unsigned FULLMASK = (1u << E) - 1u;
+   static constexpr int RS = Panel<T>::RS;
+   static constexpr int KSTEP = NT / T;     // row-contiguous map: k advance per element
+   static constexpr int RSTEP = NT / 16;    // k-contiguous map: row advance per element
+   const double* g;         // global address of element 0 of the current chunk
+   int estep;               // pointer bump element -> element (doubles)
+   int soff;                // shared-memory slot of element 0
+   unsigned rowmask;        // bit e: the row of element e is inside the tile; bit 31: rows contiguous
 
    __device__ __forceinline__ void init(const double* G, int ld, bool contig_r, int r0, int rrem, int tid) {
-      contig = contig_r;
       if (contig_r) {
-         const int r = tid % T, kb = tid / T;
-         g = G + (size_t)(r0 + r) + (size_t)kb * ld;
-         estep = (long long)(NT / T) * ld; cstep = (long long)KC * ld;
-         soff = kb * Panel<T>::SM + r; sstep = (NT / T) * Panel<T>::SM;
-         fix_ok = r < rrem; var0 = kb; varstep = NT / T; kfix = 0;
+         const int r = min(tid % T, rrem - 1);
+         const int kt = tid / T;
+         g = G + (size_t)(r0 + r) + (size_t)kt * ld;
+         estep = KSTEP * ld;
+         soff = kt * RS + tid % T;
+         rowmask = FULLMASK | 0x80000000u;
       } else {
-         const int k = tid % KC, rb = tid / KC;
-         g = G + (size_t)k + (size_t)(r0 + rb) * ld;
-         estep = (long long)(NT / KC) * ld; cstep = KC;
-         soff = rb * Panel<T>::SK + k; sstep = (NT / KC) * Panel<T>::SK;
-         fix_ok = 1; var0 = rb; varstep = NT / KC; kfix = k;
+         const int kt = tid & 15;
+         const int rt = tid >> 4;
+         g = G + (size_t)kt + (size_t)(r0 + rt) * ld;
+         estep = RSTEP * ld;
+         soff = kt * RS + rt;
+         rowmask = 0;
+#pragma unroll
+         for (int e = 0; e < E; e++) rowmask |= (rt + RSTEP * e < rrem) ? (1u << e) : 0u;
       }
    }
-   // copies the chunk that starts at k0 (kleft = K - k0 > 0 columns left); rrem = rows of the tile
-   __device__ __forceinline__ void chunk(double* P, int kleft, int rrem) {
+   // copies the chunk whose first column is the cursor position; kleft > 0 columns of the item are left
+   __device__ __forceinline__ void chunk(double* P, int kleft, const double* safe, int tid) {
       const double* p = g;
-      if (contig) {
+      double* s = P + soff;
+      const bool contig = (rowmask >> 31) != 0u;
+      if (kleft >= KC && (rowmask & FULLMASK) == FULLMASK) {
+         if (contig) {
 #pragma unroll
-         for (int e = 0; e < E; e++) {
-            const bool ok = fix_ok && (var0 + e * varstep < kleft);
-            cp_async8(P + soff + e * sstep, ok ? p : g, ok);
-            p += estep;
+            for (int e = 0; e < E; e++) { cp_async8(s + e * KSTEP * RS, p); p += estep; }
+         } else {
+#pragma unroll
+            for (int e = 0; e < E; e++) { cp_async8(s + e * RSTEP, p); p += estep; }
          }
       } else {
-         const bool kok = kfix < kleft;
+         if (contig) {
+            const int kt = tid / T;
 #pragma unroll
-         for (int e = 0; e < E; e++) {
-            const bool ok = kok && (var0 + e * varstep < rrem);
-            cp_async8(P + soff + e * sstep, ok ? p : g, ok);
-            p += estep;
+            for (int e = 0; e < E; e++) {
+               const bool ok = kt + e * KSTEP < kleft;
+               cp_async8_zfill(s + e * KSTEP * RS, ok ? p : safe, ok);
+               p += estep;
+            }
+         } else {
+            const bool kok = (tid & 15) < kleft;
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+               const bool ok = kok && ((rowmask >> e) & 1u);
+               cp_async8_zfill(s + e * RSTEP, ok ? p : safe, ok);
+               p += estep;
+            }
          }
       }
-      g += cstep;
+      g += contig ? (long long)estep * (KC / KSTEP) : (long long)KC;
    }
 };
 
-// one k-chunk of MMAs; XM / YM: the X / Y panel is m-major (compile-time so that the fragment addresses fold to immediates)
-template <int TM, int TN, int MI, int NI, bool XM, bool YM>
-__device__ __forceinline__ void mma_chunk(double (&acc)[MI][NI][2], const double* __restrict__ xs, const double* __restrict__ ys, int rbase, int cbase,
-                                          int q, int kvalid, double alpha, int mi_n, int ni_n) {
-   const double* xa = XM ? xs + q * Panel<TM>::SM + rbase : xs + rbase * Panel<TM>::SK + q;
-   const double* yb = YM ? ys + q * Panel<TN>::SM + cbase : ys + cbase * Panel<TN>::SK + q;
+// one MMA step of a k-chunk: step S multiplies k = S + 4q (q = fragment lane).  ALL: every one of the MI x NI 8x8 sub-tiles
+// of the warp is computed, no predicates (sub-tiles outside the tile see clamped / zero-filled panel rows and are never
+// stored).  SCALE: alpha != 1.
+template <int TM, int TN, int MI, int NI, bool ALL, bool SCALE, int S>
+__device__ __forceinline__ void mma_step(double (&acc)[MI][NI][2], const double* __restrict__ xa, const double* __restrict__ yb, double alpha, int mi_n, int ni_n) {
+   constexpr int RSX = Panel<TM>::RS, RSY = Panel<TN>::RS;
+   double a[MI], b[NI];
 #pragma unroll
-   for (int kk = 0; kk < KC; kk += 4) {
-      if (kk < kvalid) {
-         double a[MI], b[NI];
+   for (int i = 0; i < MI; i++) a[i] = SCALE ? alpha * xa[S * RSX + i * 8] : xa[S * RSX + i * 8];
 #pragma unroll
-         for (int i = 0; i < MI; i++) a[i] = alpha * (XM ? xa[kk * Panel<TM>::SM + i * 8] : xa[i * 8 * Panel<TM>::SK + kk]);
+   for (int j = 0; j < NI; j++) b[j] = yb[S * RSY + j * 8];
 #pragma unroll
-         for (int j = 0; j < NI; j++) b[j] = YM ? yb[kk * Panel<TN>::SM + j * 8] : yb[j * 8 * Panel<TN>::SK + kk];
+   for (int i = 0; i < MI; i++)
 #pragma unroll
-         for (int i = 0; i < MI; i++)
-#pragma unroll
-            for (int j = 0; j < NI; j++)
-               if (i < mi_n && j < ni_n) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-      }
-   }
+      for (int j = 0; j < NI; j++)
+         if (ALL || (i < mi_n && j < ni_n)) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+}
+
+// one k-chunk: the four MMA steps with the cp.async copies of a later chunk issued in between (the copies do not depend on
+// the MMAs; spreading them over the chunk keeps the DMMA pipe fed right after the barrier).  FULLK: all KC columns valid,
+// else steps >= kvalid are skipped (columns >= kvalid are zero).
+template <int TM, int TN, int MI, int NI, bool ALL, bool SCALE, bool FULLK, class FX, class FY>
+__device__ __forceinline__ void mma_chunk(double (&acc)[MI][NI][2], const double* __restrict__ xa, const double* __restrict__ yb, int kvalid, double alpha,
+                                          int mi_n, int ni_n, FX&& stage_x, FY&& stage_y) {
+   mma_step<TM, TN, MI, NI, ALL, SCALE, 0>(acc, xa, yb, alpha, mi_n, ni_n);
+   stage_x();
+   if (FULLK || 1 < kvalid) mma_step<TM, TN, MI, NI, ALL, SCALE, 1>(acc, xa, yb, alpha, mi_n, ni_n);
+   stage_y();
+   if (FULLK || 2 < kvalid) mma_step<TM, TN, MI, NI, ALL, SCALE, 2>(acc, xa, yb, alpha, mi_n, ni_n);
+   if (FULLK || 3 < kvalid) mma_step<TM, TN, MI, NI, ALL, SCALE, 3>(acc, xa, yb, alpha, mi_n, ni_n);
 }
 
 template <int TM, int TN, int WM, int WN>
-__global__ void __launch_bounds__(WM * WN * 32) k_tiles(const Tile* __restrict__ tiles, const GemmItem* __restrict__ items, DevBases bases) {
+__global__ void __launch_bounds__(WM * WN * 32, (TM == 64) ? 4 : 1) k_tiles(const Tile* __restrict__ tiles, const GemmItem* __restrict__ items, DevBases bases) {
    constexpr int NT = WM * WN * 32;
    constexpr int WTM = TM / WM, WTN = TN / WN;   // warp tile
    constexpr int MI = WTM / 8, NI = WTN / 8;     // 8x8 MMA tiles per warp
@@ -137,13 +172,14 @@ __global__ void __launch_bounds__(WM * WN * 32) k_tiles(const Tile* __restrict__
    double* Xs = smem;                    // STAGES panels
    double* Ys = smem + STAGES * XSZ;
 
-   const Tile t = tiles[blockIdx.x];
+   const Tile* __restrict__ tp = tiles + blockIdx.x;
+   const int m0 = tp->m0, n0 = tp->n0, mrem = tp->mrem, nrem = tp->nrem, item_end = tp->item_end;
    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-   const int wm = warp % WM, wn = warp / WM;
+   // the warp -> sub-tile map alternates with the CTA index: partial tiles always leave the LAST warp row / column short,
+   // and warp w of every CTA lives on scheduler w % 4, so a fixed map would systematically underload two of the four
+   const int wflip = (int)(blockIdx.x & 1u);
+   const int wm = (warp % WM) ^ (wflip & (WM - 1)), wn = (warp / WM) ^ (wflip & (WN - 1));
    const int g = lane >> 2, q = lane & 3;        // fragment coordinates
-   // 8x8 sub-tiles of this warp that lie (partly) inside the tile; the rest is skipped (warp-uniform)
-   const int mi_n = min(MI, max(0, (t.mrem - wm * WTM + 7) >> 3));
-   const int ni_n = min(NI, max(0, (t.nrem - wn * WTN + 7) >> 3));
 
    double acc[MI][NI][2];
 #pragma unroll
@@ -151,76 +187,98 @@ __global__ void __launch_bounds__(WM * WN * 32) k_tiles(const Tile* __restrict__
 #pragma unroll
       for (int j = 0; j < NI; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-   // ---- block-axpy items come first in every item range (b2_compile.cpp sorts them there)
-   int it0 = t.item_begin;
-   for (; it0 < t.item_end; it0++) {
-      const GemmItem I = items[it0];
-      if (!(I.flags & IF_AXPY)) break;
+   // ---- GEMM items: one flattened stream of k-chunks over all items, software-pipelined with cp.async.  Block-axpy
+   // items come first in every item range (b2_compile.cpp sorts them there).
+   int it0 = tp->item_begin;
+   while (it0 < item_end && (items[it0].flags & IF_AXPY)) it0++;
+   const double* safe = reinterpret_cast<const double*>(tiles);   // valid, aligned dummy source of zero-filled copies
+   int p_it = it0, p_left = 0;          // producer cursor: item, columns of K still to stage
+   Stager<TM, NT> sx;
+   Stager<TN, NT> sy;
+   auto producer_load_item = [&]() {
+      const GemmItem P = items[p_it];
+      sx.init(bases.p[P.xs] + P.xoff, P.ldx, !(P.flags & IF_TX), m0, mrem, tid);
+      sy.init(bases.p[P.ys] + P.yoff, P.ldy, (P.flags & IF_TY) != 0, n0, nrem, tid);
+      p_left = P.k;
+   };
+   if (p_it < item_end) producer_load_item();
+   auto stage_x_at = [&](int ps) {
+      if (p_it < item_end) sx.chunk(Xs + ps * XSZ, p_left, safe, tid);
+   };
+   auto stage_y_at = [&](int ps) {
+      if (p_it < item_end) {
+         sy.chunk(Ys + ps * YSZ, p_left, safe, tid);
+         p_left -= KC;
+         if (p_left <= 0 && ++p_it < item_end) producer_load_item();
+      }
+      cp_async_commit();
+   };
+#pragma unroll
+   for (int s = 0; s < STAGES - 1; s++) { stage_x_at(s); stage_y_at(s); }
+
+   // ---- block-axpy items (their global loads overlap the first panel copies)
+   for (int it = tp->item_begin; it < it0; it++) {
+      const GemmItem I = items[it];
       const double* __restrict__ X = bases.p[I.xs] + I.xoff;
 #pragma unroll
       for (int i = 0; i < MI; i++)
 #pragma unroll
          for (int j = 0; j < NI; j++) {
             const int r = wm * WTM + i * 8 + g, c = wn * WTN + j * 8 + 2 * q;
-            if (r < t.mrem) {
+            if (r < mrem) {
                if (I.flags & IF_TX) {
-                  if (c < t.nrem) acc[i][j][0] += I.alpha * X[(size_t)(t.n0 + c) + (size_t)(t.m0 + r) * I.ldx];
-                  if (c + 1 < t.nrem) acc[i][j][1] += I.alpha * X[(size_t)(t.n0 + c + 1) + (size_t)(t.m0 + r) * I.ldx];
+                  if (c < nrem) acc[i][j][0] += I.alpha * X[(size_t)(n0 + c) + (size_t)(m0 + r) * I.ldx];
+                  if (c + 1 < nrem) acc[i][j][1] += I.alpha * X[(size_t)(n0 + c + 1) + (size_t)(m0 + r) * I.ldx];
                } else {
-                  if (c < t.nrem) acc[i][j][0] += I.alpha * X[(size_t)(t.m0 + r) + (size_t)(t.n0 + c) * I.ldx];
-                  if (c + 1 < t.nrem) acc[i][j][1] += I.alpha * X[(size_t)(t.m0 + r) + (size_t)(t.n0 + c + 1) * I.ldx];
+                  if (c < nrem) acc[i][j][0] += I.alpha * X[(size_t)(m0 + r) + (size_t)(n0 + c) * I.ldx];
+                  if (c + 1 < nrem) acc[i][j][1] += I.alpha * X[(size_t)(m0 + r) + (size_t)(n0 + c + 1) * I.ldx];
                }
             }
          }
    }
 
-   // ---- GEMM items: one flattened stream of k-chunks over all items, software-pipelined with cp.async
-   int p_it = it0, p_left = 0;          // producer cursor: item, columns of K still to stage
-   Stager<TM, NT> sx;
-   Stager<TN, NT> sy;
-   auto producer_load_item = [&]() {
-      const GemmItem P = items[p_it];
-      sx.init(bases.p[P.xs] + P.xoff, P.ldx, !(P.flags & IF_TX), t.m0, t.mrem, tid);
-      sy.init(bases.p[P.ys] + P.yoff, P.ldy, (P.flags & IF_TY) != 0, t.n0, t.nrem, tid);
-      p_left = P.k;
+   int c_it = it0, c_left = 0, stage = 0;
+   double alpha = 1.0;
+   auto consumer_load_item = [&]() {
+      const GemmItem* __restrict__ Cn = items + c_it;
+      c_left = Cn->k; alpha = Cn->alpha;
    };
-   if (p_it < t.item_end) producer_load_item();
-   auto issue = [&](int stage) {
-      if (p_it < t.item_end) {
-         sx.chunk(Xs + stage * XSZ, p_left, t.mrem);
-         sy.chunk(Ys + stage * YSZ, p_left, t.nrem);
-         p_left -= KC;
-         if (p_left <= 0 && ++p_it < t.item_end) producer_load_item();
+   if (c_it < item_end) consumer_load_item();
+   const int xfrag = 4 * q * Panel<TM>::RS + wm * WTM + g, yfrag = 4 * q * Panel<TN>::RS + wn * WTN + g;
+   // 8x8 sub-tiles of this warp that lie (partly) inside the tile (warp-uniform).  A warp with >= 3/4 of its sub-tiles inside
+   // runs the predicate-free MMA path on all of them; the main loop is instantiated once per path.
+   const int mi_n = min(MI, max(0, (mrem - wm * WTM + 7) >> 3)), ni_n = min(NI, max(0, (nrem - wn * WTN + 7) >> 3));
+   auto main_loop = [&](auto wall_tag) {
+      constexpr bool WALL = decltype(wall_tag)::value;
+      while (c_it < item_end) {
+         cp_async_wait<STAGES - 2>();
+         __syncthreads();          // chunk `stage` has landed; everybody is done with the stage refilled below
+         const double* xa = Xs + stage * XSZ + xfrag;
+         const double* yb = Ys + stage * YSZ + yfrag;
+         const int ps = (stage == 0) ? STAGES - 1 : stage - 1;   // the stage consumed in the previous iteration is refilled
+         auto stage_x = [&]() { stage_x_at(ps); };
+         auto stage_y = [&]() { stage_y_at(ps); };
+         if (WALL) {
+            if (c_left >= KC) {
+               // alpha == 1 compared on the bit pattern: an FP64 compare would queue behind the DMMAs
+               if (__double2hiint(alpha) == 0x3FF00000 && __double2loint(alpha) == 0)
+                  mma_chunk<TM, TN, MI, NI, true, false, true>(acc, xa, yb, KC, alpha, MI, NI, stage_x, stage_y);
+               else mma_chunk<TM, TN, MI, NI, true, true, true>(acc, xa, yb, KC, alpha, MI, NI, stage_x, stage_y);
+            } else {
+               mma_chunk<TM, TN, MI, NI, true, true, false>(acc, xa, yb, c_left, alpha, MI, NI, stage_x, stage_y);
+            }
+         } else {
+            mma_chunk<TM, TN, MI, NI, false, true, false>(acc, xa, yb, c_left, alpha, mi_n, ni_n, stage_x, stage_y);
+         }
+         c_left -= KC;
+         if (c_left <= 0 && ++c_it < item_end) consumer_load_item();
+         stage = (stage + 1 == STAGES) ? 0 : stage + 1;
       }
-      cp_async_commit();
    };
-#pragma unroll
-   for (int s = 0; s < STAGES - 1; s++) issue(s);
-
-   int c_it = it0, c_left = 0, stage = 0, cflags = 0;
-   double alpha = 0.0;
-   if (c_it < t.item_end) { const GemmItem Cn = items[c_it]; c_left = Cn.k; cflags = Cn.flags; alpha = Cn.alpha; }
-   const int rbase = wm * WTM + g, cbase = wn * WTN + g;
-   while (c_it < t.item_end) {
-      cp_async_wait<STAGES - 2>();
-      __syncthreads();
-      issue((stage + STAGES - 1) % STAGES);   // refills the stage consumed in the previous iteration
-      const double* xs = Xs + stage * XSZ;
-      const double* ys = Ys + stage * YSZ;
-      const int kvalid = min(KC, c_left);
-      if (!(cflags & IF_TX)) {
-         if (cflags & IF_TY) mma_chunk<TM, TN, MI, NI, true, true>(acc, xs, ys, rbase, cbase, q, kvalid, alpha, mi_n, ni_n);
-         else mma_chunk<TM, TN, MI, NI, true, false>(acc, xs, ys, rbase, cbase, q, kvalid, alpha, mi_n, ni_n);
-      } else {
-         if (cflags & IF_TY) mma_chunk<TM, TN, MI, NI, false, true>(acc, xs, ys, rbase, cbase, q, kvalid, alpha, mi_n, ni_n);
-         else mma_chunk<TM, TN, MI, NI, false, false>(acc, xs, ys, rbase, cbase, q, kvalid, alpha, mi_n, ni_n);
-      }
-      c_left -= KC;
-      if (c_left <= 0 && ++c_it < t.item_end) { const GemmItem Cn = items[c_it]; c_left = Cn.k; cflags = Cn.flags; alpha = Cn.alpha; }
-      stage = (stage + 1) % STAGES;
-   }
+   if (mi_n * ni_n * 4 >= MI * NI * 3) main_loop(std::true_type{}); else main_loop(std::false_type{});
    cp_async_wait<0>();
 
+   const Tile t = *tp;
    double* __restrict__ C = bases.p[t.cspace] + t.coff;
 #pragma unroll
    for (int i = 0; i < MI; i++)

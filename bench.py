@@ -247,8 +247,15 @@ def main():
         flops_total = st["flops_ref"]
     kavg = float(np.mean(kern))
     achieved = flops_total / world / kavg / 1e12 if world > 1 else flops_total / kavg / 1e12
+    # DRAM bytes of the k_tiles launches of ONE sigma build of this workload, from the committed ncu capture (profiles/)
+    traffic = None
+    try:
+        if world == 1 and args.workload == "synth40" and args.D is None and args.dist == "gauss" and not args.work_budget and not args.chunk_k:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["k_tiles_dram_bytes_per_sigma_build"]
+    except Exception:
+        traffic = None
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s", "frac": achieved / peak.value,
-                "traffic": None, "kernel": "k_tiles (grouped FP64 DMMA contraction: stage-1 + stage-2 launches of one sigma build)",
+                "traffic": traffic, "kernel": "k_tiles (grouped FP64 DMMA contraction: stage-1 + stage-2 launches of one sigma build)",
                 "kernel_ms_per_sigma_build": kavg * 1e3,
                 "peak_source": "measured in this run: register-resident mma.sync.m8n8k4.f64 loop (b2_probe_fp64); MEASURED_PEAKS.json holds no FP64 figure"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

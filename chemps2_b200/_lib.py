@@ -98,6 +98,10 @@ SIGNATURES = [
     ("b2_dmrg_solve_site", C.c_int, [vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_ip]),
     ("b2_dmrg_sweep", C.c_int, [vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, c_dp, c_dp]),
     ("b2_update_create", C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.POINTER(vp)]),
+    ("b2_update_create_sharded", C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.POINTER(vp)]),
+    ("b2_update_set_allreduce", C.c_int, [vp, vp, vp]),
+    ("b2_dmrg_set_world", C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
+    ("b2_dmrg_timers", C.c_int, [vp, c_dp, C.c_int]),
     ("b2_update_destroy", None, [vp]),
     ("b2_update_run", C.c_int, [vp, c_dp]),
     ("b2_update_run_device", C.c_int, [vp, vp]),

@@ -194,10 +194,16 @@ class Heff:
 class Update:
     """operator renormalisation of one sweep step; stands for DMRG::updateMovingRight/Left (DMRGoperators.cpp:243-907)"""
 
-    def __init__(self, ctx, index, moving_right, old_set, new_set):
+    def __init__(self, ctx, index, moving_right, old_set, new_set, world=1, rank=0):
         self.ctx, self.old_set, self.new_set = ctx, old_set, new_set
         self.h = vp()
-        check(lib.b2_update_create(ctx.h, int(index), int(bool(moving_right)), old_set.h if old_set else None, new_set.h, C.byref(self.h)))
+        check(lib.b2_update_create_sharded(ctx.h, int(index), int(bool(moving_right)), old_set.h if old_set else None, new_set.h,
+                                           int(world), int(rank), C.byref(self.h)))
+
+    def set_allreduce(self, allreduce):
+        """allreduce: an AllReduce object (kept alive by this Update)"""
+        self._allreduce = allreduce
+        check(lib.b2_update_set_allreduce(self.h, allreduce.cfn, None))
 
     def close(self):
         if self.h:
@@ -240,6 +246,16 @@ class DMRG:
         except Exception:
             pass
 
+    def set_world(self, world, rank, allreduce=None):
+        """shard the sweep over `world` GPUs; allreduce: an AllReduce object (kept alive by this driver)"""
+        self._allreduce = allreduce
+        check(lib.b2_dmrg_set_world(self.h, int(world), int(rank), allreduce.cfn if allreduce else None, None))
+
+    def timers(self, reset=False):
+        o = np.zeros(5)
+        check(lib.b2_dmrg_timers(self.h, _dp(o), int(bool(reset))))
+        return dict(plan_s=o[0], solve_s=o[1], split_s=o[2], update_s=o[3], n_matvec=int(o[4]))
+
     def set_mps(self, site, data):
         a = np.ascontiguousarray(data, dtype=np.float64)
         check(lib.b2_dmrg_set_mps(self.h, int(site), _dp(a)))
@@ -279,6 +295,37 @@ class DMRG:
         e, dw = C.c_double(), C.c_double()
         check(lib.b2_dmrg_sweep(self.h, int(bool(to_right)), float(rtol), float(noise), int(D), int(bool(change)), C.byref(e), C.byref(dw)))
         return e.value, dw.value
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, vp, vp, C.c_int64, vp)
+
+
+class AllReduce:
+    """b2_allreduce_fn backed by torch.distributed (NCCL on the GPU box): sums a device vector over the ranks in place on the
+    stream the library hands over (the context stream = torch's current stream in bench.py).  Stands in for MPI_Allreduce of
+    the reference (Heff.cpp:350-365, DMRGoperators.cpp:449-533)."""
+
+    class _Dev:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False), "version": 3, "strides": None}
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.calls, self.doubles = 0, 0
+
+        def fn(user, ptr, n, stream):
+            try:
+                t = torch.as_tensor(AllReduce._Dev(ptr, n), device="cuda")
+                dist.all_reduce(t)
+                self.calls += 1
+                self.doubles += int(n)
+                return 0
+            except Exception as e:   # never let an exception cross the C boundary
+                print("AllReduce callback failed:", e)
+                return -1
+
+        self.cfn = ALLREDUCE_FN(fn)
 
 
 def context_from_fixture(fx, tag, device=-1):

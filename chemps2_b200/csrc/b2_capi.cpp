@@ -5,6 +5,8 @@
 #include <cstdio>
 #include <algorithm>
 #include <cmath>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -23,6 +25,7 @@
 using namespace b2;
 
 static thread_local std::string g_err;
+static double wall_seconds() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static int fail(int code, const char* fmt, ...) {
    char buf[512];
    va_list ap;
@@ -315,8 +318,11 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
    h->ctx = ctx;
    h->left = (site > 0) ? left : nullptr;
    h->right = (site < L - 2) ? right : nullptr;
+   const double tb0 = wall_seconds();
    build_sigma_plan(h->plan, ctx->bk, ctx->prob, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, site, world);
+   const double tb1 = wall_seconds();
    compile_sigma(h->comp, h->plan, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, rank, world, ctx->copt);
+   if (getenv("B2_TIMING")) fprintf(stderr, "b2_heff_create: enumerate %.3f s, schedule %.3f s, %zu terms\n", tb1 - tb0, wall_seconds() - tb1, h->plan.terms.size());
    if (ctx->device >= 0) {
       CUDA_TRY(cudaSetDevice(ctx->device));
       cudaStream_t s = ctx->stream;
@@ -588,7 +594,25 @@ struct b2_update {
    PresumJob* d_jobs = nullptr;
    PresumPart* d_parts = nullptr;
    double *d_presum = nullptr, *d_work = nullptr, *d_part = nullptr, *d_t = nullptr, *h_t = nullptr;
+   int world = 1, rank = 0;
+   std::vector<int> op_owner;              // GPU that computes new operator i in pass 0
+   b2_allreduce_fn allreduce = nullptr;
+   void* allreduce_user = nullptr;
 };
+
+// FLOPs the scheduler will spend on one update term (cheaper association order, as compile_terms picks it)
+static double term_cost(const Term3& t, const DstBlock& d) {
+   const double M = d.rows, N = d.cols;
+   const bool hp = t.p.present(), hq = t.q.present(), hr = t.r.present();
+   if (hp && hq && hr) {
+      const double k1 = t.q.op_rows(), k2 = t.q.op_cols();
+      return 2.0 * std::min(M * k1 * k2 + M * k2 * N, k1 * k2 * N + M * k1 * N);
+   }
+   if (hp && hq) return 2.0 * M * N * t.p.op_cols();
+   if (hq && hr) return 2.0 * M * N * t.q.op_cols();
+   if (hp && hr) return 2.0 * M * N * t.p.op_cols();
+   return 2.0 * M * N;
+}
 
 static void fill_worklists(const CompiledWork& c, b2_worklists* o) {
    o->items1 = c.items1.data(); o->n_items1 = (int64_t)c.items1.size();
@@ -603,7 +627,12 @@ static void fill_worklists(const CompiledWork& c, b2_worklists* o) {
 }
 
 int b2_update_create(b2_ctx* ctx, int index, int moving_right, b2_opset* old_set, b2_opset* new_set, b2_update** out) {
+   return b2_update_create_sharded(ctx, index, moving_right, old_set, new_set, 1, 0, out);
+}
+
+int b2_update_create_sharded(b2_ctx* ctx, int index, int moving_right, b2_opset* old_set, b2_opset* new_set, int world, int rank, b2_update** out) {
    if (!ctx || !ctx->have_bk || !new_set || !out) return fail(B2_ERR_STATE, "b2_update_create: bad arguments");
+   if (world < 1 || rank < 0 || rank >= world) return fail(B2_ERR_ARG, "b2_update_create: bad world/rank");
    const int L = ctx->bk.L;
    if (index < 0 || index > L - 1) return fail(B2_ERR_ARG, "b2_update_create: site %d out of range", index);
    const bool mr = moving_right != 0;
@@ -614,6 +643,29 @@ int b2_update_create(b2_ctx* ctx, int index, int moving_right, b2_opset* old_set
    std::unique_ptr<b2_update> u(new b2_update);
    u->ctx = ctx; u->old_set = need_old ? old_set : nullptr; u->new_set = new_set;
    build_update_plan(u->plan, ctx->bk, ctx->prob, u->old_set ? &u->old_set->set : nullptr, new_set->set, index, mr);
+   u->world = world; u->rank = rank;
+   {  // pass 0 is sharded by NEW operator: greedy longest-processing-time assignment of the operators to the GPUs by the
+      // FLOPs of their terms (the reference's static owner maps, MPIchemps2.h:158-231, balance counts, not work; every rank
+      // evaluates the same deterministic assignment).  The partial arenas are summed by the all-reduce callback.
+      const int nops = (int)u->plan.block_base.size();
+      std::vector<double> cost(nops, 0.0);
+      auto op_of_block = [&](int blk) { return (int)(std::upper_bound(u->plan.block_base.begin(), u->plan.block_base.end(), blk) - u->plan.block_base.begin()) - 1; };
+      for (const Term3& t : u->plan.terms) cost[op_of_block(t.dst)] += term_cost(t, u->plan.dst[t.dst]);
+      std::vector<int> order(nops);
+      for (int i = 0; i < nops; i++) order[i] = i;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+      std::vector<double> load(world, 0.0);
+      u->op_owner.assign(nops, 0);
+      for (int i : order) {
+         const int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+         u->op_owner[i] = r; load[r] += cost[i];
+      }
+      if (world > 1) {
+         std::vector<Term3> mine;
+         for (const Term3& t : u->plan.terms) if (u->op_owner[op_of_block(t.dst)] == rank) mine.push_back(t);
+         u->plan.terms.swap(mine);
+      }
+   }
    compile_terms(u->pass[0], u->plan.terms, u->plan.dst, SP_VOUT, ctx->copt);
    compile_terms(u->pass[1], u->plan.mix_terms, u->plan.dst, SP_VOUT, ctx->copt);
    for (const Presum& p : u->plan.presums) {
@@ -677,7 +729,8 @@ int b2_update_run_device(b2_update* u, const double* t_dev) {
    b.p[SP_VOUT] = u->new_set->dev;
    if (dev_launch_presum(u->d_jobs, (int)u->presum_jobs.size(), u->d_parts, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
    if (dev_fill_zero(u->new_set->dev, u->new_set->set.size, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
-   for (int p = 0; p < 2; p++)
+   if (u->world > 1 && !u->allreduce) return fail(B2_ERR_STATE, "b2_update_run: sharded update (world %d) without an all-reduce callback", u->world);
+   for (int p = 0; p < 2; p++) {
       for (const Wave& w : u->pass[p].waves) {
          for (int c = 0; c < kNumTileClasses; c++)
             if (dev_launch_tiles(c, u->d_tiles1[p][c] + w.t1_begin[c], w.t1_end[c] - w.t1_begin[c], u->d_items1[p], b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
@@ -685,6 +738,10 @@ int b2_update_run_device(b2_update* u, const double* t_dev) {
             if (dev_launch_tiles(c, u->d_tiles2[p][c] + w.t2_begin[c], w.t2_end[c] - w.t2_begin[c], u->d_items2[p], b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
          if (dev_launch_reduce(u->d_reduces[p] + w.red_begin, w.red_end - w.red_begin, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
       }
+      // every GPU computed the operators it was assigned; summing the (otherwise zero) arenas replicates all of them before
+      // the mixing pass, which every GPU then runs in full (block axpys, replaces the MPI exchanges of DMRGoperators.cpp:449-533)
+      if (p == 0 && u->world > 1 && u->allreduce(u->allreduce_user, u->new_set->dev, u->new_set->set.size, (void*)s)) return fail(B2_ERR_STATE, "b2_update_run: all-reduce callback failed");
+   }
    return B2_OK;
 }
 int b2_update_run(b2_update* u, const double* t_host) {
@@ -696,6 +753,11 @@ int b2_update_run(b2_update* u, const double* t_host) {
    int rc = b2_update_run_device(u, u->d_t);
    if (rc) return rc;
    CUDA_TRY(cudaStreamSynchronize(u->ctx->stream));
+   return B2_OK;
+}
+int b2_update_set_allreduce(b2_update* u, b2_allreduce_fn fn, void* user) {
+   if (!u) return fail(B2_ERR_ARG, "b2_update_set_allreduce: NULL");
+   u->allreduce = fn; u->allreduce_user = user;
    return B2_OK;
 }
 int b2_update_stats(const b2_update* u, double* o) {
@@ -766,6 +828,11 @@ struct b2_dmrg {
    int L = 0;
    std::vector<std::vector<double>> mps;   // TensorT storage per site in the layouts of the current bookkeeper
    std::vector<b2_opset*> left, right;     // operator sets per boundary: moving right (sites < b) / moving left (sites >= b)
+   int world = 1, rank = 0;                // GPUs sharing the sweep: sigma terms and operator updates are sharded, the rest is replicated
+   b2_allreduce_fn allreduce = nullptr;
+   void* allreduce_user = nullptr;
+   double t_solve = 0.0, t_update = 0.0, t_split = 0.0, t_plan = 0.0;   // wall-clock seconds spent per phase (b2_dmrg_timers)
+   long long n_matvec = 0;
    unsigned long long rng = 0x9E3779B97F4A7C15ULL;
    double next_uniform() {                 // xorshift64*: our own stream (the reference uses rand(), Sobject.cpp:652-659)
       rng ^= rng >> 12; rng ^= rng << 25; rng ^= rng >> 27;
@@ -825,6 +892,18 @@ int b2_dmrg_set_opset(b2_dmrg* d, int boundary, int moving_right, b2_opset* set)
    return B2_OK;
 }
 
+int b2_dmrg_set_world(b2_dmrg* d, int world, int rank, b2_allreduce_fn fn, void* user) {
+   if (!d || world < 1 || rank < 0 || rank >= world || (world > 1 && !fn)) return fail(B2_ERR_ARG, "b2_dmrg_set_world: bad arguments");
+   d->world = world; d->rank = rank; d->allreduce = fn; d->allreduce_user = user;
+   return B2_OK;
+}
+int b2_dmrg_timers(b2_dmrg* d, double* out5, int reset) {
+   if (!d || !out5) return fail(B2_ERR_ARG, "b2_dmrg_timers: NULL");
+   out5[0] = d->t_plan; out5[1] = d->t_solve; out5[2] = d->t_split; out5[3] = d->t_update; out5[4] = (double)d->n_matvec;
+   if (reset) { d->t_plan = d->t_solve = d->t_split = d->t_update = 0.0; d->n_matvec = 0; }
+   return B2_OK;
+}
+
 // DMRG::updateMovingRight(index) / updateMovingLeft(index-1): operators of the boundary next to site `index` from T = MPS[index]
 int b2_dmrg_update(b2_dmrg* d, int index, int moving_right) {
    if (!d || index < 0 || index >= d->L) return fail(B2_ERR_ARG, "b2_dmrg_update: bad arguments");
@@ -839,8 +918,13 @@ int b2_dmrg_update(b2_dmrg* d, int index, int moving_right) {
    int rc = b2_opset_create(ctx, b_new, mr, &fresh);
    if (rc) return rc;
    b2_update* u = nullptr;
-   rc = b2_update_create(ctx, index, mr, need_old ? old_set : nullptr, fresh, &u);
+   const double t0 = wall_seconds();
+   rc = b2_update_create_sharded(ctx, index, mr, need_old ? old_set : nullptr, fresh, d->world, d->rank, &u);
+   if (!rc && d->world > 1) rc = b2_update_set_allreduce(u, d->allreduce, d->allreduce_user);
+   d->t_plan += wall_seconds() - t0;
+   const double t1 = wall_seconds();
    if (!rc) rc = b2_update_run(u, d->mps[index].data());
+   d->t_update += wall_seconds() - t1;
    b2_update_destroy(u);
    if (rc) { b2_opset_destroy(fresh); return rc; }
    return b2_dmrg_set_opset(d, b_new, mr, fresh);
@@ -857,8 +941,11 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
    b2_opset* rset = index < L - 2 ? d->right[index + 2] : nullptr;
    if ((index > 0 && !lset) || (index < L - 2 && !rset)) return fail(B2_ERR_STATE, "b2_dmrg_solve_site: boundary operators for site %d are missing", index);
    b2_heff* h = nullptr;
-   int rc = b2_heff_create(ctx, index, lset, rset, 1, 0, &h);
+   const double tp0 = wall_seconds();
+   int rc = b2_heff_create(ctx, index, lset, rset, d->world, d->rank, &h);
    if (rc) return rc;
+   if (d->world > 1) b2_heff_set_allreduce(h, d->allreduce, d->allreduce_user);
+   d->t_plan += wall_seconds() - tp0;
    const SLayout& S = h->plan.S;
    TLayout TL, TR;
    TL.build(ctx->bk, index); TR.build(ctx->bk, index + 1);
@@ -881,14 +968,18 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
       if ((rc = run_compiled_once(ctx, jw, b))) break;
       // ---- Heff::SolveDAVIDSON on the device
       double ev = 0.0; int nm = 0;
+      const double ts0 = wall_seconds();
       if ((rc = b2_heff_solve_device(h, d_s, rtol, &ev, &nm))) break;
+      d->t_solve += wall_seconds() - ts0; d->n_matvec += nm;
       *energy = ev + ctx->prob.econst;
       if (n_matvec) *n_matvec = nm;
       if (cudaMemcpyAsync(s_host.data(), d_s, sizeof(double) * (size_t)S.size, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) { rc = fail(B2_ERR_CUDA, "b2_dmrg_solve_site: D2H failed"); break; }
       if (noise > 0.0) for (double& x : s_host) x += (d->next_uniform() - 0.5) * noise;   // Sobject::addNoise
       // ---- Split (host SVD + truncation); the bookkeeper dims of boundary index+1 change here
       SLayout Scopy = S;
+      const double tq0 = wall_seconds();
       const double dw = split_host(ctx->bk, index, Scopy, s_host.data(), D, moving_right != 0, change != 0, d->mps[index], d->mps[index + 1]);
+      d->t_split += wall_seconds() - tq0;
       if (discarded_weight) *discarded_weight = dw;
    } while (0);
    cudaFree(d_tl); cudaFree(d_tr); cudaFree(d_s);

@@ -10,7 +10,9 @@
 #include "b2_compile.h"
 
 #include <algorithm>
-#include <unordered_map>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace b2 {
 
@@ -31,20 +33,56 @@ inline int balanced_step(int M, int edge) {
    return std::min(s, edge);
 }
 
-struct WKey {
-   int64_t off1, off2; int32_t rows1, rows2; uint8_t s1, s2, t1, t2;
-   bool operator==(const WKey& o) const {
-      return off1 == o.off1 && off2 == o.off2 && rows1 == o.rows1 && rows2 == o.rows2 && s1 == o.s1 && s2 == o.s2 && t1 == o.t1 && t2 == o.t2;
-   }
-};
-struct WKeyHash {
-   size_t operator()(const WKey& k) const {
-      uint64_t h = (uint64_t)k.off1 * 0x9E3779B97F4A7C15ULL ^ (uint64_t)k.off2 * 0xC2B2AE3D27D4EB4FULL ^ ((uint64_t)k.s1 << 8) ^ ((uint64_t)k.s2 << 16) ^
-                   ((uint64_t)k.t1 << 4) ^ ((uint64_t)k.t2 << 5);
-      return (size_t)(h ^ (h >> 29));
-   }
-};
+// Stage-1 products shared inside a wave: open-addressing table keyed by the two operand blocks (space, transposition and
+// arena offset identify a block).  Generation-stamped slots make "clear" free; millions of look-ups per plan, so no node
+// allocations and one cache line per probe.
 struct WInfo { int64_t off; int rows, cols; };
+class WTable {
+   struct Slot { uint64_t k1, k2; uint32_t gen, idx; };
+   std::vector<Slot> slots_;
+   std::vector<WInfo> vals_;
+   uint32_t gen_ = 1;
+   size_t mask_ = 0, used_ = 0;
+   static uint64_t key_of(const MatRef& m) { return (uint64_t)m.off | ((uint64_t)m.space << 56) | ((uint64_t)m.trans << 63); }
+   static size_t hash(uint64_t a, uint64_t b) {
+      uint64_t h = a * 0x9E3779B97F4A7C15ULL ^ (b + 0x7F4A7C15ULL) * 0xC2B2AE3D27D4EB4FULL;
+      return (size_t)(h ^ (h >> 31));
+   }
+   void grow() {
+      std::vector<Slot> old;
+      old.swap(slots_);
+      slots_.assign(old.empty() ? (size_t)1 << 16 : old.size() * 2, Slot{0, 0, 0, 0});
+      mask_ = slots_.size() - 1;
+      for (const Slot& s : old)
+         if (s.gen == gen_) {
+            size_t i = hash(s.k1, s.k2) & mask_;
+            while (slots_[i].gen == gen_) i = (i + 1) & mask_;
+            slots_[i] = s;
+         }
+   }
+public:
+   void clear() {
+      if (++gen_ == 0) { for (Slot& s : slots_) s.gen = 0; gen_ = 1; }
+      used_ = 0; vals_.clear();
+   }
+   // returns the stored product or nullptr; `slot` receives the insertion position for put()
+   const WInfo* find(const MatRef& a, const MatRef& b, size_t& slot) {
+      if ((used_ + 1) * 10 >= slots_.size() * 7) grow();
+      const uint64_t k1 = key_of(a), k2 = key_of(b);
+      size_t i = hash(k1, k2) & mask_;
+      while (slots_[i].gen == gen_) {
+         if (slots_[i].k1 == k1 && slots_[i].k2 == k2) return &vals_[slots_[i].idx];
+         i = (i + 1) & mask_;
+      }
+      slot = i;
+      return nullptr;
+   }
+   void put(size_t slot, const MatRef& a, const MatRef& b, const WInfo& w) {
+      slots_[slot] = Slot{key_of(a), key_of(b), gen_, (uint32_t)vals_.size()};
+      vals_.push_back(w);
+      used_++;
+   }
+};
 
 inline void set_x(GemmItem& g, const MatRef& m) { g.xs = m.space; g.xoff = m.off; g.ldx = m.rows; if (m.trans) g.flags |= IF_TX; }
 inline void set_y(GemmItem& g, const MatRef& m) { g.ys = m.space; g.yoff = m.off; g.ldy = m.rows; if (m.trans) g.flags |= IF_TY; }
@@ -65,8 +103,10 @@ double CompiledWork::bytes() const {
    return b;
 }
 
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vector<DstBlock>& dst, uint8_t dst_space, const CompileOptions& opt) {
    out = CompiledWork();
+   double T_sort = 0, T_emit = 0, T_total = now_s(), T_part = 0;
    {  // every destination block must form ONE contiguous group: two groups would become two CTAs that read-modify-write the same
       // tile in one launch.  Generators that visit a block twice (e.g. TensorQ/TensorX: update + AddTerms) are regrouped here.
       std::vector<char> seen(dst.size(), 0);
@@ -78,7 +118,9 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
       }
       if (!grouped) std::stable_sort(terms.begin(), terms.end(), [](const Term3& a, const Term3& b) { return a.dst < b.dst; });
    }
-   std::unordered_map<WKey, WInfo, WKeyHash> wmap;
+   WTable wmap;
+   out.items2.reserve(terms.size());
+   out.items1.reserve(terms.size() / 2);
    int64_t wave_work = 0, wave_part = 0;
    Wave wave{};
    auto open_wave = [&]() {
@@ -104,6 +146,7 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
       std::copy(sorted.begin(), sorted.end(), v.begin() + b);
    };
    auto close_wave = [&]() {
+      const double t0 = now_s();
       bool any = (int)out.reduces.size() > wave.red_begin;
       for (int c = 0; c < kNumTileClasses; c++) {
          wave.t1_end[c] = (int)out.tiles1[c].size();
@@ -116,13 +159,13 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
       out.work_size = std::max(out.work_size, wave_work);
       out.part_size = std::max(out.part_size, wave_part);
       if (any) out.waves.push_back(wave);
+      T_sort += now_s() - t0;
    };
 
    // W = op(a) * op(b), shared inside the wave
    auto get_w = [&](const MatRef& a, const MatRef& b) -> WInfo {
-      WKey key{a.off, b.off, a.rows, b.rows, a.space, b.space, a.trans, b.trans};
-      auto it = wmap.find(key);
-      if (it != wmap.end()) return it->second;
+      size_t slot = 0;
+      if (const WInfo* hit = wmap.find(a, b, slot)) return *hit;
       WInfo w{};
       w.rows = a.op_rows(); w.cols = b.op_cols();
       GemmItem g{};
@@ -144,7 +187,7 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
          }
       out.flops_exec += 2.0 * w.rows * w.cols * g.k;
       out.n_stage1++;
-      wmap.emplace(key, w);
+      wmap.put(slot, a, b, w);
       return w;
    };
 
@@ -193,7 +236,7 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
       size_t i1 = i0;
       while (i1 < terms.size() && terms[i1].dst == terms[i0].dst) i1++;
       // block-axpy terms first inside every destination block: the kernel consumes them before it starts its GEMM pipeline
-      std::stable_partition(terms.begin() + i0, terms.begin() + i1, [](const Term3& t) { return !t.p.present() && !t.r.present(); });
+      { const double t0 = now_s(); std::stable_partition(terms.begin() + i0, terms.begin() + i1, [](const Term3& t) { return !t.p.present() && !t.r.present(); }); T_part += now_s() - t0; }
       const DstBlock& db = dst[terms[i0].dst];
       const int M = db.rows, N = db.cols;
       int ib = (int)out.items2.size();
@@ -227,11 +270,12 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
             ib = (int)out.items2.size();
          }
       }
-      emit_block(db, ib, (int)out.items2.size());
+      { const double t0 = now_s(); emit_block(db, ib, (int)out.items2.size()); T_emit += now_s() - t0; }
       i0 = i1;
    }
    close_wave();
    for (int c = 0; c < kNumTileClasses; c++) out.n_tiles += (long long)out.tiles1[c].size() + (long long)out.tiles2[c].size();
+   if (getenv("B2_TIMING")) fprintf(stderr, "compile_terms: total %.3f s (close_wave/sort %.3f, emit %.3f, partition %.3f)\n", now_s() - T_total, T_sort, T_emit, T_part);
 }
 
 }   // namespace b2

@@ -39,7 +39,7 @@ struct Wave {
 };
 
 struct CompileOptions {
-   int64_t work_budget = (int64_t)3 << 27;   // doubles of stage-1 workspace per wave (3 GiB): measured best on B200 (profiles/r1_tuning.md)
+   int64_t work_budget = (int64_t)3 << 30;   // doubles of stage-1 workspace per wave (24 GiB of the 180 GB): bigger waves share more stage-1 products (profiles/r1_tuning.md)
    int64_t chunk_k = 2048;                   // split-K: accumulated inner dimension per CTA
 };
 

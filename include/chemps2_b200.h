@@ -184,6 +184,12 @@ int b2_heff_worklists(const b2_heff* h, b2_worklists* out);
 typedef struct b2_update b2_update;
 int b2_update_create(b2_ctx* ctx, int index, int moving_right, b2_opset* old_set, b2_opset* new_set, b2_update** out);
 void b2_update_destroy(b2_update* u);
+/* multi-GPU: the NEW operators are distributed over `world` GPUs (deterministic FLOP-balanced assignment; replaces the static
+ * owner maps of MPIchemps2.h:158-231 for the update, whose Q/X partial exchanges are DMRGoperators.cpp:449-533); rank `rank`
+ * computes its share, the all-reduce callback sums the arenas so that every GPU ends up with every operator. */
+int b2_update_create_sharded(b2_ctx* ctx, int index, int moving_right, b2_opset* old_set, b2_opset* new_set, int world, int rank,
+                             b2_update** out);
+int b2_update_set_allreduce(b2_update* u, b2_allreduce_fn fn, void* user);
 int b2_update_run(b2_update* u, const double* t_host);
 int b2_update_run_device(b2_update* u, const double* t_dev);
 /* [0] #terms, [1] #mix terms, [2] #presums, [3] reference FLOPs, [4] executed FLOPs, [5] workspace doubles, [6] #waves, [7] launches */
@@ -211,6 +217,12 @@ int b2_dmrg_get_mps(const b2_dmrg* d, int site, double* t_storage);
 int b2_dmrg_random_mps(b2_dmrg* d, uint64_t seed);           /* random + left-normalised, DMRG.cpp:149-169 (own RNG stream) */
 b2_opset* b2_dmrg_opset(b2_dmrg* d, int boundary, int moving_right);
 int b2_dmrg_set_opset(b2_dmrg* d, int boundary, int moving_right, b2_opset* set);   /* the driver takes ownership */
+/* multi-GPU sweep: sigma terms (ownership maps) and operator updates are sharded over `world` GPUs, MPS / Davidson vectors /
+ * Split are replicated; fn sums a device vector over the ranks (NCCL).  Call before the first update / solve. */
+int b2_dmrg_set_world(b2_dmrg* d, int world, int rank, b2_allreduce_fn fn, void* user);
+/* wall-clock seconds per phase since the last reset: [0] plan building (host), [1] Davidson solves, [2] Split (host SVD),
+ * [3] operator updates, [4] number of sigma builds */
+int b2_dmrg_timers(b2_dmrg* d, double* out5, int reset);
 int b2_dmrg_update(b2_dmrg* d, int index, int moving_right);
 int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, int moving_right, int change, double* energy,
                        double* discarded_weight, int* n_matvec);

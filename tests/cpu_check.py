@@ -93,7 +93,7 @@ def emulate_worklists(ctx, left, right, heff, vec):
     return vout
 
 
-def build_update_case(fx, which, device=-1, options=None):
+def build_update_case(fx, which, device=-1, options=None, world=1, rank=0):
     """which = 'UR' (moving right after the solve at siteB) or 'UL' (moving left after the solve at siteA).
     -> (ctx, old_set, new_set, update, t_storage, expected [(kind, i, j, data)])"""
     tag = "B" if which == "UR" else "A"
@@ -114,12 +114,13 @@ def build_update_case(fx, which, device=-1, options=None):
     nb, nmr, expected = split_ops(fx, which + "/new")
     assert nmr == mr and nb == (index + 1 if mr else index)
     new = api.OpSet(ctx, nb, mr)
-    upd = api.Update(ctx, index, mr, old, new)
+    upd = api.Update(ctx, index, mr, old, new, world, rank)
     return ctx, old, new, upd, fx[f"{which}/mps/{index}"], expected
 
 
-def emulate_update(old, new, upd, t_storage):
-    """runs both passes of the compiled update work lists on the CPU (oracle/worklist_emul.cpp) -> new arena (numpy)"""
+def emulate_update(old, new, upd, t_storage, passes=(0, 1), arena=None):
+    """runs the given passes of the compiled update work lists on the CPU (oracle/worklist_emul.cpp) -> new arena (numpy);
+    `arena`: state to continue from (the all-reduced pass-0 result of a sharded update)"""
     from chemps2_b200._lib import Worklists, check, lib
     o = oracle_lib()
     o.b2o_run_update_pass.argtypes = [C.POINTER(Worklists), c_dp, c_dp, c_dp, c_dp]
@@ -130,9 +131,9 @@ def emulate_update(old, new, upd, t_storage):
     oa = old.host_arena() if old else np.zeros(1)
     presum = np.zeros(max(psize, 1))
     o.b2o_presum(parts, npp, _dp(oa), _dp(oa), _dp(presum), psize)
-    arena = np.zeros(max(lib.b2_opset_arena_size(new.h), 1))
+    arena = np.zeros(max(lib.b2_opset_arena_size(new.h), 1)) if arena is None else np.ascontiguousarray(arena, dtype=np.float64).copy()
     t = np.ascontiguousarray(t_storage, dtype=np.float64)
-    for p in (0, 1):
+    for p in passes:
         wl = Worklists()
         check(lib.b2_update_worklists(upd.h, p, C.byref(wl)))
         o.b2o_run_update_pass(C.byref(wl), _dp(oa), _dp(t), _dp(presum), _dp(arena))

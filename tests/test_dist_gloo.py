@@ -33,6 +33,17 @@ for tag in ("A", "B"):
     dist.all_reduce(fr)
     if rank == 0:
         print("B2DIST", tag, "share_of_rank0", frac / float(fr.item()))
+# operator update sharded by operator (b2_update_create_sharded): pass 0 per rank, all-reduce of the arenas, mixing pass in full
+for which in ("UR", "UL"):
+    ctx, old, new, upd, tt, expected = cpu_check.build_update_case(fx, which, world=world, rank=rank)
+    part = torch.from_numpy(cpu_check.emulate_update(old, new, upd, tt, passes=(0,)))
+    dist.all_reduce(part)
+    arena = cpu_check.emulate_update(old, new, upd, tt, passes=(1,), arena=part.numpy())
+    sl = {{(k, i, j): (off, size) for k, i, j, off, size in cpu_check.op_slices(new)}}
+    for kind, i, j, data in expected:
+        off, size = sl[(kind, i, j)]
+        if size:
+            worst = max(worst, float(np.abs(arena[off:off + size] - data).max() / max(1.0, np.abs(data).max())))
 if rank == 0:
     print("B2DIST worst", worst)
 dist.destroy_process_group()

@@ -35,6 +35,70 @@ def test_update_worklists_vs_reference_cpu(golden, which, options):
     assert st["terms"] > 0 and st["flops_ref"] > 0
 
 
+@pytest.mark.parametrize("world", [2, 5])
+@pytest.mark.parametrize("which", ["UR", "UL"])
+def test_sharded_update_sums_to_reference_cpu(golden, which, world):
+    """multi-GPU update on the CPU emulator: every rank runs pass 0 for the operators assigned to it, the arenas are summed
+    (the all-reduce), then the mixing pass runs in full -> the reference's operators"""
+    total, flops = None, []
+    for r in range(world):
+        ctx, old, new, upd, t, expected = cpu_check.build_update_case(golden, which, world=world, rank=r)
+        part = cpu_check.emulate_update(old, new, upd, t, passes=(0,))
+        total = part if total is None else total + part
+        flops.append(upd.stats()["terms"])
+    arena = cpu_check.emulate_update(old, new, upd, t, passes=(1,), arena=total)
+    _compare(lambda k, i, j, off, size: arena[off:off + size], new, expected)
+    ctx1, old1, new1, upd1, _, _ = cpu_check.build_update_case(golden, which)
+    assert sum(flops) == upd1.stats()["terms"]           # every term computed exactly once
+    if world == 2:
+        assert min(flops) > 0.2 * max(flops)                # both ranks own real work
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["UR", "UL"])
+def test_sharded_update_gpu_single_process(golden, which):
+    """GPU, world = 2 emulated in one process: rank 1 runs first and its all-reduce callback snapshots its pass-0 arena; rank 0's
+    callback adds that snapshot -> rank 0 ends with the reference's operators (b2_update_create_sharded / _set_allreduce)"""
+    import ctypes as C
+    import torch
+    snap = {}
+
+    def make(cb):
+        ar = api.AllReduce.__new__(api.AllReduce)
+        ar.cfn = api.ALLREDUCE_FN(cb)
+        return ar
+
+    def view(ptr, n):
+        return torch.as_tensor(api.AllReduce._Dev(ptr, n), device="cuda")
+
+    def cb1(user, ptr, n, stream):
+        torch.cuda.synchronize()
+        snap["x"] = view(ptr, n).clone()
+        return 0
+
+    def cb0(user, ptr, n, stream):
+        torch.cuda.synchronize()
+        view(ptr, n).add_(snap["x"])
+        torch.cuda.synchronize()
+        return 0
+
+    ctx, old, new1, upd1, t, expected = cpu_check.build_update_case(golden, which, device=0, world=2, rank=1)
+    upd1.set_allreduce(make(cb1))
+    upd1.run(t)
+    ctx0, old0, new0, upd0, t, expected = cpu_check.build_update_case(golden, which, device=0, world=2, rank=0)
+    upd0.set_allreduce(make(cb0))
+    upd0.run(t)
+    idx = {}
+    for n in range(len(new0)):
+        k, i, j, _ = new0.info(n)
+        idx[(k, i, j)] = n
+    _compare(lambda k, i, j, off, size: new0.download(idx[(k, i, j)]), new0, expected)
+    # without a callback a sharded update must refuse to run instead of producing partial operators
+    ctx2, old2, new2, upd2, t, _ = cpu_check.build_update_case(golden, which, device=0, world=2, rank=0)
+    with pytest.raises(Exception):
+        upd2.run(t)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("which", ["UR", "UL"])
 def test_update_vs_reference_gpu(golden, which):

@@ -133,16 +133,28 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
       wmap.clear();
    };
    auto weight_sort = [&](std::vector<Tile>& v, int b, int e, const std::vector<GemmItem>& items) {
-      // heaviest CTAs first (static load balance across the SMs)
-      std::vector<std::pair<long long, int>> ord(e - b);
+      // Launch order = heaviest GROUPS first (static load balance across the SMs), where a group is the set of CTAs that
+      // stream the same items (all tiles of one stage-1 product / of one split-K chunk of a destination block): they read the
+      // same operand panels, so they must be resident together for the panels to be served by L2 instead of DRAM.
+      if (e <= b) return;
+      struct Key { long long w; int ib, idx; };
+      std::vector<Key> ord(e - b);
       for (int i = b; i < e; i++) {
          long long w = 0;
          for (int it = v[i].item_begin; it < v[i].item_end; it++) w += items[it].k + 4;
-         ord[i - b] = {-w * ((v[i].mrem + 7) / 8) * ((v[i].nrem + 7) / 8), i};
+         ord[i - b] = {w * ((v[i].mrem + 7) / 8) * ((v[i].nrem + 7) / 8), v[i].item_begin, i};
       }
-      std::sort(ord.begin(), ord.end());
+      std::sort(ord.begin(), ord.end(), [](const Key& x, const Key& y) { return x.ib != y.ib ? x.ib < y.ib : x.idx < y.idx; });
+      for (size_t g0 = 0; g0 < ord.size();) {   // group weight = its heaviest tile
+         size_t g1 = g0;
+         long long wmax = 0;
+         while (g1 < ord.size() && ord[g1].ib == ord[g0].ib) { wmax = std::max(wmax, ord[g1].w); g1++; }
+         for (size_t g = g0; g < g1; g++) ord[g].w = wmax;
+         g0 = g1;
+      }
+      std::sort(ord.begin(), ord.end(), [](const Key& x, const Key& y) { return x.w != y.w ? x.w > y.w : (x.ib != y.ib ? x.ib < y.ib : x.idx < y.idx); });
       std::vector<Tile> sorted(e - b);
-      for (int i = 0; i < e - b; i++) sorted[i] = v[ord[i].second];
+      for (int i = 0; i < e - b; i++) sorted[i] = v[ord[i].idx];
       std::copy(sorted.begin(), sorted.end(), v.begin() + b);
    };
    auto close_wave = [&]() {

@@ -57,6 +57,11 @@ SIGNATURES = [
     ("b2_sobject_nkappa", C.c_int, [vp, C.c_int]),
     ("b2_sobject_table", C.c_int, [vp, C.c_int, c_ip, c_lp]),
     ("b2_opset_create", C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+    ("b2_opset_create_correlation", C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    ("b2_opset_offload", C.c_int, [vp]),
+    ("b2_opset_reload", C.c_int, [vp]),
+    ("b2_opset_resident", C.c_int, [vp]),
+    ("b2_dmrg_set_spill", C.c_int, [vp, C.c_int]),
     ("b2_opset_destroy", None, [vp]),
     ("b2_opset_count", C.c_int, [vp]),
     ("b2_opset_info", C.c_int, [vp, C.c_int, c_ip, c_ip, c_ip, c_lp]),
@@ -77,6 +82,7 @@ SIGNATURES = [
     ("b2_heff_solve", C.c_int, [vp, c_dp, C.c_double, c_dp, c_ip]),
     ("b2_heff_solve_device", C.c_int, [vp, vp, C.c_double, c_dp, c_ip]),
     ("b2_heff_set_allreduce", C.c_int, [vp, vp, vp]),
+    ("b2_heff_set_excitations", C.c_int, [vp, C.c_int, C.POINTER(c_dp)]),
     ("b2_heff_last_kernel_seconds", C.c_double, [vp]),
     ("b2_heff_num_terms", C.c_int64, [vp]),
     ("b2_heff_export_terms", C.c_int, [vp, C.POINTER(FlatTerm)]),

@@ -73,10 +73,14 @@ class Context:
 
 
 class OpSet:
-    def __init__(self, ctx, boundary, moving_right):
+    def __init__(self, ctx, boundary, moving_right, correlation=False):
+        """correlation=True: the {G, Y, Z, K, M} helper tensors of DMRG::update_correlations_tensors instead of the sweep operators"""
         self.ctx = ctx
         self.h = vp()
-        check(lib.b2_opset_create(ctx.h, int(boundary), int(bool(moving_right)), C.byref(self.h)))
+        if correlation:
+            check(lib.b2_opset_create_correlation(ctx.h, int(boundary), C.byref(self.h)))
+        else:
+            check(lib.b2_opset_create(ctx.h, int(boundary), int(bool(moving_right)), C.byref(self.h)))
 
     def close(self):
         if self.h:
@@ -120,6 +124,15 @@ class OpSet:
                 continue
             self.upload(idx, data)
 
+    def offload(self):
+        check(lib.b2_opset_offload(self.h))
+
+    def reload(self):
+        check(lib.b2_opset_reload(self.h))
+
+    def resident(self):
+        return bool(lib.b2_opset_resident(self.h))
+
     def fill_hash(self, seed, amp=1.0):
         check(lib.b2_opset_fill_hash(self.h, int(seed), float(amp)))
 
@@ -158,6 +171,12 @@ class Heff:
 
     def apply_device(self, dev_in_ptr, dev_out_ptr):
         check(lib.b2_heff_apply_device(self.h, vp(dev_in_ptr), vp(dev_out_ptr)))
+
+    def set_excitations(self, vectors):
+        """vectors: list of VeffTilde arrays (symmetric convention); [] switches the projector off (Heff.h:70 nLower / VeffTilde)"""
+        vs = [np.ascontiguousarray(v, dtype=np.float64) for v in vectors]
+        arr = (c_dp * max(len(vs), 1))(*[_dp(v) for v in vs])
+        check(lib.b2_heff_set_excitations(self.h, len(vs), arr))
 
     def kernel_seconds(self):
         return lib.b2_heff_last_kernel_seconds(self.h)
@@ -251,6 +270,9 @@ class DMRG:
         self._allreduce = allreduce
         check(lib.b2_dmrg_set_world(self.h, int(world), int(rank), allreduce.cfn if allreduce else None, None))
 
+    def set_spill(self, enabled):
+        check(lib.b2_dmrg_set_spill(self.h, int(bool(enabled))))
+
     def timers(self, reset=False):
         o = np.zeros(5)
         check(lib.b2_dmrg_timers(self.h, _dp(o), int(bool(reset))))
@@ -338,7 +360,7 @@ def context_from_fixture(fx, tag, device=-1):
     return ctx
 
 
-KIND_NAMES = ["L", "S0", "S1", "F0", "F1", "A", "B", "C", "D", "Q", "X"]
+KIND_NAMES = ["L", "S0", "S1", "F0", "F1", "A", "B", "C", "D", "Q", "X", "G", "Y", "Z", "K", "M"]
 
 
 S_KEY = (3 << 60)   # key of the synthetic two-site vector, same as op_key(3, 0, -1, -1) in oracle/ref_driver.cpp

@@ -108,6 +108,15 @@ int dev_axpy_dev(double* y, const double* x, const double* coef, double sign, in
    return 0;
 }
 
+__global__ void k_add_square(double* __restrict__ y, const double* __restrict__ x, int64_t n) {
+   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) y[e] += x[e] * x[e];
+}
+int dev_add_square(double* y, const double* x, int64_t n, void* stream) {
+   if (n <= 0) return 0;
+   k_add_square<<<grid_for(n), BT, 0, (cudaStream_t)stream>>>(y, x, n);
+   return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
+
 __global__ void k_scale_rsqrt(double* __restrict__ x, const double* __restrict__ ss, int64_t n) {
    const double a = 1.0 / sqrt(ss[0]);
    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) x[e] *= a;

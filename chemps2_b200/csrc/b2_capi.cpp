@@ -56,6 +56,8 @@ struct b2_opset {
    OpSet set;
    std::vector<double> host;   // host mirror, allocated on first use (upload / download / planning-only contexts)
    double* dev = nullptr;
+   double* spill = nullptr;    // pinned host copy while the set is offloaded (b2_opset_offload): the device arena is released
+   bool offloaded = false;
    void ensure_host() { if (host.size() != (size_t)set.size) host.assign((size_t)set.size, 0.0); }
 };
 
@@ -83,6 +85,10 @@ struct b2_heff {
    void* allreduce_user = nullptr;
    double last_kernel_s = 0.0;
    long long launches = 0;
+   int world = 1, rank = 0;
+   // excited states (Heff::addDiagramExcitations): n_exc level-shifted lower states, one vector of veclength doubles each
+   int n_exc = 0;
+   double *d_exc = nullptr, *d_exc_coef = nullptr, *d_exc_scratch = nullptr;
 };
 
 template <class T> static int upload_vec(T** dptr, const std::vector<T>& v, cudaStream_t s) {
@@ -232,7 +238,52 @@ int b2_opset_create(b2_ctx* ctx, int boundary, int moving_right, b2_opset** out)
    *out = s.release();
    return B2_OK;
 }
+int b2_opset_create_correlation(b2_ctx* ctx, int boundary, b2_opset** out) {
+   if (!ctx || !ctx->have_bk || !out) return fail(B2_ERR_STATE, "b2_opset_create_correlation: no bookkeeper");
+   if (boundary < 1 || boundary > ctx->bk.L) return fail(B2_ERR_ARG, "b2_opset_create_correlation: boundary %d out of range", boundary);
+   std::unique_ptr<b2_opset> s(new b2_opset);
+   s->ctx = ctx;
+   s->set.build_correlation(ctx->bk, boundary);
+   if (ctx->device >= 0 && s->set.size > 0) {
+      CUDA_TRY(cudaSetDevice(ctx->device));
+      CUDA_TRY(cudaMalloc(&s->dev, sizeof(double) * (size_t)s->set.size));
+      CUDA_TRY(cudaMemsetAsync(s->dev, 0, sizeof(double) * (size_t)s->set.size, ctx->stream));
+   }
+   *out = s.release();
+   return B2_OK;
+}
+
+/* Operator life-cycle (replaces DMRG::OperatorsOnDisk / deleteTensors / allocateTensors, DMRGoperators.cpp:33-231,1147-1433: the
+ * reference spills the operator tables of the boundaries it is not working on to HDF5 files; here they go to pinned host memory
+ * over PCIe/C2C and the HBM arena is released). */
+int b2_opset_offload(b2_opset* set) {
+   if (!set) return fail(B2_ERR_ARG, "b2_opset_offload: NULL");
+   if (set->ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_opset_offload: planning-only context, no CUDA device");
+   if (set->offloaded || !set->dev) return B2_OK;
+   const size_t bytes = sizeof(double) * (size_t)set->set.size;
+   if (!set->spill) CUDA_TRY(cudaMallocHost(&set->spill, bytes));
+   CUDA_TRY(cudaMemcpyAsync(set->spill, set->dev, bytes, cudaMemcpyDeviceToHost, set->ctx->stream));
+   CUDA_TRY(cudaStreamSynchronize(set->ctx->stream));
+   CUDA_TRY(cudaFree(set->dev));
+   set->dev = nullptr; set->offloaded = true;
+   return B2_OK;
+}
+int b2_opset_reload(b2_opset* set) {
+   if (!set) return fail(B2_ERR_ARG, "b2_opset_reload: NULL");
+   if (!set->offloaded) return B2_OK;
+   const size_t bytes = sizeof(double) * (size_t)set->set.size;
+   CUDA_TRY(cudaSetDevice(set->ctx->device));
+   CUDA_TRY(cudaMalloc(&set->dev, bytes));
+   CUDA_TRY(cudaMemcpyAsync(set->dev, set->spill, bytes, cudaMemcpyHostToDevice, set->ctx->stream));
+   CUDA_TRY(cudaStreamSynchronize(set->ctx->stream));
+   cudaFreeHost(set->spill);
+   set->spill = nullptr; set->offloaded = false;
+   return B2_OK;
+}
+int b2_opset_resident(const b2_opset* set) { return (set && set->dev && !set->offloaded) ? 1 : 0; }
+
 void b2_opset_destroy(b2_opset* set) {
+   if (set && set->spill) cudaFreeHost(set->spill);
    if (!set) return;
    if (set->dev) cudaFree(set->dev);
    delete set;
@@ -254,6 +305,7 @@ int b2_opset_upload(b2_opset* set, int index, const double* packed) {
    if (t.lay->size == 0) return B2_OK;
    set->ensure_host();
    std::memcpy(set->host.data() + t.off, packed, sizeof(double) * (size_t)t.lay->size);
+   if (set->offloaded) std::memcpy(set->spill + t.off, packed, sizeof(double) * (size_t)t.lay->size);
    if (set->dev) {
       CUDA_TRY(cudaMemcpyAsync(set->dev + t.off, set->host.data() + t.off, sizeof(double) * (size_t)t.lay->size, cudaMemcpyHostToDevice, set->ctx->stream));
       CUDA_TRY(cudaStreamSynchronize(set->ctx->stream));
@@ -269,6 +321,7 @@ int b2_opset_download(b2_opset* set, int index, double* packed) {
       CUDA_TRY(cudaMemcpyAsync(set->host.data() + t.off, set->dev + t.off, sizeof(double) * (size_t)t.lay->size, cudaMemcpyDeviceToHost, set->ctx->stream));
       CUDA_TRY(cudaStreamSynchronize(set->ctx->stream));
    }
+   if (set->offloaded) std::memcpy(set->host.data() + t.off, set->spill + t.off, sizeof(double) * (size_t)t.lay->size);
    std::memcpy(packed, set->host.data() + t.off, sizeof(double) * (size_t)t.lay->size);
    return B2_OK;
 }
@@ -314,8 +367,9 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
    if (site > 0 && (!left || left->set.boundary != site || !left->set.moving_right)) return fail(B2_ERR_ARG, "b2_heff_create: left operator set must sit at boundary %d moving right", site);
    if (site < L - 2 && (!right || right->set.boundary != site + 2 || right->set.moving_right)) return fail(B2_ERR_ARG, "b2_heff_create: right operator set must sit at boundary %d moving left", site + 2);
    if (world < 1 || rank < 0 || rank >= world) return fail(B2_ERR_ARG, "b2_heff_create: bad world/rank");
+   if ((site > 0 && left && left->offloaded) || (site < L - 2 && right && right->offloaded)) return fail(B2_ERR_STATE, "b2_heff_create: operator set is offloaded (b2_opset_reload first)");
    std::unique_ptr<b2_heff> h(new b2_heff);
-   h->ctx = ctx;
+   h->ctx = ctx; h->world = world; h->rank = rank;
    h->left = (site > 0) ? left : nullptr;
    h->right = (site < L - 2) ? right : nullptr;
    const double tb0 = wall_seconds();
@@ -374,6 +428,7 @@ void b2_heff_destroy(b2_heff* h) {
    cudaFree(h->d_items1); cudaFree(h->d_items2); cudaFree(h->d_reduces); cudaFree(h->d_part);
    for (int c = 0; c < kNumTileClasses; c++) { cudaFree(h->d_tiles1[c]); cudaFree(h->d_tiles2[c]); }
    cudaFree(h->d_jobs); cudaFree(h->d_parts); cudaFree(h->d_presum); cudaFree(h->d_work); cudaFree(h->d_vin); cudaFree(h->d_vout);
+   cudaFree(h->d_exc); cudaFree(h->d_exc_coef); cudaFree(h->d_exc_scratch);
    if (h->h_vin) cudaFreeHost(h->h_vin);
    if (h->h_vout) cudaFreeHost(h->h_vout);
    if (h->ev0) cudaEventDestroy(h->ev0);
@@ -398,7 +453,39 @@ int b2_heff_apply_device(b2_heff* h, const double* dev_in, double* dev_out) {
       if (dev_launch_reduce(h->d_reduces + w.red_begin, w.red_end - w.red_begin, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
       h->launches += 1;
    }
+   // level-shift projector of the lower states (HeffDiagrams1.cpp:65-85): sigma += sum_s <V_s|S> V_s.  State s belongs to GPU
+   // s % world (MPIchemps2.h owner_specific_excitation), the partial sigma vectors are summed by the caller's all-reduce.
+   for (int st = 0; st < h->n_exc; st++) {
+      if (st % h->world != h->rank) continue;
+      const double* v = h->d_exc + (size_t)st * (size_t)h->plan.S.size;
+      if (dev_multi_dot(dev_in, v, h->plan.S.size, 1, h->plan.S.size, h->d_exc_coef + st, h->d_exc_scratch, s) ||
+          dev_axpy_dev(dev_out, v, h->d_exc_coef + st, 1.0, h->plan.S.size, s))
+         return fail(B2_ERR_CUDA, "%s", dev_last_error());
+   }
    CUDA_TRY(cudaEventRecord(h->ev1, s));
+   return B2_OK;
+}
+
+int b2_heff_set_excitations(b2_heff* h, int n_lower, const double* const* veff_tilde) {
+   if (!h || n_lower < 0 || (n_lower > 0 && !veff_tilde)) return fail(B2_ERR_ARG, "b2_heff_set_excitations: bad arguments");
+   if (h->ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_heff_set_excitations: planning-only context, no CUDA device (there is no CPU fallback)");
+   cudaStream_t s = h->ctx->stream;
+   cudaFree(h->d_exc); cudaFree(h->d_exc_coef); cudaFree(h->d_exc_scratch);
+   h->d_exc = h->d_exc_coef = h->d_exc_scratch = nullptr;
+   h->n_exc = 0;
+   if (n_lower == 0) return B2_OK;
+   const size_t n = (size_t)h->plan.S.size;
+   CUDA_TRY(cudaMalloc(&h->d_exc, sizeof(double) * n * n_lower));
+   CUDA_TRY(cudaMalloc(&h->d_exc_coef, sizeof(double) * n_lower));
+   CUDA_TRY(cudaMalloc(&h->d_exc_scratch, sizeof(double) * kRedScratch));
+   CUDA_TRY(cudaMemsetAsync(h->d_exc_scratch, 0, sizeof(double) * kRedScratch, s));
+   for (int st = 0; st < n_lower; st++) {
+      if (!veff_tilde[st]) return fail(B2_ERR_ARG, "b2_heff_set_excitations: NULL vector %d", st);
+      std::memcpy(h->h_vin, veff_tilde[st], sizeof(double) * n);
+      CUDA_TRY(cudaMemcpyAsync(h->d_exc + (size_t)st * n, h->h_vin, sizeof(double) * n, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+   }
+   h->n_exc = n_lower;
    return B2_OK;
 }
 
@@ -435,6 +522,8 @@ int b2_heff_diag_device(b2_heff* h, double* dev_diag) {
    DevBases b = bases_of(h, nullptr, nullptr);
    if (dev_fill_zero(dev_diag, h->plan.S.size, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
    if (dev_launch_diag(h->d_diag_tiles, (int)h->comp.diag_tiles.size(), h->d_diag_items, b, dev_diag, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+   for (int st = 0; st < h->n_exc; st++)   // HeffDiagonal.cpp:621-640: diag += V_s .* V_s
+      if (st % h->world == h->rank && dev_add_square(dev_diag, h->d_exc + (size_t)st * (size_t)h->plan.S.size, h->plan.S.size, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
    return B2_OK;
 }
 
@@ -640,6 +729,7 @@ int b2_update_create_sharded(b2_ctx* ctx, int index, int moving_right, b2_opset*
    if (new_set->set.boundary != b_new || new_set->set.moving_right != mr) return fail(B2_ERR_ARG, "b2_update_create: new_set must sit at boundary %d", b_new);
    const bool need_old = mr ? (index > 0) : (index < L - 1);
    if (need_old && (!old_set || old_set->set.boundary != b_old || old_set->set.moving_right != mr)) return fail(B2_ERR_ARG, "b2_update_create: old_set must sit at boundary %d", b_old);
+   if ((need_old && old_set->offloaded) || new_set->offloaded) return fail(B2_ERR_STATE, "b2_update_create: operator set is offloaded (b2_opset_reload first)");
    std::unique_ptr<b2_update> u(new b2_update);
    u->ctx = ctx; u->old_set = need_old ? old_set : nullptr; u->new_set = new_set;
    build_update_plan(u->plan, ctx->bk, ctx->prob, u->old_set ? &u->old_set->set : nullptr, new_set->set, index, mr);
@@ -828,6 +918,7 @@ struct b2_dmrg {
    int L = 0;
    std::vector<std::vector<double>> mps;   // TensorT storage per site in the layouts of the current bookkeeper
    std::vector<b2_opset*> left, right;     // operator sets per boundary: moving right (sites < b) / moving left (sites >= b)
+   bool spill = false;                     // keep only the operator sets of the site being optimised in HBM (b2_dmrg_set_spill)
    int world = 1, rank = 0;                // GPUs sharing the sweep: sigma terms and operator updates are sharded, the rest is replicated
    b2_allreduce_fn allreduce = nullptr;
    void* allreduce_user = nullptr;
@@ -897,6 +988,29 @@ int b2_dmrg_set_world(b2_dmrg* d, int world, int rank, b2_allreduce_fn fn, void*
    d->world = world; d->rank = rank; d->allreduce = fn; d->allreduce_user = user;
    return B2_OK;
 }
+int b2_dmrg_set_spill(b2_dmrg* d, int enabled) {
+   if (!d) return fail(B2_ERR_ARG, "b2_dmrg_set_spill: NULL");
+   d->spill = enabled != 0;
+   if (!d->spill)
+      for (int b = 0; b <= d->L; b++) {
+         int rc;
+         if (d->left[b] && (rc = b2_opset_reload(d->left[b]))) return rc;
+         if (d->right[b] && (rc = b2_opset_reload(d->right[b]))) return rc;
+      }
+   return B2_OK;
+}
+// make the sets `keep_l` (moving right) and `keep_r` (moving left) resident and, in spill mode, offload every other set
+static int dmrg_residency(b2_dmrg* d, int keep_l, int keep_r) {
+   int rc;
+   if (keep_l >= 0 && keep_l <= d->L && d->left[keep_l] && (rc = b2_opset_reload(d->left[keep_l]))) return rc;
+   if (keep_r >= 0 && keep_r <= d->L && d->right[keep_r] && (rc = b2_opset_reload(d->right[keep_r]))) return rc;
+   if (!d->spill) return B2_OK;
+   for (int b = 0; b <= d->L; b++) {
+      if (b != keep_l && d->left[b] && (rc = b2_opset_offload(d->left[b]))) return rc;
+      if (b != keep_r && d->right[b] && (rc = b2_opset_offload(d->right[b]))) return rc;
+   }
+   return B2_OK;
+}
 int b2_dmrg_timers(b2_dmrg* d, double* out5, int reset) {
    if (!d || !out5) return fail(B2_ERR_ARG, "b2_dmrg_timers: NULL");
    out5[0] = d->t_plan; out5[1] = d->t_solve; out5[2] = d->t_split; out5[3] = d->t_update; out5[4] = (double)d->n_matvec;
@@ -913,6 +1027,7 @@ int b2_dmrg_update(b2_dmrg* d, int index, int moving_right) {
    if (b_new < 1 || b_new > d->L - 1) return fail(B2_ERR_ARG, "b2_dmrg_update: no operators live at boundary %d", b_new);
    b2_opset* old_set = mr ? d->left[b_old] : d->right[b_old];
    const bool need_old = mr ? (index > 0) : (index < d->L - 1);
+   if (need_old && old_set) { int rr = b2_opset_reload(old_set); if (rr) return rr; }
    if (need_old && !old_set) return fail(B2_ERR_STATE, "b2_dmrg_update: operators of boundary %d are missing", b_old);
    b2_opset* fresh = nullptr;
    int rc = b2_opset_create(ctx, b_new, mr, &fresh);
@@ -937,6 +1052,7 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
    b2_ctx* ctx = d->ctx;
    const int L = d->L;
    cudaStream_t s = ctx->stream;
+   { int rr = dmrg_residency(d, index > 0 ? index : -1, index < L - 2 ? index + 2 : -1); if (rr) return rr; }
    b2_opset* lset = index > 0 ? d->left[index] : nullptr;
    b2_opset* rset = index < L - 2 ? d->right[index + 2] : nullptr;
    if ((index > 0 && !lset) || (index < L - 2 && !rset)) return fail(B2_ERR_STATE, "b2_dmrg_solve_site: boundary operators for site %d are missing", index);

@@ -84,6 +84,8 @@ struct Coefs { double c[kMaxVec]; };
 int dev_multi_dot(const double* x, const double* ybase, int64_t ystride, int m, int64_t n, double* out, double* scratch, void* stream);
 // y += sign * coef[0] * x   (coef on device)
 int dev_axpy_dev(double* y, const double* x, const double* coef, double sign, int64_t n, void* stream);
+// y += x .* x   (diagonal of the excited-state projector, HeffDiagonal.cpp:621-640)
+int dev_add_square(double* y, const double* x, int64_t n, void* stream);
 // x *= 1/sqrt(ss[0])
 int dev_scale_rsqrt(double* x, const double* ss, int64_t n, void* stream);
 // u = sum_j a.c[j] V_j ; t = sum_j a.c[j] HV_j - theta*u ; out[0] = ||t||^2

@@ -15,7 +15,9 @@ std::shared_ptr<const OpLayout> OpSet::layout(const Bookkeeper& bk, int two_j, i
 int OpSet::add(const Bookkeeper& bk, int kind, int i, int j) {
    OpTensor t;
    t.kind = kind; t.i = i; t.j = j;
-   t.irrep = (kind == K_X) ? 0 : ((i == j && (kind == K_L || kind == K_Q)) ? bk.orb_irrep[i] : xorp(bk.orb_irrep[i], bk.orb_irrep[j]));
+   if (kind == K_X || kind == K_G || kind == K_Y || kind == K_Z) t.irrep = 0;
+   else if (i == j && (kind == K_L || kind == K_Q || kind == K_K || kind == K_M)) t.irrep = bk.orb_irrep[i];
+   else t.irrep = xorp(bk.orb_irrep[i], bk.orb_irrep[j]);
    t.prime_last = (kind == K_F1 || kind == K_D) ? moving_right : true;
    t.lay = layout(bk, kind_two_j(kind), kind_nelec(kind), t.irrep);
    t.off = size;
@@ -49,6 +51,14 @@ void OpSet::build_all(const Bookkeeper& bk, int boundary_, bool moving_right_) {
       }
    for (int s = out_lo; s <= out_hi; s++) add(bk, K_Q, s, s);
    add(bk, K_X, -1, -1);
+}
+
+void OpSet::build_correlation(const Bookkeeper& bk, int boundary_) {
+   boundary = boundary_; moving_right = true;
+   ops.clear(); index.clear(); layouts.clear(); size = 0;
+   for (int s = 0; s < boundary; s++) {
+      add(bk, K_G, s, s); add(bk, K_Y, s, s); add(bk, K_Z, s, s); add(bk, K_K, s, s); add(bk, K_M, s, s);
+   }
 }
 
 }   // namespace b2

@@ -12,15 +12,17 @@
 
 namespace b2 {
 
-enum OpKind { K_L = 0, K_S0, K_S1, K_F0, K_F1, K_A, K_B, K_C, K_D, K_Q, K_X, K_NKINDS };
+enum OpKind { K_L = 0, K_S0, K_S1, K_F0, K_F1, K_A, K_B, K_C, K_D, K_Q, K_X, K_G, K_Y, K_Z, K_K, K_M, K_NKINDS };
 
 // (two_j, n_elec) per kind: TensorL.cpp:29-37, TensorS0.cpp:27-35, TensorS1.cpp:28-36, TensorF0.cpp:27-35,
 // TensorF1.cpp:28-36, DMRGoperators.cpp:977-987 (A,B,C,D), TensorQ.cpp:28-36, TensorX.cpp:28-36
-inline int kind_two_j(int k) { static const int t[K_NKINDS] = {1, 0, 2, 0, 2, 0, 2, 0, 2, 1, 0}; return t[k]; }
-inline int kind_nelec(int k) { static const int t[K_NKINDS] = {1, 2, 2, 0, 0, 2, 2, 0, 0, 1, 0}; return t[k]; }
+// G, Y, Z (TensorGYZ.cpp:26-36: two_j 0, n_elec 0, irrep 0) and K, M (TensorKM.cpp:26-36: two_j 1, n_elec 1, irrep of the site)
+// are the helper operators of the two-orbital correlation functions; they never carry a Jordan-Wigner phase.
+inline int kind_two_j(int k) { static const int t[K_NKINDS] = {1, 0, 2, 0, 2, 0, 2, 0, 2, 1, 0, 0, 0, 0, 1, 1}; return t[k]; }
+inline int kind_nelec(int k) { static const int t[K_NKINDS] = {1, 2, 2, 0, 0, 2, 2, 0, 0, 1, 0, 0, 0, 0, 1, 1}; return t[k]; }
 inline bool kind_jw(int k) { return k == K_L || k == K_Q; }
 inline const char* kind_name(int k) {
-   static const char* n[K_NKINDS] = {"L", "S0", "S1", "F0", "F1", "A", "B", "C", "D", "Q", "X"};
+   static const char* n[K_NKINDS] = {"L", "S0", "S1", "F0", "F1", "A", "B", "C", "D", "Q", "X", "G", "Y", "Z", "K", "M"};
    return n[k];
 }
 
@@ -46,6 +48,8 @@ struct OpSet {
    int add(const Bookkeeper& bk, int kind, int i, int j);
    // allocate the full complement the reference keeps at this boundary (DMRGoperators.cpp:909-1140)
    void build_all(const Bookkeeper& bk, int boundary, bool moving_right);
+   // the G, Y, Z, K, M tensors of every site left of `boundary` (DMRG::update_correlations_tensors, DMRGoperators3RDM.cpp:415-479)
+   void build_correlation(const Bookkeeper& bk, int boundary);
 };
 
 }   // namespace b2

@@ -260,6 +260,36 @@ struct UGen {
       }
    }
 
+   // ============================================================================ TensorGYZ::construct (TensorGYZ.cpp:42-98), TensorKM::construct (TensorKM.cpp:42-95)
+   // site-local helper operators of the two-orbital correlation functions, built from T alone (moving right only):
+   //   new[U -> Dn] = sum alpha * T[s -> U]^T * T[s -> Dn]
+   void construct_corr(int new_op) {
+      const OpTensor& t = new_set.ops[new_op];
+      const OpLayout& l = *t.lay;
+      for (int k = 0; k < l.nkappa(); k++) {
+         Sec U, Dn;
+         block_secs(t, k, U, Dn);
+         switch (t.kind) {
+            case K_Y: emit(new_op, k, U, Dn, U, U, nullptr, 1.0); break;                                        // site empty
+            case K_Z: { const Sec s{U.n - 2, U.ts, U.ir}; emit(new_op, k, U, Dn, s, s, nullptr, 1.0); break; }  // site doubly occupied
+            case K_G:                                                                                           // site singly occupied
+               for (int dts = -1; dts <= 1; dts += 2) {
+                  const Sec s{U.n - 1, U.ts + dts, xorp(U.ir, site_irr)};
+                  if (s.ts >= 0) emit(new_op, k, U, Dn, s, s, nullptr, std::sqrt(0.5));
+               }
+               break;
+            case K_K: emit(new_op, k, U, Dn, U, U, nullptr, 1.0); break;                                        // <empty| ... |single>
+            case K_M: {                                                                                         // <single| ... |double>
+               const Sec s{U.n - 1, Dn.ts, Dn.ir};
+               const int fase = ((((Dn.ts - U.ts + 1) / 2) % 2) != 0) ? -1 : 1;
+               emit(new_op, k, U, Dn, s, s, nullptr, fase * std::sqrt((U.ts + 1.0) / (Dn.ts + 1)));
+               break;
+            }
+            default: break;
+         }
+      }
+   }
+
 #include "b2_update_plan_qx.inc"
 
    // ============================================================================ orchestration (DMRGoperators.cpp:243-907)
@@ -285,6 +315,9 @@ struct UGen {
                break;
             case K_Q: update_Q(n); break;
             case K_X: update_X(n); break;
+            case K_G: case K_Y: case K_Z: case K_K: case K_M:   // DMRG::update_correlations_tensors (DMRGoperators3RDM.cpp:415-479)
+               if (t.i == i) construct_corr(n); else generic_update(n, oldf(t.kind, t.i, t.i));
+               break;
          }
       }
    }

@@ -30,7 +30,9 @@ extern "C" {
 #define B2_ERR_STATE (-4)
 
 /* operator kinds; (two_j, n_elec): L(1,1) S0(0,2) S1(2,2) F0(0,0) F1(2,0) A(0,2) B(2,2) C(0,0) D(2,0) Q(1,1) X(0,0) */
-enum { B2_L = 0, B2_S0, B2_S1, B2_F0, B2_F1, B2_A, B2_B, B2_C, B2_D, B2_Q, B2_X };
+enum { B2_L = 0, B2_S0, B2_S1, B2_F0, B2_F1, B2_A, B2_B, B2_C, B2_D, B2_Q, B2_X,
+       /* helper operators of the two-orbital correlation functions: G, Y, Z (0,0) TensorGYZ.cpp, K, M (1,1) TensorKM.cpp */
+       B2_G, B2_Y, B2_Z, B2_K, B2_M };
 
 typedef struct b2_ctx b2_ctx;
 typedef struct b2_opset b2_opset;
@@ -93,6 +95,11 @@ int b2_sobject_table(const b2_ctx* ctx, int site, int* labels, int64_t* offsets)
  * the pointer tables Ltensors/F0tensors/.../Xtensors[boundary-1] of DMRG.h:211-226 allocated by
  * DMRG::allocateTensors (DMRGoperators.cpp:909-1145).  moving_right != 0: operators of the block left of `boundary`. */
 int b2_opset_create(b2_ctx* ctx, int boundary, int moving_right, b2_opset** out);
+/* the set {G, Y, Z, K, M}(site s) for every s < boundary, as DMRG::update_correlations_tensors keeps it
+ * (DMRGoperators3RDM.cpp:415-479; moving right only, 1 <= boundary <= L-1).  b2_update_create on two such sets (old at boundary
+ * index, new at index+1; old = NULL for index 0) replaces update_correlations_tensors(index+1): TensorGYZ::construct /
+ * TensorKM::construct for the newest site, TensorOperator::update without Jordan-Wigner phase for the others. */
+int b2_opset_create_correlation(b2_ctx* ctx, int boundary, b2_opset** out);
 void b2_opset_destroy(b2_opset* set);
 int b2_opset_count(const b2_opset* set);
 int b2_opset_info(const b2_opset* set, int index, int* kind, int* site_i, int* site_j, int64_t* size);
@@ -101,6 +108,12 @@ int b2_opset_find(const b2_opset* set, int kind, int site_i, int site_j);   /* i
 int b2_opset_upload(b2_opset* set, int index, const double* packed);
 int b2_opset_download(b2_opset* set, int index, double* packed);
 int b2_opset_clear(b2_opset* set);
+/* life-cycle: move the arena of a set to pinned host memory and release its HBM / bring it back.  Replaces DMRG::OperatorsOnDisk,
+ * deleteTensors, allocateTensors (DMRGoperators.cpp:33-231, 1147-1433; the reference spills to HDF5 files).  Compute entry points
+ * refuse offloaded sets (B2_ERR_STATE); upload / download keep working on the host copy. */
+int b2_opset_offload(b2_opset* set);
+int b2_opset_reload(b2_opset* set);
+int b2_opset_resident(const b2_opset* set);
 /* synthetic contents: element e of operator (kind,i,j) = amp * hash(seed, side, kind, i, j, e) in [-amp/2, amp/2); the
  * identical fill is produced by oracle/ref_driver.cpp `synth`, which lets bench.py compare with the reference at full size */
 int b2_opset_fill_hash(b2_opset* set, uint64_t seed, double amp);
@@ -122,6 +135,11 @@ int b2_heff_apply(b2_heff* h, const double* vec_in, double* vec_out);
 int b2_heff_apply_device(b2_heff* h, const double* dev_in, double* dev_out);
 int b2_heff_diag(b2_heff* h, double* diag);
 int b2_heff_diag_device(b2_heff* h, double* dev_diag);
+/* Excited states: the nLower / VeffTilde arguments of Heff::makeHeff / fillHeffDiag / SolveDAVIDSON (Heff.h:70).  veff_tilde[s] =
+ * level-shifted lower state s projected on this site pair (HOST, veclength doubles, symmetric convention).  Afterwards every
+ * apply adds sum_s <V_s|S> V_s (addDiagramExcitations, HeffDiagrams1.cpp:65-85) and the diagonal adds V_s .* V_s
+ * (addDiagonalExcitations, HeffDiagonal.cpp:621-640).  n_lower = 0 switches it off. */
+int b2_heff_set_excitations(b2_heff* h, int n_lower, const double* const* veff_tilde);
 /* b2_heff_solve = Heff::SolveDAVIDSON (Heff.cpp:317-386) with CheMPS2::Davidson (Davidson.cpp) running on the device:
  * s (HOST, Sobject storage in the reference's "program" convention) holds the initial guess on entry and the lowest
  * eigenvector on exit; *eigenvalue excludes Econst exactly like the reference's return value; rtol = the sweep
@@ -220,6 +238,9 @@ int b2_dmrg_set_opset(b2_dmrg* d, int boundary, int moving_right, b2_opset* set)
 /* multi-GPU sweep: sigma terms (ownership maps) and operator updates are sharded over `world` GPUs, MPS / Davidson vectors /
  * Split are replicated; fn sums a device vector over the ranks (NCCL).  Call before the first update / solve. */
 int b2_dmrg_set_world(b2_dmrg* d, int world, int rank, b2_allreduce_fn fn, void* user);
+/* enabled != 0: only the two operator sets of the site pair being optimised (and the set being built) stay in HBM, every
+ * other boundary is offloaded to pinned host memory (the reference's disk mode, DMRG.cpp:57-65 makecheckpoints / OperatorsOnDisk) */
+int b2_dmrg_set_spill(b2_dmrg* d, int enabled);
 /* wall-clock seconds per phase since the last reset: [0] plan building (host), [1] Davidson solves, [2] Split (host SVD),
  * [3] operator updates, [4] number of sigma builds */
 int b2_dmrg_timers(b2_dmrg* d, double* out5, int reset);

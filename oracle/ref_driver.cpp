@@ -62,7 +62,7 @@ struct Writer {
    void dbls(const std::string & name, const double * p, long long n){ rec(name, 1, n, p); }
 };
 
-enum { K_L = 0, K_S0, K_S1, K_F0, K_F1, K_A, K_B, K_C, K_D, K_Q, K_X };
+enum { K_L = 0, K_S0, K_S1, K_F0, K_F1, K_A, K_B, K_C, K_D, K_Q, K_X, K_G, K_Y, K_Z, K_K, K_M };
 
 static void push_op(std::vector<int> & meta, std::vector<double> & data, int kind, int i, int j, Tensor * t){
    if (t == NULL) return;
@@ -181,8 +181,48 @@ static void dump_sigma(Writer & w, const std::string & prefix, DMRG & d, int ind
                    d.F0tensors, d.F1tensors, d.Qtensors, d.Xtensors, 0, NULL);
    w.dbls(prefix + "/rnd_in", rin);
    w.dbls(prefix + "/rnd_out", rout);
+   /* excited-state level-shift projector (Heff::addDiagramExcitations, HeffDiagrams1.cpp:65-85; addDiagonalExcitations,
+      HeffDiagonal.cpp:621-640): two random "VeffTilde" vectors */
+   {
+      std::vector<double> v0(n), v1(n), eout(n), ediag(n);
+      for (int i = 0; i < n; i++){ st = st * 1664525u + 1013904223u; v0[i] = ((st >> 8) & 0xFFFF) / 65536.0 - 0.5; }
+      for (int i = 0; i < n; i++){ st = st * 1664525u + 1013904223u; v1[i] = ((st >> 8) & 0xFFFF) / 65536.0 - 0.5; }
+      double * vt[2] = { v0.data(), v1.data() };
+      solver.makeHeff(rin.data(), eout.data(), &S, d.Ltensors, d.Atensors, d.Btensors, d.Ctensors, d.Dtensors, d.S0tensors, d.S1tensors,
+                      d.F0tensors, d.F1tensors, d.Qtensors, d.Xtensors, 2, vt);
+      solver.fillHeffDiag(ediag.data(), &S, d.Ctensors, d.Dtensors, d.F0tensors, d.F1tensors, d.Xtensors, 2, vt);
+      w.dbls(prefix + "/exc_v0", v0); w.dbls(prefix + "/exc_v1", v1);
+      w.dbls(prefix + "/exc_out", eout); w.dbls(prefix + "/exc_diag", ediag);
+   }
    if (index > 0) dump_ops(w, prefix + "/left", d, index - 1, true);
    if (index < d.L - 2) dump_ops(w, prefix + "/right", d, index + 1, false);
+}
+
+/* G/Y/Z/K/M tensors of the two-orbital correlation functions along the chain: DMRG::update_correlations_tensors
+   (DMRGoperators3RDM.cpp:415-479) called for siteindex = 1 .. L-1 on the current MPS, every table dumped */
+static void dump_correlation_tensors(Writer & w, const std::string & prefix, DMRG & d){
+   const int L = d.L;
+   dump_bk(w, prefix + "/bk", d.denBK);
+   dump_mps(w, prefix + "/mps", d);
+   d.Gtensors = new TensorGYZ*[L - 1]; d.Ytensors = new TensorGYZ*[L - 1]; d.Ztensors = new TensorGYZ*[L - 1];
+   d.Ktensors = new TensorKM*[L - 1];  d.Mtensors = new TensorKM*[L - 1];
+   for (int siteindex = 1; siteindex < L; siteindex++){
+      d.update_correlations_tensors(siteindex);
+      std::vector<int> meta; std::vector<double> data;
+      for (int prev = 0; prev < siteindex; prev++){
+         push_op(meta, data, K_G, prev, prev, d.Gtensors[prev]);
+         push_op(meta, data, K_Y, prev, prev, d.Ytensors[prev]);
+         push_op(meta, data, K_Z, prev, prev, d.Ztensors[prev]);
+         push_op(meta, data, K_K, prev, prev, d.Ktensors[prev]);
+         push_op(meta, data, K_M, prev, prev, d.Mtensors[prev]);
+      }
+      std::ostringstream nm; nm << prefix << "/b" << siteindex;
+      std::vector<int> hdr; hdr.push_back(siteindex); hdr.push_back(1);
+      w.ints(nm.str() + "/hdr", hdr); w.ints(nm.str() + "/meta", meta); w.dbls(nm.str() + "/data", data);
+   }
+   for (int prev = 0; prev < L - 1; prev++){ delete d.Gtensors[prev]; delete d.Ytensors[prev]; delete d.Ztensors[prev]; delete d.Ktensors[prev]; delete d.Mtensors[prev]; }
+   delete [] d.Gtensors; delete [] d.Ytensors; delete [] d.Ztensors; delete [] d.Ktensors; delete [] d.Mtensors;
+   d.Gtensors = NULL; d.Ytensors = NULL; d.Ztensors = NULL; d.Ktensors = NULL; d.Mtensors = NULL;
 }
 
 struct Setup {
@@ -446,6 +486,7 @@ int main(int argc, char ** argv){
          if (index == siteB) dump_ops(w, "UR/new", d, index, true);
       }
       w.dbls("energies", energies);
+      dump_correlation_tensors(w, "corr", d);
       printf("B2REF dumped; last energy %.12f\n", energies.back());
       return 0;
    }

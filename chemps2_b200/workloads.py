@@ -45,6 +45,37 @@ def synthetic_integrals(L, irreps, seed, naux, width, amp, local=False):
     return tmat, vmat
 
 
+# carbon positions (Angstrom) of tetracene, reference sphinx/tetracene.fcidump.in:6-23
+TETRACENE_C = [(4.888883611380, -0.715374463486), (4.888883611380, 0.715374463486), (-4.888883611380, -0.715374463486),
+               (-4.888883611380, 0.715374463486), (3.711144499602, -1.409316610825), (3.711144499602, 1.409316610825),
+               (-3.711144499602, -1.409316610825), (-3.711144499602, 1.409316610825), (2.450542389320, -0.725895641808),
+               (2.450542389320, 0.725895641808), (-2.450542389320, -0.725895641808), (-2.450542389320, 0.725895641808),
+               (1.235393613403, -1.406341384439), (1.235393613403, 1.406341384439), (-1.235393613403, -1.406341384439),
+               (-1.235393613403, 1.406341384439), (0.000000000000, -0.726150477978), (0.000000000000, 0.726150477978)]
+
+
+def ppp_tetracene_integrals():
+    """SURVEY.md 8(d) config 3 stand-in (the 20 GB psi4 FCIDUMP of sphinx/handson.rst:57 cannot be regenerated here): 18e/18o
+    Pariser-Parr-Pople model on the tetracene carbon skeleton.  t = -2.4 eV for C-C < 1.6 A, Ohno gamma_ij = U / sqrt(1 + (U r_ij /
+    14.397)^2) with U = 11.26 eV, <ij|kl> = delta_ik delta_jl gamma_ij, T_ii = -sum_{j != i} gamma_ij, everything / 27.2114 (Hartree);
+    sites ordered along the long molecular axis (x, then y).  Known answer from the unmodified reference:
+    E(D = 600) = -23.892594067 Eh.  -> (tmat[L,L], vmat[L,L,L,L] physicist)"""
+    xy = np.array(sorted(TETRACENE_C, key=lambda p: (round(p[0], 6), round(p[1], 6))))
+    L = len(xy)
+    r = np.sqrt(((xy[:, None, :] - xy[None, :, :]) ** 2).sum(-1))
+    U = 11.26
+    gamma = U / np.sqrt(1.0 + (U * r / 14.397) ** 2)
+    t = np.zeros((L, L))
+    t[(r < 1.6) & (r > 1e-9)] = -2.4
+    for i in range(L):
+        t[i, i] = -(gamma[i].sum() - gamma[i, i])
+    v = np.zeros((L, L, L, L))
+    for i in range(L):
+        for j in range(L):
+            v[i, j, i, j] = gamma[i, j]
+    return t / 27.2114, v / 27.2114
+
+
 class Workload:
     def __init__(self, name, L, group, N, twoS, irrep, irreps, D, site, seed, **gen):
         self.name, self.L, self.group, self.N, self.twoS, self.irrep = name, L, group, N, twoS, irrep
@@ -53,7 +84,7 @@ class Workload:
 
     def integrals(self):
         if self._ints is None:
-            self._ints = synthetic_integrals(self.L, self.irreps, self.seed, **self.gen)
+            self._ints = ppp_tetracene_integrals() if self.gen.get("model") == "ppp_tetracene" else synthetic_integrals(self.L, self.irreps, self.seed, **self.gen)
         return self._ints
 
     def context(self, device):
@@ -134,6 +165,8 @@ def get(name, D=None, site=None):
         w = Workload(name, 28, 7, 14, 0, 0, N2_CCPVDZ_IRREPS, 2000, 13, 14282000, naux=96, width=6.0, amp=0.3)
     elif name == "tetracene":  # config 3: 18e/18o C1
         w = Workload(name, 18, 0, 18, 0, 0, [0] * 18, 3000, 8, 18183000, naux=36, width=3.0, amp=0.4, local=True)
+    elif name == "tetracene_ppp":   # config 3 stand-in with a known answer from the reference
+        w = Workload(name, 18, 0, 18, 0, 0, [0] * 18, 600, 8, 0, model="ppp_tetracene")
     elif name == "tiny":       # CPU-checkable stand-in used by smoke() and the fast tests
         w = Workload(name, 8, 5, 8, 0, 0, [0, 0, 2, 3, 0, 0, 2, 3], 40, 3, 8080, naux=16, width=3.0, amp=0.4)
     else:

@@ -90,6 +90,7 @@ SIGNATURES = [
     ("b2_heff_presum_size", C.c_int64, [vp]),
     ("b2_heff_export_presums", C.c_int, [vp, C.POINTER(FlatPresum)]),
     ("b2_probe_fp64", C.c_int, [vp, C.c_int, c_dp]),
+    ("b2_svd_batch", C.c_int, [vp, C.c_int, c_ip, c_ip, C.POINTER(c_dp), C.POINTER(c_dp), C.POINTER(c_dp), C.POINTER(c_dp)]),
     ("b2_heff_worklists", C.c_int, [vp, vp]),
     ("b2_ctx_set_option", C.c_int, [vp, C.c_char_p, C.c_double]),
     ("b2_dmrg_create", C.c_int, [vp, C.POINTER(vp)]),

@@ -72,6 +72,20 @@ class Context:
         return labels, offs
 
 
+def svd_batch(ctx, mats):
+    """thin SVDs of a list of 2-D arrays on the GPU -> [(u, s, vt)]   (b2_svd_batch; stands for dgesdd_ in Sobject::Split)"""
+    As = [np.asfortranarray(m, dtype=np.float64) for m in mats]
+    ms = np.array([a.shape[0] for a in As], dtype=np.int32)
+    ns = np.array([a.shape[1] for a in As], dtype=np.int32)
+    ks = np.minimum(ms, ns)
+    S = [np.zeros(k) for k in ks]
+    U = [np.zeros((m, k), order="F") for m, k in zip(ms, ks)]
+    VT = [np.zeros((k, n), order="F") for k, n in zip(ks, ns)]
+    arr = lambda xs: (c_dp * max(len(xs), 1))(*[x.ctypes.data_as(c_dp) for x in xs])   # noqa: E731
+    check(lib.b2_svd_batch(ctx.h, len(As), ms.ctypes.data_as(c_ip), ns.ctypes.data_as(c_ip), arr(As), arr(S), arr(U), arr(VT)))
+    return list(zip(U, S, VT))
+
+
 class OpSet:
     def __init__(self, ctx, boundary, moving_right, correlation=False):
         """correlation=True: the {G, Y, Z, K, M} helper tensors of DMRG::update_correlations_tensors instead of the sweep operators"""

@@ -1094,8 +1094,11 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
       // ---- Split (host SVD + truncation); the bookkeeper dims of boundary index+1 change here
       SLayout Scopy = S;
       const double tq0 = wall_seconds();
-      const double dw = split_host(ctx->bk, index, Scopy, s_host.data(), D, moving_right != 0, change != 0, d->mps[index], d->mps[index + 1]);
+      char svd_err[256] = "";
+      SvdBatchFn svd = [&](std::vector<SvdJob>& jobs) { return dev_svd_batch(jobs, (void*)s, svd_err, (int)sizeof(svd_err)); };
+      const double dw = split_host(ctx->bk, index, Scopy, s_host.data(), D, moving_right != 0, change != 0, d->mps[index], d->mps[index + 1], svd);
       d->t_split += wall_seconds() - tq0;
+      if (dw < 0.0) { rc = fail(B2_ERR_CUDA, "b2_dmrg_solve_site: Split: %s", svd_err); break; }
       if (discarded_weight) *discarded_weight = dw;
    } while (0);
    cudaFree(d_tl); cudaFree(d_tr); cudaFree(d_s);
@@ -1130,6 +1133,21 @@ int b2_dmrg_sweep(b2_dmrg* d, int to_right, double rtol, double noise, int D, in
    }
    *min_energy = emin;
    if (max_discarded) *max_discarded = dmax;
+   return B2_OK;
+}
+
+/* thin SVDs of a batch of host matrices on the GPU (what Sobject::Split needs from dgesdd_, Sobject.cpp:412-419) */
+int b2_svd_batch(b2_ctx* ctx, int count, const int* m, const int* n, const double* const* a, double* const* sv, double* const* u, double* const* vt) {
+   if (!ctx || count < 0 || (count > 0 && (!m || !n || !a || !sv || !u || !vt))) return fail(B2_ERR_ARG, "b2_svd_batch: bad arguments");
+   if (ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_svd_batch: planning-only context, no CUDA device (there is no CPU fallback)");
+   CUDA_TRY(cudaSetDevice(ctx->device));
+   std::vector<SvdJob> jobs(count);
+   for (int i = 0; i < count; i++) {
+      if (m[i] < 1 || n[i] < 1) return fail(B2_ERR_ARG, "b2_svd_batch: empty matrix %d", i);
+      jobs[i].m = m[i]; jobs[i].n = n[i]; jobs[i].a = a[i]; jobs[i].s = sv[i]; jobs[i].u = u[i]; jobs[i].vt = vt[i];
+   }
+   char err[256] = "";
+   if (dev_svd_batch(jobs, (void*)ctx->stream, err, (int)sizeof(err))) return fail(B2_ERR_CUDA, "%s", err);
    return B2_OK;
 }
 

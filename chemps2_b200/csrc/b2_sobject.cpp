@@ -40,62 +40,6 @@ void join_terms(std::vector<Term3>& terms, std::vector<DstBlock>& dst, const Boo
    }
 }
 
-// thin SVD of the column-major m x n matrix a (ld = m): a = U diag(s) V^T with k = min(m, n); u is m x k (ld m), vt is k x n (ld k).
-// One-sided Jacobi (Hestenes) on the columns of the taller orientation; singular values sorted in decreasing order.
-void jacobi_svd(int m, int n, const double* a, double* s, double* u, double* vt) {
-   const bool flip = m < n;                 // work on the transpose so that rows >= cols
-   const int R = flip ? n : m, C = flip ? m : n;
-   std::vector<double> W((size_t)R * C), V((size_t)C * C, 0.0);
-   for (int j = 0; j < C; j++)
-      for (int i = 0; i < R; i++) W[i + (size_t)R * j] = flip ? a[j + (size_t)m * i] : a[i + (size_t)m * j];
-   for (int j = 0; j < C; j++) V[j + (size_t)C * j] = 1.0;
-   double scale = 0.0;
-   for (double x : W) scale = std::max(scale, std::fabs(x));
-   const double tiny = scale * scale * 1e-300;
-   for (int sweep = 0; sweep < 60; sweep++) {
-      bool rotated = false;
-      for (int p = 0; p < C - 1; p++)
-         for (int q = p + 1; q < C; q++) {
-            double* wp = &W[(size_t)R * p];
-            double* wq = &W[(size_t)R * q];
-            double alpha = 0.0, beta = 0.0, gamma = 0.0;
-            for (int i = 0; i < R; i++) { alpha += wp[i] * wp[i]; beta += wq[i] * wq[i]; gamma += wp[i] * wq[i]; }
-            if (std::fabs(gamma) <= 1e-15 * std::sqrt(alpha * beta) || std::fabs(gamma) <= tiny) continue;
-            rotated = true;
-            const double zeta = (beta - alpha) / (2.0 * gamma);
-            const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
-            const double c = 1.0 / std::sqrt(1.0 + t * t), sn = c * t;
-            for (int i = 0; i < R; i++) { const double x = wp[i], y = wq[i]; wp[i] = c * x - sn * y; wq[i] = sn * x + c * y; }
-            double* vp = &V[(size_t)C * p];
-            double* vq = &V[(size_t)C * q];
-            for (int i = 0; i < C; i++) { const double x = vp[i], y = vq[i]; vp[i] = c * x - sn * y; vq[i] = sn * x + c * y; }
-         }
-      if (!rotated) break;
-   }
-   std::vector<double> nrm(C);
-   std::vector<int> idx(C);
-   for (int j = 0; j < C; j++) {
-      double x = 0.0;
-      for (int i = 0; i < R; i++) x += W[i + (size_t)R * j] * W[i + (size_t)R * j];
-      nrm[j] = std::sqrt(x); idx[j] = j;
-   }
-   std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return nrm[x] > nrm[y]; });
-   const int k = C;   // = min(m, n)
-   for (int jj = 0; jj < k; jj++) {
-      const int j = idx[jj];
-      s[jj] = nrm[j];
-      const double inv = nrm[j] > 0.0 ? 1.0 / nrm[j] : 0.0;
-      // W(:,j)/s = left vectors of the worked-on matrix; V(:,j) = right vectors
-      if (!flip) {
-         for (int i = 0; i < m; i++) u[i + (size_t)m * jj] = W[i + (size_t)R * j] * inv;
-         for (int i = 0; i < n; i++) vt[jj + (size_t)k * i] = V[i + (size_t)C * j];
-      } else {   // a^T = W V^T  =>  a = V W^T : U = V, V^T rows = normalised W columns
-         for (int i = 0; i < m; i++) u[i + (size_t)m * jj] = V[i + (size_t)C * j];
-         for (int i = 0; i < n; i++) vt[jj + (size_t)k * i] = W[i + (size_t)R * j] * inv;
-      }
-   }
-}
-
 namespace {
 struct Center { int NM, TwoJM, IM; };
 struct Piece { int n, ts, ir, dim, start; };
@@ -131,13 +75,15 @@ std::vector<Piece> right_pieces(const Bookkeeper& bk, int ix, const Center& c) {
 }   // namespace
 
 double split_host(Bookkeeper& bk, int ix, const SLayout& S, const double* s_storage, int D, bool moving_right, bool change,
-                  std::vector<double>& t_left, std::vector<double>& t_right) {
+                  std::vector<double>& t_left, std::vector<double>& t_right, const SvdBatchFn& svd_batch) {
    std::vector<Center> centers;
    bk.for_sectors(ix + 1, [&](int n, int ts, int ir) { if (bk.fcidim(ix + 1, n, ts, ir) > 0) centers.push_back({n, ts, ir}); });
    const int nc = (int)centers.size();
    std::vector<std::vector<double>> Lam(nc), Us(nc), VTs(nc);
    std::vector<int> cdim(nc, 0), dimLtot(nc, 0), dimRtot(nc, 0);
    std::vector<std::vector<Piece>> LP(nc), RP(nc);
+   std::vector<std::vector<double>> mems(nc);
+   std::vector<SvdJob> jobs;
    for (int ic = 0; ic < nc; ic++) {
       const Center& c = centers[ic];
       LP[ic] = left_pieces(bk, ix, c);
@@ -147,7 +93,8 @@ double split_host(Bookkeeper& bk, int ix, const SLayout& S, const double* s_stor
       cdim[ic] = std::min(dimLtot[ic], dimRtot[ic]);
       if (cdim[ic] <= 0) continue;
       const int M = dimLtot[ic], N = dimRtot[ic];
-      std::vector<double> mem((size_t)M * N, 0.0);
+      std::vector<double>& mem = mems[ic];
+      mem.assign((size_t)M * N, 0.0);
       for (auto& pl : LP[ic]) {
          const int TwoS1 = (pl.n + 1 == c.NM) ? 1 : 0;
          for (auto& pr : RP[ic]) {
@@ -165,8 +112,13 @@ double split_host(Bookkeeper& bk, int ix, const SLayout& S, const double* s_stor
          }
       }
       Lam[ic].resize(cdim[ic]); Us[ic].resize((size_t)cdim[ic] * M); VTs[ic].resize((size_t)cdim[ic] * N);
-      jacobi_svd(M, N, mem.data(), Lam[ic].data(), Us[ic].data(), VTs[ic].data());
+      SvdJob job;
+      job.m = M; job.n = N; job.a = mem.data(); job.s = Lam[ic].data(); job.u = Us[ic].data(); job.vt = VTs[ic].data();
+      jobs.push_back(job);
    }
+   // the decomposition itself (dgesdd_ per centre sector in the reference, Sobject.cpp:412-419): all sectors in one device batch
+   if (!svd_batch || svd_batch(jobs) != 0) return -1.0;   // negative = failed (the caller reports the device error)
+   mems.clear();
 
    double discarded = 0.0;
    if (change) {   // Sobject.cpp:437-499

@@ -249,6 +249,12 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
                        double* discarded_weight, int* n_matvec);
 int b2_dmrg_sweep(b2_dmrg* d, int to_right, double rtol, double noise, int D, int change, double* min_energy, double* max_discarded);
 
+/* Batched thin SVD on the GPU: a[i] (HOST, column-major m[i] x n[i], ld = m[i]) = U diag(s) V^T with k = min(m, n); u[i] is m x k
+ * (ld m), vt[i] is k x n (ld k), s[i] decreasing.  Stands for the dgesdd_ call per centre sector of Sobject::Split
+ * (Sobject.cpp:412-419); one-sided Jacobi, all matrices of the batch progress together (b2_svd.cu).  b2_dmrg_solve_site uses it. */
+int b2_svd_batch(b2_ctx* ctx, int count, const int* m, const int* n, const double* const* a, double* const* s, double* const* u,
+                 double* const* vt);
+
 /* scheduling knobs of plans created afterwards: "work_budget" (doubles of stage-1 workspace per wave), "chunk_k" */
 int b2_ctx_set_option(b2_ctx* ctx, const char* name, double value);
 /* host mirrors of the operator arenas (valid until the set is destroyed) */

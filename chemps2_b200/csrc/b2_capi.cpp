@@ -49,6 +49,7 @@ struct b2_ctx {
    Bookkeeper bk;
    bool have_problem = false, have_bk = false;
    CompileOptions copt;
+   double parallel_plan_flops = 2e11;   // plans below this many reference FLOPs per apply are compiled on all host cores
 };
 
 struct b2_opset {
@@ -375,7 +376,10 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
    const double tb0 = wall_seconds();
    build_sigma_plan(h->plan, ctx->bk, ctx->prob, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, site, world);
    const double tb1 = wall_seconds();
-   compile_sigma(h->comp, h->plan, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, rank, world, ctx->copt);
+   CompileOptions copt = ctx->copt;
+   // plans whose sigma build is a few milliseconds are dominated by the time to BUILD them: compile those on all host cores
+   copt.threads = (h->plan.flops_ref < ctx->parallel_plan_flops) ? plan_threads(h->plan.S.nkappa()) : 1;
+   compile_sigma(h->comp, h->plan, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, rank, world, copt);
    if (getenv("B2_TIMING")) fprintf(stderr, "b2_heff_create: enumerate %.3f s, schedule %.3f s, %zu terms\n", tb1 - tb0, wall_seconds() - tb1, h->plan.terms.size());
    if (ctx->device >= 0) {
       CUDA_TRY(cudaSetDevice(ctx->device));
@@ -664,6 +668,8 @@ int b2_ctx_set_option(b2_ctx* ctx, const char* name, double value) {
    if (!ctx || !name) return fail(B2_ERR_ARG, "b2_ctx_set_option: NULL");
    if (!std::strcmp(name, "work_budget")) { if (value < 1024) return fail(B2_ERR_ARG, "work_budget too small"); ctx->copt.work_budget = (int64_t)value; }
    else if (!std::strcmp(name, "chunk_k")) { if (value < 8) return fail(B2_ERR_ARG, "chunk_k too small"); ctx->copt.chunk_k = (int64_t)value; }
+   else if (!std::strcmp(name, "parallel_plan_flops")) ctx->parallel_plan_flops = value;
+   else if (!std::strcmp(name, "parallel_min_terms")) ctx->copt.parallel_min_terms = (int64_t)value;
    else return fail(B2_ERR_ARG, "b2_ctx_set_option: unknown option %s", name);
    return B2_OK;
 }
@@ -756,8 +762,10 @@ int b2_update_create_sharded(b2_ctx* ctx, int index, int moving_right, b2_opset*
          u->plan.terms.swap(mine);
       }
    }
-   compile_terms(u->pass[0], u->plan.terms, u->plan.dst, SP_VOUT, ctx->copt);
-   compile_terms(u->pass[1], u->plan.mix_terms, u->plan.dst, SP_VOUT, ctx->copt);
+   CompileOptions copt = ctx->copt;
+   copt.threads = (u->plan.flops_ref < ctx->parallel_plan_flops) ? plan_threads((int)u->plan.dst.size()) : 1;
+   compile_terms(u->pass[0], u->plan.terms, u->plan.dst, SP_VOUT, copt);
+   compile_terms(u->pass[1], u->plan.mix_terms, u->plan.dst, SP_VOUT, copt);
    for (const Presum& p : u->plan.presums) {
       PresumJob j{};
       j.dst_off = p.off; j.size = p.lay->size; j.part_begin = (int)u->presum_parts.size();

@@ -11,6 +11,8 @@
 
 #include <algorithm>
 #include <chrono>
+#include <functional>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 
@@ -104,9 +106,20 @@ double CompiledWork::bytes() const {
 }
 
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+namespace {
+
+// the launch order of the tiles [b, e) of one wave: see weight_sort in compile_range
+void group_sort(std::vector<Tile>& v, int b, int e, const std::vector<GemmItem>& items);
+
+// compiles terms[0, n) (grouped by dst) into `out`; sort_waves = false leaves the launch order to the caller
+void compile_range(CompiledWork& out, Term3* terms, size_t nterms, const std::vector<DstBlock>& dst, uint8_t dst_space, const CompileOptions& opt,
+                   bool sort_waves);
+
+}   // namespace
+
 void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vector<DstBlock>& dst, uint8_t dst_space, const CompileOptions& opt) {
    out = CompiledWork();
-   double T_sort = 0, T_emit = 0, T_total = now_s(), T_part = 0;
+   const double T_total = now_s();
    {  // every destination block must form ONE contiguous group: two groups would become two CTAs that read-modify-write the same
       // tile in one launch.  Generators that visit a block twice (e.g. TensorQ/TensorX: update + AddTerms) are regrouped here.
       std::vector<char> seen(dst.size(), 0);
@@ -118,21 +131,109 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
       }
       if (!grouped) std::stable_sort(terms.begin(), terms.end(), [](const Term3& a, const Term3& b) { return a.dst < b.dst; });
    }
-   WTable wmap;
-   out.items2.reserve(terms.size());
-   out.items1.reserve(terms.size() / 2);
-   int64_t wave_work = 0, wave_part = 0;
-   Wave wave{};
-   auto open_wave = [&]() {
-      for (int c = 0; c < kNumTileClasses; c++) {
-         wave.t1_begin[c] = (int)out.tiles1[c].size();
-         wave.t2_begin[c] = (int)out.tiles2[c].size();
+   const int T = std::max(1, std::min<int>(opt.threads, (int)(terms.size() / std::max<int64_t>(opt.parallel_min_terms, 1))));
+   if (T <= 1) {
+      compile_range(out, terms.data(), terms.size(), dst, dst_space, opt, true);
+   } else {
+      // Small plans are dominated by the time to BUILD them (the tiny-block regime of a first sweep): the term list is cut at
+      // destination-block boundaries into T segments that are compiled concurrently, each with 1/T of the workspace budget, and
+      // merged wave by wave (workspace / partial-slot / item offsets shifted per segment).  Stage-1 products are then shared only
+      // inside a segment, which is why large plans (where the FLOPs matter, not the planning) keep the sequential path.
+      std::vector<size_t> cut(T + 1, terms.size());
+      cut[0] = 0;
+      for (int t = 1; t < T; t++) {
+         size_t i = std::max(cut[t - 1], terms.size() * t / T);
+         while (i < terms.size() && i > 0 && terms[i].dst == terms[i - 1].dst) i++;
+         cut[t] = i;
       }
-      wave.red_begin = (int)out.reduces.size();
-      wave_work = 0; wave_part = 0;
-      wmap.clear();
-   };
-   auto weight_sort = [&](std::vector<Tile>& v, int b, int e, const std::vector<GemmItem>& items) {
+      std::vector<CompiledWork> seg(T);
+      CompileOptions o = opt;
+      o.work_budget = std::max<int64_t>(opt.work_budget / T, 1 << 20);
+      auto run_all = [&](const std::function<void(int)>& fn) {
+         std::vector<std::thread> pool;
+         for (int t = 1; t < T; t++) pool.emplace_back(fn, t);
+         fn(0);
+         for (std::thread& th : pool) th.join();
+      };
+      // every segment orders its own waves (heaviest group first); the merged wave is the concatenation of the segments' waves
+      run_all([&](int t) { compile_range(seg[t], terms.data() + cut[t], cut[t + 1] - cut[t], dst, dst_space, o, true); });
+      std::vector<int64_t> wbase(T + 1, 0), pbase(T + 1, 0);
+      std::vector<int> i1base(T + 1, 0), i2base(T + 1, 0);
+      size_t nwaves = 0;
+      for (int t = 0; t < T; t++) {
+         wbase[t + 1] = wbase[t] + (seg[t].work_size + 15) / 16 * 16;
+         pbase[t + 1] = pbase[t] + (seg[t].part_size + 15) / 16 * 16;
+         i1base[t + 1] = i1base[t] + (int)seg[t].items1.size();
+         i2base[t + 1] = i2base[t] + (int)seg[t].items2.size();
+         nwaves = std::max(nwaves, seg[t].waves.size());
+         out.flops_exec += seg[t].flops_exec; out.n_stage1 += seg[t].n_stage1;
+      }
+      out.work_size = wbase[T]; out.part_size = pbase[T];
+      out.items1.resize(i1base[T]); out.items2.resize(i2base[T]);
+      // positions of every (wave, segment) slice in the merged tile / reduce lists
+      struct Pos { int t1[kNumTileClasses], t2[kNumTileClasses], red; };
+      std::vector<std::vector<Pos>> pos(nwaves, std::vector<Pos>(T));
+      int n1[kNumTileClasses] = {}, n2[kNumTileClasses] = {}, nred = 0;
+      out.waves.resize(nwaves);
+      for (size_t w = 0; w < nwaves; w++) {
+         Wave& gw = out.waves[w];
+         for (int c = 0; c < kNumTileClasses; c++) { gw.t1_begin[c] = n1[c]; gw.t2_begin[c] = n2[c]; }
+         gw.red_begin = nred;
+         for (int t = 0; t < T; t++) {
+            Pos& ps = pos[w][t];
+            for (int c = 0; c < kNumTileClasses; c++) { ps.t1[c] = n1[c]; ps.t2[c] = n2[c]; }
+            ps.red = nred;
+            if (w >= seg[t].waves.size()) continue;
+            const Wave& sw = seg[t].waves[w];
+            for (int c = 0; c < kNumTileClasses; c++) { n1[c] += sw.t1_end[c] - sw.t1_begin[c]; n2[c] += sw.t2_end[c] - sw.t2_begin[c]; }
+            nred += sw.red_end - sw.red_begin;
+         }
+         for (int c = 0; c < kNumTileClasses; c++) { gw.t1_end[c] = n1[c]; gw.t2_end[c] = n2[c]; }
+         gw.red_end = nred;
+      }
+      for (int c = 0; c < kNumTileClasses; c++) { out.tiles1[c].resize(n1[c]); out.tiles2[c].resize(n2[c]); }
+      out.reduces.resize(nred);
+      run_all([&](int t) {   // every segment copies its own slices, shifting item indices and workspace / partial-slot offsets
+         std::copy(seg[t].items1.begin(), seg[t].items1.end(), out.items1.begin() + i1base[t]);
+         for (size_t i = 0; i < seg[t].items2.size(); i++) {
+            GemmItem g = seg[t].items2[i];
+            if (g.xs == SP_WORK) g.xoff += wbase[t];
+            if (g.ys == SP_WORK) g.yoff += wbase[t];
+            out.items2[i2base[t] + i] = g;
+         }
+         for (size_t w = 0; w < seg[t].waves.size(); w++) {
+            const Wave& sw = seg[t].waves[w];
+            const Pos& ps = pos[w][t];
+            for (int c = 0; c < kNumTileClasses; c++) {
+               for (int i = sw.t1_begin[c]; i < sw.t1_end[c]; i++) {
+                  Tile x = seg[t].tiles1[c][i];
+                  x.item_begin += i1base[t]; x.item_end += i1base[t];
+                  if (x.cspace == SP_WORK) x.coff += wbase[t];
+                  out.tiles1[c][ps.t1[c] + (i - sw.t1_begin[c])] = x;
+               }
+               for (int i = sw.t2_begin[c]; i < sw.t2_end[c]; i++) {
+                  Tile x = seg[t].tiles2[c][i];
+                  x.item_begin += i2base[t]; x.item_end += i2base[t];
+                  if (x.cspace == SP_PART) x.coff += pbase[t];
+                  out.tiles2[c][ps.t2[c] + (i - sw.t2_begin[c])] = x;
+               }
+            }
+            for (int i = sw.red_begin; i < sw.red_end; i++) {
+               ReduceJob r = seg[t].reduces[i];
+               r.part_off += pbase[t];
+               out.reduces[ps.red + (i - sw.red_begin)] = r;
+            }
+         }
+         seg[t] = CompiledWork();
+      });
+   }
+   for (int c = 0; c < kNumTileClasses; c++) out.n_tiles += (long long)out.tiles1[c].size() + (long long)out.tiles2[c].size();
+   if (getenv("B2_TIMING")) fprintf(stderr, "compile_terms: total %.3f s, %d thread(s)\n", now_s() - T_total, T);
+}
+
+namespace {
+
+void group_sort(std::vector<Tile>& v, int b, int e, const std::vector<GemmItem>& items) {
       // Launch order = heaviest GROUPS first (static load balance across the SMs), where a group is the set of CTAs that
       // stream the same items (all tiles of one stage-1 product / of one split-K chunk of a destination block): they read the
       // same operand panels, so they must be resident together for the panels to be served by L2 instead of DRAM.
@@ -156,9 +257,27 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
       std::vector<Tile> sorted(e - b);
       for (int i = 0; i < e - b; i++) sorted[i] = v[ord[i].idx];
       std::copy(sorted.begin(), sorted.end(), v.begin() + b);
+   }
+
+void compile_range(CompiledWork& out, Term3* terms, size_t nterms, const std::vector<DstBlock>& dst, uint8_t dst_space, const CompileOptions& opt,
+                   bool sort_waves) {
+   out = CompiledWork();
+   WTable wmap;
+   out.items2.reserve(nterms);
+   out.items1.reserve(nterms / 2);
+   int64_t wave_work = 0, wave_part = 0;
+   Wave wave{};
+   auto open_wave = [&]() {
+      for (int c = 0; c < kNumTileClasses; c++) {
+         wave.t1_begin[c] = (int)out.tiles1[c].size();
+         wave.t2_begin[c] = (int)out.tiles2[c].size();
+      }
+      wave.red_begin = (int)out.reduces.size();
+      wave_work = 0; wave_part = 0;
+      wmap.clear();
    };
+   auto weight_sort = [&](std::vector<Tile>& v, int b, int e, const std::vector<GemmItem>& items) { if (sort_waves) group_sort(v, b, e, items); };
    auto close_wave = [&]() {
-      const double t0 = now_s();
       bool any = (int)out.reduces.size() > wave.red_begin;
       for (int c = 0; c < kNumTileClasses; c++) {
          wave.t1_end[c] = (int)out.tiles1[c].size();
@@ -171,7 +290,6 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
       out.work_size = std::max(out.work_size, wave_work);
       out.part_size = std::max(out.part_size, wave_part);
       if (any) out.waves.push_back(wave);
-      T_sort += now_s() - t0;
    };
 
    // W = op(a) * op(b), shared inside the wave
@@ -244,11 +362,11 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
 
    open_wave();
    size_t i0 = 0;
-   while (i0 < terms.size()) {
+   while (i0 < nterms) {
       size_t i1 = i0;
-      while (i1 < terms.size() && terms[i1].dst == terms[i0].dst) i1++;
+      while (i1 < nterms && terms[i1].dst == terms[i0].dst) i1++;
       // block-axpy terms first inside every destination block: the kernel consumes them before it starts its GEMM pipeline
-      { const double t0 = now_s(); std::stable_partition(terms.begin() + i0, terms.begin() + i1, [](const Term3& t) { return !t.p.present() && !t.r.present(); }); T_part += now_s() - t0; }
+      std::stable_partition(terms + i0, terms + i1, [](const Term3& t) { return !t.p.present() && !t.r.present(); });
       const DstBlock& db = dst[terms[i0].dst];
       const int M = db.rows, N = db.cols;
       int ib = (int)out.items2.size();
@@ -282,12 +400,12 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
             ib = (int)out.items2.size();
          }
       }
-      { const double t0 = now_s(); emit_block(db, ib, (int)out.items2.size()); T_emit += now_s() - t0; }
+      emit_block(db, ib, (int)out.items2.size());
       i0 = i1;
    }
    close_wave();
-   for (int c = 0; c < kNumTileClasses; c++) out.n_tiles += (long long)out.tiles1[c].size() + (long long)out.tiles2[c].size();
-   if (getenv("B2_TIMING")) fprintf(stderr, "compile_terms: total %.3f s (close_wave/sort %.3f, emit %.3f, partition %.3f)\n", now_s() - T_total, T_sort, T_emit, T_part);
 }
+
+}   // namespace
 
 }   // namespace b2

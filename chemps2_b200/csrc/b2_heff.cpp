@@ -6,6 +6,7 @@
 #include "b2_heff.h"
 
 #include <algorithm>
+#include <thread>
 
 namespace b2 {
 
@@ -60,14 +61,23 @@ void compile_sigma(CompiledSigma& out, const SigmaPlan& plan, const OpSet* left,
    std::vector<DstBlock> dst(nk);
    for (int k = 0; k < nk; k++) dst[k] = DstBlock{S.blk[k].off, S.blk[k].rows, S.blk[k].cols};
    std::vector<Term3> terms(order.size());
-   for (size_t i = 0; i < order.size(); i++) {
-      const SigmaTerm& t = plan.terms[order[i]];
-      const Block& sb = S.blk[t.src];
-      Term3& x = terms[i];
-      x.dst = t.dst; x.f = t.factor;
-      x.p = resolve(t.l, plan, left, right);
-      x.r = resolve(t.r, plan, left, right);
-      x.q.space = SP_VIN; x.q.off = sb.off; x.q.rows = sb.rows; x.q.cols = sb.cols; x.q.trans = 0;
+   auto resolve_range = [&](size_t b, size_t e) {
+      for (size_t i = b; i < e; i++) {
+         const SigmaTerm& t = plan.terms[order[i]];
+         const Block& sb = S.blk[t.src];
+         Term3& x = terms[i];
+         x.dst = t.dst; x.f = t.factor;
+         x.p = resolve(t.l, plan, left, right);
+         x.r = resolve(t.r, plan, left, right);
+         x.q.space = SP_VIN; x.q.off = sb.off; x.q.rows = sb.rows; x.q.cols = sb.cols; x.q.trans = 0;
+      }
+   };
+   {
+      const int T = std::max(1, std::min<int>(opt.threads, (int)(order.size() / 20000)));
+      std::vector<std::thread> pool;
+      for (int t = 1; t < T; t++) pool.emplace_back(resolve_range, order.size() * t / T, order.size() * (t + 1) / T);
+      resolve_range(0, order.size() / T);
+      for (std::thread& th : pool) th.join();
    }
    // ---- diagonal of H_eff (Heff::fillHeffDiag, Heff.cpp:250-315 + HeffDiagonal.cpp): exactly the terms that map a block
    // onto itself — families 1A-1D, 2d3, 2b3/2c3/2e3/2f3 and 2a3 — restricted to the operator-block diagonals:

@@ -54,6 +54,8 @@ struct SigmaPlan {
    double flops_ref = 0.0;
 };
 
+int plan_threads(int nblocks);   // host threads for plan building (B2_PLAN_THREADS)
+
 // world = number of GPUs the ownership maps are evaluated for (1 = everything owned by GPU 0)
 void build_sigma_plan(SigmaPlan& plan, const Bookkeeper& bk, const Problem& prob, const OpSet* left, const OpSet* right,
                       int site, int world);

@@ -7,11 +7,25 @@
 #include <cassert>
 #include <cmath>
 #include <cstdio>
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <map>
+#include <thread>
 
 #include "b2_sigma.h"
 
 namespace b2 {
+
+// host threads used to build plans: B2_PLAN_THREADS, else the hardware concurrency (at most 32); small plans stay sequential
+int plan_threads(int nblocks) {
+   static const int configured = [] {
+      const char* e = getenv("B2_PLAN_THREADS");
+      int n = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+      return std::max(1, std::min(n, 32));
+   }();
+   return std::max(1, std::min(configured, nblocks / 8));
+}
 
 namespace {
 
@@ -446,13 +460,85 @@ void build_sigma_plan(SigmaPlan& plan, const Bookkeeper& bk, const Problem& prob
    plan.terms.clear(); plan.presums.clear(); plan.presum_size = 0; plan.skipped_zero = 0; plan.flops_ref = 0.0;
    if (plan.at_left) left = nullptr;
    if (plan.at_right) right = nullptr;
-   Gen g(plan, bk, prob, left, right, site, world < 1 ? 1 : world);
-   for (int k = 0; k < plan.S.nkappa(); k++) {
+   const int nk = plan.S.nkappa();
+   auto enumerate_block = [&](Gen& g, int k) {
       g.set_block(k);
       g.d1(); g.d2d(); g.d3EH();
       g.d2bcef(); g.d2bcef3(); g.d3_onesided();
       g.d4_onesided();
       if (left && right) { g.d2a(); g.d3CJ(); g.d4_twosided(); g.d5(); }
+   };
+   const int nthreads = plan_threads(nk);
+   if (nthreads <= 1) {
+      Gen g(plan, bk, prob, left, right, site, world < 1 ? 1 : world);
+      for (int k = 0; k < nk; k++) enumerate_block(g, k);
+      return;
+   }
+   // Target blocks are independent: every host thread enumerates the blocks it grabs into a private fragment (terms, pre-sums,
+   // FLOP count); the fragments are stitched together in block order, pre-sums de-duplicated by their keys and re-indexed, so the
+   // resulting plan has exactly the terms (and the per-block term order) of the sequential enumeration.
+   struct Frag {
+      SigmaPlan plan;
+      std::vector<int> blk_k, blk_begin;             // blocks this thread enumerated and where their terms start
+      std::map<std::string, int> keys;
+   };
+   std::vector<Frag> frags(nthreads);
+   std::atomic<int> next{0};
+   auto worker = [&](int t) {
+      Frag& f = frags[t];
+      f.plan.site = site; f.plan.at_left = plan.at_left; f.plan.at_right = plan.at_right; f.plan.S = plan.S;
+      Gen g(f.plan, bk, prob, left, right, site, world < 1 ? 1 : world);
+      for (;;) {
+         const int k0 = next.fetch_add(4);
+         if (k0 >= nk) break;
+         for (int k = k0; k < std::min(nk, k0 + 4); k++) {
+            f.blk_k.push_back(k); f.blk_begin.push_back((int)f.plan.terms.size());
+            enumerate_block(g, k);
+         }
+      }
+      f.blk_begin.push_back((int)f.plan.terms.size());
+      f.keys.swap(g.presum_index);
+   };
+   std::vector<std::thread> pool;
+   for (int t = 1; t < nthreads; t++) pool.emplace_back(worker, t);
+   worker(0);
+   for (std::thread& th : pool) th.join();
+   // ---- pre-sums: global registry in thread order
+   std::map<std::string, int> global;
+   std::vector<std::vector<int>> remap(nthreads);
+   size_t nterms = 0;
+   for (int t = 0; t < nthreads; t++) {
+      Frag& f = frags[t];
+      remap[t].assign(f.plan.presums.size(), -1);
+      for (auto& kv : f.keys) {
+         auto it = global.find(kv.first);
+         if (it == global.end()) {
+            Presum p = f.plan.presums[kv.second];
+            p.off = plan.presum_size;
+            plan.presum_size += (p.lay->size + 15) / 16 * 16;
+            plan.presums.push_back(p);
+            it = global.emplace(kv.first, (int)plan.presums.size() - 1).first;
+         }
+         remap[t][kv.second] = it->second;
+      }
+      plan.skipped_zero += f.plan.skipped_zero;
+      plan.flops_ref += f.plan.flops_ref;
+      nterms += f.plan.terms.size();
+   }
+   // ---- terms in block order
+   std::vector<std::pair<int, int>> where(nk, {-1, -1});   // block -> (thread, position in its block list)
+   for (int t = 0; t < nthreads; t++)
+      for (size_t i = 0; i < frags[t].blk_k.size(); i++) where[frags[t].blk_k[i]] = {t, (int)i};
+   plan.terms.reserve(nterms);
+   for (int k = 0; k < nk; k++) {
+      const int t = where[k].first, i = where[k].second;
+      const Frag& f = frags[t];
+      for (int e = f.blk_begin[i]; e < f.blk_begin[i + 1]; e++) {
+         SigmaTerm x = f.plan.terms[e];
+         if (x.l.src == SRC_PRESUM && x.l.op >= 0) x.l.op = remap[t][x.l.op];
+         if (x.r.src == SRC_PRESUM && x.r.op >= 0) x.r.op = remap[t][x.r.op];
+         plan.terms.push_back(x);
+      }
    }
 }
 

@@ -255,7 +255,8 @@ int b2_dmrg_sweep(b2_dmrg* d, int to_right, double rtol, double noise, int D, in
 int b2_svd_batch(b2_ctx* ctx, int count, const int* m, const int* n, const double* const* a, double* const* s, double* const* u,
                  double* const* vt);
 
-/* scheduling knobs of plans created afterwards: "work_budget" (doubles of stage-1 workspace per wave), "chunk_k" */
+/* scheduling knobs of plans created afterwards: "work_budget" (doubles of stage-1 workspace per wave), "chunk_k",
+ * "parallel_plan_flops" (plans below this many reference FLOPs per apply are compiled on all host cores; env B2_PLAN_THREADS) */
 int b2_ctx_set_option(b2_ctx* ctx, const char* name, double value);
 /* host mirrors of the operator arenas (valid until the set is destroyed) */
 const double* b2_opset_host_arena(const b2_opset* set);

@@ -101,8 +101,9 @@ def test_sigma_plan_owner_sharding(golden, world):
     assert np.abs(tot - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
 
 
-@pytest.mark.parametrize("options", [{}, {"work_budget": 2048, "chunk_k": 64}, {"work_budget": 50000, "chunk_k": 16}],
-                         ids=["default", "tiny-waves", "tiny-chunks"])
+@pytest.mark.parametrize("options", [{}, {"work_budget": 2048, "chunk_k": 64}, {"work_budget": 50000, "chunk_k": 16},
+                                     {"parallel_min_terms": 16}, {"parallel_min_terms": 16, "work_budget": 16384, "chunk_k": 32}],
+                         ids=["default", "tiny-waves", "tiny-chunks", "parallel-plan", "parallel-plan-tiny-waves"])
 @pytest.mark.parametrize("tag", ["A", "B"])
 def test_compiled_worklists_vs_reference(golden, tag, options):
     """the device work lists (waves, split-K chunks, reduces, shared intermediates) executed by the CPU emulator

@@ -23,7 +23,8 @@ def _compare(arena_of, new, expected):
     return seen
 
 
-@pytest.mark.parametrize("options", [{}, {"work_budget": 4096, "chunk_k": 32}], ids=["default", "tiny-waves"])
+@pytest.mark.parametrize("options", [{}, {"work_budget": 4096, "chunk_k": 32}, {"parallel_min_terms": 16}, {"parallel_min_terms": 16, "work_budget": 8192, "chunk_k": 32}],
+                         ids=["default", "tiny-waves", "parallel-plan", "parallel-plan-tiny-waves"])
 @pytest.mark.parametrize("which", ["UR", "UL"])
 def test_update_worklists_vs_reference_cpu(golden, which, options):
     """CPU: the compiled update work lists executed by the emulator in oracle/ (no GPU needed to pin the plan)"""

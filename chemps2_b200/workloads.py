@@ -155,6 +155,24 @@ class Workload:
         return f"{self.name}: {self.N}e/{self.L}o group {self.group} D={self.D} site pair ({self.site},{self.site + 1})"
 
 
+class FixtureWorkload(Workload):
+    """a real Hamiltonian whose folded integral table travels as a problem-only fixture (tests/golden/problem_*.npz, written by
+    tests/golden/make_golden.py from the reference's own FCIDUMP through the reference's Hamiltonian / Problem classes)"""
+
+    def __init__(self, name, fixture, D, site):
+        fx = np.load(os.path.join(ROOT, "tests", "golden", fixture))
+        L, group, N, twoS, irrep = [int(x) for x in fx["problem/hdr"]]
+        super().__init__(name, L, group, N, twoS, irrep, [int(x) for x in fx["problem/orb_irrep"]], D, site, 0)
+        self._mx, self._econst = fx["problem/mx"], float(fx["problem/econst"][0])
+
+    def context(self, device):
+        from . import api
+        ctx = api.Context(device)
+        ctx.set_problem(self.L, self.group, self.N, self.twoS, self.irrep, self.irreps, mx=self._mx, econst=self._econst)
+        ctx.bk_init(self.D)
+        return ctx
+
+
 def get(name, D=None, site=None):
     """named workloads = the BASELINE.json configs (shape + symmetry), synthetic integrals"""
     if name == "synth40":      # config 5: 40e/40o C1, no locality (SURVEY 8(d))
@@ -165,6 +183,9 @@ def get(name, D=None, site=None):
         w = Workload(name, 28, 7, 14, 0, 0, N2_CCPVDZ_IRREPS, 2000, 13, 14282000, naux=96, width=6.0, amp=0.3)
     elif name == "tetracene":  # config 3: 18e/18o C1
         w = Workload(name, 18, 0, 18, 0, 0, [0] * 18, 3000, 8, 18183000, naux=36, width=3.0, amp=0.4, local=True)
+    elif name == "n2_ccpvdz":   # config 2 itself: N2/cc-pVDZ 14e/28o D2h X1Sigma_g+, orbitals reordered by Problem::SetupReorderD2h;
+        # published (sphinx/resources.rst:50-56): E(D=1000) = -109.28209711, E(D=2000) = -109.28216077 (219 s/sweep on 16 cores)
+        w = FixtureWorkload(name, "problem_n2_ccpvdz.npz", 2000, 13)
     elif name == "tetracene_ppp":   # config 3 stand-in with a known answer from the reference
         w = Workload(name, 18, 0, 18, 0, 0, [0] * 18, 600, 8, 0, model="ppp_tetracene")
     elif name == "tiny":       # CPU-checkable stand-in used by smoke() and the fast tests

@@ -421,6 +421,14 @@ int main(int argc, char ** argv){
    }
 
    if (mode == "synth") return run_synth(argc, argv);
+   if (mode == "problem"){   /* only the problem (orbital irreps in DMRG order + folded integral table): input of full calculations */
+      Setup s = make_setup(argc, argv);
+      s.prob->construct_mxelem();
+      Writer w(args(argc, argv, "--out", "problem.b2fx"));
+      dump_problem(w, s.prob, s.ham, s.group);
+      printf("B2REF problem dumped\n");
+      return 0;
+   }
 
    Setup s = make_setup(argc, argv);
    const int D = argi(argc, argv, "--D", 20);

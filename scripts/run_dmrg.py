@@ -23,7 +23,10 @@ def run(name, schedule, rtol=1e-5, noise=0.0, seed=12345, device=0, spill=False,
         d.update(i, True)                       # DMRG::PreSolve (DMRG.cpp:257-266)
     log(f"presolve {time.time() - t0:.2f} s")
     out, change, first = [], False, True
-    for D, nsweeps in schedule:
+    for entry in schedule:
+        D, nsweeps = entry[0], entry[1]
+        if len(entry) > 2:
+            noise = entry[2]
         for _ in range(nsweeps):
             for to_right in (False, True):
                 d.timers(reset=True)
@@ -41,13 +44,13 @@ def run(name, schedule, rtol=1e-5, noise=0.0, seed=12345, device=0, spill=False,
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("workload")
-    ap.add_argument("schedule", help="D:sweeps,D:sweeps,...")
+    ap.add_argument("schedule", help="D:sweeps[:noise],D:sweeps[:noise],...")
     ap.add_argument("--rtol", type=float, default=1e-5)
     ap.add_argument("--noise", type=float, default=0.0)
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--json", default=None)
     a = ap.parse_args()
-    sched = [(int(x.split(":")[0]), int(x.split(":")[1])) for x in a.schedule.split(",")]
+    sched = [tuple([int(x.split(":")[0]), int(x.split(":")[1])] + [float(v) for v in x.split(":")[2:3]]) for x in a.schedule.split(",")]
     res = run(a.workload, sched, a.rtol, a.noise, a.seed)
     if a.json:
         json.dump(res, open(a.json, "w"), indent=1)

@@ -17,7 +17,8 @@ def pytest_configure(config):
         subprocess.run(["make", "-j8"], cwd=ROOT, check=True, stdout=subprocess.DEVNULL)
 
 
-GOLDEN = sorted(p for p in glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")) if not p.endswith("wigner.npz"))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz"))
+                if not p.endswith("wigner.npz") and not os.path.basename(p).startswith("problem_"))
 
 
 @pytest.fixture(scope="session", params=GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])

@@ -41,6 +41,14 @@ def main():
         fx = read_b2fx(tmp)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
         print(name, os.path.getsize(os.path.join(HERE, name + ".npz")) // 1024, "KiB")
+    # problem-only fixture of BASELINE config 2 (N2/cc-pVDZ, 14e/28o, D2h, SetupReorderD2h): the input of scripts/run_dmrg.py n2_ccpvdz,
+    # whose known answers are the published energies of sphinx/resources.rst:50-56.  Only the folded table gMxElement is kept.
+    tmp = "/tmp/n2_ccpvdz_problem.b2fx"
+    subprocess.run([DRV, "problem", "--fcidump", f"{ME}/N2.CCPVDZ.FCIDUMP", "--group", "7", "--twoS", "0", "--N", "14", "--irrep", "0", "--reorder",
+                    "--out", tmp], check=True, env=env, stdout=subprocess.DEVNULL)
+    fx = read_b2fx(tmp)
+    np.savez_compressed(os.path.join(HERE, "problem_n2_ccpvdz.npz"), **{k: v for k, v in fx.items() if k not in ("problem/vmat", "problem/tmat")})
+    print("problem_n2_ccpvdz", os.path.getsize(os.path.join(HERE, "problem_n2_ccpvdz.npz")) // 1024, "KiB")
     tmp = "/tmp/wigner.b2fx"
     subprocess.run([DRV, "wigner", "--out", tmp], check=True, env=env)
     np.savez_compressed(os.path.join(HERE, "wigner.npz"), **read_b2fx(tmp))

@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--dist", default="gauss", choices=["gauss", "flat"])
     ap.add_argument("--cpu-flops-cap", type=float, default=6e11, help="FLOPs of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the secondary metric (DMRG sweep time at D on the PPP tetracene model)")
+    ap.add_argument("--sweep-ref", action="store_true", help="also time the unmodified reference's DMRG::Solve on the same schedule (minutes)")
     ap.add_argument("--work-budget", type=float, default=0)
     ap.add_argument("--chunk-k", type=float, default=0)
     return ap.parse_args()
@@ -109,6 +111,54 @@ def cpu_baseline(args, w_full, flops_full, threads=None):
               f"FLOP ratio {flops_full / flops:.1f}")
     return {"value": value, "unit": UNIT, "cores": ref["threads"], "kind": "reference", "sample": sample, "gflops": gflops,
             "sample_seconds": ref["best_s"]}, ref, w, dims
+
+
+SWEEP_SCHEDULE = [(100, 1), (300, 1), (600, 2)]   # (D, full sweeps); rtol 1e-5, no noise — the ramp of SURVEY Appendix D.3, shortened
+SWEEP_KNOWN_ANSWER = -23.892594067                # E(D=600) of the unmodified reference on this model
+
+
+def sweep_metric(device, with_reference):
+    """Secondary metric of BASELINE.json ("DMRG sweep time at D"): a complete DMRG calculation — own random MPS, PreSolve, scheduled
+    two-site sweeps (Join, device Davidson, device-SVD Split, operator updates) — on the 18e/18o PPP tetracene model (config 3 stand-in),
+    timed by wall clock around b2_dmrg_sweep; the last full sweep runs at D = 600.  with_reference: the same schedule through
+    DMRG::Solve of the unmodified reference (oracle/_ref) on the host cores."""
+    from chemps2_b200 import api, workloads
+    w = workloads.get("tetracene_ppp")
+    ctx = w.context(device)
+    ctx.bk_init(SWEEP_SCHEDULE[0][0])
+    d = api.DMRG(ctx)
+    d.random_mps(12345)
+    t_begin = time.time()
+    for i in range(w.L - 2):
+        d.update(i, True)
+    change, last, e, dw = False, None, 0.0, 0.0
+    for D, nsweeps in SWEEP_SCHEDULE:
+        for _ in range(nsweeps):
+            d.timers(reset=True)
+            t0 = time.time()
+            el, dl = d.sweep(False, 1e-5, 0.0, D, change)
+            change = True
+            er, dr = d.sweep(True, 1e-5, 0.0, D, change)
+            last = dict(D=D, seconds=time.time() - t0, **d.timers())
+            e, dw = min(el, er), max(dl, dr)
+    out = {"workload": "tetracene_ppp: 18e/18o C1 Pariser-Parr-Pople model on the tetracene skeleton (BASELINE config 3 stand-in), schedule D=100,300,600,600",
+           "seconds_per_sweep_at_D600": last["seconds"], "total_seconds": time.time() - t_begin, "energy": e, "max_discarded_weight": dw,
+           "energy_minus_reference_known_answer": e - SWEEP_KNOWN_ANSWER,
+           "last_sweep_phases_s": {k: last[k] for k in ("plan_s", "solve_s", "split_s", "update_s")}, "last_sweep_sigma_builds": last["n_matvec"]}
+    if with_reference and os.path.exists(workloads.REF_DRIVER):
+        pfile = f"/tmp/b2_ppp_{os.getpid()}.bin"
+        w.write_problem_file(pfile)
+        sched = ",".join(f"{D}:1e-14:{n}:0.0:1e-5" for D, n in SWEEP_SCHEDULE)
+        env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count()), OPENBLAS_NUM_THREADS="1")
+        t0 = time.time()
+        res = subprocess.run([workloads.REF_DRIVER, "energies", "--problem", pfile, "--schedule", sched, "--seed", "12345"], capture_output=True, text=True, env=env)
+        walls = [float(ln.split("=")[1].split()[0]) for ln in res.stdout.splitlines() if "Elapsed wall time" in ln]
+        fin = [ln for ln in res.stdout.splitlines() if ln.startswith("B2REF final_energy")]
+        os.remove(pfile)
+        if fin and len(walls) >= 2:
+            out["reference"] = {"kind": "reference", "cores": os.cpu_count(), "seconds_per_sweep_at_D600": walls[-2] + walls[-1], "total_seconds": time.time() - t0,
+                                "energy": float(fin[-1].split()[2])}
+    return out
 
 
 def run_reference(args):
@@ -282,6 +332,11 @@ def main():
                                            "veclength": int(h2.n), "D": ws.D}
         except Exception as e:   # the baseline must not take the bench line down
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
+    if world == 1 and not args.no_sweep:
+        try:
+            line["sweep"] = sweep_metric(local, args.sweep_ref)
+        except Exception as e:   # the secondary metric must not take the bench line down
+            line["sweep"] = {"failed": str(e)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -926,6 +926,7 @@ struct b2_dmrg {
    int L = 0;
    std::vector<std::vector<double>> mps;   // TensorT storage per site in the layouts of the current bookkeeper
    std::vector<b2_opset*> left, right;     // operator sets per boundary: moving right (sites < b) / moving left (sites >= b)
+   double max_disc_last_sweep = 0.0;       // DMRG::MaxDiscWeightLastSweep (DMRG.cpp:360-362): scales the noise of the next half sweep
    bool spill = false;                     // keep only the operator sets of the site being optimised in HBM (b2_dmrg_set_spill)
    int world = 1, rank = 0;                // GPUs sharing the sweep: sigma terms and operator updates are sharded, the rest is replicated
    b2_allreduce_fn allreduce = nullptr;
@@ -1124,6 +1125,8 @@ int b2_dmrg_sweep(b2_dmrg* d, int to_right, double rtol, double noise, int D, in
    const int L = d->L;
    double emin = 1e300, dmax = 0.0;
    int rc;
+   // DMRG.cpp:360,391: the noise added before Split is |noise prefactor| x (largest discarded weight of the previous half sweep)
+   noise = std::fabs(noise) * d->max_disc_last_sweep;
    if (!to_right) {
       for (int index = L - 2; index > 0; index--) {
          double e, dw;
@@ -1139,6 +1142,7 @@ int b2_dmrg_sweep(b2_dmrg* d, int to_right, double rtol, double noise, int D, in
          if ((rc = b2_dmrg_update(d, index, 1))) return rc;
       }
    }
+   d->max_disc_last_sweep = dmax;
    *min_energy = emin;
    if (max_discarded) *max_discarded = dmax;
    return B2_OK;

@@ -225,7 +225,10 @@ int b2_update_export_presums(const b2_update* u, b2_flat_presum* out);
  *                         / updateMovingLeft (moving_right == 0: operators of boundary index from MPS[index])
  *   b2_dmrg_solve_site  = DMRG::solve_site: Sobject::Join (device) -> Heff::SolveDAVIDSON (device) -> addNoise -> Sobject::Split
  *                         (host SVD; virtual dimensions of boundary index+1 are rewritten when change != 0); *energy includes Econst
- *   b2_dmrg_sweep       = DMRG::sweepleft (to_right == 0: index L-2 .. 1) / sweepright (index 0 .. L-3) incl. the operator updates */
+ *   b2_dmrg_sweep       = DMRG::sweepleft (to_right == 0: index L-2 .. 1) / sweepright (index 0 .. L-3) incl. the operator updates;
+ *                         `noise` is the ConvergenceScheme noise PREFACTOR: like DMRG.cpp:360,391 the level handed to solve_site is
+ *                         |noise| x the largest discarded weight of the previous half sweep (0 before the first one);
+ *                         b2_dmrg_solve_site takes the absolute level, exactly like DMRG::solve_site */
 typedef struct b2_dmrg b2_dmrg;
 int b2_dmrg_create(b2_ctx* ctx, b2_dmrg** out);
 void b2_dmrg_destroy(b2_dmrg* d);

@@ -231,7 +231,7 @@ struct Setup {
 };
 
 static Setup make_setup(int argc, char ** argv){
-   Setup s; std::string fcidump; int twoS = 0, N = 0, irrep = 0, hubL = 0; double hubU = 0.0; bool reorder = false;
+   Setup s; std::string fcidump, problem; int twoS = 0, N = 0, irrep = 0, hubL = 0; double hubU = 0.0; bool reorder = false;
    for (int i = 2; i < argc; i++){
       std::string a = argv[i];
       if (a == "--fcidump") fcidump = argv[++i];
@@ -241,6 +241,24 @@ static Setup make_setup(int argc, char ** argv){
       else if (a == "--irrep") irrep = atoi(argv[++i]);
       else if (a == "--hubbard"){ hubL = atoi(argv[++i]); hubU = atof(argv[++i]); }
       else if (a == "--reorder") reorder = true;
+      else if (a == "--problem") problem = argv[++i];
+   }
+   if (!problem.empty()){   /* binary problem file of chemps2_b200/workloads.py (write_problem_file): synthetic / model Hamiltonians */
+      FILE * f = fopen(problem.c_str(), "rb");
+      if (!f){ perror(problem.c_str()); exit(2); }
+      int hdr[5]; if (fread(hdr, 4, 5, f) != 5) exit(2);
+      const int L = hdr[0]; s.group = hdr[1]; N = hdr[2]; twoS = hdr[3]; irrep = hdr[4];
+      std::vector<int> irr(L); double econst = 0.0;
+      std::vector<double> tm((size_t) L * L), vm((size_t) L * L * L * L);
+      if (fread(irr.data(), 4, L, f) != (size_t) L || fread(&econst, 8, 1, f) != 1 || fread(tm.data(), 8, tm.size(), f) != tm.size() || fread(vm.data(), 8, vm.size(), f) != vm.size()) exit(2);
+      fclose(f);
+      s.ham = new Hamiltonian(L, s.group, irr.data());
+      s.ham->setEconst(econst);
+      for (int i = 0; i < L; i++) for (int j = i; j < L; j++) if (Irreps::directProd(irr[i], irr[j]) == 0) s.ham->setTmat(i, j, tm[i + (size_t) L * j]);
+      for (int i = 0; i < L; i++) for (int j = 0; j < L; j++) for (int k = 0; k < L; k++) for (int l = 0; l < L; l++)
+         if (Irreps::directProd(Irreps::directProd(irr[i], irr[j]), Irreps::directProd(irr[k], irr[l])) == 0) s.ham->setVmat(i, j, k, l, vm[i + L * (j + L * (k + (size_t) L * l))]);
+      s.prob = new Problem(s.ham, twoS, N, irrep);
+      return s;
    }
    if (hubL > 0){   /* 1-D Hubbard chain, open ends, C1 (pattern of the reference's tests/test4) */
       std::vector<int> irr(hubL, 0);

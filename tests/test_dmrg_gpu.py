@@ -86,7 +86,7 @@ def test_full_dmrg_n2_sto3g_known_answer():
         d.update(i, True)                                   # DMRG::PreSolve (DMRG.cpp:257-266)
     e_prev, change = 0.0, False
     for it in range(8):
-        noise = 0.05 * 1e-3 if it < 3 else 0.0
+        noise = 0.05 if it < 3 else 0.0      # noise PREFACTOR, as ConvergenceScheme (test5.cpp.in uses 0.05)
         el, _ = d.sweep(False, 1e-8, noise, D, change)
         change = True
         er, _ = d.sweep(True, 1e-8, noise, D, change)

@@ -49,6 +49,7 @@ struct b2_ctx {
    Bookkeeper bk;
    bool have_problem = false, have_bk = false;
    CompileOptions copt;
+   int simulate_oom = 0;                // test hook: the next N device allocations of operator sets / plans report B2_ERR_CUDA
    double parallel_plan_flops = 2e11;   // plans below this many reference FLOPs per apply are compiled on all host cores
 };
 
@@ -60,6 +61,7 @@ struct b2_opset {
    double* spill = nullptr;    // pinned host copy while the set is offloaded (b2_opset_offload): the device arena is released
    bool offloaded = false;
    void ensure_host() { if (host.size() != (size_t)set.size) host.assign((size_t)set.size, 0.0); }
+   ~b2_opset() { if (spill) cudaFreeHost(spill); if (dev) cudaFree(dev); }
 };
 
 struct b2_heff {
@@ -90,7 +92,29 @@ struct b2_heff {
    // excited states (Heff::addDiagramExcitations): n_exc level-shifted lower states, one vector of veclength doubles each
    int n_exc = 0;
    double *d_exc = nullptr, *d_exc_coef = nullptr, *d_exc_scratch = nullptr;
+   ~b2_heff() {   // also runs when b2_heff_create bails out half-way (e.g. out of HBM): nothing leaks
+      cudaFree(d_diag_items); cudaFree(d_diag_tiles); cudaFree(d_blk_off); cudaFree(d_p2s); cudaFree(d_s2p);
+      cudaFree(d_items1); cudaFree(d_items2); cudaFree(d_reduces); cudaFree(d_part);
+      for (int c = 0; c < kNumTileClasses; c++) { cudaFree(d_tiles1[c]); cudaFree(d_tiles2[c]); }
+      cudaFree(d_jobs); cudaFree(d_parts); cudaFree(d_presum); cudaFree(d_work); cudaFree(d_vin); cudaFree(d_vout);
+      cudaFree(d_exc); cudaFree(d_exc_coef); cudaFree(d_exc_scratch);
+      if (h_vin) cudaFreeHost(h_vin);
+      if (h_vout) cudaFreeHost(h_vout);
+      if (ev0) cudaEventDestroy(ev0);
+      if (ev1) cudaEventDestroy(ev1);
+   }
 };
+
+// stage-1 workspace budget of a plan: the configured value, capped by half of the HBM that is free right now
+static CompileOptions budgeted(const b2_ctx* ctx) {
+   CompileOptions o = ctx->copt;
+   if (ctx->device >= 0) {
+      size_t free_b = 0, total_b = 0;
+      if (cudaSetDevice(ctx->device) == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+         o.work_budget = std::max<int64_t>((int64_t)1 << 22, std::min<int64_t>(o.work_budget, (int64_t)(free_b / 2 / sizeof(double))));
+   }
+   return o;
+}
 
 template <class T> static int upload_vec(T** dptr, const std::vector<T>& v, cudaStream_t s) {
    *dptr = nullptr;
@@ -231,6 +255,7 @@ int b2_opset_create(b2_ctx* ctx, int boundary, int moving_right, b2_opset** out)
    std::unique_ptr<b2_opset> s(new b2_opset);
    s->ctx = ctx;
    s->set.build_all(ctx->bk, boundary, moving_right != 0);
+   if (ctx->device >= 0 && ctx->simulate_oom > 0) { ctx->simulate_oom--; return fail(B2_ERR_CUDA, "b2_opset_create: out of memory (simulated)"); }
    if (ctx->device >= 0 && s->set.size > 0) {
       CUDA_TRY(cudaSetDevice(ctx->device));
       CUDA_TRY(cudaMalloc(&s->dev, sizeof(double) * (size_t)s->set.size));
@@ -283,12 +308,7 @@ int b2_opset_reload(b2_opset* set) {
 }
 int b2_opset_resident(const b2_opset* set) { return (set && set->dev && !set->offloaded) ? 1 : 0; }
 
-void b2_opset_destroy(b2_opset* set) {
-   if (set && set->spill) cudaFreeHost(set->spill);
-   if (!set) return;
-   if (set->dev) cudaFree(set->dev);
-   delete set;
-}
+void b2_opset_destroy(b2_opset* set) { delete set; }
 int b2_opset_count(const b2_opset* set) { return set ? (int)set->set.ops.size() : 0; }
 int b2_opset_info(const b2_opset* set, int index, int* kind, int* si, int* sj, int64_t* size) {
    if (!set || index < 0 || index >= (int)set->set.ops.size()) return fail(B2_ERR_ARG, "b2_opset_info: bad index");
@@ -368,6 +388,7 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
    if (site > 0 && (!left || left->set.boundary != site || !left->set.moving_right)) return fail(B2_ERR_ARG, "b2_heff_create: left operator set must sit at boundary %d moving right", site);
    if (site < L - 2 && (!right || right->set.boundary != site + 2 || right->set.moving_right)) return fail(B2_ERR_ARG, "b2_heff_create: right operator set must sit at boundary %d moving left", site + 2);
    if (world < 1 || rank < 0 || rank >= world) return fail(B2_ERR_ARG, "b2_heff_create: bad world/rank");
+   if (ctx->device >= 0 && ctx->simulate_oom > 0) { ctx->simulate_oom--; return fail(B2_ERR_CUDA, "b2_heff_create: out of memory (simulated)"); }
    if ((site > 0 && left && left->offloaded) || (site < L - 2 && right && right->offloaded)) return fail(B2_ERR_STATE, "b2_heff_create: operator set is offloaded (b2_opset_reload first)");
    std::unique_ptr<b2_heff> h(new b2_heff);
    h->ctx = ctx; h->world = world; h->rank = rank;
@@ -376,7 +397,7 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
    const double tb0 = wall_seconds();
    build_sigma_plan(h->plan, ctx->bk, ctx->prob, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, site, world);
    const double tb1 = wall_seconds();
-   CompileOptions copt = ctx->copt;
+   CompileOptions copt = budgeted(ctx);
    // plans whose sigma build is a few milliseconds are dominated by the time to BUILD them: compile those on all host cores
    copt.threads = (h->plan.flops_ref < ctx->parallel_plan_flops) ? plan_threads(h->plan.S.nkappa()) : 1;
    compile_sigma(h->comp, h->plan, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, rank, world, copt);
@@ -426,19 +447,7 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
    return B2_OK;
 }
 
-void b2_heff_destroy(b2_heff* h) {
-   if (!h) return;
-   cudaFree(h->d_diag_items); cudaFree(h->d_diag_tiles); cudaFree(h->d_blk_off); cudaFree(h->d_p2s); cudaFree(h->d_s2p);
-   cudaFree(h->d_items1); cudaFree(h->d_items2); cudaFree(h->d_reduces); cudaFree(h->d_part);
-   for (int c = 0; c < kNumTileClasses; c++) { cudaFree(h->d_tiles1[c]); cudaFree(h->d_tiles2[c]); }
-   cudaFree(h->d_jobs); cudaFree(h->d_parts); cudaFree(h->d_presum); cudaFree(h->d_work); cudaFree(h->d_vin); cudaFree(h->d_vout);
-   cudaFree(h->d_exc); cudaFree(h->d_exc_coef); cudaFree(h->d_exc_scratch);
-   if (h->h_vin) cudaFreeHost(h->h_vin);
-   if (h->h_vout) cudaFreeHost(h->h_vout);
-   if (h->ev0) cudaEventDestroy(h->ev0);
-   if (h->ev1) cudaEventDestroy(h->ev1);
-   delete h;
-}
+void b2_heff_destroy(b2_heff* h) { delete h; }
 
 int64_t b2_heff_veclength(const b2_heff* h) { return h ? h->plan.S.size : 0; }
 
@@ -669,6 +678,7 @@ int b2_ctx_set_option(b2_ctx* ctx, const char* name, double value) {
    if (!std::strcmp(name, "work_budget")) { if (value < 1024) return fail(B2_ERR_ARG, "work_budget too small"); ctx->copt.work_budget = (int64_t)value; }
    else if (!std::strcmp(name, "chunk_k")) { if (value < 8) return fail(B2_ERR_ARG, "chunk_k too small"); ctx->copt.chunk_k = (int64_t)value; }
    else if (!std::strcmp(name, "parallel_plan_flops")) ctx->parallel_plan_flops = value;
+   else if (!std::strcmp(name, "simulate_oom")) ctx->simulate_oom = (int)value;
    else if (!std::strcmp(name, "parallel_min_terms")) ctx->copt.parallel_min_terms = (int64_t)value;
    else return fail(B2_ERR_ARG, "b2_ctx_set_option: unknown option %s", name);
    return B2_OK;
@@ -693,6 +703,14 @@ struct b2_update {
    std::vector<int> op_owner;              // GPU that computes new operator i in pass 0
    b2_allreduce_fn allreduce = nullptr;
    void* allreduce_user = nullptr;
+   ~b2_update() {
+      for (int p = 0; p < 2; p++) {
+         cudaFree(d_items1[p]); cudaFree(d_items2[p]); cudaFree(d_reduces[p]);
+         for (int c = 0; c < kNumTileClasses; c++) { cudaFree(d_tiles1[p][c]); cudaFree(d_tiles2[p][c]); }
+      }
+      cudaFree(d_jobs); cudaFree(d_parts); cudaFree(d_presum); cudaFree(d_work); cudaFree(d_part); cudaFree(d_t);
+      if (h_t) cudaFreeHost(h_t);
+   }
 };
 
 // FLOPs the scheduler will spend on one update term (cheaper association order, as compile_terms picks it)
@@ -762,7 +780,7 @@ int b2_update_create_sharded(b2_ctx* ctx, int index, int moving_right, b2_opset*
          u->plan.terms.swap(mine);
       }
    }
-   CompileOptions copt = ctx->copt;
+   CompileOptions copt = budgeted(ctx);
    copt.threads = (u->plan.flops_ref < ctx->parallel_plan_flops) ? plan_threads((int)u->plan.dst.size()) : 1;
    compile_terms(u->pass[0], u->plan.terms, u->plan.dst, SP_VOUT, copt);
    compile_terms(u->pass[1], u->plan.mix_terms, u->plan.dst, SP_VOUT, copt);
@@ -805,16 +823,7 @@ int b2_update_create_sharded(b2_ctx* ctx, int index, int moving_right, b2_opset*
    *out = u.release();
    return B2_OK;
 }
-void b2_update_destroy(b2_update* u) {
-   if (!u) return;
-   for (int p = 0; p < 2; p++) {
-      cudaFree(u->d_items1[p]); cudaFree(u->d_items2[p]); cudaFree(u->d_reduces[p]);
-      for (int c = 0; c < kNumTileClasses; c++) { cudaFree(u->d_tiles1[p][c]); cudaFree(u->d_tiles2[p][c]); }
-   }
-   cudaFree(u->d_jobs); cudaFree(u->d_parts); cudaFree(u->d_presum); cudaFree(u->d_work); cudaFree(u->d_part); cudaFree(u->d_t);
-   if (u->h_t) cudaFreeHost(u->h_t);
-   delete u;
-}
+void b2_update_destroy(b2_update* u) { delete u; }
 int b2_update_run_device(b2_update* u, const double* t_dev) {
    if (!u || !t_dev) return fail(B2_ERR_ARG, "b2_update_run_device: NULL");
    if (u->ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_update_run: planning-only context, no CUDA device (there is no CPU fallback)");
@@ -1039,12 +1048,23 @@ int b2_dmrg_update(b2_dmrg* d, int index, int moving_right) {
    if (need_old && old_set) { int rr = b2_opset_reload(old_set); if (rr) return rr; }
    if (need_old && !old_set) return fail(B2_ERR_STATE, "b2_dmrg_update: operators of boundary %d are missing", b_old);
    b2_opset* fresh = nullptr;
-   int rc = b2_opset_create(ctx, b_new, mr, &fresh);
-   if (rc) return rc;
    b2_update* u = nullptr;
    const double t0 = wall_seconds();
-   rc = b2_update_create_sharded(ctx, index, mr, need_old ? old_set : nullptr, fresh, d->world, d->rank, &u);
-   if (!rc && d->world > 1) rc = b2_update_set_allreduce(u, d->allreduce, d->allreduce_user);
+   int rc = B2_OK;
+   for (int attempt = 0; attempt < 2; attempt++) {
+      rc = b2_opset_create(ctx, b_new, mr, &fresh);
+      if (!rc) rc = b2_update_create_sharded(ctx, index, mr, need_old ? old_set : nullptr, fresh, d->world, d->rank, &u);
+      if (rc != B2_ERR_CUDA || attempt == 1 || d->spill) break;
+      // HBM exhausted (O(L) boundaries x O(L^2 D^2) operators): from now on only the sets in use stay resident — the
+      // reference's OperatorsOnDisk mode, switched on when it is needed instead of by the user
+      cudaGetLastError();
+      b2_update_destroy(u); u = nullptr;
+      b2_opset_destroy(fresh); fresh = nullptr;
+      d->spill = true;
+      if ((rc = dmrg_residency(d, mr ? b_old : -1, mr ? -1 : b_old))) return rc;
+   }
+   if (rc) { b2_update_destroy(u); b2_opset_destroy(fresh); return rc; }
+   if (d->world > 1) rc = b2_update_set_allreduce(u, d->allreduce, d->allreduce_user);
    d->t_plan += wall_seconds() - t0;
    const double t1 = wall_seconds();
    if (!rc) rc = b2_update_run(u, d->mps[index].data());
@@ -1068,6 +1088,13 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
    b2_heff* h = nullptr;
    const double tp0 = wall_seconds();
    int rc = b2_heff_create(ctx, index, lset, rset, d->world, d->rank, &h);
+   if (rc == B2_ERR_CUDA && !d->spill) {   // out of HBM: park every operator set that this site does not use and retry
+      cudaGetLastError();
+      b2_heff_destroy(h); h = nullptr;
+      d->spill = true;
+      if ((rc = dmrg_residency(d, index > 0 ? index : -1, index < L - 2 ? index + 2 : -1))) return rc;
+      rc = b2_heff_create(ctx, index, lset, rset, d->world, d->rank, &h);
+   }
    if (rc) return rc;
    if (d->world > 1) b2_heff_set_allreduce(h, d->allreduce, d->allreduce_user);
    d->t_plan += wall_seconds() - tp0;

@@ -234,30 +234,29 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
 namespace {
 
 void group_sort(std::vector<Tile>& v, int b, int e, const std::vector<GemmItem>& items) {
-      // Launch order = heaviest GROUPS first (static load balance across the SMs), where a group is the set of CTAs that
-      // stream the same items (all tiles of one stage-1 product / of one split-K chunk of a destination block): they read the
-      // same operand panels, so they must be resident together for the panels to be served by L2 instead of DRAM.
-      if (e <= b) return;
-      struct Key { long long w; int ib, idx; };
-      std::vector<Key> ord(e - b);
-      for (int i = b; i < e; i++) {
-         long long w = 0;
-         for (int it = v[i].item_begin; it < v[i].item_end; it++) w += items[it].k + 4;
-         ord[i - b] = {w * ((v[i].mrem + 7) / 8) * ((v[i].nrem + 7) / 8), v[i].item_begin, i};
-      }
-      std::sort(ord.begin(), ord.end(), [](const Key& x, const Key& y) { return x.ib != y.ib ? x.ib < y.ib : x.idx < y.idx; });
-      for (size_t g0 = 0; g0 < ord.size();) {   // group weight = its heaviest tile
-         size_t g1 = g0;
-         long long wmax = 0;
-         while (g1 < ord.size() && ord[g1].ib == ord[g0].ib) { wmax = std::max(wmax, ord[g1].w); g1++; }
-         for (size_t g = g0; g < g1; g++) ord[g].w = wmax;
-         g0 = g1;
-      }
-      std::sort(ord.begin(), ord.end(), [](const Key& x, const Key& y) { return x.w != y.w ? x.w > y.w : (x.ib != y.ib ? x.ib < y.ib : x.idx < y.idx); });
-      std::vector<Tile> sorted(e - b);
-      for (int i = 0; i < e - b; i++) sorted[i] = v[ord[i].idx];
-      std::copy(sorted.begin(), sorted.end(), v.begin() + b);
+   // Launch order = heaviest GROUPS first (static load balance across the SMs), where a group is the set of CTAs that
+   // stream the same items (all tiles of one stage-1 product / of one split-K chunk of a destination block): they read the
+   // same operand panels, so they must be resident together for the panels to be served by L2 instead of DRAM.
+   if (e <= b) return;
+   struct Key { long long w; int ib, idx; };
+   std::vector<Key> ord(e - b);
+   int ib_lo = v[b].item_begin, ib_hi = v[b].item_begin;
+   for (int i = b; i < e; i++) { ib_lo = std::min(ib_lo, v[i].item_begin); ib_hi = std::max(ib_hi, v[i].item_begin); }
+   std::vector<long long> wmax((size_t)(ib_hi - ib_lo) + 1, 0);   // group weight = its heaviest tile, indexed by the group's first item
+   for (int i = b; i < e; i++) {
+      long long w = 0;
+      for (int it = v[i].item_begin; it < v[i].item_end; it++) w += items[it].k + 4;
+      w *= (long long)((v[i].mrem + 7) / 8) * ((v[i].nrem + 7) / 8);
+      ord[i - b] = {w, v[i].item_begin, i};
+      long long& g = wmax[v[i].item_begin - ib_lo];
+      g = std::max(g, w);
    }
+   for (Key& k : ord) k.w = wmax[k.ib - ib_lo];
+   std::sort(ord.begin(), ord.end(), [](const Key& x, const Key& y) { return x.w != y.w ? x.w > y.w : (x.ib != y.ib ? x.ib < y.ib : x.idx < y.idx); });
+   std::vector<Tile> sorted(e - b);
+   for (int i = 0; i < e - b; i++) sorted[i] = v[ord[i].idx];
+   std::copy(sorted.begin(), sorted.end(), v.begin() + b);
+}
 
 void compile_range(CompiledWork& out, Term3* terms, size_t nterms, const std::vector<DstBlock>& dst, uint8_t dst_space, const CompileOptions& opt,
                    bool sort_waves) {

@@ -90,6 +90,16 @@ SIGNATURES = [
     ("b2_heff_presum_size", C.c_int64, [vp]),
     ("b2_heff_export_presums", C.c_int, [vp, C.POINTER(FlatPresum)]),
     ("b2_probe_fp64", C.c_int, [vp, C.c_int, c_dp]),
+    ("b2_twodm_fill_site", C.c_int, [vp, C.c_int, c_dp, vp, vp, c_dp, c_dp]),
+    ("b2_twodm_create", C.c_int, [vp, C.c_int, vp, vp, C.POINTER(vp)]),
+    ("b2_twodm_destroy", None, [vp]),
+    ("b2_twodm_run", C.c_int, [vp, c_dp, c_dp, c_dp]),
+    ("b2_twodm_worklists", C.c_int, [vp, vp]),
+    ("b2_twodm_m_size", C.c_int64, [vp]),
+    ("b2_twodm_num_groups", C.c_int, [vp]),
+    ("b2_twodm_group_info", C.c_int, [vp, C.c_int, c_ip, c_lp, c_lp, c_lp, c_ip, c_ip, c_ip, C.c_int]),
+    ("b2_twodm_d1_scale", C.c_int, [vp, c_dp, C.c_int]),
+    ("b2_twodm_scatter", C.c_int, [vp, C.POINTER(c_dp), C.c_double, c_dp, c_dp]),
     ("b2_svd_batch", C.c_int, [vp, C.c_int, c_ip, c_ip, C.POINTER(c_dp), C.POINTER(c_dp), C.POINTER(c_dp), C.POINTER(c_dp)]),
     ("b2_heff_worklists", C.c_int, [vp, vp]),
     ("b2_ctx_set_option", C.c_int, [vp, C.c_char_p, C.c_double]),

@@ -72,6 +72,16 @@ class Context:
         return labels, offs
 
 
+def twodm_fill_site(ctx, site, t_storage, left, right, A=None, B=None):
+    """TwoDM::FillSite on the GPU: -> (A, B) flat L^4 arrays (created zeroed when not given); see b2_twodm_fill_site"""
+    n = ctx.L ** 4
+    A = np.zeros(n) if A is None else A
+    B = np.zeros(n) if B is None else B
+    t = np.ascontiguousarray(t_storage, dtype=np.float64)
+    check(lib.b2_twodm_fill_site(ctx.h, int(site), _dp(t), left.h if left else None, right.h if right else None, _dp(A), _dp(B)))
+    return A, B
+
+
 def svd_batch(ctx, mats):
     """thin SVDs of a list of 2-D arrays on the GPU -> [(u, s, vt)]   (b2_svd_batch; stands for dgesdd_ in Sobject::Split)"""
     As = [np.asfortranarray(m, dtype=np.float64) for m in mats]

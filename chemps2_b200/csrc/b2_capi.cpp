@@ -20,6 +20,7 @@
 #include "b2_ops.h"
 #include "b2_sigma.h"
 #include "b2_sobject.h"
+#include "b2_twodm.h"
 #include "b2_update.h"
 
 using namespace b2;
@@ -1173,6 +1174,176 @@ int b2_dmrg_sweep(b2_dmrg* d, int to_right, double rtol, double noise, int D, in
    *min_energy = emin;
    if (max_discarded) *max_discarded = dmax;
    return B2_OK;
+}
+
+/* TwoDM::FillSite (TwoDM.cpp:445-628): contribution of one site to the spin-summed 2-RDM arrays A and B.  See b2_twodm.cpp. */
+struct b2_twodm {
+   b2_ctx* ctx = nullptr;
+   b2_opset *left = nullptr, *right = nullptr;
+   TwoDMPlan plan;
+   CompiledWork build;    // pass 1: the effective operators
+};
+
+int b2_twodm_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, b2_twodm** out) {
+   if (!ctx || !ctx->have_bk || !out) return fail(B2_ERR_ARG, "b2_twodm_create: bad arguments");
+   const int L = ctx->bk.L;
+   if (site < 0 || site >= L) return fail(B2_ERR_ARG, "b2_twodm_create: site %d out of range", site);
+   if (site > 0 && (!left || left->set.boundary != site || !left->set.moving_right)) return fail(B2_ERR_ARG, "b2_twodm_create: left set must sit at boundary %d moving right", site);
+   if (site < L - 1 && (!right || right->set.boundary != site + 1 || right->set.moving_right)) return fail(B2_ERR_ARG, "b2_twodm_create: right set must sit at boundary %d moving left", site + 1);
+   std::unique_ptr<b2_twodm> p(new b2_twodm);
+   p->ctx = ctx;
+   p->left = site > 0 ? left : nullptr;
+   p->right = site < L - 1 ? right : nullptr;
+   build_twodm_plan(p->plan, ctx->bk, site, p->left ? &p->left->set : nullptr, p->right ? &p->right->set : nullptr);
+   CompileOptions copt = budgeted(ctx);
+   copt.threads = plan_threads((int)p->plan.dst.size());
+   compile_terms(p->build, p->plan.terms, p->plan.dst, SP_VOUT, copt);
+   *out = p.release();
+   return B2_OK;
+}
+void b2_twodm_destroy(b2_twodm* p) { delete p; }
+int b2_twodm_worklists(const b2_twodm* p, b2_worklists* o) {
+   if (!p || !o) return fail(B2_ERR_ARG, "b2_twodm_worklists: NULL");
+   fill_worklists(p->build, o);
+   return B2_OK;
+}
+int64_t b2_twodm_m_size(const b2_twodm* p) { return p ? p->plan.m_size : 0; }
+int b2_twodm_num_groups(const b2_twodm* p) { return p ? (int)p->plan.groups.size() : 0; }
+int b2_twodm_group_info(const b2_twodm* p, int g, int* left_side, int64_t* off, int64_t* stride, int64_t* op_size, int* n_members, int* n_partners,
+                        int* partners, int cap) {
+   if (!p || g < 0 || g >= (int)p->plan.groups.size()) return fail(B2_ERR_ARG, "b2_twodm_group_info: bad arguments");
+   const TwoDMPlan::Group& grp = p->plan.groups[g];
+   if (left_side) *left_side = grp.left_side;
+   if (off) *off = grp.off;
+   if (stride) *stride = grp.stride;
+   if (op_size) *op_size = grp.members.empty() ? 0 : p->plan.mops[grp.members[0]].lay->size;
+   if (n_members) *n_members = (int)grp.members.size();
+   if (n_partners) *n_partners = (int)grp.partners.size();
+   if (partners) for (int i = 0; i < std::min<int>(cap, (int)grp.partners.size()); i++) partners[i] = grp.partners[i];
+   return B2_OK;
+}
+int b2_twodm_d1_scale(const b2_twodm* p, double* per_block, int cap) {
+   if (!p || !per_block) return fail(B2_ERR_ARG, "b2_twodm_d1_scale: NULL");
+   for (int k = 0; k < std::min<int>(cap, (int)p->plan.d1_scale.size()); k++) per_block[k] = p->plan.d1_scale[k];
+   return (int)p->plan.d1_scale.size();
+}
+int b2_twodm_scatter(const b2_twodm* p, const double* const* gram, double d1, double* two_rdm_A, double* two_rdm_B) {
+   if (!p || !gram || !two_rdm_A || !two_rdm_B) return fail(B2_ERR_ARG, "b2_twodm_scatter: NULL");
+   std::vector<std::vector<double>> g(p->plan.groups.size());
+   for (size_t i = 0; i < g.size(); i++) {
+      const size_t n = p->plan.groups[i].members.size() * p->plan.groups[i].partners.size();
+      if (n) g[i].assign(gram[i], gram[i] + n);
+   }
+   twodm_scatter(p->plan, p->ctx->bk, p->left ? &p->left->set : nullptr, p->right ? &p->right->set : nullptr, d1, g, two_rdm_A, two_rdm_B);
+   return B2_OK;
+}
+
+int b2_twodm_run(b2_twodm* tp, const double* t_host, double* two_rdm_A, double* two_rdm_B) {
+   if (!tp || !t_host || !two_rdm_A || !two_rdm_B) return fail(B2_ERR_ARG, "b2_twodm_run: bad arguments");
+   b2_ctx* ctx = tp->ctx;
+   if (ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_twodm_run: planning-only context, no CUDA device (there is no CPU fallback)");
+   b2_opset *left = tp->left, *right = tp->right;
+   if ((left && left->offloaded) || (right && right->offloaded)) return fail(B2_ERR_STATE, "b2_twodm_run: operator set is offloaded (b2_opset_reload first)");
+   CUDA_TRY(cudaSetDevice(ctx->device));
+   cudaStream_t s = ctx->stream;
+   const TwoDMPlan& plan = tp->plan;
+   const int64_t tsize = plan.T.size;
+   struct Buf { double* p = nullptr; ~Buf() { cudaFree(p); } } dT, dTs, dM, dY, dG, dScal, dScale;
+   struct IBuf { int64_t* p = nullptr; ~IBuf() { cudaFree(p); } } dOff;
+   CUDA_TRY(cudaMalloc(&dT.p, sizeof(double) * (size_t)std::max<int64_t>(tsize, 1)));
+   CUDA_TRY(cudaMalloc(&dTs.p, sizeof(double) * (size_t)std::max<int64_t>(tsize, 1)));
+   CUDA_TRY(cudaMalloc(&dM.p, sizeof(double) * (size_t)std::max<int64_t>(plan.m_size, 1)));
+   CUDA_TRY(cudaMemcpyAsync(dT.p, t_host, sizeof(double) * (size_t)tsize, cudaMemcpyHostToDevice, s));
+   CUDA_TRY(cudaMemcpyAsync(dTs.p, dT.p, sizeof(double) * (size_t)tsize, cudaMemcpyDeviceToDevice, s));
+   CUDA_TRY(cudaMemsetAsync(dM.p, 0, sizeof(double) * (size_t)std::max<int64_t>(plan.m_size, 1), s));
+   // ---- effective operators
+   {
+      DevBases b;
+      for (int i = 0; i < SP_COUNT; i++) b.p[i] = nullptr;
+      b.p[SP_LEFT] = left ? left->dev : nullptr; b.p[SP_RIGHT] = dT.p; b.p[SP_VOUT] = dM.p;
+      int rc = run_compiled_once(ctx, tp->build, b);
+      if (rc) return rc;
+   }
+   // ---- diagram 1: < T , (2SL+1)-scaled doubly-occupied blocks of T >
+   double d1 = 0.0;
+   {
+      const int nk = plan.T.nkappa();
+      std::vector<int64_t> off(nk + 1);
+      for (int k = 0; k < nk; k++) off[k] = plan.T.blk[k].off;
+      off[nk] = tsize;
+      CUDA_TRY(cudaMalloc(&dOff.p, sizeof(int64_t) * (nk + 1)));
+      CUDA_TRY(cudaMalloc(&dScale.p, sizeof(double) * std::max(nk, 1)));
+      CUDA_TRY(cudaMalloc(&dScal.p, sizeof(double) * (kRedScratch + 8)));
+      CUDA_TRY(cudaMemcpyAsync(dOff.p, off.data(), sizeof(int64_t) * (nk + 1), cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemcpyAsync(dScale.p, plan.d1_scale.data(), sizeof(double) * nk, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemsetAsync(dScal.p, 0, sizeof(double) * (kRedScratch + 8), s));
+      if (nk > 0 && dev_scale_blocks(dTs.p, dOff.p, dScale.p, nk, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+      if (tsize > 0 && dev_multi_dot(dT.p, dTs.p, tsize, 1, tsize, dScal.p + kRedScratch, dScal.p, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+      CUDA_TRY(cudaMemcpyAsync(&d1, dScal.p + kRedScratch, sizeof(double), cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+   }
+   // ---- Gram matrices  G[member, partner] = < M_member , stored operator >: the partners of a group are gathered into a dense
+   // [stride x count] matrix, then one K-concatenated GEMM per group through the grouped contraction kernels
+   std::vector<std::vector<double>> gram(plan.groups.size());
+   {
+      std::vector<int64_t> yoff(plan.groups.size(), 0), goff(plan.groups.size(), 0);
+      int64_t ytot = 0, gtot = 0;
+      for (size_t gi = 0; gi < plan.groups.size(); gi++) {
+         const TwoDMPlan::Group& grp = plan.groups[gi];
+         yoff[gi] = ytot; goff[gi] = gtot;
+         ytot += grp.stride * (int64_t)grp.partners.size();
+         gtot += ((int64_t)grp.members.size() * (int64_t)grp.partners.size() + 15) / 16 * 16;
+      }
+      CUDA_TRY(cudaMalloc(&dY.p, sizeof(double) * (size_t)std::max<int64_t>(ytot, 1)));
+      CUDA_TRY(cudaMalloc(&dG.p, sizeof(double) * (size_t)std::max<int64_t>(gtot, 1)));
+      CUDA_TRY(cudaMemsetAsync(dY.p, 0, sizeof(double) * (size_t)std::max<int64_t>(ytot, 1), s));
+      CUDA_TRY(cudaMemsetAsync(dG.p, 0, sizeof(double) * (size_t)std::max<int64_t>(gtot, 1), s));
+      std::vector<Term3> terms;
+      std::vector<DstBlock> dst;
+      for (size_t gi = 0; gi < plan.groups.size(); gi++) {
+         const TwoDMPlan::Group& grp = plan.groups[gi];
+         const b2_opset* set = grp.left_side ? left : right;
+         if (!set || grp.partners.empty() || grp.members.empty() || grp.stride == 0) continue;
+         for (size_t c = 0; c < grp.partners.size(); c++) {
+            const OpTensor& t = set->set.ops[grp.partners[c]];
+            if (t.lay->size > 0)
+               CUDA_TRY(cudaMemcpyAsync(dY.p + yoff[gi] + (int64_t)c * grp.stride, set->dev + t.off, sizeof(double) * (size_t)t.lay->size, cudaMemcpyDeviceToDevice, s));
+         }
+         Term3 x;
+         x.dst = (int)dst.size(); x.f = 1.0;
+         x.p.space = SP_LEFT; x.p.off = grp.off; x.p.rows = (int32_t)grp.stride; x.p.cols = (int32_t)grp.members.size(); x.p.trans = 1;
+         x.q.space = SP_RIGHT; x.q.off = yoff[gi]; x.q.rows = (int32_t)grp.stride; x.q.cols = (int32_t)grp.partners.size(); x.q.trans = 0;
+         terms.push_back(x);
+         dst.push_back(DstBlock{goff[gi], (int32_t)grp.members.size(), (int32_t)grp.partners.size()});
+      }
+      if (!terms.empty()) {
+         CompiledWork w;
+         CompileOptions copt = budgeted(ctx);
+         compile_terms(w, terms, dst, SP_VOUT, copt);
+         DevBases b;
+         for (int i = 0; i < SP_COUNT; i++) b.p[i] = nullptr;
+         b.p[SP_LEFT] = dM.p; b.p[SP_RIGHT] = dY.p; b.p[SP_VOUT] = dG.p;
+         int rc = run_compiled_once(ctx, w, b);
+         if (rc) return rc;
+      }
+      std::vector<double> gh((size_t)std::max<int64_t>(gtot, 1));
+      CUDA_TRY(cudaMemcpyAsync(gh.data(), dG.p, sizeof(double) * (size_t)gtot, cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      for (size_t gi = 0; gi < plan.groups.size(); gi++) {
+         const size_t n = plan.groups[gi].members.size() * plan.groups[gi].partners.size();
+         gram[gi].assign(gh.begin() + goff[gi], gh.begin() + goff[gi] + n);
+      }
+   }
+   twodm_scatter(plan, ctx->bk, left ? &left->set : nullptr, right ? &right->set : nullptr, d1, gram, two_rdm_A, two_rdm_B);
+   return B2_OK;
+}
+
+int b2_twodm_fill_site(b2_ctx* ctx, int site, const double* t_host, b2_opset* left, b2_opset* right, double* two_rdm_A, double* two_rdm_B) {
+   b2_twodm* p = nullptr;
+   int rc = b2_twodm_create(ctx, site, left, right, &p);
+   if (!rc) rc = b2_twodm_run(p, t_host, two_rdm_A, two_rdm_B);
+   b2_twodm_destroy(p);
+   return rc;
 }
 
 /* thin SVDs of a batch of host matrices on the GPU (what Sobject::Split needs from dgesdd_, Sobject.cpp:412-419) */

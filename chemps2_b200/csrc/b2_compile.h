@@ -39,7 +39,7 @@ struct Wave {
 };
 
 struct CompileOptions {
-   int64_t work_budget = (int64_t)3 << 30;   // doubles of stage-1 workspace per wave (24 GiB of the 180 GB): bigger waves share more stage-1 products (profiles/r1_tuning.md)
+   int64_t work_budget = (int64_t)6 << 30;   // doubles of stage-1 workspace per wave (48 GiB of the 180 GB, capped by half of the free HBM): bigger waves share more stage-1 products (profiles/r1_tuning.md)
    int64_t chunk_k = 2048;                   // split-K: accumulated inner dimension per CTA
    int threads = 1;                          // host threads compile_terms may use (small plans only, see b2_compile.cpp)
    int64_t parallel_min_terms = 20000;       // ... and only when every thread gets at least this many terms

@@ -252,6 +252,31 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
                        double* discarded_weight, int* n_matvec);
 int b2_dmrg_sweep(b2_dmrg* d, int to_right, double rtol, double noise, int D, int change, double* min_energy, double* max_discarded);
 
+/* ------------------------------------------------------------------------------------------------ 2-RDM
+ * b2_twodm_fill_site = TwoDM::FillSite (TwoDM.cpp:445-628 with its 24 diagram functions doD1..doD24, :642-1592): the entries of the
+ * spin-summed 2-RDM arrays two_rdm_A / two_rdm_B (L^4 doubles each, index c1 + L*(c2 + L*(c3 + L*c4)), DMRG orbital order, the four
+ * symmetry-equivalent positions of set_2rdm_A_DMRG written together) that involve orbital `site` as the orthogonality centre.
+ * t_host = TensorT::gStorage() of MPS[site]; left = operator set of boundary `site` moving right (NULL for site 0), right = operator
+ * set of boundary site+1 moving left (NULL for site L-1); only their L / S0 / S1 / F0 / F1 operators are read.  The chain around it
+ * (left/right normalisation, updateMovingLeftSafe2DM, correct_higher_multiplicities: DMRGtechnics.cpp:40-113) is host-side glue. */
+int b2_twodm_fill_site(b2_ctx* ctx, int site, const double* t_host, b2_opset* left, b2_opset* right, double* two_rdm_A, double* two_rdm_B);
+/* the same in two steps (plan once, run per tensor); planning works on planning-only contexts */
+typedef struct b2_twodm b2_twodm;
+int b2_twodm_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, b2_twodm** out);
+void b2_twodm_destroy(b2_twodm* p);
+int b2_twodm_run(b2_twodm* p, const double* t_host, double* two_rdm_A, double* two_rdm_B);
+/* inspection for the CPU checker in oracle/ (tests only): work lists that build the effective operators (spaces: LEFT = left
+ * operator arena, RIGHT = T, VOUT = arena of b2_twodm_m_size doubles); the groups of effective operators (dense [stride x members]
+ * matrices at `off`, op_size valid doubles per column) with the operators of the left/right set they are paired with; the per-block
+ * weights of diagram 1; and the scatter of externally computed inner products gram[group][member + members*partner] into A and B */
+int b2_twodm_worklists(const b2_twodm* p, b2_worklists* out);
+int64_t b2_twodm_m_size(const b2_twodm* p);
+int b2_twodm_num_groups(const b2_twodm* p);
+int b2_twodm_group_info(const b2_twodm* p, int g, int* left_side, int64_t* off, int64_t* stride, int64_t* op_size, int* n_members, int* n_partners,
+                        int* partners, int cap);
+int b2_twodm_d1_scale(const b2_twodm* p, double* per_block, int cap);
+int b2_twodm_scatter(const b2_twodm* p, const double* const* gram, double d1, double* two_rdm_A, double* two_rdm_B);
+
 /* Batched thin SVD on the GPU: a[i] (HOST, column-major m[i] x n[i], ld = m[i]) = U diag(s) V^T with k = min(m, n); u[i] is m x k
  * (ld m), vt[i] is k x n (ld k), s[i] decreasing.  Stands for the dgesdd_ call per centre sector of Sobject::Split
  * (Sobject.cpp:412-419); one-sided Jacobi, all matrices of the batch progress together (b2_svd.cu).  b2_dmrg_solve_site uses it. */

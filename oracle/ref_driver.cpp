@@ -42,6 +42,7 @@
 #include "Sobject.h"
 #include "Heff.h"
 #include "DMRG.h"
+#include "TwoDM.h"
 #include "Wigner.h"
 #undef private
 #undef protected
@@ -496,6 +497,20 @@ int main(int argc, char ** argv){
          energies.push_back(e);
          if (index == siteA){   /* operator update moving left: inputs = A/right ops + new MPS[index+1]; outputs = table `index` */
             dump_bk(w, "UL/bk", d.denBK); dump_mps(w, "UL/mps", d);
+         }
+         if (index == siteA){
+            /* TwoDM::FillSite at this site (TwoDM.cpp:445-628): T = MPS[siteA], left operators of boundary siteA (A/left, table siteA-1),
+               right operators of boundary siteA+1 (UL/new, table siteA).  updateMovingLeftSafe frees table siteA-1 at its end, so the
+               right table is built first by the same steps updateMovingLeftSafe starts with (DMRGoperators.cpp:124-132); the Safe call
+               below then only repeats updateMovingLeft and does the life-cycle bookkeeping. */
+            if (d.isAllocated[index] == 1){ d.deleteTensors(index, true); d.isAllocated[index] = 0; }
+            if (d.isAllocated[index] == 0){ d.allocateTensors(index, false); d.isAllocated[index] = 2; }
+            d.updateMovingLeft(index);
+            TwoDM tdm(d.denBK, d.Prob);
+            tdm.FillSite(d.MPS[index], d.Ltensors, d.F0tensors, d.F1tensors, d.S0tensors, d.S1tensors);
+            const long long n4 = (long long) L * L * L * L;
+            w.dbls("UL/twodm_A", tdm.two_rdm_A, n4);
+            w.dbls("UL/twodm_B", tdm.two_rdm_B, n4);
          }
          d.updateMovingLeftSafe(index);
          if (index == siteA) dump_ops(w, "UL/new", d, index, false);

@@ -136,18 +136,20 @@ def test_sweep_with_spill_matches_resident_sweep(golden):
 def test_sweep_survives_out_of_memory_by_spilling(golden):
     """when HBM runs out while a new operator set or a sigma plan is allocated (simulated through the 'simulate_oom' option), the driver
     switches to spill mode (only the sets in use stay resident) and carries on with bit-identical energies"""
-    def run(oom_at):
+    def run(oom_before):
         ctx, d = _start_from_fixture(golden, "A")
         L, D = ctx.L, _fixture_D(golden)
         for i in range(L - 2):
             d.update(i, True)
         out = []
         for it in range(2):
-            if it == oom_at:
-                ctx.set_option("simulate_oom", 1)
+            if oom_before == ("left", it):
+                ctx.set_option("simulate_oom", 1)      # hits b2_heff_create of the first site of the left sweep
             out += list(d.sweep(False, 1e-8, 0.0, D, it > 0))
-            if it == oom_at:
+            if oom_before == ("right", it):
                 ctx.set_option("simulate_oom", 1)
             out += list(d.sweep(True, 1e-8, 0.0, D, True))
         return np.array(out)
-    assert np.array_equal(run(0), run(-1))
+    ref = run(None)
+    assert np.array_equal(run(("left", 0)), ref)
+    assert np.array_equal(run(("right", 1)), ref)

@@ -96,3 +96,38 @@ def test_davidson_solve_vs_reference(golden, tag):
     assert abs(np.linalg.norm(x) - 1.0) < 1e-10
     r = heff.apply(x) - e * x
     assert np.linalg.norm(r) < 5e-8
+
+
+def test_full_size_properties_synth40():
+    """BASELINE config 5 shape (40e/40o C1, 'gauss' sector model) at D = 2000 — too large for the CPU checkers — through size-independent
+    properties of the sigma build: H_eff symmetric in the symmetric convention, linear, bitwise reproducible, diagonal consistent with
+    <e_i|H e_i> on sampled unit vectors, and the owner shards of 2 GPUs summing to the full result."""
+    w = workloads.get("synth40", D=2000)
+    ctx = w.context(0)
+    w.apply_distribution(ctx, "gauss")
+    left, right = api.OpSet(ctx, w.site, True), api.OpSet(ctx, w.site + 2, False)
+    left.fill_hash(5, 1.0)
+    right.fill_hash(5, 1.0)
+    heff = api.Heff(ctx, w.site, left, right)
+    n = heff.n
+    x, y = api.hash_fill(n, 21), api.hash_fill(n, 22)
+    hx, hy = heff.apply(x), heff.apply(y)
+    scale = np.abs(hx).max()
+    a, b = float(x @ hy), float(y @ hx)
+    assert abs(a - b) <= 1e-11 * max(abs(a), np.linalg.norm(x) * np.linalg.norm(hy))
+    hz = heff.apply(2.0 * x - 3.0 * y)
+    assert np.abs(hz - (2.0 * hx - 3.0 * hy)).max() <= 1e-11 * scale
+    assert np.array_equal(heff.apply(x), hx)
+    diag = heff.diag()
+    rng = np.random.default_rng(3)
+    for i in rng.integers(0, n, 3):
+        e = np.zeros(n)
+        e[i] = 1.0
+        assert abs(heff.apply(e)[i] - diag[i]) <= 1e-10 * max(1.0, abs(diag[i]))
+    del heff
+    tot = np.zeros(n)
+    for r in range(2):
+        h = api.Heff(ctx, w.site, left, right, 2, r)
+        tot += h.apply(x)
+        del h
+    assert np.abs(tot - hx).max() <= 1e-11 * scale

@@ -294,6 +294,13 @@ class DMRG:
         self._allreduce = allreduce
         check(lib.b2_dmrg_set_world(self.h, int(world), int(rank), allreduce.cfn if allreduce else None, None))
 
+    def calc_2rdm(self):
+        """-> (A, B) as [L,L,L,L] arrays indexed [i,j,k,l] (TwoDM::getTwoDMA_DMRG / getTwoDMB_DMRG); see b2_dmrg_calc_2rdm"""
+        L = self.ctx.L
+        A, B = np.zeros(L ** 4), np.zeros(L ** 4)
+        check(lib.b2_dmrg_calc_2rdm(self.h, _dp(A), _dp(B)))
+        return A.reshape((L, L, L, L), order="F"), B.reshape((L, L, L, L), order="F")
+
     def set_spill(self, enabled):
         check(lib.b2_dmrg_set_spill(self.h, int(bool(enabled))))
 

@@ -1147,6 +1147,160 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
    return rc;
 }
 
+// Move the orthogonality centre of the MPS by one site (TensorT::QR + LeftMultiply = DMRG::left_normalize, TensorT::LQ +
+// RightMultiply = DMRG::right_normalize; TensorT.cpp:188-420, DMRGtechnics.cpp).  The orthogonal factor comes from the batched
+// device SVD (any orthonormal basis of the same space is a valid gauge: Q = U resp. V^T, the other factor S V^T resp. U S), the
+// neighbour absorbs that factor through the grouped contraction kernels.
+//   to_left  = 0: MPS[site] becomes left-normalised, the factor goes into MPS[site+1]      (left_normalize)
+//   to_left != 0: MPS[site] becomes right-normalised (U-convention weights sqrt((2SR+1)/(2SL+1)), TensorT.cpp:289-299),
+//                 the factor goes into MPS[site-1]                                         (right_normalize)
+static int dmrg_gauge_move(b2_dmrg* d, int site, bool to_left) {
+   b2_ctx* ctx = d->ctx;
+   const Bookkeeper& bk = ctx->bk;
+   const int L = d->L;
+   TLayout T;
+   T.build(bk, site);
+   std::vector<double>& t = d->mps[site];
+   const int b_fix = to_left ? site : site + 1;        // boundary whose sectors index the decompositions
+   struct Sector { int n, ts, ir, dim, tot; std::vector<int> blocks; std::vector<int> start; };
+   std::vector<Sector> secs;
+   bk.for_sectors(b_fix, [&](int n, int ts, int ir) {
+      const int dm = bk.dim(b_fix, n, ts, ir);
+      if (dm <= 0) return;
+      Sector sc{n, ts, ir, dm, 0, {}, {}};
+      for (int k = 0; k < T.nkappa(); k++) {
+         const bool match = to_left ? (T.NL[k] == n && T.twoSL[k] == ts && T.IL[k] == ir) : (T.NR[k] == n && T.twoSR[k] == ts && T.IR[k] == ir);
+         if (!match) continue;
+         sc.blocks.push_back(k); sc.start.push_back(sc.tot);
+         sc.tot += to_left ? T.blk[k].cols : T.blk[k].rows;
+      }
+      if (sc.tot > 0) secs.push_back(sc);
+   });
+   // stacked matrices: to_left: dim x tot (blocks side by side, weighted); else tot x dim (blocks on top of each other)
+   std::vector<std::vector<double>> mem(secs.size()), sv(secs.size()), U(secs.size()), VT(secs.size());
+   std::vector<SvdJob> jobs(secs.size());
+   for (size_t i = 0; i < secs.size(); i++) {
+      const Sector& sc = secs[i];
+      const int m = to_left ? sc.dim : sc.tot, n = to_left ? sc.tot : sc.dim, kk = std::min(m, n);
+      mem[i].assign((size_t)m * n, 0.0);
+      for (size_t bi = 0; bi < sc.blocks.size(); bi++) {
+         const int k = sc.blocks[bi];
+         const Block& B = T.blk[k];
+         const double f = to_left ? std::sqrt((T.twoSR[k] + 1.0) / (sc.ts + 1.0)) : 1.0;
+         for (int c = 0; c < B.cols; c++)
+            for (int r = 0; r < B.rows; r++) {
+               const double x = f * t[B.off + r + (size_t)B.rows * c];
+               if (to_left) mem[i][r + (size_t)m * (sc.start[bi] + c)] = x;
+               else mem[i][sc.start[bi] + r + (size_t)m * c] = x;
+            }
+      }
+      sv[i].resize(kk); U[i].resize((size_t)m * kk); VT[i].resize((size_t)kk * n);
+      jobs[i].m = m; jobs[i].n = n; jobs[i].a = mem[i].data(); jobs[i].s = sv[i].data(); jobs[i].u = U[i].data(); jobs[i].vt = VT[i].data();
+   }
+   char err[256] = "";
+   if (dev_svd_batch(jobs, (void*)ctx->stream, err, (int)sizeof(err))) return fail(B2_ERR_CUDA, "gauge move: %s", err);
+   // ---- the orthonormal factor goes back into MPS[site]; the square factor F (dim x dim per sector) is collected for the neighbour
+   std::vector<int64_t> foff(secs.size());
+   int64_t ftot = 0;
+   for (size_t i = 0; i < secs.size(); i++) { foff[i] = ftot; ftot += ((int64_t)secs[i].dim * secs[i].dim + 15) / 16 * 16; }
+   std::vector<double> F((size_t)std::max<int64_t>(ftot, 1), 0.0);
+   for (size_t i = 0; i < secs.size(); i++) {
+      const Sector& sc = secs[i];
+      const int m = to_left ? sc.dim : sc.tot, n = to_left ? sc.tot : sc.dim, kk = std::min(m, n), dm = sc.dim;
+      double* Fi = F.data() + foff[i];
+      if (to_left) {   // mem = (U S) V^T : F = U S (dim x kk, zero-padded to dim x dim), Q = V^T (kk x tot, zero rows below)
+         for (int j = 0; j < kk; j++)
+            for (int r = 0; r < dm; r++) Fi[r + (size_t)dm * j] = U[i][r + (size_t)m * j] * sv[i][j];
+      } else {         // mem = U (S V^T) : Q = U (tot x kk, zero columns beyond), F = S V^T (kk x dim, zero rows below)
+         for (int c = 0; c < dm; c++)
+            for (int j = 0; j < kk; j++) Fi[j + (size_t)dm * c] = sv[i][j] * VT[i][j + (size_t)kk * c];
+      }
+      for (size_t bi = 0; bi < sc.blocks.size(); bi++) {
+         const int k = sc.blocks[bi];
+         const Block& B = T.blk[k];
+         const double f = to_left ? std::sqrt((sc.ts + 1.0) / (T.twoSR[k] + 1.0)) : 1.0;
+         for (int c = 0; c < B.cols; c++)
+            for (int r = 0; r < B.rows; r++) {
+               double x;
+               if (to_left) x = (r < kk) ? f * VT[i][r + (size_t)kk * (sc.start[bi] + c)] : 0.0;
+               else x = (c < kk) ? U[i][sc.start[bi] + r + (size_t)m * c] : 0.0;
+               t[B.off + r + (size_t)B.rows * c] = x;
+            }
+      }
+   }
+   // ---- neighbour:  T_prev[. -> sector] <- T_prev F   resp.   T_next[sector -> .] <- F T_next      (device GEMMs)
+   const int nb = to_left ? site - 1 : site + 1;
+   if (nb < 0 || nb >= L) return B2_OK;
+   TLayout N;
+   N.build(bk, nb);
+   std::vector<Term3> terms;
+   std::vector<DstBlock> dst;
+   for (int k = 0; k < N.nkappa(); k++) {
+      dst.push_back(DstBlock{N.blk[k].off, N.blk[k].rows, N.blk[k].cols});
+      const int sn = to_left ? N.NR[k] : N.NL[k], sts = to_left ? N.twoSR[k] : N.twoSL[k], sir = to_left ? N.IR[k] : N.IL[k];
+      for (size_t i = 0; i < secs.size(); i++) {
+         if (secs[i].n != sn || secs[i].ts != sts || secs[i].ir != sir) continue;
+         Term3 x;
+         x.dst = k; x.f = 1.0;
+         MatRef tb, fb;
+         tb.space = SP_LEFT; tb.off = N.blk[k].off; tb.rows = N.blk[k].rows; tb.cols = N.blk[k].cols;
+         fb.space = SP_RIGHT; fb.off = foff[i]; fb.rows = secs[i].dim; fb.cols = secs[i].dim;
+         if (to_left) { x.q = tb; x.r = fb; } else { x.p = fb; x.q = tb; }
+         terms.push_back(x);
+      }
+   }
+   cudaStream_t s = ctx->stream;
+   struct Buf { double* p = nullptr; ~Buf() { cudaFree(p); } } dOld, dNew, dF;
+   const size_t nbytes = sizeof(double) * (size_t)std::max<int64_t>(N.size, 1);
+   CUDA_TRY(cudaMalloc(&dOld.p, nbytes));
+   CUDA_TRY(cudaMalloc(&dNew.p, nbytes));
+   CUDA_TRY(cudaMalloc(&dF.p, sizeof(double) * F.size()));
+   CUDA_TRY(cudaMemcpyAsync(dOld.p, d->mps[nb].data(), sizeof(double) * (size_t)N.size, cudaMemcpyHostToDevice, s));
+   CUDA_TRY(cudaMemcpyAsync(dF.p, F.data(), sizeof(double) * F.size(), cudaMemcpyHostToDevice, s));
+   CUDA_TRY(cudaMemsetAsync(dNew.p, 0, nbytes, s));
+   CompiledWork w;
+   compile_terms(w, terms, dst, SP_VOUT, budgeted(ctx));
+   DevBases b;
+   for (int i = 0; i < SP_COUNT; i++) b.p[i] = nullptr;
+   b.p[SP_LEFT] = dOld.p; b.p[SP_RIGHT] = dF.p; b.p[SP_VOUT] = dNew.p;
+   int rc = run_compiled_once(ctx, w, b);
+   if (rc) return rc;
+   CUDA_TRY(cudaMemcpyAsync(d->mps[nb].data(), dNew.p, sizeof(double) * (size_t)N.size, cudaMemcpyDeviceToHost, s));
+   CUDA_TRY(cudaStreamSynchronize(s));
+   return B2_OK;
+}
+
+// DMRG::calc_rdms_and_correlations, 2-RDM part (DMRGtechnics.cpp:40-113): whole MPS into left-canonical form, moving-right operators
+// of every boundary, then site by site from the right: TwoDM::FillSite, right-normalise, moving-left operators one boundary further.
+int b2_dmrg_calc_2rdm(b2_dmrg* d, double* two_rdm_A, double* two_rdm_B) {
+   if (!d || !two_rdm_A || !two_rdm_B) return fail(B2_ERR_ARG, "b2_dmrg_calc_2rdm: NULL");
+   const int L = d->L;
+   const size_t n4 = (size_t)L * L * L * L;
+   std::fill(two_rdm_A, two_rdm_A + n4, 0.0);
+   std::fill(two_rdm_B, two_rdm_B + n4, 0.0);
+   int rc;
+   for (int s = 0; s < L; s++) {
+      if ((rc = dmrg_gauge_move(d, s, false))) return rc;          // the last one discards the norm (left_normalize(MPS[L-1], NULL))
+      if (s < L - 1 && (rc = b2_dmrg_update(d, s, 1))) return rc;  // operators of boundary s+1 from the left-normalised MPS[s]
+   }
+   for (int site = L - 1; site >= 0; site--) {
+      b2_opset* lset = site > 0 ? d->left[site] : nullptr;
+      b2_opset* rset = site < L - 1 ? d->right[site + 1] : nullptr;
+      if (lset && (rc = b2_opset_reload(lset))) return rc;
+      if (rset && (rc = b2_opset_reload(rset))) return rc;
+      if ((rc = b2_twodm_fill_site(d->ctx, site, d->mps[site].data(), lset, rset, two_rdm_A, two_rdm_B))) return rc;
+      if (site > 0) {
+         if ((rc = dmrg_gauge_move(d, site, true))) return rc;
+         if ((rc = b2_dmrg_update(d, site, 0))) return rc;         // updateMovingLeftSafe2DM(site-1): operators of boundary `site`
+      }
+   }
+   if (d->ctx->prob.twoS != 0) {                                    // TwoDM::correct_higher_multiplicities (TwoDM.cpp:630-640)
+      const double alpha = 1.0 / (d->ctx->prob.twoS + 1.0);
+      for (size_t i = 0; i < n4; i++) { two_rdm_A[i] *= alpha; two_rdm_B[i] *= alpha; }
+   }
+   return B2_OK;
+}
+
 // DMRG::sweepleft / sweepright (DMRG.cpp:357-417): returns the lowest site energy of the half sweep
 int b2_dmrg_sweep(b2_dmrg* d, int to_right, double rtol, double noise, int D, int change, double* min_energy, double* max_discarded) {
    if (!d || !min_energy) return fail(B2_ERR_ARG, "b2_dmrg_sweep: bad arguments");

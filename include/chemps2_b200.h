@@ -238,6 +238,12 @@ int b2_dmrg_get_mps(const b2_dmrg* d, int site, double* t_storage);
 int b2_dmrg_random_mps(b2_dmrg* d, uint64_t seed);           /* random + left-normalised, DMRG.cpp:149-169 (own RNG stream) */
 b2_opset* b2_dmrg_opset(b2_dmrg* d, int boundary, int moving_right);
 int b2_dmrg_set_opset(b2_dmrg* d, int boundary, int moving_right, b2_opset* set);   /* the driver takes ownership */
+/* 2-RDM of the current MPS: the TwoDM part of DMRG::calc_rdms_and_correlations (DMRGtechnics.cpp:40-113) — MPS into left-canonical form
+ * (device-SVD gauge moves), operators of every boundary, then from the right site by site b2_twodm_fill_site, right-normalise, next
+ * moving-left operators; finally TwoDM::correct_higher_multiplicities.  two_rdm_A / two_rdm_B: L^4 doubles each, DMRG orbital order,
+ * A(i,j,k,l) at i + L*(j + L*(k + L*l)) as TwoDM::getTwoDMA_DMRG.  The MPS is left in right-canonical form with its norm set to 1;
+ * afterwards only the moving-left operator sets are current. */
+int b2_dmrg_calc_2rdm(b2_dmrg* d, double* two_rdm_A, double* two_rdm_B);
 /* multi-GPU sweep: sigma terms (ownership maps) and operator updates are sharded over `world` GPUs, MPS / Davidson vectors /
  * Split are replicated; fn sums a device vector over the ranks (NCCL).  Call before the first update / solve. */
 int b2_dmrg_set_world(b2_dmrg* d, int world, int rank, b2_allreduce_fn fn, void* user);

@@ -528,6 +528,15 @@ int main(int argc, char ** argv){
       }
       w.dbls("energies", energies);
       dump_correlation_tensors(w, "corr", d);
+      /* the full 2-RDM of the final MPS (= corr/mps): DMRG::calc2DMandCorrelations -> TwoDM arrays A and B in DMRG orbital order */
+      d.calc2DMandCorrelations();
+      {
+         const long long n4 = (long long) L * L * L * L;
+         w.dbls("twodm/A", d.the2DM->two_rdm_A, n4);
+         w.dbls("twodm/B", d.the2DM->two_rdm_B, n4);
+         std::vector<double> te; te.push_back(d.the2DM->trace()); te.push_back(d.the2DM->energy());
+         w.dbls("twodm/trace_energy", te);
+      }
       printf("B2REF dumped; last energy %.12f\n", energies.back());
       return 0;
    }

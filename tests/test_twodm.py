@@ -121,3 +121,27 @@ def test_fill_site_gpu(golden):
     assert np.abs(B - refB).max() <= TOL * max(1.0, np.abs(refB).max())
     A2, B2 = api.twodm_fill_site(ctx, site, t, left, right)
     assert np.array_equal(A, A2) and np.array_equal(B, B2)                # deterministic
+
+
+@pytest.mark.gpu
+def test_full_2rdm_vs_reference(golden):
+    """b2_dmrg_calc_2rdm on the reference's final MPS (golden corr/mps, corr/bk) against the 2-RDM DMRG::calc2DMandCorrelations of the
+    reference computed from the same state (golden twodm/A, twodm/B): north_star tolerance 1e-8 on every element (gauge moves differ,
+    so only rounding separates the two); trace = N(N-1) and the energy 0.5 * sum A * gMxElement + Econst equal the reference's."""
+    ctx = api.context_from_fixture(golden, "corr", device=0)
+    L = ctx.L
+    d = api.DMRG(ctx)
+    for s in range(L):
+        d.set_mps(s, golden[f"corr/mps/{s}"])
+    A, B = d.calc_2rdm()
+    refA = golden["twodm/A"].reshape((L, L, L, L), order="F")
+    refB = golden["twodm/B"].reshape((L, L, L, L), order="F")
+    assert np.abs(A - refA).max() < 1e-8
+    assert np.abs(B - refB).max() < 1e-8
+    N = int(golden["problem/hdr"][2])
+    trace = float(np.einsum("ijij->", A))
+    assert abs(trace - N * (N - 1)) < 1e-8 and abs(trace - golden["twodm/trace_energy"][0]) < 1e-8
+    mx = golden["problem/mx"].reshape((L, L, L, L), order="F")
+    energy = float(golden["problem/econst"][0]) + 0.5 * float(np.sum(A * mx))
+    assert abs(energy - golden["twodm/trace_energy"][1]) < 1e-8
+    assert abs(energy - golden["energies"][-1]) < 1e-6          # and it is the energy of the last sweep step

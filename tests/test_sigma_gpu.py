@@ -100,8 +100,9 @@ def test_davidson_solve_vs_reference(golden, tag):
 
 def test_full_size_properties_synth40():
     """BASELINE config 5 shape (40e/40o C1, 'gauss' sector model) at D = 2000 — too large for the CPU checkers — through size-independent
-    properties of the sigma build: H_eff symmetric in the symmetric convention, linear, bitwise reproducible, diagonal consistent with
-    <e_i|H e_i> on sampled unit vectors, and the owner shards of 2 GPUs summing to the full result."""
+    properties of the sigma build: linear, bitwise reproducible, diagonal consistent with <e_i|H e_i> on sampled unit vectors, and the
+    owner shards of 2 GPUs summing to the full result.  (The operators are hash-filled, i.e. not the renormalized operators of any state,
+    so H_eff is not symmetric here; symmetry is tested on the golden systems.)"""
     w = workloads.get("synth40", D=2000)
     ctx = w.context(0)
     w.apply_distribution(ctx, "gauss")
@@ -113,8 +114,6 @@ def test_full_size_properties_synth40():
     x, y = api.hash_fill(n, 21), api.hash_fill(n, 22)
     hx, hy = heff.apply(x), heff.apply(y)
     scale = np.abs(hx).max()
-    a, b = float(x @ hy), float(y @ hx)
-    assert abs(a - b) <= 1e-11 * max(abs(a), np.linalg.norm(x) * np.linalg.norm(hy))
     hz = heff.apply(2.0 * x - 3.0 * y)
     assert np.abs(hz - (2.0 * hx - 3.0 * hy)).max() <= 1e-11 * scale
     assert np.array_equal(heff.apply(x), hx)

@@ -118,6 +118,8 @@ SIGNATURES = [
     ("b2_update_create_sharded", C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.POINTER(vp)]),
     ("b2_update_set_allreduce", C.c_int, [vp, vp, vp]),
     ("b2_dmrg_calc_2rdm", C.c_int, [vp, c_dp, c_dp]),
+    ("b2_dmrg_calc_correlations", C.c_int, [vp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+    ("b2_corr_fill_site", C.c_int, [vp, C.c_int, c_dp, vp, c_dp, c_dp, c_dp, c_dp]),
     ("b2_dmrg_set_world", C.c_int, [vp, C.c_int, C.c_int, vp, vp]),
     ("b2_dmrg_timers", C.c_int, [vp, c_dp, C.c_int]),
     ("b2_update_destroy", None, [vp]),

@@ -301,6 +301,15 @@ class DMRG:
         check(lib.b2_dmrg_calc_2rdm(self.h, _dp(A), _dp(B)))
         return A.reshape((L, L, L, L), order="F"), B.reshape((L, L, L, L), order="F")
 
+    def calc_correlations(self, A, B):
+        """A, B from calc_2rdm -> dict of [L,L] tables Cspin, Cdens, Cspinflip, Cdirad, MutInfo (Correlations::get*_DMRG)"""
+        L = self.ctx.L
+        a = np.ascontiguousarray(A.ravel(order="F"))
+        b = np.ascontiguousarray(B.ravel(order="F"))
+        out = {k: np.zeros(L * L) for k in ("Cspin", "Cdens", "Cspinflip", "Cdirad", "MutInfo")}
+        check(lib.b2_dmrg_calc_correlations(self.h, _dp(a), _dp(b), *[_dp(out[k]) for k in ("Cspin", "Cdens", "Cspinflip", "Cdirad", "MutInfo")]))
+        return {k: v.reshape((L, L), order="F") for k, v in out.items()}
+
     def set_spill(self, enabled):
         check(lib.b2_dmrg_set_spill(self.h, int(bool(enabled))))
 

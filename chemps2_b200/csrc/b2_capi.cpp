@@ -265,6 +265,18 @@ int b2_opset_create(b2_ctx* ctx, int boundary, int moving_right, b2_opset** out)
    *out = s.release();
    return B2_OK;
 }
+static int opset_create_reduced(b2_ctx* ctx, int boundary, bool mr, bool only_L, b2_opset** out) {
+   std::unique_ptr<b2_opset> s(new b2_opset);
+   s->ctx = ctx;
+   s->set.build_reduced(ctx->bk, boundary, mr, only_L);
+   if (ctx->device >= 0 && s->set.size > 0) {
+      CUDA_TRY(cudaSetDevice(ctx->device));
+      CUDA_TRY(cudaMalloc(&s->dev, sizeof(double) * (size_t)s->set.size));
+      CUDA_TRY(cudaMemsetAsync(s->dev, 0, sizeof(double) * (size_t)s->set.size, ctx->stream));
+   }
+   *out = s.release();
+   return B2_OK;
+}
 int b2_opset_create_correlation(b2_ctx* ctx, int boundary, b2_opset** out) {
    if (!ctx || !ctx->have_bk || !out) return fail(B2_ERR_STATE, "b2_opset_create_correlation: no bookkeeper");
    if (boundary < 1 || boundary > ctx->bk.L) return fail(B2_ERR_ARG, "b2_opset_create_correlation: boundary %d out of range", boundary);
@@ -389,6 +401,7 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
    if (site > 0 && (!left || left->set.boundary != site || !left->set.moving_right)) return fail(B2_ERR_ARG, "b2_heff_create: left operator set must sit at boundary %d moving right", site);
    if (site < L - 2 && (!right || right->set.boundary != site + 2 || right->set.moving_right)) return fail(B2_ERR_ARG, "b2_heff_create: right operator set must sit at boundary %d moving left", site + 2);
    if (world < 1 || rank < 0 || rank >= world) return fail(B2_ERR_ARG, "b2_heff_create: bad world/rank");
+   if ((site > 0 && left && left->set.reduced) || (site < L - 2 && right && right->set.reduced)) return fail(B2_ERR_STATE, "b2_heff_create: a reduced operator set (2-RDM chain / correlation tensors) cannot drive a sigma build");
    if (ctx->device >= 0 && ctx->simulate_oom > 0) { ctx->simulate_oom--; return fail(B2_ERR_CUDA, "b2_heff_create: out of memory (simulated)"); }
    if ((site > 0 && left && left->offloaded) || (site < L - 2 && right && right->offloaded)) return fail(B2_ERR_STATE, "b2_heff_create: operator set is offloaded (b2_opset_reload first)");
    std::unique_ptr<b2_heff> h(new b2_heff);
@@ -1038,7 +1051,10 @@ int b2_dmrg_timers(b2_dmrg* d, double* out5, int reset) {
 }
 
 // DMRG::updateMovingRight(index) / updateMovingLeft(index-1): operators of the boundary next to site `index` from T = MPS[index]
-int b2_dmrg_update(b2_dmrg* d, int index, int moving_right) {
+static int dmrg_update_mode(b2_dmrg* d, int index, int moving_right, int mode);
+int b2_dmrg_update(b2_dmrg* d, int index, int moving_right) { return dmrg_update_mode(d, index, moving_right, 0); }
+// mode 0: the full operator complement of a sweep; 1: L, S0, S1, F0, F1 (updateMovingLeftSafe2DM); 2: L only
+static int dmrg_update_mode(b2_dmrg* d, int index, int moving_right, int mode) {
    if (!d || index < 0 || index >= d->L) return fail(B2_ERR_ARG, "b2_dmrg_update: bad arguments");
    b2_ctx* ctx = d->ctx;
    const bool mr = moving_right != 0;
@@ -1053,7 +1069,7 @@ int b2_dmrg_update(b2_dmrg* d, int index, int moving_right) {
    const double t0 = wall_seconds();
    int rc = B2_OK;
    for (int attempt = 0; attempt < 2; attempt++) {
-      rc = b2_opset_create(ctx, b_new, mr, &fresh);
+      rc = mode == 0 ? b2_opset_create(ctx, b_new, mr, &fresh) : opset_create_reduced(ctx, b_new, mr, mode == 2, &fresh);
       if (!rc) rc = b2_update_create_sharded(ctx, index, mr, need_old ? old_set : nullptr, fresh, d->world, d->rank, &u);
       if (rc != B2_ERR_CUDA || attempt == 1 || d->spill) break;
       // HBM exhausted (O(L) boundaries x O(L^2 D^2) operators): from now on only the sets in use stay resident — the
@@ -1281,7 +1297,7 @@ int b2_dmrg_calc_2rdm(b2_dmrg* d, double* two_rdm_A, double* two_rdm_B) {
    int rc;
    for (int s = 0; s < L; s++) {
       if ((rc = dmrg_gauge_move(d, s, false))) return rc;          // the last one discards the norm (left_normalize(MPS[L-1], NULL))
-      if (s < L - 1 && (rc = b2_dmrg_update(d, s, 1))) return rc;  // operators of boundary s+1 from the left-normalised MPS[s]
+      if (s < L - 1 && (rc = dmrg_update_mode(d, s, 1, 2))) return rc;   // L operators of boundary s+1 from the left-normalised MPS[s]
    }
    for (int site = L - 1; site >= 0; site--) {
       b2_opset* lset = site > 0 ? d->left[site] : nullptr;
@@ -1291,13 +1307,55 @@ int b2_dmrg_calc_2rdm(b2_dmrg* d, double* two_rdm_A, double* two_rdm_B) {
       if ((rc = b2_twodm_fill_site(d->ctx, site, d->mps[site].data(), lset, rset, two_rdm_A, two_rdm_B))) return rc;
       if (site > 0) {
          if ((rc = dmrg_gauge_move(d, site, true))) return rc;
-         if ((rc = b2_dmrg_update(d, site, 0))) return rc;         // updateMovingLeftSafe2DM(site-1): operators of boundary `site`
+         if ((rc = dmrg_update_mode(d, site, 0, 1))) return rc;    // updateMovingLeftSafe2DM(site-1): L, S0, S1, F0, F1 of boundary `site`
       }
    }
    if (d->ctx->prob.twoS != 0) {                                    // TwoDM::correct_higher_multiplicities (TwoDM.cpp:630-640)
       const double alpha = 1.0 / (d->ctx->prob.twoS + 1.0);
       for (size_t i = 0; i < n4; i++) { two_rdm_A[i] *= alpha; two_rdm_B[i] *= alpha; }
    }
+   return B2_OK;
+}
+
+// The Correlations part of DMRG::calc_rdms_and_correlations (DMRGtechnics.cpp:150-175): spin / density / spin-flip / singlet-diradical
+// correlation functions from the 2-RDM (Correlations::FillSpinDensSpinflip, Correlations.cpp:69-103) and the two-orbital mutual
+// information from the G/Y/Z/K/M tensors, site by site from the left.
+int b2_dmrg_calc_correlations(b2_dmrg* d, const double* A, const double* B, double* Cspin, double* Cdens, double* Cspinflip, double* Cdirad,
+                              double* MutInfo) {
+   if (!d || !A || !B || !Cspin || !Cdens || !Cspinflip || !Cdirad || !MutInfo) return fail(B2_ERR_ARG, "b2_dmrg_calc_correlations: NULL");
+   b2_ctx* ctx = d->ctx;
+   const int L = d->L, N = ctx->prob.N;
+   auto irr = [&](int o) { return ctx->bk.orb_irrep[o]; };
+   auto getA = [&](int i, int j, int k, int l) { return (xorp(irr(i), irr(j)) == xorp(irr(k), irr(l))) ? A[i + L * (j + L * (k + L * (size_t)l))] : 0.0; };
+   auto getB = [&](int i, int j, int k, int l) { return (xorp(irr(i), irr(j)) == xorp(irr(k), irr(l))) ? B[i + L * (j + L * (k + L * (size_t)l))] : 0.0; };
+   std::vector<double> n1(L);
+   for (int i = 0; i < L; i++) { double v = 0.0; for (int o = 0; o < L; o++) v += getA(i, o, i, o); n1[i] = v / (N - 1.0); }
+   for (int r = 0; r < L; r++)
+      for (int c = 0; c < L; c++) {
+         Cspin[r + L * c] = getB(r, c, r, c) + (r == c ? n1[r] : 0.0);
+         Cdens[r + L * c] = getA(r, c, r, c) - n1[r] * n1[c] + (r == c ? n1[r] : 0.0);
+         Cspinflip[r + L * c] = 0.5 * (getB(r, c, c, r) - getA(r, c, c, r)) + (r == c ? n1[r] : 0.0);
+         Cdirad[r + L * c] = -0.5 * (n1[r] - getA(r, r, r, r)) * (n1[c] - getA(c, c, c, c));
+         MutInfo[r + L * c] = 0.0;
+      }
+   int rc;
+   for (int site = L - 1; site >= 1; site--)
+      if ((rc = dmrg_gauge_move(d, site, true))) return rc;        // right-canonical, orthogonality centre on site 0
+   b2_opset* old_set = nullptr;
+   for (int site = 1; site < L; site++) {
+      if ((rc = dmrg_gauge_move(d, site - 1, false))) { b2_opset_destroy(old_set); return rc; }   // left_normalize(MPS[site-1], MPS[site])
+      b2_opset* fresh = nullptr;
+      b2_update* u = nullptr;
+      rc = b2_opset_create_correlation(ctx, site, &fresh);                                        // update_correlations_tensors(site)
+      if (!rc) rc = b2_update_create(ctx, site - 1, 1, old_set, fresh, &u);
+      if (!rc) rc = b2_update_run(u, d->mps[site - 1].data());
+      b2_update_destroy(u);
+      if (!rc) rc = b2_corr_fill_site(ctx, site, d->mps[site].data(), fresh, A, B, Cdirad, MutInfo);
+      b2_opset_destroy(old_set);
+      old_set = fresh;
+      if (rc) { b2_opset_destroy(old_set); return rc; }
+   }
+   b2_opset_destroy(old_set);
    return B2_OK;
 }
 
@@ -1392,15 +1450,13 @@ int b2_twodm_scatter(const b2_twodm* p, const double* const* gram, double d1, do
    return B2_OK;
 }
 
-int b2_twodm_run(b2_twodm* tp, const double* t_host, double* two_rdm_A, double* two_rdm_B) {
-   if (!tp || !t_host || !two_rdm_A || !two_rdm_B) return fail(B2_ERR_ARG, "b2_twodm_run: bad arguments");
-   b2_ctx* ctx = tp->ctx;
-   if (ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_twodm_run: planning-only context, no CUDA device (there is no CPU fallback)");
-   b2_opset *left = tp->left, *right = tp->right;
-   if ((left && left->offloaded) || (right && right->offloaded)) return fail(B2_ERR_STATE, "b2_twodm_run: operator set is offloaded (b2_opset_reload first)");
+// executes a TwoDMPlan on the device: effective operators, diagram-1 weight sum, Gram matrices with the stored operators
+static int twodm_execute(b2_ctx* ctx, const TwoDMPlan& plan, const CompiledWork& build, const double* t_host, b2_opset* left, b2_opset* right, double* d1_out,
+                         std::vector<std::vector<double>>& gram) {
+   if (ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "2-RDM / correlations: planning-only context, no CUDA device (there is no CPU fallback)");
+   if ((left && left->offloaded) || (right && right->offloaded)) return fail(B2_ERR_STATE, "2-RDM / correlations: operator set is offloaded (b2_opset_reload first)");
    CUDA_TRY(cudaSetDevice(ctx->device));
    cudaStream_t s = ctx->stream;
-   const TwoDMPlan& plan = tp->plan;
    const int64_t tsize = plan.T.size;
    struct Buf { double* p = nullptr; ~Buf() { cudaFree(p); } } dT, dTs, dM, dY, dG, dScal, dScale;
    struct IBuf { int64_t* p = nullptr; ~IBuf() { cudaFree(p); } } dOff;
@@ -1415,7 +1471,7 @@ int b2_twodm_run(b2_twodm* tp, const double* t_host, double* two_rdm_A, double* 
       DevBases b;
       for (int i = 0; i < SP_COUNT; i++) b.p[i] = nullptr;
       b.p[SP_LEFT] = left ? left->dev : nullptr; b.p[SP_RIGHT] = dT.p; b.p[SP_VOUT] = dM.p;
-      int rc = run_compiled_once(ctx, tp->build, b);
+      int rc = run_compiled_once(ctx, build, b);
       if (rc) return rc;
    }
    // ---- diagram 1: < T , (2SL+1)-scaled doubly-occupied blocks of T >
@@ -1438,7 +1494,7 @@ int b2_twodm_run(b2_twodm* tp, const double* t_host, double* two_rdm_A, double* 
    }
    // ---- Gram matrices  G[member, partner] = < M_member , stored operator >: the partners of a group are gathered into a dense
    // [stride x count] matrix, then one K-concatenated GEMM per group through the grouped contraction kernels
-   std::vector<std::vector<double>> gram(plan.groups.size());
+   gram.assign(plan.groups.size(), std::vector<double>());
    {
       std::vector<int64_t> yoff(plan.groups.size(), 0), goff(plan.groups.size(), 0);
       int64_t ytot = 0, gtot = 0;
@@ -1488,7 +1544,85 @@ int b2_twodm_run(b2_twodm* tp, const double* t_host, double* two_rdm_A, double* 
          gram[gi].assign(gh.begin() + goff[gi], gh.begin() + goff[gi] + n);
       }
    }
-   twodm_scatter(plan, ctx->bk, left ? &left->set : nullptr, right ? &right->set : nullptr, d1, gram, two_rdm_A, two_rdm_B);
+   if (d1_out) *d1_out = d1;
+   return B2_OK;
+}
+
+int b2_twodm_run(b2_twodm* tp, const double* t_host, double* two_rdm_A, double* two_rdm_B) {
+   if (!tp || !t_host || !two_rdm_A || !two_rdm_B) return fail(B2_ERR_ARG, "b2_twodm_run: bad arguments");
+   double d1 = 0.0;
+   std::vector<std::vector<double>> gram;
+   int rc = twodm_execute(tp->ctx, tp->plan, tp->build, t_host, tp->left, tp->right, &d1, gram);
+   if (rc) return rc;
+   twodm_scatter(tp->plan, tp->ctx->bk, tp->left ? &tp->left->set : nullptr, tp->right ? &tp->right->set : nullptr, d1, gram, two_rdm_A, two_rdm_B);
+   return B2_OK;
+}
+
+/* Correlations::FillSite (Correlations.cpp:212-351) for site `site` (>= 1): T = MPS[site] (orthogonality centre), corr = correlation
+ * operator set of boundary `site`; A, B = the finished 2-RDM arrays (TwoDM, after correct_higher_multiplicities).  Fills row/column
+ * `site` of MutInfo and adds the two-orbital part to Cdirad, exactly like the reference. */
+int b2_corr_fill_site(b2_ctx* ctx, int site, const double* t_host, b2_opset* corr, const double* A, const double* B, double* Cdirad, double* MutInfo) {
+   if (!ctx || !ctx->have_bk || !t_host || !corr || !A || !B || !Cdirad || !MutInfo) return fail(B2_ERR_ARG, "b2_corr_fill_site: bad arguments");
+   const int L = ctx->bk.L;
+   if (site < 1 || site >= L || corr->set.boundary != site) return fail(B2_ERR_ARG, "b2_corr_fill_site: the correlation set must sit at boundary %d", site);
+   TwoDMPlan plan;
+   build_corr_plan(plan, ctx->bk, site, corr->set);
+   CompiledWork build;
+   CompileOptions copt = budgeted(ctx);
+   compile_terms(build, plan.terms, plan.dst, SP_VOUT, copt);
+   std::vector<std::vector<double>> gram;
+   int rc = twodm_execute(ctx, plan, build, t_host, corr, nullptr, nullptr, gram);
+   if (rc) return rc;
+   const Problem& pr = ctx->prob;
+   auto irr = [&](int o) { return ctx->bk.orb_irrep[o]; };
+   auto getA = [&](int i, int j, int k, int l) { return (xorp(irr(i), irr(j)) == xorp(irr(k), irr(l))) ? A[i + L * (j + L * (k + L * (size_t)l))] : 0.0; };
+   auto getB = [&](int i, int j, int k, int l) { return (xorp(irr(i), irr(j)) == xorp(irr(k), irr(l))) ? B[i + L * (j + L * (k + L * (size_t)l))] : 0.0; };
+   auto rdm1 = [&](int i, int j) {   // TwoDM::get1RDM_DMRG (TwoDM.cpp:128-142)
+      if (irr(i) != irr(j)) return 0.0;
+      double v = 0.0;
+      for (int o = 0; o < L; o++) v += getA(i, o, j, o);
+      return v / (pr.N - 1.0);
+   };
+   auto entropy1 = [&](int i) {      // Correlations::SingleOrbitalEntropy_DMRG (Correlations.cpp:165-177)
+      const double v4 = 0.5 * getA(i, i, i, i), v23 = 0.5 * (rdm1(i, i) - getA(i, i, i, i)), v1 = 1.0 - v4 - 2 * v23;
+      double e = 0.0;
+      if (v1 > 1e-100) e -= v1 * std::log(v1);
+      if (v23 > 1e-100) e -= 2 * v23 * std::log(v23);
+      if (v4 > 1e-100) e -= v4 * std::log(v4);
+      return e;
+   };
+   const double ps = 1.0 / (pr.twoS + 1.0), s5 = std::sqrt(0.5);
+   const OpSet& cs = corr->set;
+   auto v = [&](int tag, int kind, int p) { return corr_value(plan, cs, gram, tag, kind, p); };
+   for (int p = 0; p < site; p++) {
+      const bool eq = irr(p) == irr(site);
+      const double diag1 = v(CORR_D3, K_G, p) * ps * 0.5 * s5;
+      const double diag2 = 0.125 * (getB(p, site, site, p) - getA(p, site, site, p));
+      const double val1 = v(CORR_D1, K_Y, p) * ps, val2 = v(CORR_D2, K_Z, p) * ps, val3 = diag1 + diag2;
+      const double val4 = v(CORR_D1, K_G, p) * ps * s5, val5 = v(CORR_D3, K_Y, p) * ps * 0.5, val6 = eq ? v(CORR_D4, K_K, p) * ps * 0.5 : 0.0;
+      const double val7 = v(CORR_D2, K_G, p) * ps * s5, val8 = v(CORR_D3, K_Z, p) * ps * 0.5, val9 = eq ? v(CORR_D5, K_M, p) * ps * 0.5 : 0.0;
+      const double alpha = v(CORR_D2, K_Y, p) * ps, gamma = v(CORR_D1, K_Z, p) * ps, beta = diag1 - diag2, lambda = 2 * diag2;
+      const double delta = eq ? -v(CORR_D5, K_K, p) * ps * 0.5 : 0.0, epsilon = eq ? v(CORR_D4, K_M, p) * ps * 0.5 : 0.0;
+      const double kappa = 0.5 * getA(p, p, site, site);
+      double R[256] = {0.0}, ev[16], evec[256];
+      auto at = [&](int r, int c) -> double& { return R[r + 16 * c]; };
+      at(0, 0) = val1; at(15, 15) = val2; at(5, 5) = at(10, 10) = val3;
+      at(1, 1) = at(3, 3) = val4; at(2, 2) = at(4, 4) = val5;
+      at(1, 2) = at(2, 1) = at(3, 4) = at(4, 3) = val6;
+      at(11, 11) = at(13, 13) = val7; at(12, 12) = at(14, 14) = val8;
+      at(11, 12) = at(12, 11) = at(13, 14) = at(14, 13) = val9;
+      at(6, 6) = alpha; at(7, 7) = at(8, 8) = beta; at(9, 9) = gamma;
+      at(6, 7) = at(7, 6) = delta; at(6, 8) = at(8, 6) = -delta;
+      at(7, 9) = at(9, 7) = epsilon; at(8, 9) = at(9, 8) = -epsilon;
+      at(6, 9) = at(9, 6) = kappa; at(7, 8) = at(8, 7) = lambda;
+      if (b2_small_symmetric_eig(16, R, ev, evec)) return fail(B2_ERR_STATE, "b2_corr_fill_site: eigenvalue problem failed");
+      double ent = 0.0;
+      for (int c = 0; c < 16; c++) if (ev[c] > 1e-100) ent -= ev[c] * std::log(ev[c]);
+      const double mi = 0.5 * (entropy1(p) + entropy1(site) - ent);
+      MutInfo[p + L * site] = MutInfo[site + L * p] = mi;
+      Cdirad[p + L * site] += 2 * beta;
+      Cdirad[site + L * p] += 2 * beta;
+   }
    return B2_OK;
 }
 

@@ -53,8 +53,24 @@ void OpSet::build_all(const Bookkeeper& bk, int boundary_, bool moving_right_) {
    add(bk, K_X, -1, -1);
 }
 
+void OpSet::build_reduced(const Bookkeeper& bk, int boundary_, bool moving_right_, bool only_L) {
+   boundary = boundary_; moving_right = moving_right_; reduced = true;
+   ops.clear(); index.clear(); layouts.clear(); size = 0;
+   const int L = bk.L, b = boundary;
+   const int in_lo = moving_right ? 0 : b, in_hi = moving_right ? b - 1 : L - 1;
+   for (int s = in_lo; s <= in_hi; s++) add(bk, K_L, s, s);
+   if (only_L) return;
+   for (int i = in_lo; i <= in_hi; i++)
+      for (int j = i; j <= in_hi; j++) {
+         add(bk, K_S0, i, j);
+         if (j > i) add(bk, K_S1, i, j);
+         add(bk, K_F0, i, j);
+         add(bk, K_F1, i, j);
+      }
+}
+
 void OpSet::build_correlation(const Bookkeeper& bk, int boundary_) {
-   boundary = boundary_; moving_right = true;
+   boundary = boundary_; moving_right = true; reduced = true;
    ops.clear(); index.clear(); layouts.clear(); size = 0;
    for (int s = 0; s < boundary; s++) {
       add(bk, K_G, s, s); add(bk, K_Y, s, s); add(bk, K_Z, s, s); add(bk, K_K, s, s); add(bk, K_M, s, s);

@@ -50,6 +50,9 @@ struct OpSet {
    void build_all(const Bookkeeper& bk, int boundary, bool moving_right);
    // the G, Y, Z, K, M tensors of every site left of `boundary` (DMRG::update_correlations_tensors, DMRGoperators3RDM.cpp:415-479)
    void build_correlation(const Bookkeeper& bk, int boundary);
+   // reduced complement for the 2-RDM chain (DMRG::updateMovingLeftSafe2DM keeps L, S0, S1, F0, F1 only; the left blocks need L only)
+   void build_reduced(const Bookkeeper& bk, int boundary, bool moving_right, bool only_L);
+   bool reduced = false;                     // not a full sweep set: b2_heff_create refuses it
 };
 
 }   // namespace b2

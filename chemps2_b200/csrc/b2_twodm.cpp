@@ -267,12 +267,105 @@ void build_twodm_plan(TwoDMPlan& plan, const Bookkeeper& bk, int site, const OpS
       if (!set) continue;
       for (size_t i = 0; i < set->ops.size(); i++) {
          const OpTensor& t = set->ops[i];
-         if (t.kind != grp.kind || t.irrep != grp.irrep) continue;
+         const bool kind_ok = grp.partner_kinds.empty() ? (t.kind == grp.kind) : (std::find(grp.partner_kinds.begin(), grp.partner_kinds.end(), t.kind) != grp.partner_kinds.end());
+         if (!kind_ok || t.irrep != grp.irrep) continue;
          if (grp.left_side && !(t.i < th)) continue;
          grp.partners.push_back((int)i);
       }
    }
    (void)L;
+}
+
+void build_corr_plan(TwoDMPlan& plan, const Bookkeeper& bk, int site, const OpSet& corr) {
+   plan = TwoDMPlan();
+   plan.site = site;
+   plan.T.build(bk, site);
+   const int th = site, I_th = bk.orb_irrep[site];
+   const TLayout& T = plan.T;
+   // N1, N2, N3 pair with G / Y / Z (two_j 0, n_elec 0, irrep 0); N4, N5 with K / M of the sites that carry the irrep of this site
+   const int tags[5] = {CORR_D1, CORR_D2, CORR_D3, CORR_D4, CORR_D5};
+   for (int a = 0; a < 5; a++) {
+      TwoDMPlan::MOp m;
+      m.tag = tags[a]; m.g = -1; m.left_side = true;
+      m.kind = a < 3 ? K_G : K_K;
+      m.irrep = a < 3 ? 0 : I_th;
+      auto lay = std::make_shared<OpLayout>();
+      lay->build(bk, th, kind_two_j(m.kind), kind_nelec(m.kind), m.irrep);
+      m.lay = lay;
+      plan.mops.push_back(m);
+   }
+   for (int gi = 0; gi < 2; gi++) {
+      TwoDMPlan::Group grp;
+      grp.left_side = true; grp.kind = gi == 0 ? K_G : K_K; grp.irrep = gi == 0 ? 0 : I_th;
+      grp.partner_kinds = gi == 0 ? std::vector<int>{K_G, K_Y, K_Z} : std::vector<int>{K_K, K_M};
+      const int first = gi == 0 ? 0 : 3, count = gi == 0 ? 3 : 2;
+      grp.stride = (plan.mops[first].lay->size + 15) / 16 * 16;
+      grp.off = plan.m_size;
+      for (int c = 0; c < count; c++) {
+         plan.mops[first + c].group = gi; plan.mops[first + c].col = c; plan.mops[first + c].off = grp.off + (int64_t)c * grp.stride;
+         grp.members.push_back(first + c);
+      }
+      plan.m_size += grp.stride * count;
+      for (size_t i = 0; i < corr.ops.size(); i++) {
+         const OpTensor& t = corr.ops[i];
+         if (std::find(grp.partner_kinds.begin(), grp.partner_kinds.end(), t.kind) == grp.partner_kinds.end() || t.irrep != grp.irrep) continue;
+         grp.partners.push_back((int)i);
+      }
+      plan.groups.push_back(grp);
+   }
+   plan.block_base.resize(plan.mops.size());
+   for (size_t i = 0; i < plan.mops.size(); i++) {
+      plan.block_base[i] = (int)plan.dst.size();
+      for (const Block& b : plan.mops[i].lay->blk) plan.dst.push_back(DstBlock{plan.mops[i].off + b.off, b.rows, b.cols});
+   }
+   auto tref = [&](int nl, int tsl, int il, int nr, int tsr, int ir, bool trans) {
+      MatRef m;
+      const int k = T.kappa(bk, nl, tsl, il, nr, tsr, ir);
+      if (k < 0) return m;
+      m.space = SP_RIGHT; m.off = T.blk[k].off; m.rows = T.blk[k].rows; m.cols = T.blk[k].cols; m.trans = trans;
+      return m;
+   };
+   // N[mop][block a -> b] += f * Ta * Tb^T       (value = < N , stored tensor block a -> b >)
+   auto emit = [&](int mop, int an, int ats, int air, int bn, int bts, int bir, const MatRef& ta, const MatRef& tbT, double f) {
+      if (!ta.present() || !tbT.present() || f == 0.0) return;
+      const int k = plan.mops[mop].lay->kappa(bk, an, ats, air, bn, bts, bir);
+      if (k < 0) return;
+      Term3 t;
+      t.dst = plan.block_base[mop] + k; t.f = f; t.p = ta; t.r = tbT;
+      plan.terms.push_back(t);
+   };
+   bk.for_sectors(th + 1, [&](int NR, int TwoSR, int IR) {
+      if (bk.dim(th + 1, NR, TwoSR, IR) <= 0) return;
+      const int Ix = xorp(IR, I_th);
+      // diagram1 (Correlations.cpp:353-387): site empty;  < T , Y T >  =  < Y , T T^T >
+      emit(0, NR, TwoSR, IR, NR, TwoSR, IR, tref(NR, TwoSR, IR, NR, TwoSR, IR, false), tref(NR, TwoSR, IR, NR, TwoSR, IR, true), TwoSR + 1.0);
+      // diagram2 (:389-423): site doubly occupied
+      emit(1, NR - 2, TwoSR, IR, NR - 2, TwoSR, IR, tref(NR - 2, TwoSR, IR, NR, TwoSR, IR, false), tref(NR - 2, TwoSR, IR, NR, TwoSR, IR, true), TwoSR + 1.0);
+      for (int TwoSL = TwoSR - 1; TwoSL <= TwoSR + 1; TwoSL += 2) {
+         if (TwoSL < 0) continue;
+         // diagram3 (:425-467): site singly occupied
+         emit(2, NR - 1, TwoSL, Ix, NR - 1, TwoSL, Ix, tref(NR - 1, TwoSL, Ix, NR, TwoSR, IR, false), tref(NR - 1, TwoSL, Ix, NR, TwoSR, IR, true), TwoSR + 1.0);
+         // diagram4 (:469-513): K block (ld -> lu) with lu = (NR, TwoSR, IR) [site empty], ld = (NR-1, TwoSL, Ix) [site single]:  < Tdown , K Tup >
+         emit(3, NR - 1, TwoSL, Ix, NR, TwoSR, IR, tref(NR - 1, TwoSL, Ix, NR, TwoSR, IR, false), tref(NR, TwoSR, IR, NR, TwoSR, IR, true), TwoSR + 1.0);
+         // diagram5 (:515-560): M block (ld -> lu) with ld = (NR-2, TwoSR, IR) [double], lu = (NR-1, TwoSL, Ix) [single]
+         const int fase = ((((TwoSL + 1 - TwoSR) / 2) % 2) != 0) ? -1 : 1;
+         emit(4, NR - 2, TwoSR, IR, NR - 1, TwoSL, Ix, tref(NR - 2, TwoSR, IR, NR, TwoSR, IR, false), tref(NR - 1, TwoSL, Ix, NR, TwoSR, IR, true),
+              fase * std::sqrt((TwoSL + 1.0) * (TwoSR + 1)));
+      }
+   });
+   for (int k = 0; k < T.nkappa(); k++) plan.d1_scale.push_back(0.0);
+}
+
+double corr_value(const TwoDMPlan& plan, const OpSet& corr, const std::vector<std::vector<double>>& gram, int tag, int kind, int p) {
+   const int op = corr.find(kind, p, p);
+   if (op < 0) return 0.0;
+   for (const TwoDMPlan::MOp& mo : plan.mops) {
+      if (mo.tag != tag) continue;
+      const TwoDMPlan::Group& grp = plan.groups[mo.group];
+      for (size_t c = 0; c < grp.partners.size(); c++)
+         if (grp.partners[c] == op) return gram[mo.group][mo.col + grp.members.size() * c];
+   }
+   return 0.0;
 }
 
 // scatter the Gram entries into the 2-RDM exactly like TwoDM::FillSite (TwoDM.cpp:445-628)

@@ -22,7 +22,8 @@ struct TwoDMPlan {
       int kind = 0, irrep = 0;
       int64_t off = 0, stride = 0;
       std::vector<int> members;      // indices into mops
-      std::vector<int> partners;     // operator indices in the left / right OpSet with the same (kind, irrep): the Gram columns
+      std::vector<int> partner_kinds;   // kinds of stored operators this group is paired with (empty: just `kind`)
+      std::vector<int> partners;     // operator indices in the left / right OpSet with a matching kind and irrep: the Gram columns
    };
    int site = 0;
    TLayout T;
@@ -36,6 +37,14 @@ struct TwoDMPlan {
 };
 
 void build_twodm_plan(TwoDMPlan& plan, const Bookkeeper& bk, int site, const OpSet* left, const OpSet* right);
+
+// Correlations::FillSite (Correlations.cpp:212-351): the five diagram functions (:353-560) between the MPS tensor of `site` and the
+// G / Y / Z / K / M tensors of every previous site, as Gram matrices of the effective operators N = f * T_a T_b^T (left boundary) with
+// the tensors of the correlation operator set `corr` (boundary `site`).  Same plan structure as the 2-RDM (mops tags CORR_D1..D5).
+enum { CORR_D1 = 100, CORR_D2, CORR_D3, CORR_D4, CORR_D5 };
+void build_corr_plan(TwoDMPlan& plan, const Bookkeeper& bk, int site, const OpSet& corr);
+// < N(tag) , tensor (kind, p) of the correlation set >
+double corr_value(const TwoDMPlan& plan, const OpSet& corr, const std::vector<std::vector<double>>& gram, int tag, int kind, int p);
 // gram[group][member + members * partner] = < M_member , partner operator >
 void twodm_scatter(const TwoDMPlan& plan, const Bookkeeper& bk, const OpSet* left, const OpSet* right, double d1,
                    const std::vector<std::vector<double>>& gram, double* A, double* B);

@@ -241,9 +241,19 @@ int b2_dmrg_set_opset(b2_dmrg* d, int boundary, int moving_right, b2_opset* set)
 /* 2-RDM of the current MPS: the TwoDM part of DMRG::calc_rdms_and_correlations (DMRGtechnics.cpp:40-113) — MPS into left-canonical form
  * (device-SVD gauge moves), operators of every boundary, then from the right site by site b2_twodm_fill_site, right-normalise, next
  * moving-left operators; finally TwoDM::correct_higher_multiplicities.  two_rdm_A / two_rdm_B: L^4 doubles each, DMRG orbital order,
- * A(i,j,k,l) at i + L*(j + L*(k + L*l)) as TwoDM::getTwoDMA_DMRG.  The MPS is left in right-canonical form with its norm set to 1;
- * afterwards only the moving-left operator sets are current. */
+ * A(i,j,k,l) at i + L*(j + L*(k + L*l)) as TwoDM::getTwoDMA_DMRG.  The MPS is left in right-canonical form with its norm set to 1.
+ * The chain keeps REDUCED operator sets (L only on the left, L/S0/S1/F0/F1 on the right, like updateMovingLeftSafe2DM); a sigma
+ * build refuses them (B2_ERR_STATE): rebuild the sweep operators with b2_dmrg_update before sweeping again. */
 int b2_dmrg_calc_2rdm(b2_dmrg* d, double* two_rdm_A, double* two_rdm_B);
+/* Correlations (Correlations.cpp; the second half of DMRG::calc_rdms_and_correlations, DMRGtechnics.cpp:150-175): from the finished
+ * 2-RDM arrays A, B (b2_dmrg_calc_2rdm) the L x L tables Cspin, Cdens, Cspinflip, Cdirad (FillSpinDensSpinflip, :69-103) and the
+ * two-orbital mutual information MutInfo (Correlations::FillSite, :212-351) of the current MPS; element (row, col) at row + L*col as
+ * Correlations::getCspin_DMRG etc.  b2_corr_fill_site is the per-site step (T = MPS[site] as orthogonality centre, corr = the
+ * correlation operator set of boundary `site`). */
+int b2_dmrg_calc_correlations(b2_dmrg* d, const double* two_rdm_A, const double* two_rdm_B, double* Cspin, double* Cdens, double* Cspinflip,
+                              double* Cdirad, double* MutInfo);
+int b2_corr_fill_site(b2_ctx* ctx, int site, const double* t_host, b2_opset* corr, const double* two_rdm_A, const double* two_rdm_B, double* Cdirad,
+                      double* MutInfo);
 /* multi-GPU sweep: sigma terms (ownership maps) and operator updates are sharded over `world` GPUs, MPS / Davidson vectors /
  * Split are replicated; fn sums a device vector over the ranks (NCCL).  Call before the first update / solve. */
 int b2_dmrg_set_world(b2_dmrg* d, int world, int rank, b2_allreduce_fn fn, void* user);

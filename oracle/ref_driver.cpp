@@ -43,6 +43,7 @@
 #include "Heff.h"
 #include "DMRG.h"
 #include "TwoDM.h"
+#include "Correlations.h"
 #include "Wigner.h"
 #undef private
 #undef protected
@@ -536,6 +537,10 @@ int main(int argc, char ** argv){
          w.dbls("twodm/B", d.the2DM->two_rdm_B, n4);
          std::vector<double> te; te.push_back(d.the2DM->trace()); te.push_back(d.the2DM->energy());
          w.dbls("twodm/trace_energy", te);
+         const long long n2 = (long long) L * L;   /* Correlations tables of the same state (Correlations.cpp), DMRG orbital order */
+         w.dbls("corrfun/Cspin", d.theCorr->Cspin, n2); w.dbls("corrfun/Cdens", d.theCorr->Cdens, n2);
+         w.dbls("corrfun/Cspinflip", d.theCorr->Cspinflip, n2); w.dbls("corrfun/Cdirad", d.theCorr->Cdirad, n2);
+         w.dbls("corrfun/MutInfo", d.theCorr->MutInfo, n2);
       }
       printf("B2REF dumped; last energy %.12f\n", energies.back());
       return 0;

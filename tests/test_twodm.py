@@ -145,3 +145,21 @@ def test_full_2rdm_vs_reference(golden):
     energy = float(golden["problem/econst"][0]) + 0.5 * float(np.sum(A * mx))
     assert abs(energy - golden["twodm/trace_energy"][1]) < 1e-8
     assert abs(energy - golden["energies"][-1]) < 1e-6          # and it is the energy of the last sweep step
+
+
+@pytest.mark.gpu
+def test_correlations_vs_reference(golden):
+    """b2_dmrg_calc_correlations (after b2_dmrg_calc_2rdm) on the reference's final MPS against the Correlations object of the reference
+    for the same state (golden corrfun/*): spin, density, spin-flip and singlet-diradical correlation functions and the two-orbital
+    mutual information (Correlations.cpp:69-103, 212-560; G/Y/Z/K/M tensors of DMRGoperators3RDM.cpp:415-479)."""
+    ctx = api.context_from_fixture(golden, "corr", device=0)
+    L = ctx.L
+    d = api.DMRG(ctx)
+    for s in range(L):
+        d.set_mps(s, golden[f"corr/mps/{s}"])
+    A, B = d.calc_2rdm()
+    tables = d.calc_correlations(A, B)
+    for key in ("Cspin", "Cdens", "Cspinflip", "Cdirad", "MutInfo"):
+        ref = golden["corrfun/" + key].reshape((L, L), order="F")
+        assert np.abs(tables[key] - ref).max() < 1e-8, key
+    assert np.abs(tables["MutInfo"]).max() > 1e-6

@@ -294,6 +294,10 @@ class DMRG:
         self._allreduce = allreduce
         check(lib.b2_dmrg_set_world(self.h, int(world), int(rank), allreduce.cfn if allreduce else None, None))
 
+    def new_excitation(self, eshift, D, seed):
+        """DMRG::newExcitation: store the current MPS as a lower state (level shift eshift), restart from a random MPS at dimension D"""
+        check(lib.b2_dmrg_new_excitation(self.h, float(eshift), int(D), int(seed)))
+
     def calc_2rdm(self):
         """-> (A, B) as [L,L,L,L] arrays indexed [i,j,k,l] (TwoDM::getTwoDMA_DMRG / getTwoDMB_DMRG); see b2_dmrg_calc_2rdm"""
         L = self.ctx.L

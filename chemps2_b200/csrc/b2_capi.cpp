@@ -944,9 +944,30 @@ static int run_compiled_once(b2_ctx* ctx, const CompiledWork& w, DevBases b) {
    return rc;
 }
 
+// overlap tensor <current MPS | stored lower state> on one boundary (CheMPS2::TensorO, TensorO.cpp): one block dim_current x dim_stored per
+// symmetry sector that is populated in both bookkeepers
+struct Overlap {
+   struct Blk { int n, ts, ir, rows, cols; int64_t off; };
+   std::vector<Blk> blk;
+   std::vector<double> data;
+   bool valid = false;
+   const Blk* find(int n, int ts, int ir) const {
+      for (const Blk& b : blk) if (b.n == n && b.ts == ts && b.ir == ir) return &b;
+      return nullptr;
+   }
+};
+// a converged lower state kept for the level-shift projector (DMRG::newExcitation, DMRG.cpp:475-505): Exc_MPSs, Exc_BKs, Exc_Eshifts, Exc_Overlaps
+struct ExcState {
+   double eshift = 0.0;
+   Bookkeeper bk;
+   std::vector<std::vector<double>> mps;
+   std::vector<Overlap> left, right;   // per boundary: built moving right (covers sites < b) / moving left (sites >= b)
+};
+
 struct b2_dmrg {
    b2_ctx* ctx = nullptr;
    int L = 0;
+   std::vector<ExcState> exc;              // lower states (excited-state calculations)
    std::vector<std::vector<double>> mps;   // TensorT storage per site in the layouts of the current bookkeeper
    std::vector<b2_opset*> left, right;     // operator sets per boundary: moving right (sites < b) / moving left (sites >= b)
    double max_disc_last_sweep = 0.0;       // DMRG::MaxDiscWeightLastSweep (DMRG.cpp:360-362): scales the noise of the next half sweep
@@ -1051,6 +1072,180 @@ int b2_dmrg_timers(b2_dmrg* d, double* out5, int reset) {
 }
 
 // DMRG::updateMovingRight(index) / updateMovingLeft(index-1): operators of the boundary next to site `index` from T = MPS[index]
+// TensorO::update_ownmem / create (TensorO.cpp:38-196, formulas of TensorOperator::update with two_j = 0, no Jordan-Wigner phase) for every
+// stored state: the overlap tensor of the boundary next to site `index` from MPS[index] of both states.
+static int dmrg_update_overlaps(b2_dmrg* d, int index, bool mr) {
+   if (d->exc.empty()) return B2_OK;
+   b2_ctx* ctx = d->ctx;
+   const Bookkeeper& bk = ctx->bk;
+   const int L = d->L, b_old = mr ? index : index + 1, b_new = mr ? index + 1 : index;
+   cudaStream_t s = ctx->stream;
+   for (ExcState& e : d->exc) {
+      if ((int)e.left.size() != L + 1) { e.left.assign(L + 1, Overlap()); e.right.assign(L + 1, Overlap()); }
+      const Overlap& oldo = mr ? e.left[b_old] : e.right[b_old];
+      const bool edge = mr ? (index == 0) : (index == L - 1);
+      if (!edge && !oldo.valid) return fail(B2_ERR_STATE, "overlap tensor of boundary %d is missing", b_old);
+      Overlap fresh;
+      int64_t off = 0;
+      bk.for_sectors(b_new, [&](int n, int ts, int ir) {
+         const int r = bk.dim(b_new, n, ts, ir), c = e.bk.dim(b_new, n, ts, ir);
+         if (r > 0 && c > 0) { fresh.blk.push_back({n, ts, ir, r, c, off}); off += ((int64_t)r * c + 15) / 16 * 16; }
+      });
+      fresh.data.assign((size_t)std::max<int64_t>(off, 1), 0.0);
+      TLayout Tc, Te;
+      Tc.build(bk, index); Te.build(e.bk, index);
+      std::vector<Term3> terms;
+      std::vector<DstBlock> dst;
+      for (size_t k = 0; k < fresh.blk.size(); k++) {
+         const Overlap::Blk& nb = fresh.blk[k];
+         dst.push_back(DstBlock{nb.off, nb.rows, nb.cols});
+         for (int geval = 0; geval < 4; geval++) {   // site empty / doubly occupied / singly occupied with spin down or up coupling
+            int on, ots, oir;
+            const int sg = mr ? -1 : +1;
+            if (geval == 0) { on = nb.n; ots = nb.ts; oir = nb.ir; }
+            else if (geval == 1) { on = nb.n + 2 * sg; ots = nb.ts; oir = nb.ir; }
+            else { on = nb.n + sg; ots = nb.ts + (geval == 2 ? -1 : 1); oir = xorp(nb.ir, bk.orb_irrep[index]); }
+            if (ots < 0) continue;
+            const int kc = mr ? Tc.kappa(bk, on, ots, oir, nb.n, nb.ts, nb.ir) : Tc.kappa(bk, nb.n, nb.ts, nb.ir, on, ots, oir);
+            const int ke = mr ? Te.kappa(e.bk, on, ots, oir, nb.n, nb.ts, nb.ir) : Te.kappa(e.bk, nb.n, nb.ts, nb.ir, on, ots, oir);
+            if (kc < 0 || ke < 0) continue;
+            Term3 t;
+            t.dst = (int)k;
+            t.f = (!mr && geval >= 2) ? (ots + 1.0) / (nb.ts + 1.0) : 1.0;                       // TensorOperator.cpp:370-372 with two_j = 0
+            t.p.space = SP_LEFT; t.p.off = Tc.blk[kc].off; t.p.rows = Tc.blk[kc].rows; t.p.cols = Tc.blk[kc].cols; t.p.trans = mr ? 1 : 0;
+            t.r.space = SP_RIGHT; t.r.off = Te.blk[ke].off; t.r.rows = Te.blk[ke].rows; t.r.cols = Te.blk[ke].cols; t.r.trans = mr ? 0 : 1;
+            if (edge) {   // TensorO::create: the outer boundary carries the 1 x 1 identity
+               if (bk.dim(b_old, on, ots, oir) != e.bk.dim(b_old, on, ots, oir)) continue;
+            } else {
+               const Overlap::Blk* ob = oldo.find(on, ots, oir);
+               if (!ob) continue;
+               t.q.space = SP_VIN; t.q.off = ob->off; t.q.rows = ob->rows; t.q.cols = ob->cols;
+            }
+            terms.push_back(t);
+         }
+      }
+      struct Buf { double* p = nullptr; ~Buf() { cudaFree(p); } } dTc, dTe, dOld, dNew;
+      CUDA_TRY(cudaMalloc(&dTc.p, sizeof(double) * (size_t)std::max<int64_t>(Tc.size, 1)));
+      CUDA_TRY(cudaMalloc(&dTe.p, sizeof(double) * (size_t)std::max<int64_t>(Te.size, 1)));
+      CUDA_TRY(cudaMalloc(&dOld.p, sizeof(double) * std::max<size_t>(oldo.data.size(), 1)));
+      CUDA_TRY(cudaMalloc(&dNew.p, sizeof(double) * fresh.data.size()));
+      CUDA_TRY(cudaMemcpyAsync(dTc.p, d->mps[index].data(), sizeof(double) * (size_t)Tc.size, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemcpyAsync(dTe.p, e.mps[index].data(), sizeof(double) * (size_t)Te.size, cudaMemcpyHostToDevice, s));
+      if (!oldo.data.empty()) CUDA_TRY(cudaMemcpyAsync(dOld.p, oldo.data.data(), sizeof(double) * oldo.data.size(), cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemsetAsync(dNew.p, 0, sizeof(double) * fresh.data.size(), s));
+      CompiledWork w;
+      compile_terms(w, terms, dst, SP_VOUT, budgeted(ctx));
+      DevBases b;
+      for (int i = 0; i < SP_COUNT; i++) b.p[i] = nullptr;
+      b.p[SP_LEFT] = dTc.p; b.p[SP_RIGHT] = dTe.p; b.p[SP_VIN] = dOld.p; b.p[SP_VOUT] = dNew.p;
+      int rc = run_compiled_once(ctx, w, b);
+      if (rc) return rc;
+      CUDA_TRY(cudaMemcpyAsync(fresh.data.data(), dNew.p, sizeof(double) * fresh.data.size(), cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(cudaStreamSynchronize(s));
+      fresh.valid = true;
+      (mr ? e.left[b_new] : e.right[b_new]) = std::move(fresh);
+   }
+   return B2_OK;
+}
+
+// DMRG::calcVeffTilde (DMRGtechnics.cpp:540-620) for every stored state, straight into the device slab of the sigma plan:
+//   Vtilde[kappa] = sqrt(Eshift) / (2S+1) * sqrt(2SR+1) * O_left[l] * Sup[kappa] * O_right[r]^T ,   Sup = Join of the stored state's two tensors
+static int dmrg_attach_excitations(b2_dmrg* d, b2_heff* h, int index) {
+   if (d->exc.empty()) return B2_OK;
+   b2_ctx* ctx = d->ctx;
+   const int L = d->L, nexc = (int)d->exc.size();
+   cudaStream_t s = ctx->stream;
+   const SLayout& S = h->plan.S;
+   const size_t n = (size_t)S.size;
+   cudaFree(h->d_exc); cudaFree(h->d_exc_coef); cudaFree(h->d_exc_scratch);
+   h->d_exc = h->d_exc_coef = h->d_exc_scratch = nullptr; h->n_exc = 0;
+   CUDA_TRY(cudaMalloc(&h->d_exc, sizeof(double) * std::max<size_t>(n, 1) * nexc));
+   CUDA_TRY(cudaMalloc(&h->d_exc_coef, sizeof(double) * nexc));
+   CUDA_TRY(cudaMalloc(&h->d_exc_scratch, sizeof(double) * kRedScratch));
+   CUDA_TRY(cudaMemsetAsync(h->d_exc_scratch, 0, sizeof(double) * kRedScratch, s));
+   CUDA_TRY(cudaMemsetAsync(h->d_exc, 0, sizeof(double) * std::max<size_t>(n, 1) * nexc, s));
+   for (int st = 0; st < nexc; st++) {
+      ExcState& e = d->exc[st];
+      const Overlap* ol = index > 0 ? &e.left[index] : nullptr;
+      const Overlap* orr = index < L - 2 ? &e.right[index + 2] : nullptr;
+      if ((ol && !ol->valid) || (orr && !orr->valid)) return fail(B2_ERR_STATE, "overlap tensors for site %d are missing", index);
+      SLayout Se;
+      Se.build(e.bk, index);
+      TLayout TLe, TRe;
+      TLe.build(e.bk, index); TRe.build(e.bk, index + 1);
+      struct Buf { double* p = nullptr; ~Buf() { cudaFree(p); } } dTl, dTr, dSup, dOl, dOr;
+      CUDA_TRY(cudaMalloc(&dTl.p, sizeof(double) * (size_t)std::max<int64_t>(TLe.size, 1)));
+      CUDA_TRY(cudaMalloc(&dTr.p, sizeof(double) * (size_t)std::max<int64_t>(TRe.size, 1)));
+      CUDA_TRY(cudaMalloc(&dSup.p, sizeof(double) * (size_t)std::max<int64_t>(Se.size, 1)));
+      CUDA_TRY(cudaMemcpyAsync(dTl.p, e.mps[index].data(), sizeof(double) * (size_t)TLe.size, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemcpyAsync(dTr.p, e.mps[index + 1].data(), sizeof(double) * (size_t)TRe.size, cudaMemcpyHostToDevice, s));
+      CUDA_TRY(cudaMemsetAsync(dSup.p, 0, sizeof(double) * (size_t)std::max<int64_t>(Se.size, 1), s));
+      {  // Sup = Join of the stored state (Sobject::Join with its own bookkeeper)
+         std::vector<Term3> jt; std::vector<DstBlock> jd;
+         join_terms(jt, jd, e.bk, Se, TLe, TRe);
+         CompiledWork jw;
+         compile_terms(jw, jt, jd, SP_VOUT, budgeted(ctx));
+         DevBases b;
+         for (int i = 0; i < SP_COUNT; i++) b.p[i] = nullptr;
+         b.p[SP_LEFT] = dTl.p; b.p[SP_RIGHT] = dTr.p; b.p[SP_VOUT] = dSup.p;
+         int rc = run_compiled_once(ctx, jw, b);
+         if (rc) return rc;
+      }
+      if (ol) { CUDA_TRY(cudaMalloc(&dOl.p, sizeof(double) * ol->data.size())); CUDA_TRY(cudaMemcpyAsync(dOl.p, ol->data.data(), sizeof(double) * ol->data.size(), cudaMemcpyHostToDevice, s)); }
+      if (orr) { CUDA_TRY(cudaMalloc(&dOr.p, sizeof(double) * orr->data.size())); CUDA_TRY(cudaMemcpyAsync(dOr.p, orr->data.data(), sizeof(double) * orr->data.size(), cudaMemcpyHostToDevice, s)); }
+      std::vector<Term3> terms;
+      std::vector<DstBlock> dst(S.nkappa());
+      const double pref = std::sqrt(e.eshift) / (ctx->prob.twoS + 1.0);
+      for (int k = 0; k < S.nkappa(); k++) {
+         dst[k] = DstBlock{S.blk[k].off, S.blk[k].rows, S.blk[k].cols};
+         const int ke = Se.kappa(e.bk, S.NL[k], S.twoSL[k], S.IL[k], S.N1[k], S.N2[k], S.twoJ[k], S.NR[k], S.twoSR[k], S.IR[k]);
+         if (ke < 0) continue;
+         Term3 t;
+         t.dst = k; t.f = pref * std::sqrt(S.twoSR[k] + 1.0);
+         t.q.space = SP_VIN; t.q.off = Se.blk[ke].off; t.q.rows = Se.blk[ke].rows; t.q.cols = Se.blk[ke].cols;
+         if (ol) {
+            const Overlap::Blk* ob = ol->find(S.NL[k], S.twoSL[k], S.IL[k]);
+            if (!ob) continue;
+            t.p.space = SP_LEFT; t.p.off = ob->off; t.p.rows = ob->rows; t.p.cols = ob->cols;
+         } else if (S.blk[k].rows != Se.blk[ke].rows) continue;
+         if (orr) {
+            const Overlap::Blk* ob = orr->find(S.NR[k], S.twoSR[k], S.IR[k]);
+            if (!ob) continue;
+            t.r.space = SP_RIGHT; t.r.off = ob->off; t.r.rows = ob->rows; t.r.cols = ob->cols; t.r.trans = 1;
+         } else if (S.blk[k].cols != Se.blk[ke].cols) continue;
+         terms.push_back(t);
+      }
+      CompiledWork w;
+      compile_terms(w, terms, dst, SP_VOUT, budgeted(ctx));
+      DevBases b;
+      for (int i = 0; i < SP_COUNT; i++) b.p[i] = nullptr;
+      b.p[SP_LEFT] = dOl.p; b.p[SP_RIGHT] = dOr.p; b.p[SP_VIN] = dSup.p; b.p[SP_VOUT] = h->d_exc + (size_t)st * n;
+      int rc = run_compiled_once(ctx, w, b);
+      if (rc) return rc;
+   }
+   h->n_exc = nexc;
+   return B2_OK;
+}
+
+// DMRG::activateExcitations + newExcitation (DMRG.cpp:464-505): the current MPS becomes lower state number nStates-1 with level shift
+// `eshift`; a fresh random MPS (bookkeeper re-initialised for virtual dimension D) takes its place and every operator set is dropped.
+int b2_dmrg_new_excitation(b2_dmrg* d, double eshift, int D, uint64_t seed) {
+   if (!d || D < 1) return fail(B2_ERR_ARG, "b2_dmrg_new_excitation: bad arguments");
+   ExcState e;
+   e.eshift = eshift; e.bk = d->ctx->bk; e.mps = d->mps;
+   e.left.assign(d->L + 1, Overlap()); e.right.assign(d->L + 1, Overlap());
+   d->exc.push_back(std::move(e));
+   for (int b = 0; b <= d->L; b++) {
+      if (d->left[b]) { b2_opset_destroy(d->left[b]); d->left[b] = nullptr; }
+      if (d->right[b]) { b2_opset_destroy(d->right[b]); d->right[b] = nullptr; }
+   }
+   for (ExcState& x : d->exc) { x.left.assign(d->L + 1, Overlap()); x.right.assign(d->L + 1, Overlap()); }
+   d->ctx->bk.init(d->ctx->prob, D);
+   d->max_disc_last_sweep = 0.0;
+   return b2_dmrg_random_mps(d, seed);
+}
+int b2_dmrg_num_lower_states(const b2_dmrg* d) { return d ? (int)d->exc.size() : 0; }
+
 static int dmrg_update_mode(b2_dmrg* d, int index, int moving_right, int mode);
 int b2_dmrg_update(b2_dmrg* d, int index, int moving_right) { return dmrg_update_mode(d, index, moving_right, 0); }
 // mode 0: the full operator complement of a sweep; 1: L, S0, S1, F0, F1 (updateMovingLeftSafe2DM); 2: L only
@@ -1088,7 +1283,8 @@ static int dmrg_update_mode(b2_dmrg* d, int index, int moving_right, int mode) {
    d->t_update += wall_seconds() - t1;
    b2_update_destroy(u);
    if (rc) { b2_opset_destroy(fresh); return rc; }
-   return b2_dmrg_set_opset(d, b_new, mr, fresh);
+   if ((rc = b2_dmrg_set_opset(d, b_new, mr, fresh))) return rc;
+   return dmrg_update_overlaps(d, index, mr);   // DMRGoperators.cpp:556-567 / :889-900
 }
 
 // DMRG::solve_site (DMRG.cpp:419-452): Join -> Heff::SolveDAVIDSON -> (noise) -> Split.  *energy includes Econst.
@@ -1114,6 +1310,7 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
    }
    if (rc) return rc;
    if (d->world > 1) b2_heff_set_allreduce(h, d->allreduce, d->allreduce_user);
+   if ((rc = dmrg_attach_excitations(d, h, index))) { b2_heff_destroy(h); return rc; }   // DMRG::prepare_excitations (DMRG.cpp:434)
    d->t_plan += wall_seconds() - tp0;
    const SLayout& S = h->plan.S;
    TLayout TL, TR;

@@ -238,6 +238,13 @@ int b2_dmrg_get_mps(const b2_dmrg* d, int site, double* t_storage);
 int b2_dmrg_random_mps(b2_dmrg* d, uint64_t seed);           /* random + left-normalised, DMRG.cpp:149-169 (own RNG stream) */
 b2_opset* b2_dmrg_opset(b2_dmrg* d, int boundary, int moving_right);
 int b2_dmrg_set_opset(b2_dmrg* d, int boundary, int moving_right, b2_opset* set);   /* the driver takes ownership */
+/* Excited states (DMRG::activateExcitations / newExcitation, DMRG.cpp:464-505): the current MPS is stored as a lower state with level shift
+ * `eshift`; a fresh random MPS (bookkeeper re-initialised like b2_bk_init(D)) takes its place and all operator sets are dropped — run
+ * the PreSolve updates again, then sweep: every b2_dmrg_update also renews the overlap tensors with the stored states (TensorO,
+ * DMRGoperators.cpp:556-567, 889-900) and every b2_dmrg_solve_site adds the projector sum_s Eshift_s |s><s| through calcVeffTilde
+ * (DMRGtechnics.cpp:540-620) + Heff::addDiagramExcitations. */
+int b2_dmrg_new_excitation(b2_dmrg* d, double eshift, int D, uint64_t seed);
+int b2_dmrg_num_lower_states(const b2_dmrg* d);
 /* 2-RDM of the current MPS: the TwoDM part of DMRG::calc_rdms_and_correlations (DMRGtechnics.cpp:40-113) — MPS into left-canonical form
  * (device-SVD gauge moves), operators of every boundary, then from the right site by site b2_twodm_fill_site, right-normalise, next
  * moving-left operators; finally TwoDM::correct_higher_multiplicities.  two_rdm_A / two_rdm_B: L^4 doubles each, DMRG orbital order,

@@ -153,3 +153,41 @@ def test_sweep_survives_out_of_memory_by_spilling(golden):
     ref = run(None)
     assert np.array_equal(run(("left", 0)), ref)
     assert np.array_equal(run(("right", 1)), ref)
+
+
+def test_excited_states_n2_sto3g_known_answers():
+    """The reference's own test5 (tests/test5.cpp.in:55-85): ground state and the first two excited 1Ag states of N2/STO-3G with a level
+    shift of 20 Eh on the converged lower states (DMRG::activateExcitations / newExcitation -> TensorO overlaps, calcVeffTilde,
+    Heff::addDiagramExcitations).  Known answers pinned there to 1e-8: -107.648250974014, -106.944757308768, -106.92314213886."""
+    import os
+    fx = fixtures.load(os.path.join(os.path.dirname(__file__), "golden", "n2_sto3g_singlet.npz"))
+    L, group, N, twoS, irrep = [int(x) for x in fx["problem/hdr"]]
+    ctx = api.Context(0)
+    ctx.set_problem(L, group, N, twoS, irrep, fx["problem/orb_irrep"], mx=fx["problem/mx"], econst=float(fx["problem/econst"][0]))
+    D = 1000
+    ctx.bk_init(D)
+    d = api.DMRG(ctx)
+    d.random_mps(4321)
+
+    def solve():
+        for i in range(L - 2):
+            d.update(i, True)                                   # DMRG::PreSolve
+        e_prev, change, e = 0.0, False, 0.0
+        for it in range(30):
+            el, _ = d.sweep(False, 1e-10, 0.0, D, change)
+            change = True
+            er, _ = d.sweep(True, 1e-10, 0.0, D, change)
+            e = min(el, er)
+            if it >= 2 and abs(e - e_prev) < 1e-11:
+                break
+            e_prev = e
+        return e
+
+    e0 = solve()
+    assert abs(e0 - (-107.648250974014)) < 1e-8, e0
+    d.new_excitation(20.0, D, 777)
+    e1 = solve()
+    assert abs(e1 - (-106.944757308768)) < 1e-8, e1
+    d.new_excitation(20.0, D, 778)
+    e2 = solve()
+    assert abs(e2 - (-106.92314213886)) < 1e-8, e2

@@ -161,6 +161,34 @@ def sweep_metric(device, with_reference):
     return out
 
 
+def update_metric(torch, ctx, w, old_set, stream, steps=3):
+    """Second half of the north-star hot path: the renormalized-operator update DMRG::updateMovingRight (DMRGoperators.cpp:243-574) at the
+    bench shape — every operator of boundary site+1 (L, S0/S1, F0/F1, A/B/C/D, Q, X) from the hash-filled operators of boundary `site` and a
+    synthetic site tensor, through b2_update_run_device; CUDA events on the context stream.  FLOPs = 2mnk per reference dgemm_ of
+    TensorOperator::update & co (SURVEY 8(d) F_upd), computed analytically by the plan."""
+    from chemps2_b200 import api
+    from chemps2_b200._lib import lib
+    new_set = api.OpSet(ctx, w.site + 1, True)
+    t0 = time.time()
+    upd = api.Update(ctx, w.site, True, old_set, new_set)
+    plan_s = time.time() - t0
+    st = upd.stats()
+    nt = lib.b2_tensor_t_size(ctx.h, w.site)
+    t_dev = torch.from_numpy(api.hash_fill(nt, 55) * 0.1).cuda()
+    upd.run_device(t_dev.data_ptr())              # warm-up
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        upd.run_device(t_dev.data_ptr())
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {"what": "DMRG::updateMovingRight at the bench shape (all operators of boundary site+1)", "ms_per_update": ms,
+            "gflop_per_update": st["flops_ref"] / 1e9, "tflops_fp64": st["flops_ref"] / (ms * 1e-3) / 1e12, "terms": st["terms"] + st["mix_terms"],
+            "launches": st["launches"], "plan_build_s": plan_s}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -333,6 +361,13 @@ def main():
         except Exception as e:   # the baseline must not take the bench line down
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
     if world == 1 and not args.no_sweep:
+        try:
+            del heff                                     # frees the sigma plan (workspace + work lists) before the update plan is built
+            um = update_metric(torch, ctx, w, left, stream)
+            um["frac_of_fp64_peak"] = um["tflops_fp64"] / peak.value
+            line["operator_update"] = um
+        except Exception as e:
+            line["operator_update"] = {"failed": str(e)}
         try:
             line["sweep"] = sweep_metric(local, args.sweep_ref)
         except Exception as e:   # the secondary metric must not take the bench line down

@@ -263,6 +263,10 @@ class Update:
         t = np.ascontiguousarray(t_storage, dtype=np.float64)
         check(lib.b2_update_run(self.h, _dp(t)))
 
+    def run_device(self, t_dev_ptr):
+        """T already resident on the device (asynchronous on the context stream)"""
+        check(lib.b2_update_run_device(self.h, vp(t_dev_ptr)))
+
     def stats(self):
         o = np.zeros(8)
         check(lib.b2_update_stats(self.h, _dp(o)))
@@ -293,6 +297,17 @@ class DMRG:
         """shard the sweep over `world` GPUs; allreduce: an AllReduce object (kept alive by this driver)"""
         self._allreduce = allreduce
         check(lib.b2_dmrg_set_world(self.h, int(world), int(rank), allreduce.cfn if allreduce else None, None))
+
+    def solve(self, scheme):
+        """DMRG::Solve; scheme = [(D, energy_conv, max_sweeps, noise_prefactor, davidson_rtol), ...] like ConvergenceScheme::set_instruction"""
+        Ds = np.array([x[0] for x in scheme], dtype=np.int32)
+        ec = np.array([x[1] for x in scheme], dtype=np.float64)
+        ms = np.array([x[2] for x in scheme], dtype=np.int32)
+        nz = np.array([x[3] for x in scheme], dtype=np.float64)
+        rt = np.array([x[4] for x in scheme], dtype=np.float64)
+        e = C.c_double()
+        check(lib.b2_dmrg_solve(self.h, len(scheme), Ds.ctypes.data_as(c_ip), _dp(ec), ms.ctypes.data_as(c_ip), _dp(nz), _dp(rt), C.byref(e)))
+        return e.value
 
     def new_excitation(self, eshift, D, seed):
         """DMRG::newExcitation: store the current MPS as a lower state (level shift eshift), restart from a random MPS at dimension D"""

@@ -970,6 +970,7 @@ struct b2_dmrg {
    std::vector<ExcState> exc;              // lower states (excited-state calculations)
    std::vector<std::vector<double>> mps;   // TensorT storage per site in the layouts of the current bookkeeper
    std::vector<b2_opset*> left, right;     // operator sets per boundary: moving right (sites < b) / moving left (sites >= b)
+   bool swept_once = false;                // false until the first left sweep (which runs with fixed virtual dimensions, DMRG.cpp:270)
    double max_disc_last_sweep = 0.0;       // DMRG::MaxDiscWeightLastSweep (DMRG.cpp:360-362): scales the noise of the next half sweep
    bool spill = false;                     // keep only the operator sets of the site being optimised in HBM (b2_dmrg_set_spill)
    int world = 1, rank = 0;                // GPUs sharing the sweep: sigma terms and operator updates are sharded, the rest is replicated
@@ -1242,6 +1243,7 @@ int b2_dmrg_new_excitation(b2_dmrg* d, double eshift, int D, uint64_t seed) {
    for (ExcState& x : d->exc) { x.left.assign(d->L + 1, Overlap()); x.right.assign(d->L + 1, Overlap()); }
    d->ctx->bk.init(d->ctx->prob, D);
    d->max_disc_last_sweep = 0.0;
+   d->swept_once = false;
    return b2_dmrg_random_mps(d, seed);
 }
 int b2_dmrg_num_lower_states(const b2_dmrg* d) { return d ? (int)d->exc.size() : 0; }
@@ -1358,6 +1360,43 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
       b2_dmrg_set_opset(d, index + 1, 0, nullptr);
    }
    return rc;
+}
+
+// DMRG::PreSolve (DMRG.cpp:257-266): the moving-right operators of every boundary from the current MPS
+int b2_dmrg_presolve(b2_dmrg* d) {
+   if (!d) return fail(B2_ERR_ARG, "b2_dmrg_presolve: NULL");
+   for (int i = 0; i < d->L - 2; i++) { int rc = b2_dmrg_update(d, i, 1); if (rc) return rc; }
+   return B2_OK;
+}
+
+// DMRG::Solve (DMRG.cpp:268-355) for a ConvergenceScheme given as arrays: per instruction the virtual dimension, the energy convergence
+// threshold, the maximum number of (left + right) sweeps, the noise prefactor and the Davidson residual tolerance.  The very first left
+// sweep of a fresh MPS keeps the virtual dimensions fixed (`change` = false), exactly like the reference; returns the lowest energy met.
+int b2_dmrg_solve(b2_dmrg* d, int n_instructions, const int* D, const double* energy_conv, const int* max_sweeps, const double* noise_prefactor,
+                  const double* davidson_rtol, double* energy_out) {
+   if (!d || n_instructions < 1 || !D || !energy_conv || !max_sweeps || !noise_prefactor || !davidson_rtol || !energy_out)
+      return fail(B2_ERR_ARG, "b2_dmrg_solve: bad arguments");
+   bool have_ops = true;
+   for (int b = 1; b <= d->L - 2 && have_ops; b++) have_ops = d->left[b] != nullptr && !d->left[b]->set.reduced;
+   int rc;
+   if (!have_ops && (rc = b2_dmrg_presolve(d))) return rc;
+   double energy = 0.0, lowest = 1e300;
+   for (int ins = 0; ins < n_instructions; ins++) {
+      int it = 0;
+      double prev = energy + 10 * energy_conv[ins];   // at least one left-right sweep per instruction (DMRG.cpp:283)
+      while (std::fabs(energy - prev) > energy_conv[ins] && it < max_sweeps[ins]) {
+         prev = energy;
+         double el, er, dw;
+         if ((rc = b2_dmrg_sweep(d, 0, davidson_rtol[ins], noise_prefactor[ins], D[ins], d->swept_once ? 1 : 0, &el, &dw))) return rc;
+         d->swept_once = true;
+         if ((rc = b2_dmrg_sweep(d, 1, davidson_rtol[ins], noise_prefactor[ins], D[ins], 1, &er, &dw))) return rc;
+         energy = std::min(el, er);
+         lowest = std::min(lowest, energy);
+         it++;
+      }
+   }
+   *energy_out = lowest;
+   return B2_OK;
 }
 
 // Move the orthogonality centre of the MPS by one site (TensorT::QR + LeftMultiply = DMRG::left_normalize, TensorT::LQ +

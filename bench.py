@@ -228,6 +228,7 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: the bench prints exactly one JSON line there
     import torch
     import torch.distributed as dist
 

@@ -1,0 +1,44 @@
+"""Host-side plan building on several threads (b2_sigma_plan.cpp fragments stitched in block order, b2_compile.cpp segments merged
+wave by wave) must give the same plan as the sequential build: identical term list (order included) and, for the compiled work
+lists, the same arithmetic (checked through the work-list emulator against the reference's sigma vector)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r"""
+import sys, os
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import cpu_check
+from chemps2_b200 import fixtures
+fx = fixtures.load(os.path.join({root!r}, "tests", "golden", "h2o_631g.npz"))
+out = []
+for tag in ("A", "B"):
+    ctx, left, right, heff = cpu_check.build_case(fx, tag, options={{"parallel_min_terms": 16}})
+    terms, nt, parts, npp, psize = heff.export()
+    st = heff.stats()
+    sig = cpu_check.emulate_worklists(ctx, left, right, heff, fx[tag + "/rnd_in"])
+    err = float(np.abs(sig - fx[tag + "/rnd_out"]).max() / max(1.0, np.abs(fx[tag + "/rnd_out"]).max()))
+    out.append((int(nt), st["flops_ref"], st["terms"], err))
+print("B2PLAN", out)
+"""
+
+
+def _run(threads):
+    env = dict(os.environ, B2_PLAN_THREADS=str(threads))
+    res = subprocess.run([sys.executable, "-c", WORKER.format(root=ROOT)], capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("B2PLAN")][-1]
+    return eval(line[len("B2PLAN"):])
+
+
+def test_parallel_plan_equals_sequential_plan():
+    seq, par = _run(1), _run(5)
+    for (n1, f1, t1, e1), (n2, f2, t2, e2) in zip(seq, par):
+        assert n1 == n2 and t1 == t2                      # same number of terms
+        assert abs(f1 - f2) <= 1e-9 * f1                  # same algorithmic FLOP count (summed per thread, so only rounding may differ)
+        assert e1 < 1e-12 and e2 < 1e-12                  # both reproduce Heff::makeHeff through the emulated work lists

@@ -118,6 +118,8 @@ SIGNATURES = [
     ("b2_update_create_sharded", C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.POINTER(vp)]),
     ("b2_update_set_allreduce", C.c_int, [vp, vp, vp]),
     ("b2_dmrg_presolve", C.c_int, [vp]),
+    ("b2_dmrg_save_mps", C.c_int, [vp, C.c_char_p, C.c_int]),
+    ("b2_dmrg_load_mps", C.c_int, [vp, C.c_char_p, c_ip]),
     ("b2_dmrg_solve", C.c_int, [vp, C.c_int, c_ip, c_dp, c_ip, c_dp, c_dp, c_dp]),
     ("b2_dmrg_new_excitation", C.c_int, [vp, C.c_double, C.c_int, C.c_uint64]),
     ("b2_dmrg_num_lower_states", C.c_int, [vp]),

@@ -298,6 +298,18 @@ class DMRG:
         self._allreduce = allreduce
         check(lib.b2_dmrg_set_world(self.h, int(world), int(rank), allreduce.cfn if allreduce else None, None))
 
+    def save_mps(self, path, converged=False):
+        check(lib.b2_dmrg_save_mps(self.h, str(path).encode(), int(bool(converged))))
+
+    def load_mps(self, path):
+        """-> converged flag stored in the checkpoint; operator sets are dropped (call presolve())"""
+        c = C.c_int()
+        check(lib.b2_dmrg_load_mps(self.h, str(path).encode(), C.byref(c)))
+        return bool(c.value)
+
+    def presolve(self):
+        check(lib.b2_dmrg_presolve(self.h))
+
     def solve(self, scheme):
         """DMRG::Solve; scheme = [(D, energy_conv, max_sweeps, noise_prefactor, davidson_rtol), ...] like ConvergenceScheme::set_instruction"""
         Ds = np.array([x[0] for x in scheme], dtype=np.int32)

@@ -1362,6 +1362,58 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
    return rc;
 }
 
+// MPS checkpoint: the content of DMRG::saveMPS / loadDIM / loadMPS (DMRGmpsio.cpp:30-131: converged flag, every virtual dimension in
+// the bookkeeper's enumeration order, the packed TensorT storage of every site) as one flat little-endian binary file — this image has
+// no HDF5 library, so the reference's HDF5 container is not reproduced, only its payload (a shim can copy dataset by dataset).
+int b2_dmrg_save_mps(const b2_dmrg* d, const char* path, int converged) {
+   if (!d || !path) return fail(B2_ERR_ARG, "b2_dmrg_save_mps: NULL");
+   FILE* f = std::fopen(path, "wb");
+   if (!f) return fail(B2_ERR_ARG, "b2_dmrg_save_mps: cannot open %s", path);
+   const Bookkeeper& bk = d->ctx->bk;
+   const char magic[8] = {'B', '2', 'M', 'P', 'S', '0', '0', '1'};
+   const int32_t hdr[6] = {bk.L, bk.N, bk.twoS, bk.irrep, bk.nirr, converged ? 1 : 0};
+   bool ok = std::fwrite(magic, 1, 8, f) == 8 && std::fwrite(hdr, 4, 6, f) == 6;
+   for (int b = 0; b <= bk.L && ok; b++)
+      bk.for_sectors(b, [&](int n, int ts, int ir) { const int32_t v = bk.dim(b, n, ts, ir); ok = ok && std::fwrite(&v, 4, 1, f) == 1; });
+   for (int sdx = 0; sdx < d->L && ok; sdx++) {
+      const int64_t n = (int64_t)d->mps[sdx].size();
+      ok = std::fwrite(&n, 8, 1, f) == 1 && (n == 0 || std::fwrite(d->mps[sdx].data(), 8, (size_t)n, f) == (size_t)n);
+   }
+   std::fclose(f);
+   return ok ? B2_OK : fail(B2_ERR_STATE, "b2_dmrg_save_mps: write to %s failed", path);
+}
+int b2_dmrg_load_mps(b2_dmrg* d, const char* path, int* converged) {
+   if (!d || !path) return fail(B2_ERR_ARG, "b2_dmrg_load_mps: NULL");
+   FILE* f = std::fopen(path, "rb");
+   if (!f) return fail(B2_ERR_ARG, "b2_dmrg_load_mps: cannot open %s", path);
+   Bookkeeper& bk = d->ctx->bk;
+   char magic[8];
+   int32_t hdr[6];
+   bool ok = std::fread(magic, 1, 8, f) == 8 && std::memcmp(magic, "B2MPS001", 8) == 0 && std::fread(hdr, 4, 6, f) == 6;
+   if (ok && (hdr[0] != bk.L || hdr[1] != bk.N || hdr[2] != bk.twoS || hdr[3] != bk.irrep || hdr[4] != bk.nirr)) {
+      std::fclose(f);
+      return fail(B2_ERR_STATE, "b2_dmrg_load_mps: %s belongs to another problem (L, N, 2S, irrep, group differ)", path);
+   }
+   for (int b = 0; b <= bk.L && ok; b++)
+      bk.for_sectors(b, [&](int n, int ts, int ir) { int32_t v = 0; ok = ok && std::fread(&v, 4, 1, f) == 1; if (ok) bk.set_dim(b, n, ts, ir, v); });
+   for (int sdx = 0; sdx < d->L && ok; sdx++) {
+      TLayout lay;
+      lay.build(bk, sdx);
+      int64_t n = -1;
+      ok = std::fread(&n, 8, 1, f) == 1 && n == lay.size;
+      if (ok) { d->mps[sdx].resize((size_t)n); ok = n == 0 || std::fread(d->mps[sdx].data(), 8, (size_t)n, f) == (size_t)n; }
+   }
+   std::fclose(f);
+   if (!ok) return fail(B2_ERR_STATE, "b2_dmrg_load_mps: %s is truncated or inconsistent with the bookkeeper", path);
+   if (converged) *converged = hdr[5];
+   for (int b = 0; b <= d->L; b++) {   // the operators of the previous MPS are stale
+      if (d->left[b]) { b2_opset_destroy(d->left[b]); d->left[b] = nullptr; }
+      if (d->right[b]) { b2_opset_destroy(d->right[b]); d->right[b] = nullptr; }
+   }
+   for (ExcState& x : d->exc) { x.left.assign(d->L + 1, Overlap()); x.right.assign(d->L + 1, Overlap()); }
+   return B2_OK;
+}
+
 // DMRG::PreSolve (DMRG.cpp:257-266): the moving-right operators of every boundary from the current MPS
 int b2_dmrg_presolve(b2_dmrg* d) {
    if (!d) return fail(B2_ERR_ARG, "b2_dmrg_presolve: NULL");

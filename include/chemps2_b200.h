@@ -238,6 +238,11 @@ int b2_dmrg_get_mps(const b2_dmrg* d, int site, double* t_storage);
 int b2_dmrg_random_mps(b2_dmrg* d, uint64_t seed);           /* random + left-normalised, DMRG.cpp:149-169 (own RNG stream) */
 b2_opset* b2_dmrg_opset(b2_dmrg* d, int boundary, int moving_right);
 int b2_dmrg_set_opset(b2_dmrg* d, int boundary, int moving_right, b2_opset* set);   /* the driver takes ownership */
+/* MPS checkpoint (DMRG::saveMPS / loadDIM / loadMPS, DMRGmpsio.cpp:30-131): converged flag, all virtual dimensions, the TensorT storage of
+ * every site in one flat binary file (no HDF5 in this image: same payload, different container).  Loading re-dimensions the bookkeeper,
+ * replaces the MPS and drops every operator set (run b2_dmrg_presolve again). */
+int b2_dmrg_save_mps(const b2_dmrg* d, const char* path, int converged);
+int b2_dmrg_load_mps(b2_dmrg* d, const char* path, int* converged);
 /* b2_dmrg_presolve = DMRG::PreSolve (DMRG.cpp:257-266).  b2_dmrg_solve = DMRG::Solve (DMRG.cpp:268-355) with the ConvergenceScheme
  * (ConvergenceScheme.h) passed as arrays of length n_instructions; *energy = lowest energy encountered (Econst included). */
 int b2_dmrg_presolve(b2_dmrg* d);

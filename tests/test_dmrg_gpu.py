@@ -212,3 +212,28 @@ def test_solve_with_convergence_scheme_h2o():
     assert abs(e - e_rdm) < 1e-7                                  # Solve's energy is the energy of the final MPS
     assert abs(float(np.einsum("ijij->", A)) - N * (N - 1)) < 1e-8
     assert e < -76.12 and e < float(fx["energies"][-1]) + 1e-6    # at least as low as the reference's D=20 fixture run
+
+
+def test_mps_checkpoint_resume(golden, tmp_path):
+    """b2_dmrg_save_mps / _load_mps (payload of DMRG::saveMPS / loadDIM / loadMPS): a fresh driver that loads the checkpoint continues
+    the sweeps with bit-identical energies; a checkpoint of another problem is refused."""
+    ctx, d = _start_from_fixture(golden, "A")
+    L, D = ctx.L, _fixture_D(golden)
+    d.presolve()
+    d.sweep(False, 1e-8, 0.0, D, False)
+    d.sweep(True, 1e-8, 0.0, D, True)
+    path = tmp_path / "mps.b2"
+    d.save_mps(path, converged=True)
+    ref = list(d.sweep(False, 1e-8, 0.0, D, True)) + list(d.sweep(True, 1e-8, 0.0, D, True))
+    ctx2 = api.context_from_fixture(golden, "A", device=0)
+    d2 = api.DMRG(ctx2)
+    assert d2.load_mps(path) is True
+    d2.presolve()
+    got = list(d2.sweep(False, 1e-8, 0.0, D, True)) + list(d2.sweep(True, 1e-8, 0.0, D, True))
+    assert got == ref
+    other = api.Context(0)
+    other.set_problem(L, int(golden["problem/hdr"][1]), int(golden["problem/hdr"][2]) - 2, int(golden["problem/hdr"][3]), int(golden["problem/hdr"][4]),
+                      golden["problem/orb_irrep"], mx=golden["problem/mx"], econst=0.0)
+    other.bk_init(D)
+    with pytest.raises(Exception):
+        api.DMRG(other).load_mps(path)

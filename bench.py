@@ -195,7 +195,7 @@ def run_reference(args):
         return
     from chemps2_b200 import api, workloads
     if not os.path.exists(workloads.REF_DRIVER):
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_driver not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/ref_driver not built (needs /root/reference at build time)"})
         return
     w, ctx, dims = workload_and_dims(args, -1)
     left = api.OpSet(ctx, w.site, True)
@@ -215,7 +215,7 @@ def run_reference(args):
             "dtype": "f64", "data": "synthetic", "config": config_of(args, w, flops_full),
             "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": best["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def config_of(args, w, flops):
@@ -224,11 +224,23 @@ def config_of(args, w, flops):
             "gflop_per_sigma_build": flops / 1e9, "l2_policy": "inputs_exceed_l2 (operator arenas >> 126 MB)"}
 
 
+def emit(line):
+    """the ONE JSON line of the contract, on the process's real stdout (fd 1 is pointed at stderr while the bench runs, so that
+    banners of libraries — NCCL prints its version to stdout — cannot end up in front of it)"""
+    os.write(REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+REAL_STDOUT = 1
+
+
 def main():
+    global REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
-    os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep NCCL's version banner off stdout: the bench prints exactly one JSON line there
     import torch
     import torch.distributed as dist
 
@@ -373,7 +385,7 @@ def main():
             line["sweep"] = sweep_metric(local, args.sweep_ref)
         except Exception as e:   # the secondary metric must not take the bench line down
             line["sweep"] = {"failed": str(e)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

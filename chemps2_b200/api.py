@@ -307,6 +307,14 @@ class DMRG:
         check(lib.b2_dmrg_load_mps(self.h, str(path).encode(), C.byref(c)))
         return bool(c.value)
 
+    def set_plan_cache(self, enabled):
+        check(lib.b2_dmrg_set_plan_cache(self.h, int(bool(enabled))))
+
+    def plan_cache_stats(self):
+        hits, misses = C.c_longlong(), C.c_longlong()
+        check(lib.b2_dmrg_plan_cache_stats(self.h, C.byref(hits), C.byref(misses)))
+        return hits.value, misses.value
+
     def presolve(self):
         check(lib.b2_dmrg_presolve(self.h))
 

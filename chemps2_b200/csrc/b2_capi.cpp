@@ -90,6 +90,7 @@ struct b2_heff {
    double last_kernel_s = 0.0;
    long long launches = 0;
    int world = 1, rank = 0;
+   double list_bytes = 0.0;                      // size of the device work lists (decides whether the sweep driver keeps the plan)
    // excited states (Heff::addDiagramExcitations): n_exc level-shifted lower states, one vector of veclength doubles each
    int n_exc = 0;
    double *d_exc = nullptr, *d_exc_coef = nullptr, *d_exc_scratch = nullptr;
@@ -415,6 +416,7 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
    // plans whose sigma build is a few milliseconds are dominated by the time to BUILD them: compile those on all host cores
    copt.threads = (h->plan.flops_ref < ctx->parallel_plan_flops) ? plan_threads(h->plan.S.nkappa()) : 1;
    compile_sigma(h->comp, h->plan, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, rank, world, copt);
+   h->list_bytes = h->comp.bytes();
    if (getenv("B2_TIMING")) fprintf(stderr, "b2_heff_create: enumerate %.3f s, schedule %.3f s, %zu terms\n", tb1 - tb0, wall_seconds() - tb1, h->plan.terms.size());
    if (ctx->device >= 0) {
       CUDA_TRY(cudaSetDevice(ctx->device));
@@ -462,6 +464,39 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
 }
 
 void b2_heff_destroy(b2_heff* h) { delete h; }
+
+// a plan parked in the sweep driver's cache keeps only its device work lists: workspaces, vectors and host copies of the lists go
+static void heff_park(b2_heff* h) {
+   cudaFree(h->d_work); cudaFree(h->d_part); cudaFree(h->d_vin); cudaFree(h->d_vout); cudaFree(h->d_presum);
+   cudaFree(h->d_exc); cudaFree(h->d_exc_coef); cudaFree(h->d_exc_scratch);
+   h->d_work = h->d_part = h->d_vin = h->d_vout = h->d_presum = h->d_exc = h->d_exc_coef = h->d_exc_scratch = nullptr;
+   h->n_exc = 0;
+   if (h->h_vin) { cudaFreeHost(h->h_vin); h->h_vin = nullptr; }
+   if (h->h_vout) { cudaFreeHost(h->h_vout); h->h_vout = nullptr; }
+   std::vector<SigmaTerm>().swap(h->plan.terms);
+   std::vector<GemmItem>().swap(h->comp.items1); std::vector<GemmItem>().swap(h->comp.items2);
+   std::vector<ReduceJob>().swap(h->comp.reduces);
+   for (int c = 0; c < kNumTileClasses; c++) { std::vector<Tile>().swap(h->comp.tiles1[c]); std::vector<Tile>().swap(h->comp.tiles2[c]); }
+   h->left = h->right = nullptr;
+}
+// brings a parked plan back: new operator sets (same layouts: same dimensions), workspaces, pre-summed operators of the new contents
+static int heff_unpark(b2_heff* h, b2_opset* left, b2_opset* right) {
+   b2_ctx* ctx = h->ctx;
+   cudaStream_t s = ctx->stream;
+   h->left = left; h->right = right;
+   const size_t n = (size_t)h->plan.S.size;
+   if (h->comp.part_size > 0) CUDA_TRY(cudaMalloc(&h->d_part, sizeof(double) * (size_t)h->comp.part_size));
+   if (h->plan.presum_size > 0) CUDA_TRY(cudaMalloc(&h->d_presum, sizeof(double) * (size_t)h->plan.presum_size));
+   if (h->comp.work_size > 0) CUDA_TRY(cudaMalloc(&h->d_work, sizeof(double) * (size_t)h->comp.work_size));
+   CUDA_TRY(cudaMalloc(&h->d_vin, sizeof(double) * (n ? n : 1)));
+   CUDA_TRY(cudaMalloc(&h->d_vout, sizeof(double) * (n ? n : 1)));
+   CUDA_TRY(cudaMallocHost(&h->h_vin, sizeof(double) * (n ? n : 1)));
+   CUDA_TRY(cudaMallocHost(&h->h_vout, sizeof(double) * (n ? n : 1)));
+   DevBases b = bases_of(h, nullptr, nullptr);
+   if (dev_launch_presum(h->d_jobs, (int)h->comp.presum_jobs.size(), h->d_parts, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+   CUDA_TRY(cudaStreamSynchronize(s));
+   return B2_OK;
+}
 
 int64_t b2_heff_veclength(const b2_heff* h) { return h ? h->plan.S.size : 0; }
 
@@ -970,6 +1005,13 @@ struct b2_dmrg {
    std::vector<ExcState> exc;              // lower states (excited-state calculations)
    std::vector<std::vector<double>> mps;   // TensorT storage per site in the layouts of the current bookkeeper
    std::vector<b2_opset*> left, right;     // operator sets per boundary: moving right (sites < b) / moving left (sites >= b)
+   // Sigma plans of earlier visits, one slot per site: at a fixed virtual dimension the sector dimensions stop changing once the sweeps
+   // converge, and a plan depends on nothing but those dimensions — re-using it removes the host-side plan building (the largest part
+   // of a small/medium-D sweep) from every later visit.  Key = the exact dimension tables of the three boundaries + the sharding.
+   struct PlanSlot { std::vector<int> key; b2_heff* h = nullptr; };
+   std::vector<PlanSlot> plan_cache;
+   bool use_plan_cache = true;
+   long long plan_hits = 0, plan_misses = 0;
    bool swept_once = false;                // false until the first left sweep (which runs with fixed virtual dimensions, DMRG.cpp:270)
    double max_disc_last_sweep = 0.0;       // DMRG::MaxDiscWeightLastSweep (DMRG.cpp:360-362): scales the noise of the next half sweep
    bool spill = false;                     // keep only the operator sets of the site being optimised in HBM (b2_dmrg_set_spill)
@@ -996,8 +1038,12 @@ int b2_dmrg_create(b2_ctx* ctx, b2_dmrg** out) {
    *out = d.release();
    return B2_OK;
 }
+static void dmrg_clear_plan_cache(b2_dmrg* d) {
+   for (b2_dmrg::PlanSlot& p : d->plan_cache) { b2_heff_destroy(p.h); p.h = nullptr; p.key.clear(); }
+}
 void b2_dmrg_destroy(b2_dmrg* d) {
    if (!d) return;
+   dmrg_clear_plan_cache(d);
    for (b2_opset* s : d->left) b2_opset_destroy(s);
    for (b2_opset* s : d->right) b2_opset_destroy(s);
    delete d;
@@ -1063,6 +1109,18 @@ static int dmrg_residency(b2_dmrg* d, int keep_l, int keep_r) {
       if (b != keep_l && d->left[b] && (rc = b2_opset_offload(d->left[b]))) return rc;
       if (b != keep_r && d->right[b] && (rc = b2_opset_offload(d->right[b]))) return rc;
    }
+   return B2_OK;
+}
+int b2_dmrg_set_plan_cache(b2_dmrg* d, int enabled) {
+   if (!d) return fail(B2_ERR_ARG, "b2_dmrg_set_plan_cache: NULL");
+   d->use_plan_cache = enabled != 0;
+   if (!d->use_plan_cache) dmrg_clear_plan_cache(d);
+   return B2_OK;
+}
+int b2_dmrg_plan_cache_stats(const b2_dmrg* d, long long* hits, long long* misses) {
+   if (!d) return fail(B2_ERR_ARG, "b2_dmrg_plan_cache_stats: NULL");
+   if (hits) *hits = d->plan_hits;
+   if (misses) *misses = d->plan_misses;
    return B2_OK;
 }
 int b2_dmrg_timers(b2_dmrg* d, double* out5, int reset) {
@@ -1242,6 +1300,7 @@ int b2_dmrg_new_excitation(b2_dmrg* d, double eshift, int D, uint64_t seed) {
    }
    for (ExcState& x : d->exc) { x.left.assign(d->L + 1, Overlap()); x.right.assign(d->L + 1, Overlap()); }
    d->ctx->bk.init(d->ctx->prob, D);
+   dmrg_clear_plan_cache(d);
    d->max_disc_last_sweep = 0.0;
    d->swept_once = false;
    return b2_dmrg_random_mps(d, seed);
@@ -1302,11 +1361,25 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
    if ((index > 0 && !lset) || (index < L - 2 && !rset)) return fail(B2_ERR_STATE, "b2_dmrg_solve_site: boundary operators for site %d are missing", index);
    b2_heff* h = nullptr;
    const double tp0 = wall_seconds();
-   int rc = b2_heff_create(ctx, index, lset, rset, d->world, d->rank, &h);
+   std::vector<int> key;
+   if (d->use_plan_cache) {
+      if ((int)d->plan_cache.size() != L) d->plan_cache.assign(L, b2_dmrg::PlanSlot());
+      key.push_back(d->world); key.push_back(d->rank);
+      for (int b = index; b <= index + 2; b++) key.insert(key.end(), ctx->bk.cur[b].begin(), ctx->bk.cur[b].end());
+      b2_dmrg::PlanSlot& slot = d->plan_cache[index];
+      if (slot.h && slot.key == key) {
+         h = slot.h; slot.h = nullptr;
+         int ur = heff_unpark(h, lset, rset);
+         if (ur) { b2_heff_destroy(h); h = nullptr; cudaGetLastError(); } else d->plan_hits++;
+      }
+   }
+   int rc = B2_OK;
+   if (!h) { d->plan_misses++; rc = b2_heff_create(ctx, index, lset, rset, d->world, d->rank, &h); }
    if (rc == B2_ERR_CUDA && !d->spill) {   // out of HBM: park every operator set that this site does not use and retry
       cudaGetLastError();
       b2_heff_destroy(h); h = nullptr;
       d->spill = true;
+      dmrg_clear_plan_cache(d);
       if ((rc = dmrg_residency(d, index > 0 ? index : -1, index < L - 2 ? index + 2 : -1))) return rc;
       rc = b2_heff_create(ctx, index, lset, rset, d->world, d->rank, &h);
    }
@@ -1354,7 +1427,12 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
       if (discarded_weight) *discarded_weight = dw;
    } while (0);
    cudaFree(d_tl); cudaFree(d_tr); cudaFree(d_s);
-   b2_heff_destroy(h);
+   if (!rc && d->use_plan_cache && h->list_bytes <= 1.0e9) {   // keep the plan for the next visit of this site (device work lists only, < 1 GB)
+      b2_dmrg::PlanSlot& slot = d->plan_cache[index];
+      b2_heff_destroy(slot.h);
+      heff_park(h);
+      slot.h = h; slot.key = key;
+   } else b2_heff_destroy(h);
    if (!rc) {   // operator sets living at the re-dimensioned boundary are stale now
       b2_dmrg_set_opset(d, index + 1, 1, nullptr);
       b2_dmrg_set_opset(d, index + 1, 0, nullptr);
@@ -1411,6 +1489,7 @@ int b2_dmrg_load_mps(b2_dmrg* d, const char* path, int* converged) {
       if (d->right[b]) { b2_opset_destroy(d->right[b]); d->right[b] = nullptr; }
    }
    for (ExcState& x : d->exc) { x.left.assign(d->L + 1, Overlap()); x.right.assign(d->L + 1, Overlap()); }
+   dmrg_clear_plan_cache(d);
    return B2_OK;
 }
 

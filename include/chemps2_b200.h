@@ -277,6 +277,11 @@ int b2_dmrg_set_world(b2_dmrg* d, int world, int rank, b2_allreduce_fn fn, void*
 /* enabled != 0: only the two operator sets of the site pair being optimised (and the set being built) stay in HBM, every
  * other boundary is offloaded to pinned host memory (the reference's disk mode, DMRG.cpp:57-65 makecheckpoints / OperatorsOnDisk) */
 int b2_dmrg_set_spill(b2_dmrg* d, int enabled);
+/* The driver keeps the sigma plan of the last visit of every site (device work lists only) and re-uses it when the dimension tables of
+ * the three boundaries of the site pair are unchanged — the normal situation in converged sweeps at a fixed virtual dimension.
+ * enabled = 0 switches the cache off and frees it; the statistics count re-used and newly built plans. */
+int b2_dmrg_set_plan_cache(b2_dmrg* d, int enabled);
+int b2_dmrg_plan_cache_stats(const b2_dmrg* d, long long* hits, long long* misses);
 /* wall-clock seconds per phase since the last reset: [0] plan building (host), [1] Davidson solves, [2] Split (host SVD),
  * [3] operator updates, [4] number of sigma builds */
 int b2_dmrg_timers(b2_dmrg* d, double* out5, int reset);

@@ -237,3 +237,23 @@ def test_mps_checkpoint_resume(golden, tmp_path):
     other.bk_init(D)
     with pytest.raises(Exception):
         api.DMRG(other).load_mps(path)
+
+
+def test_plan_cache_gives_identical_sweeps(golden):
+    """the sweep driver re-uses the sigma plan of the previous visit of a site when the dimension tables of its three boundaries are
+    unchanged (b2_dmrg_set_plan_cache): energies and discarded weights are bit-identical to sweeps that rebuild every plan, and the
+    later sweeps at fixed virtual dimension really hit the cache"""
+    def run(cache):
+        ctx, d = _start_from_fixture(golden, "A")
+        D = _fixture_D(golden)
+        d.set_plan_cache(cache)
+        d.presolve()
+        out = []
+        for it in range(4):
+            out += list(d.sweep(False, 1e-9, 0.0, D, it > 0))
+            out += list(d.sweep(True, 1e-9, 0.0, D, True))
+        return np.array(out), d.plan_cache_stats()
+    on, (hits, misses) = run(True)
+    off, (hits0, _) = run(False)
+    assert np.array_equal(on, off)
+    assert hits > 0 and hits0 == 0

@@ -749,6 +749,7 @@ struct b2_update {
    PresumPart* d_parts = nullptr;
    double *d_presum = nullptr, *d_work = nullptr, *d_part = nullptr, *d_t = nullptr, *h_t = nullptr;
    int world = 1, rank = 0;
+   double list_bytes[2] = {0.0, 0.0};      // device work-list bytes per pass
    std::vector<int> op_owner;              // GPU that computes new operator i in pass 0
    b2_allreduce_fn allreduce = nullptr;
    void* allreduce_user = nullptr;
@@ -833,6 +834,7 @@ int b2_update_create_sharded(b2_ctx* ctx, int index, int moving_right, b2_opset*
    copt.threads = (u->plan.flops_ref < ctx->parallel_plan_flops) ? plan_threads((int)u->plan.dst.size()) : 1;
    compile_terms(u->pass[0], u->plan.terms, u->plan.dst, SP_VOUT, copt);
    compile_terms(u->pass[1], u->plan.mix_terms, u->plan.dst, SP_VOUT, copt);
+   for (int p = 0; p < 2; p++) u->list_bytes[p] = u->pass[p].bytes();
    for (const Presum& p : u->plan.presums) {
       PresumJob j{};
       j.dst_off = p.off; j.size = p.lay->size; j.part_begin = (int)u->presum_parts.size();
@@ -873,6 +875,31 @@ int b2_update_create_sharded(b2_ctx* ctx, int index, int moving_right, b2_opset*
    return B2_OK;
 }
 void b2_update_destroy(b2_update* u) { delete u; }
+// update plans kept by the sweep driver between visits of a boundary (same idea as heff_park / heff_unpark)
+static void update_park(b2_update* u) {
+   cudaFree(u->d_presum); cudaFree(u->d_work); cudaFree(u->d_part); cudaFree(u->d_t);
+   u->d_presum = u->d_work = u->d_part = u->d_t = nullptr;
+   if (u->h_t) { cudaFreeHost(u->h_t); u->h_t = nullptr; }
+   std::vector<Term3>().swap(u->plan.terms); std::vector<Term3>().swap(u->plan.mix_terms);
+   for (int p = 0; p < 2; p++) {
+      std::vector<GemmItem>().swap(u->pass[p].items1); std::vector<GemmItem>().swap(u->pass[p].items2);
+      std::vector<ReduceJob>().swap(u->pass[p].reduces);
+      for (int c = 0; c < kNumTileClasses; c++) { std::vector<Tile>().swap(u->pass[p].tiles1[c]); std::vector<Tile>().swap(u->pass[p].tiles2[c]); }
+   }
+   u->old_set = u->new_set = nullptr;
+}
+static int update_unpark(b2_update* u, b2_opset* old_set, b2_opset* new_set) {
+   u->old_set = old_set; u->new_set = new_set;
+   int64_t work = 0, part = 0;
+   for (int p = 0; p < 2; p++) { work = std::max(work, u->pass[p].work_size); part = std::max(part, u->pass[p].part_size); }
+   if (u->plan.presum_size > 0) CUDA_TRY(cudaMalloc(&u->d_presum, sizeof(double) * (size_t)u->plan.presum_size));
+   if (work > 0) CUDA_TRY(cudaMalloc(&u->d_work, sizeof(double) * (size_t)work));
+   if (part > 0) CUDA_TRY(cudaMalloc(&u->d_part, sizeof(double) * (size_t)part));
+   const size_t nt = (size_t)(u->plan.T.size ? u->plan.T.size : 1);
+   CUDA_TRY(cudaMalloc(&u->d_t, sizeof(double) * nt));
+   CUDA_TRY(cudaMallocHost(&u->h_t, sizeof(double) * nt));
+   return B2_OK;
+}
 int b2_update_run_device(b2_update* u, const double* t_dev) {
    if (!u || !t_dev) return fail(B2_ERR_ARG, "b2_update_run_device: NULL");
    if (u->ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_update_run: planning-only context, no CUDA device (there is no CPU fallback)");
@@ -1010,6 +1037,8 @@ struct b2_dmrg {
    // of a small/medium-D sweep) from every later visit.  Key = the exact dimension tables of the three boundaries + the sharding.
    struct PlanSlot { std::vector<int> key; b2_heff* h = nullptr; };
    std::vector<PlanSlot> plan_cache;
+   struct UpdSlot { std::vector<int> key; b2_update* u = nullptr; };
+   std::vector<UpdSlot> upd_cache;        // index = 2 * site + moving_right
    bool use_plan_cache = true;
    long long plan_hits = 0, plan_misses = 0;
    bool swept_once = false;                // false until the first left sweep (which runs with fixed virtual dimensions, DMRG.cpp:270)
@@ -1040,6 +1069,7 @@ int b2_dmrg_create(b2_ctx* ctx, b2_dmrg** out) {
 }
 static void dmrg_clear_plan_cache(b2_dmrg* d) {
    for (b2_dmrg::PlanSlot& p : d->plan_cache) { b2_heff_destroy(p.h); p.h = nullptr; p.key.clear(); }
+   for (b2_dmrg::UpdSlot& p : d->upd_cache) { b2_update_destroy(p.u); p.u = nullptr; p.key.clear(); }
 }
 void b2_dmrg_destroy(b2_dmrg* d) {
    if (!d) return;
@@ -1324,9 +1354,24 @@ static int dmrg_update_mode(b2_dmrg* d, int index, int moving_right, int mode) {
    b2_update* u = nullptr;
    const double t0 = wall_seconds();
    int rc = B2_OK;
+   std::vector<int> key;
+   b2_dmrg::UpdSlot* slot = nullptr;
+   if (d->use_plan_cache) {
+      if ((int)d->upd_cache.size() != 2 * d->L) d->upd_cache.assign(2 * d->L, b2_dmrg::UpdSlot());
+      slot = &d->upd_cache[2 * index + (mr ? 1 : 0)];
+      key.push_back(d->world); key.push_back(d->rank); key.push_back(mode);
+      for (int b = index; b <= index + 1; b++) key.insert(key.end(), ctx->bk.cur[b].begin(), ctx->bk.cur[b].end());
+   }
    for (int attempt = 0; attempt < 2; attempt++) {
       rc = mode == 0 ? b2_opset_create(ctx, b_new, mr, &fresh) : opset_create_reduced(ctx, b_new, mr, mode == 2, &fresh);
-      if (!rc) rc = b2_update_create_sharded(ctx, index, mr, need_old ? old_set : nullptr, fresh, d->world, d->rank, &u);
+      if (!rc && slot && slot->u && slot->key == key) {   // the plan of the previous visit fits: re-bind it to the new arenas
+         u = slot->u; slot->u = nullptr;
+         rc = update_unpark(u, need_old ? old_set : nullptr, fresh);
+         if (!rc) d->plan_hits++;
+      } else if (!rc) {
+         d->plan_misses++;
+         rc = b2_update_create_sharded(ctx, index, mr, need_old ? old_set : nullptr, fresh, d->world, d->rank, &u);
+      }
       if (rc != B2_ERR_CUDA || attempt == 1 || d->spill) break;
       // HBM exhausted (O(L) boundaries x O(L^2 D^2) operators): from now on only the sets in use stay resident — the
       // reference's OperatorsOnDisk mode, switched on when it is needed instead of by the user
@@ -1334,6 +1379,7 @@ static int dmrg_update_mode(b2_dmrg* d, int index, int moving_right, int mode) {
       b2_update_destroy(u); u = nullptr;
       b2_opset_destroy(fresh); fresh = nullptr;
       d->spill = true;
+      dmrg_clear_plan_cache(d);
       if ((rc = dmrg_residency(d, mr ? b_old : -1, mr ? -1 : b_old))) return rc;
    }
    if (rc) { b2_update_destroy(u); b2_opset_destroy(fresh); return rc; }
@@ -1342,7 +1388,13 @@ static int dmrg_update_mode(b2_dmrg* d, int index, int moving_right, int mode) {
    const double t1 = wall_seconds();
    if (!rc) rc = b2_update_run(u, d->mps[index].data());
    d->t_update += wall_seconds() - t1;
-   b2_update_destroy(u);
+   double ubytes = 0.0;
+   if (u) for (int p = 0; p < 2; p++) ubytes += u->list_bytes[p];
+   if (!rc && slot && ubytes <= 1.0e9) {
+      b2_update_destroy(slot->u);
+      update_park(u);
+      slot->u = u; slot->key = key;
+   } else b2_update_destroy(u);
    if (rc) { b2_opset_destroy(fresh); return rc; }
    if ((rc = b2_dmrg_set_opset(d, b_new, mr, fresh))) return rc;
    return dmrg_update_overlaps(d, index, mr);   // DMRGoperators.cpp:556-567 / :889-900

@@ -114,6 +114,7 @@ SIGNATURES = [
     ("b2_dmrg_update", C.c_int, [vp, C.c_int, C.c_int]),
     ("b2_dmrg_solve_site", C.c_int, [vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, c_dp, c_dp, c_ip]),
     ("b2_dmrg_sweep", C.c_int, [vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, c_dp, c_dp]),
+    ("b2_dmrg_sweep_info", C.c_int, [vp, c_dp]),
     ("b2_update_create", C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.POINTER(vp)]),
     ("b2_update_create_sharded", C.c_int, [vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.POINTER(vp)]),
     ("b2_update_set_allreduce", C.c_int, [vp, vp, vp]),

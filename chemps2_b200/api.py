@@ -392,6 +392,11 @@ class DMRG:
                                      C.byref(e), C.byref(dw), C.byref(nm)))
         return e.value, dw.value, nm.value
 
+    def sweep_info(self):
+        out = (C.c_double * 4)()
+        check(lib.b2_dmrg_sweep_info(self.h, out))
+        return dict(last_energy=out[0], last_min_energy=out[1], max_discarded=out[2], total_min_energy=out[3])
+
     def sweep(self, to_right, rtol, noise, D, change):
         e, dw = C.c_double(), C.c_double()
         check(lib.b2_dmrg_sweep(self.h, int(bool(to_right)), float(rtol), float(noise), int(D), int(bool(change)), C.byref(e), C.byref(dw)))

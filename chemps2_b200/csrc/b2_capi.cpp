@@ -1043,6 +1043,9 @@ struct b2_dmrg {
    long long plan_hits = 0, plan_misses = 0;
    bool swept_once = false;                // false until the first left sweep (which runs with fixed virtual dimensions, DMRG.cpp:270)
    double max_disc_last_sweep = 0.0;       // DMRG::MaxDiscWeightLastSweep (DMRG.cpp:360-362): scales the noise of the next half sweep
+   double last_energy = 0.0;               // energy of the last site solved (what DMRG::sweepleft / sweepright return)
+   double last_min_energy = 1e8;           // DMRG::LastMinEnergy: lowest energy of the last half sweep
+   double total_min_energy = 1e8;          // DMRG::TotalMinEnergy: lowest energy since the last PreSolve
    bool spill = false;                     // keep only the operator sets of the site being optimised in HBM (b2_dmrg_set_spill)
    int world = 1, rank = 0;                // GPUs sharing the sweep: sigma terms and operator updates are sharded, the rest is replicated
    b2_allreduce_fn allreduce = nullptr;
@@ -1549,6 +1552,8 @@ int b2_dmrg_load_mps(b2_dmrg* d, const char* path, int* converged) {
 int b2_dmrg_presolve(b2_dmrg* d) {
    if (!d) return fail(B2_ERR_ARG, "b2_dmrg_presolve: NULL");
    for (int i = 0; i < d->L - 2; i++) { int rc = b2_dmrg_update(d, i, 1); if (rc) return rc; }
+   d->total_min_energy = 1e8;       // DMRG.cpp:263-264
+   d->max_disc_last_sweep = 0.0;
    return B2_OK;
 }
 
@@ -1573,8 +1578,8 @@ int b2_dmrg_solve(b2_dmrg* d, int n_instructions, const int* D, const double* en
          if ((rc = b2_dmrg_sweep(d, 0, davidson_rtol[ins], noise_prefactor[ins], D[ins], d->swept_once ? 1 : 0, &el, &dw))) return rc;
          d->swept_once = true;
          if ((rc = b2_dmrg_sweep(d, 1, davidson_rtol[ins], noise_prefactor[ins], D[ins], 1, &er, &dw))) return rc;
-         energy = std::min(el, er);
-         lowest = std::min(lowest, energy);
+         energy = d->last_energy;         // the convergence test compares what sweepright returns: the energy of its last site
+         lowest = std::min(lowest, std::min(el, er));
          it++;
       }
    }
@@ -1790,20 +1795,27 @@ int b2_dmrg_sweep(b2_dmrg* d, int to_right, double rtol, double noise, int D, in
       for (int index = L - 2; index > 0; index--) {
          double e, dw;
          if ((rc = b2_dmrg_solve_site(d, index, rtol, noise, D, 0, change, &e, &dw, nullptr))) return rc;
-         emin = std::min(emin, e); dmax = std::max(dmax, dw);
+         emin = std::min(emin, e); dmax = std::max(dmax, dw); d->last_energy = e;
          if ((rc = b2_dmrg_update(d, index + 1, 0))) return rc;
       }
    } else {
       for (int index = 0; index < L - 2; index++) {
          double e, dw;
          if ((rc = b2_dmrg_solve_site(d, index, rtol, noise, D, 1, change, &e, &dw, nullptr))) return rc;
-         emin = std::min(emin, e); dmax = std::max(dmax, dw);
+         emin = std::min(emin, e); dmax = std::max(dmax, dw); d->last_energy = e;
          if ((rc = b2_dmrg_update(d, index, 1))) return rc;
       }
    }
    d->max_disc_last_sweep = dmax;
+   d->last_min_energy = emin;
+   d->total_min_energy = std::min(d->total_min_energy, emin);
    *min_energy = emin;
    if (max_discarded) *max_discarded = dmax;
+   return B2_OK;
+}
+int b2_dmrg_sweep_info(const b2_dmrg* d, double* out4) {
+   if (!d || !out4) return fail(B2_ERR_ARG, "b2_dmrg_sweep_info: NULL");
+   out4[0] = d->last_energy; out4[1] = d->last_min_energy; out4[2] = d->max_disc_last_sweep; out4[3] = d->total_min_energy;
    return B2_OK;
 }
 

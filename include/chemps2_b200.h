@@ -289,6 +289,9 @@ int b2_dmrg_update(b2_dmrg* d, int index, int moving_right);
 int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, int moving_right, int change, double* energy,
                        double* discarded_weight, int* n_matvec);
 int b2_dmrg_sweep(b2_dmrg* d, int to_right, double rtol, double noise, int D, int change, double* min_energy, double* max_discarded);
+/* the sweep counters DMRG keeps (DMRG.cpp:356-414): [0] energy of the last site solved (the value sweepleft / sweepright return and
+ * DMRG::Solve tests for convergence), [1] LastMinEnergy, [2] MaxDiscWeightLastSweep, [3] TotalMinEnergy since the last PreSolve */
+int b2_dmrg_sweep_info(const b2_dmrg* d, double* out4);
 
 /* ------------------------------------------------------------------------------------------------ 2-RDM
  * b2_twodm_fill_site = TwoDM::FillSite (TwoDM.cpp:445-628 with its 24 diagram functions doD1..doD24, :642-1592): the entries of the

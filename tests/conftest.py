@@ -13,7 +13,9 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     # the product library and the CPU checker are built in-tree; build them if this checkout has not been built yet
-    if not (os.path.exists(os.path.join(ROOT, "chemps2_b200", "libchemps2_b200.so")) and os.path.exists(os.path.join(ROOT, "oracle", "libb2oracle.so"))):
+    built = [os.path.join(ROOT, "chemps2_b200", "libchemps2_b200.so"), os.path.join(ROOT, "oracle", "libb2oracle.so"),
+             os.path.join(ROOT, "tests", "cpp", "_bin", "dmrg_caller")]
+    if not all(os.path.exists(p) for p in built):
         subprocess.run(["make", "-j8"], cwd=ROOT, check=True, stdout=subprocess.DEVNULL)
 
 

@@ -51,7 +51,10 @@ struct b2_ctx {
    bool have_problem = false, have_bk = false;
    CompileOptions copt;
    int simulate_oom = 0;                // test hook: the next N device allocations of operator sets / plans report B2_ERR_CUDA
-   double parallel_plan_flops = 2e11;   // plans below this many reference FLOPs per apply are compiled on all host cores
+   // plans below this many reference FLOPs per apply are scheduled on all host cores: segment-wise scheduling shares stage-1 products
+   // only inside a segment (+1-3 % executed FLOPs, measured on the N2/cc-pVDZ D=2000 and tetracene D=3000 shapes) but builds the plan
+   // 2-4x faster, which wins as long as a Davidson solve (~15 sigma builds) is shorter than the planning it saves
+   double parallel_plan_flops = 1e13;
 };
 
 struct b2_opset {

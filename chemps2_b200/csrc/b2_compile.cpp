@@ -8,6 +8,7 @@
 //     one CTA each; a tile with one chunk adds straight into the destination, otherwise the chunks write partial slots
 //     and a reduce job sums them in a fixed order.
 #include "b2_compile.h"
+#include "b2_core.h"
 
 #include <algorithm>
 #include <chrono>
@@ -149,14 +150,11 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
       std::vector<CompiledWork> seg(T);
       CompileOptions o = opt;
       o.work_budget = std::max<int64_t>(opt.work_budget / T, 1 << 20);
-      auto run_all = [&](const std::function<void(int)>& fn) {
-         std::vector<std::thread> pool;
-         for (int t = 1; t < T; t++) pool.emplace_back(fn, t);
-         fn(0);
-         for (std::thread& th : pool) th.join();
-      };
+      auto run_all = [&](const std::function<void(int)>& fn) { parallel_run(T, fn); };
       // every segment orders its own waves (heaviest group first); the merged wave is the concatenation of the segments' waves
+      const double t_seg0 = now_s();
       run_all([&](int t) { compile_range(seg[t], terms.data() + cut[t], cut[t + 1] - cut[t], dst, dst_space, o, true); });
+      const double t_seg1 = now_s();
       std::vector<int64_t> wbase(T + 1, 0), pbase(T + 1, 0);
       std::vector<int> i1base(T + 1, 0), i2base(T + 1, 0);
       size_t nwaves = 0;
@@ -226,6 +224,7 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
          }
          seg[t] = CompiledWork();
       });
+      if (getenv("B2_TIMING")) fprintf(stderr, "compile_terms: regroup %.3f s, segments %.3f s, merge %.3f s\n", t_seg0 - T_total, t_seg1 - t_seg0, now_s() - t_seg1);
    }
    for (int c = 0; c < kNumTileClasses; c++) out.n_tiles += (long long)out.tiles1[c].size() + (long long)out.tiles2[c].size();
    if (getenv("B2_TIMING")) fprintf(stderr, "compile_terms: total %.3f s, %d thread(s)\n", now_s() - T_total, T);

@@ -4,9 +4,92 @@
 #include <algorithm>
 #include <cassert>
 #include <cmath>
+#include <condition_variable>
 #include <mutex>
+#include <new>
+#include <thread>
+#include <unistd.h>
 
 namespace b2 {
+
+// ------------------------------------------------------------------------------------------------ host worker pool
+namespace {
+struct WorkerPool {
+   std::mutex run_mutex;                 // one parallel_run at a time
+   std::mutex m;
+   std::condition_variable wake, finished;
+   std::vector<std::thread> workers;     // worker w executes piece w + 1
+   const std::function<void(int)>* job = nullptr;
+   int job_n = 0, pending = 0;
+   long long generation = 0;
+   bool quit = false;
+
+   void worker_main(int piece, long long seen) {
+      for (;;) {
+         const std::function<void(int)>* fn = nullptr;
+         {
+            std::unique_lock<std::mutex> lk(m);
+            wake.wait(lk, [&] { return quit || generation != seen; });
+            if (quit) return;
+            seen = generation;
+            if (piece < job_n) fn = job;
+         }
+         if (!fn) continue;
+         (*fn)(piece);
+         std::lock_guard<std::mutex> lk(m);
+         if (--pending == 0) finished.notify_one();
+      }
+   }
+   void run(int n, const std::function<void(int)>& fn) {
+      std::unique_lock<std::mutex> busy(run_mutex, std::try_to_lock);
+      if (n <= 1 || !busy.owns_lock()) { for (int t = 0; t < n; t++) fn(t); return; }
+      {
+         std::lock_guard<std::mutex> lk(m);
+         while ((int)workers.size() < n - 1) { const int piece = (int)workers.size() + 1; workers.emplace_back(&WorkerPool::worker_main, this, piece, generation); }
+         job = &fn; job_n = n; pending = n - 1;
+         generation++;
+      }
+      wake.notify_all();
+      fn(0);
+      std::unique_lock<std::mutex> lk(m);
+      finished.wait(lk, [&] { return pending == 0; });
+      job = nullptr; job_n = 0;
+   }
+   void shutdown() {
+      { std::lock_guard<std::mutex> lk(m); quit = true; }
+      wake.notify_all();
+      for (std::thread& th : workers) th.join();
+      workers.clear();
+   }
+};
+
+// The pool lives on the heap and belongs to one process: a forked child inherits the object but neither its threads nor a usable
+// copy of its mutexes / condition variables (their waiter bookkeeping describes threads that do not exist there), so the child
+// abandons the inherited object and starts a fresh one.
+struct PoolHolder {
+   WorkerPool* pool = nullptr;
+   pid_t owner = 0;
+   std::mutex guard;
+   WorkerPool* get() {
+      const pid_t me = getpid();
+      if (owner != 0 && owner != me) new (&guard) std::mutex();   // first call in a forked child: the copy may be in the locked state
+      std::lock_guard<std::mutex> lk(guard);
+      if (owner != me) {
+         pool = new WorkerPool;                                     // an inherited pool is leaked on purpose
+         owner = me;
+      }
+      return pool;
+   }
+   ~PoolHolder() {
+      if (pool && owner == getpid()) { pool->shutdown(); delete pool; }
+   }
+};
+}   // namespace
+
+void parallel_run(int n, const std::function<void(int)>& fn) {
+   static PoolHolder holder;
+   holder.get()->run(n, fn);
+}
 
 // ------------------------------------------------------------------------------------------------ Wigner
 // Racah's closed form for the 6j symbol with long-double factorials (arguments are doubled spins).

@@ -74,10 +74,7 @@ void compile_sigma(CompiledSigma& out, const SigmaPlan& plan, const OpSet* left,
    };
    {
       const int T = std::max(1, std::min<int>(opt.threads, (int)(order.size() / 20000)));
-      std::vector<std::thread> pool;
-      for (int t = 1; t < T; t++) pool.emplace_back(resolve_range, order.size() * t / T, order.size() * (t + 1) / T);
-      resolve_range(0, order.size() / T);
-      for (std::thread& th : pool) th.join();
+      parallel_run(T, [&](int t) { resolve_range(order.size() * t / T, order.size() * (t + 1) / T); });
    }
    // ---- diagonal of H_eff (Heff::fillHeffDiag, Heff.cpp:250-315 + HeffDiagonal.cpp): exactly the terms that map a block
    // onto itself — families 1A-1D, 2d3, 2b3/2c3/2e3/2f3 and 2a3 — restricted to the operator-block diagonals:

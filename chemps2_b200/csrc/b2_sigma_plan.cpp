@@ -13,6 +13,8 @@
 #include <map>
 #include <thread>
 
+#include <chrono>
+
 #include "b2_sigma.h"
 
 namespace b2 {
@@ -499,10 +501,9 @@ void build_sigma_plan(SigmaPlan& plan, const Bookkeeper& bk, const Problem& prob
       f.blk_begin.push_back((int)f.plan.terms.size());
       f.keys.swap(g.presum_index);
    };
-   std::vector<std::thread> pool;
-   for (int t = 1; t < nthreads; t++) pool.emplace_back(worker, t);
-   worker(0);
-   for (std::thread& th : pool) th.join();
+   const auto tp0 = std::chrono::steady_clock::now();
+   parallel_run(nthreads, worker);
+   const auto tp1 = std::chrono::steady_clock::now();
    // ---- pre-sums: global registry in thread order
    std::map<std::string, int> global;
    std::vector<std::vector<int>> remap(nthreads);
@@ -540,6 +541,9 @@ void build_sigma_plan(SigmaPlan& plan, const Bookkeeper& bk, const Problem& prob
          plan.terms.push_back(x);
       }
    }
+   if (getenv("B2_TIMING"))
+      fprintf(stderr, "build_sigma_plan: %d blocks on %d threads, enumerate %.3f s, stitch %.3f s\n", nk, nthreads,
+              std::chrono::duration<double>(tp1 - tp0).count(), std::chrono::duration<double>(std::chrono::steady_clock::now() - tp1).count());
 }
 
 }   // namespace b2

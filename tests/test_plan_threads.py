@@ -42,3 +42,45 @@ def test_parallel_plan_equals_sequential_plan():
         assert n1 == n2 and t1 == t2                      # same number of terms
         assert abs(f1 - f2) <= 1e-9 * f1                  # same algorithmic FLOP count (summed per thread, so only rounding may differ)
         assert e1 < 1e-12 and e2 < 1e-12                  # both reproduce Heff::makeHeff through the emulated work lists
+
+
+POOL_WORKER = r"""
+import sys, os, threading
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import cpu_check
+from chemps2_b200 import fixtures
+fx = fixtures.load(os.path.join({root!r}, "tests", "golden", "h2o_631g.npz"))
+
+def one(tag):
+    ctx, left, right, heff = cpu_check.build_case(fx, tag, options={{"parallel_min_terms": 16}})
+    sig = cpu_check.emulate_worklists(ctx, left, right, heff, fx[tag + "/rnd_in"])
+    return float(np.abs(sig - fx[tag + "/rnd_out"]).max() / max(1.0, np.abs(fx[tag + "/rnd_out"]).max()))
+
+errs = [one("A")]                                   # creates the parked workers
+res = {{}}
+ths = [threading.Thread(target=lambda t=t: res.__setitem__(t, one("AB"[t % 2]))) for t in range(4)]
+for th in ths: th.start()                           # concurrent builds: one owns the pool, the others run their pieces inline
+for th in ths: th.join()
+errs += [res[t] for t in range(4)]
+pid = os.fork()                                     # the child inherits the pool object but not its threads
+if pid == 0:
+    ok = one("B") < 1e-12
+    os._exit(0 if ok else 3)
+_, status = os.waitpid(pid, 0)
+errs.append(one("B"))                               # and the parent's pool still works
+print("B2POOL", errs, os.WEXITSTATUS(status))
+"""
+
+
+def test_worker_pool_concurrent_callers_and_fork():
+    """the parked host workers (b2_core.cpp parallel_run) are shared by every caller: concurrent builds fall back to inline pieces,
+    a forked child starts its own workers; every plan still reproduces the reference's sigma vector"""
+    env = dict(os.environ, B2_PLAN_THREADS="4")
+    res = subprocess.run([sys.executable, "-c", POOL_WORKER.format(root=ROOT)], capture_output=True, text=True, env=env, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("B2POOL")][-1]
+    payload = line[len("B2POOL"):].strip()
+    errs, child = eval("(" + payload.rsplit("]", 1)[0] + "]," + payload.rsplit("]", 1)[1] + ")")
+    assert child == 0
+    assert len(errs) == 6 and max(errs) < 1e-12, errs

@@ -421,6 +421,7 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
    compile_sigma(h->comp, h->plan, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, rank, world, copt);
    h->list_bytes = h->comp.bytes();
    if (getenv("B2_TIMING")) fprintf(stderr, "b2_heff_create: enumerate %.3f s, schedule %.3f s, %zu terms\n", tb1 - tb0, wall_seconds() - tb1, h->plan.terms.size());
+   const double tb2 = wall_seconds();
    if (ctx->device >= 0) {
       CUDA_TRY(cudaSetDevice(ctx->device));
       cudaStream_t s = ctx->stream;
@@ -461,6 +462,9 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
       DevBases b = bases_of(h.get(), nullptr, nullptr);
       if (dev_launch_presum(h->d_jobs, (int)h->comp.presum_jobs.size(), h->d_parts, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
       CUDA_TRY(cudaStreamSynchronize(s));
+      if (getenv("B2_TIMING"))
+         fprintf(stderr, "b2_heff_create: device setup %.3f s (work lists %.1f MB uploaded, workspace %.2f GB, pre-sums %.1f MB)\n", wall_seconds() - tb2,
+                 h->list_bytes / 1e6, h->comp.work_size * 8e-9, h->plan.presum_size * 8e-6);
    }
    *out = h.release();
    return B2_OK;
@@ -1055,6 +1059,7 @@ struct b2_dmrg {
    void* allreduce_user = nullptr;
    double t_solve = 0.0, t_update = 0.0, t_split = 0.0, t_plan = 0.0;   // wall-clock seconds spent per phase (b2_dmrg_timers)
    long long n_matvec = 0;
+   double t_join = 0.0, t_release = 0.0, t_tail = 0.0;   // B2_TIMING diagnostics: Join + vector copies, releasing plans / buffers / stale sets, update epilogue
    unsigned long long rng = 0x9E3779B97F4A7C15ULL;
    double next_uniform() {                 // xorshift64*: our own stream (the reference uses rand(), Sobject.cpp:652-659)
       rng ^= rng >> 12; rng ^= rng << 25; rng ^= rng >> 27;
@@ -1394,6 +1399,7 @@ static int dmrg_update_mode(b2_dmrg* d, int index, int moving_right, int mode) {
    const double t1 = wall_seconds();
    if (!rc) rc = b2_update_run(u, d->mps[index].data());
    d->t_update += wall_seconds() - t1;
+   const double t2 = wall_seconds();
    double ubytes = 0.0;
    if (u) for (int p = 0; p < 2; p++) ubytes += u->list_bytes[p];
    if (!rc && slot && ubytes <= 1.0e9) {
@@ -1403,7 +1409,9 @@ static int dmrg_update_mode(b2_dmrg* d, int index, int moving_right, int mode) {
    } else b2_update_destroy(u);
    if (rc) { b2_opset_destroy(fresh); return rc; }
    if ((rc = b2_dmrg_set_opset(d, b_new, mr, fresh))) return rc;
-   return dmrg_update_overlaps(d, index, mr);   // DMRGoperators.cpp:556-567 / :889-900
+   rc = dmrg_update_overlaps(d, index, mr);   // DMRGoperators.cpp:556-567 / :889-900
+   d->t_tail += wall_seconds() - t2;
+   return rc;
 }
 
 // DMRG::solve_site (DMRG.cpp:419-452): Join -> Heff::SolveDAVIDSON -> (noise) -> Split.  *energy includes Econst.
@@ -1445,6 +1453,7 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
    if (d->world > 1) b2_heff_set_allreduce(h, d->allreduce, d->allreduce_user);
    if ((rc = dmrg_attach_excitations(d, h, index))) { b2_heff_destroy(h); return rc; }   // DMRG::prepare_excitations (DMRG.cpp:434)
    d->t_plan += wall_seconds() - tp0;
+   const double tj0 = wall_seconds();
    const SLayout& S = h->plan.S;
    TLayout TL, TR;
    TL.build(ctx->bk, index); TR.build(ctx->bk, index + 1);
@@ -1468,6 +1477,7 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
       // ---- Heff::SolveDAVIDSON on the device
       double ev = 0.0; int nm = 0;
       const double ts0 = wall_seconds();
+      d->t_join += ts0 - tj0;
       if ((rc = b2_heff_solve_device(h, d_s, rtol, &ev, &nm))) break;
       d->t_solve += wall_seconds() - ts0; d->n_matvec += nm;
       *energy = ev + ctx->prob.econst;
@@ -1484,6 +1494,7 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
       if (dw < 0.0) { rc = fail(B2_ERR_CUDA, "b2_dmrg_solve_site: Split: %s", svd_err); break; }
       if (discarded_weight) *discarded_weight = dw;
    } while (0);
+   const double tr0 = wall_seconds();
    cudaFree(d_tl); cudaFree(d_tr); cudaFree(d_s);
    if (!rc && d->use_plan_cache && h->list_bytes <= 1.0e9) {   // keep the plan for the next visit of this site (device work lists only, < 1 GB)
       b2_dmrg::PlanSlot& slot = d->plan_cache[index];
@@ -1495,6 +1506,7 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
       b2_dmrg_set_opset(d, index + 1, 1, nullptr);
       b2_dmrg_set_opset(d, index + 1, 0, nullptr);
    }
+   d->t_release += wall_seconds() - tr0;
    return rc;
 }
 
@@ -1792,6 +1804,8 @@ int b2_dmrg_sweep(b2_dmrg* d, int to_right, double rtol, double noise, int D, in
    const int L = d->L;
    double emin = 1e300, dmax = 0.0;
    int rc;
+   const double tw0 = wall_seconds();
+   const double base[7] = {d->t_plan, d->t_join, d->t_solve, d->t_split, d->t_release, d->t_update, d->t_tail};
    // DMRG.cpp:360,391: the noise added before Split is |noise prefactor| x (largest discarded weight of the previous half sweep)
    noise = std::fabs(noise) * d->max_disc_last_sweep;
    if (!to_right) {
@@ -1809,6 +1823,10 @@ int b2_dmrg_sweep(b2_dmrg* d, int to_right, double rtol, double noise, int D, in
          if ((rc = b2_dmrg_update(d, index, 1))) return rc;
       }
    }
+   if (getenv("B2_TIMING"))
+      fprintf(stderr, "b2_dmrg_sweep %s D=%d: wall %.3f s = plan %.3f + join %.3f + solve %.3f + split %.3f + release %.3f + update %.3f + update epilogue %.3f + rest\n",
+              to_right ? "->" : "<-", D, wall_seconds() - tw0, d->t_plan - base[0], d->t_join - base[1], d->t_solve - base[2], d->t_split - base[3],
+              d->t_release - base[4], d->t_update - base[5], d->t_tail - base[6]);
    d->max_disc_last_sweep = dmax;
    d->last_min_energy = emin;
    d->total_min_energy = std::min(d->total_min_energy, emin);

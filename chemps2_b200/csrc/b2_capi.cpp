@@ -74,6 +74,11 @@ static int set_problem_common(b2_ctx* ctx, int L, int group, int N, int twoS, in
    if (nirr < 0) return fail(B2_ERR_ARG, "b2_problem_set: group %d out of range", group);
    if (irrep < 0 || irrep >= nirr) return fail(B2_ERR_ARG, "b2_problem_set: target irrep %d out of range", irrep);
    if (N < 2) return fail(B2_ERR_ARG, "b2_problem_set: N must be >= 2 (one-body part is folded in with 1/(N-1))");
+   // Problem::checkConsistency (Problem.cpp:386-430)
+   if (twoS < 0) return fail(B2_ERR_ARG, "b2_problem_set: TwoS = %d", twoS);
+   if (N > 2 * L) return fail(B2_ERR_ARG, "b2_problem_set: N > 2*L ; N = %d and L = %d", N, L);
+   if ((N % 2) != (twoS % 2)) return fail(B2_ERR_ARG, "b2_problem_set: N %% 2 != TwoS %% 2 ; N = %d and TwoS = %d", N, twoS);
+   if (twoS > L - std::abs(N - L)) return fail(B2_ERR_ARG, "b2_problem_set: TwoS > L - |N-L| ; N = %d and TwoS = %d and L = %d", N, twoS, L);
    for (int i = 0; i < L; i++)
       if (orb_irrep[i] < 0 || orb_irrep[i] >= nirr) return fail(B2_ERR_ARG, "b2_problem_set: orbital irrep out of range");
    Problem& p = ctx->prob;
@@ -122,20 +127,35 @@ int b2_bk_init(b2_ctx* ctx, int D) {
 }
 int b2_bk_set_dim(b2_ctx* ctx, int boundary, int N, int twoS, int irrep, int dim) {
    if (!ctx || !ctx->have_bk) return fail(B2_ERR_STATE, "b2_bk_set_dim: no bookkeeper");
-   ctx->bk.set_dim(boundary, N, twoS, irrep, dim);
+   if (dim < 0) return fail(B2_ERR_ARG, "b2_bk_set_dim: negative dimension");
+   ctx->bk.set_dim(boundary, N, twoS, irrep, dim);     // sectors outside the table or with FCI dimension 0 are ignored (SyBookkeeper.cpp:163-169)
    return B2_OK;
 }
 int b2_bk_dim(const b2_ctx* ctx, int b, int N, int twoS, int irrep) { return (ctx && ctx->have_bk) ? ctx->bk.dim(b, N, twoS, irrep) : 0; }
 int b2_bk_fcidim(const b2_ctx* ctx, int b, int N, int twoS, int irrep) { return (ctx && ctx->have_bk) ? ctx->bk.fcidim(b, N, twoS, irrep) : 0; }
-int b2_bk_nmin(const b2_ctx* ctx, int b) { return ctx->bk.Nmin[b]; }
-int b2_bk_nmax(const b2_ctx* ctx, int b) { return ctx->bk.Nmax[b]; }
-int b2_bk_twosmin(const b2_ctx* ctx, int b, int N) { return ctx->bk.tsmin[b][N - ctx->bk.Nmin[b]]; }
-int b2_bk_twosmax(const b2_ctx* ctx, int b, int N) { return ctx->bk.tsmax[b][N - ctx->bk.Nmin[b]]; }
+// range queries follow the reference's sentinels instead of crashing: nothing set / boundary or N outside the table -> an empty range
+static bool bk_boundary_ok(const b2_ctx* ctx, int b) { return ctx && ctx->have_bk && b >= 0 && b <= ctx->bk.L; }
+static bool bk_n_ok(const b2_ctx* ctx, int b, int N) { return bk_boundary_ok(ctx, b) && N >= ctx->bk.Nmin[b] && N <= ctx->bk.Nmax[b]; }
+int b2_bk_nmin(const b2_ctx* ctx, int b) { return bk_boundary_ok(ctx, b) ? ctx->bk.Nmin[b] : 0; }
+int b2_bk_nmax(const b2_ctx* ctx, int b) { return bk_boundary_ok(ctx, b) ? ctx->bk.Nmax[b] : -1; }
+int b2_bk_twosmin(const b2_ctx* ctx, int b, int N) { return bk_n_ok(ctx, b, N) ? ctx->bk.tsmin[b][N - ctx->bk.Nmin[b]] : 0; }
+int b2_bk_twosmax(const b2_ctx* ctx, int b, int N) { return bk_n_ok(ctx, b, N) ? ctx->bk.tsmax[b][N - ctx->bk.Nmin[b]] : -1; }
 
-int64_t b2_tensor_t_size(const b2_ctx* ctx, int site) { TLayout t; t.build(ctx->bk, site); return t.size; }
-int64_t b2_sobject_size(const b2_ctx* ctx, int site) { SLayout s; s.build(ctx->bk, site); return s.size; }
-int b2_sobject_nkappa(const b2_ctx* ctx, int site) { SLayout s; s.build(ctx->bk, site); return s.nkappa(); }
+static bool site_ok(const b2_ctx* ctx, int site, int last) { return ctx && ctx->have_bk && site >= 0 && site <= last; }
+int64_t b2_tensor_t_size(const b2_ctx* ctx, int site) {
+   if (!site_ok(ctx, site, ctx ? ctx->bk.L - 1 : 0)) { fail(B2_ERR_ARG, "b2_tensor_t_size: no bookkeeper or site %d out of range", site); return -1; }
+   TLayout t; t.build(ctx->bk, site); return t.size;
+}
+int64_t b2_sobject_size(const b2_ctx* ctx, int site) {
+   if (!site_ok(ctx, site, ctx ? ctx->bk.L - 2 : 0)) { fail(B2_ERR_ARG, "b2_sobject_size: no bookkeeper or site %d out of range", site); return -1; }
+   SLayout s; s.build(ctx->bk, site); return s.size;
+}
+int b2_sobject_nkappa(const b2_ctx* ctx, int site) {
+   if (!site_ok(ctx, site, ctx ? ctx->bk.L - 2 : 0)) { fail(B2_ERR_ARG, "b2_sobject_nkappa: no bookkeeper or site %d out of range", site); return -1; }
+   SLayout s; s.build(ctx->bk, site); return s.nkappa();
+}
 int b2_sobject_table(const b2_ctx* ctx, int site, int* labels, int64_t* offsets) {
+   if (!site_ok(ctx, site, ctx ? ctx->bk.L - 2 : 0) || !labels || !offsets) return fail(B2_ERR_ARG, "b2_sobject_table: no bookkeeper, NULL output or site %d out of range", site);
    SLayout s; s.build(ctx->bk, site);
    for (int k = 0; k < s.nkappa(); k++) {
       int* l = labels + 9 * k;

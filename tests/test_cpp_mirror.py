@@ -138,3 +138,21 @@ def test_cpp_caller_n2_sto3g_known_answers(tmp_path):
     assert abs(out["n_elec"] - N) < 1e-8 and out["rdm1_asym"] < 1e-9
     assert out["entropy_sum"] > 0.0 and out["mutinfo_sum"] > 0.0
     assert "Information on completed instruction" in res.stdout
+
+
+@pytest.mark.parametrize("std", ["c++11", "c++17"])
+def test_header_compiles_cleanly(tmp_path, std):
+    """the mirror is header-only C++11, warning-free, and its namespace can be renamed for programs that also link the reference"""
+    inc = os.path.join(ROOT, "include")
+    res = subprocess.run(["g++", f"-std={std}", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", f"-I{inc}", os.path.join(ROOT, "tests", "cpp", "dmrg_caller.cpp")],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    src = tmp_path / "ns.cpp"
+    src.write_text('#include "chemps2_b200.hpp"\nint main(){ b2shim::ConvergenceScheme s(1); s.setInstruction(0, 10, 1e-8, 3, 0.0);\n'
+                   ' b2shim::Irreps g(7); return (s.get_D(0) == 10 && g.getNumberOfIrreps() == 8 && b2shim::Irreps::directProd(5, 7) == 2) ? 0 : 1; }\n')
+    exe = tmp_path / "ns"
+    lib_dir = os.path.join(ROOT, "chemps2_b200")
+    res = subprocess.run(["g++", f"-std={std}", "-DCHEMPS2_B200_NAMESPACE=b2shim", f"-I{inc}", str(src), "-o", str(exe), f"-L{lib_dir}", "-lchemps2_b200",
+                          f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert subprocess.run([str(exe)]).returncode == 0

@@ -38,3 +38,18 @@ def test_version_and_error_strings():
     assert lib.b2_bk_init(out, 10) != 0      # no problem set yet -> error code + message, never a crash
     assert b"problem" in lib.b2_last_error()
     lib.b2_ctx_destroy(out)
+
+
+def test_header_is_plain_c(tmp_path):
+    """the boundary is a C ABI: include/chemps2_b200.h compiles as strict C99 and a C program can drive the library"""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "chemps2_b200.h"\n'
+                   'int main(void){ b2_ctx* c = 0; if (b2_ctx_create(-1, &c)) return 1; if (b2_bk_init(c, 8) != B2_ERR_STATE) return 3;\n'
+                   '  b2_ctx_destroy(c); return b2_version()[0] ? 0 : 2; }\n')
+    exe = tmp_path / "abi"
+    lib_dir = os.path.join(ROOT, "chemps2_b200")
+    res = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{os.path.join(ROOT, 'include')}", str(src), "-o", str(exe),
+                          f"-L{lib_dir}", "-lchemps2_b200", f"-Wl,-rpath,{lib_dir}"], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert subprocess.run([str(exe)]).returncode == 0

@@ -2,7 +2,6 @@
 // states, MPS checkpoints, and the 2-RDM / correlation chains of DMRG::calc_rdms_and_correlations (DMRGtechnics.cpp:40-215).
 #include "b2_capi_internal.h"
 
-// upload a compiled work list, run it once on the context stream, free it (used for small one-shot contractions: Join)
 int b2capi::run_compiled_once(b2_ctx* ctx, const CompiledWork& w, DevBases b) {
    cudaStream_t s = ctx->stream;
    GemmItem *i1 = nullptr, *i2 = nullptr;
@@ -129,6 +128,7 @@ int b2_dmrg_get_mps(const b2_dmrg* d, int site, double* t) {
 int b2_dmrg_random_mps(b2_dmrg* d, uint64_t seed) {
    if (!d) return fail(B2_ERR_ARG, "b2_dmrg_random_mps: NULL");
    d->rng = seed * 0x9E3779B97F4A7C15ULL + 0xD1B54A32D192ED03ULL;
+   if (d->rng == 0) d->rng = 0x9E3779B97F4A7C15ULL;   // the all-zero state is the one fixed point of xorshift
    for (int s = 0; s < d->L; s++) {   // DMRG::setupBookkeeperAndMPS (DMRG.cpp:149-169): random() then left_normalize with R discarded
       TLayout lay; lay.build(d->ctx->bk, s);
       d->mps[s].resize((size_t)lay.size);
@@ -196,9 +196,9 @@ int b2_dmrg_timers(b2_dmrg* d, double* out5, int reset) {
    return B2_OK;
 }
 
-// DMRG::updateMovingRight(index) / updateMovingLeft(index-1): operators of the boundary next to site `index` from T = MPS[index]
 // TensorO::update_ownmem / create (TensorO.cpp:38-196, formulas of TensorOperator::update with two_j = 0, no Jordan-Wigner phase) for every
-// stored state: the overlap tensor of the boundary next to site `index` from MPS[index] of both states.
+// stored state: the overlap tensor of the boundary next to site `index` from MPS[index] of both states
+// (DMRG::updateMovingRight / updateMovingLeft, DMRGoperators.cpp:556-567, 889-900).
 static int dmrg_update_overlaps(b2_dmrg* d, int index, bool mr) {
    if (d->exc.empty()) return B2_OK;
    b2_ctx* ctx = d->ctx;

@@ -130,7 +130,14 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
          if (seen[terms[i].dst]) grouped = false;
          seen[terms[i].dst] = 1;
       }
-      if (!grouped) std::stable_sort(terms.begin(), terms.end(), [](const Term3& a, const Term3& b) { return a.dst < b.dst; });
+      if (!grouped) {   // stable counting sort by destination block (ids are dense): one pass to count, one to scatter
+         std::vector<size_t> pos(dst.size() + 1, 0);
+         for (const Term3& t : terms) pos[t.dst + 1]++;
+         for (size_t k = 0; k < dst.size(); k++) pos[k + 1] += pos[k];
+         std::vector<Term3> sorted(terms.size());
+         for (const Term3& t : terms) sorted[pos[t.dst]++] = t;
+         terms.swap(sorted);
+      }
    }
    const int T = std::max(1, std::min<int>(opt.threads, (int)(terms.size() / std::max<int64_t>(opt.parallel_min_terms, 1))));
    if (T <= 1) {

@@ -45,8 +45,10 @@ int b2_update_create_sharded(b2_ctx* ctx, int index, int moving_right, b2_opset*
    if ((need_old && old_set->offloaded) || new_set->offloaded) return fail(B2_ERR_STATE, "b2_update_create: operator set is offloaded (b2_opset_reload first)");
    std::unique_ptr<b2_update> u(new b2_update);
    u->ctx = ctx; u->old_set = need_old ? old_set : nullptr; u->new_set = new_set;
+   const double tb0 = wall_seconds();
    build_update_plan(u->plan, ctx->bk, ctx->prob, u->old_set ? &u->old_set->set : nullptr, new_set->set, index, mr);
    u->world = world; u->rank = rank;
+   const double tb1 = wall_seconds();
    {  // pass 0 is sharded by NEW operator: greedy longest-processing-time assignment of the operators to the GPUs by the
       // FLOPs of their terms (the reference's static owner maps, MPIchemps2.h:158-231, balance counts, not work; every rank
       // evaluates the same deterministic assignment).  The partial arenas are summed by the all-reduce callback.
@@ -69,11 +71,15 @@ int b2_update_create_sharded(b2_ctx* ctx, int index, int moving_right, b2_opset*
          u->plan.terms.swap(mine);
       }
    }
+   const double tb2 = wall_seconds();
    CompileOptions copt = budgeted(ctx);
    copt.threads = (u->plan.flops_ref < ctx->parallel_plan_flops) ? plan_threads((int)u->plan.dst.size()) : 1;
    compile_terms(u->pass[0], u->plan.terms, u->plan.dst, SP_VOUT, copt);
    compile_terms(u->pass[1], u->plan.mix_terms, u->plan.dst, SP_VOUT, copt);
    for (int p = 0; p < 2; p++) u->list_bytes[p] = u->pass[p].bytes();
+   if (getenv("B2_TIMING"))
+      fprintf(stderr, "b2_update_create: enumerate %.3f s, owners %.3f s, schedule %.3f s, %zu + %zu terms\n", tb1 - tb0, tb2 - tb1, wall_seconds() - tb2,
+              u->plan.terms.size(), u->plan.mix_terms.size());
    for (const Presum& p : u->plan.presums) {
       PresumJob j{};
       j.dst_off = p.off; j.size = p.lay->size; j.part_begin = (int)u->presum_parts.size();

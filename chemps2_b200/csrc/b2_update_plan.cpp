@@ -11,6 +11,8 @@
 
 #include "b2_update.h"
 
+#include <atomic>
+
 namespace b2 {
 
 namespace {
@@ -18,7 +20,8 @@ namespace {
 struct Sec { int n, ts, ir; };
 
 struct UGen {
-   UpdatePlan& plan;
+   UpdatePlan& plan;               // receives terms, mixing terms, pre-sums and the FLOP count (the whole plan, or one thread's fragment)
+   const UpdatePlan& shared;       // T layout, destination blocks, block_base: read only
    const Bookkeeper& bk;
    const Problem& prob;
    const OpSet* old_set;
@@ -28,8 +31,8 @@ struct UGen {
    const int b_old, b_new;    // boundaries
    const int site_irr;        // irrep of the site T lives on
 
-   UGen(UpdatePlan& p, const Bookkeeper& b, const Problem& pr, const OpSet* o, const OpSet& n, int index, bool moving_right)
-       : plan(p), bk(b), prob(pr), old_set(o), new_set(n), ix(index), L(b.L), mr(moving_right), b_old(moving_right ? index : index + 1),
+   UGen(UpdatePlan& p, const UpdatePlan& sh, const Bookkeeper& b, const Problem& pr, const OpSet* o, const OpSet& n, int index, bool moving_right)
+       : plan(p), shared(sh), bk(b), prob(pr), old_set(o), new_set(n), ix(index), L(b.L), mr(moving_right), b_old(moving_right ? index : index + 1),
          b_new(moving_right ? index + 1 : index), site_irr(b.orb_irrep[index]) {}
 
    double V(int a, int b, int c, int d) const { return prob.V(a, b, c, d); }
@@ -39,9 +42,9 @@ struct UGen {
    // T block between an old-boundary sector and a new-boundary sector
    MatRef tref(const Sec& so, const Sec& sn, bool is_up) const {
       MatRef m;
-      const int k = mr ? plan.T.kappa(bk, so.n, so.ts, so.ir, sn.n, sn.ts, sn.ir) : plan.T.kappa(bk, sn.n, sn.ts, sn.ir, so.n, so.ts, so.ir);
+      const int k = mr ? shared.T.kappa(bk, so.n, so.ts, so.ir, sn.n, sn.ts, sn.ir) : shared.T.kappa(bk, sn.n, sn.ts, sn.ir, so.n, so.ts, so.ir);
       if (k < 0) return m;
-      m.space = SP_RIGHT; m.off = plan.T.blk[k].off; m.rows = plan.T.blk[k].rows; m.cols = plan.T.blk[k].cols;
+      m.space = SP_RIGHT; m.off = shared.T.blk[k].off; m.rows = shared.T.blk[k].rows; m.cols = shared.T.blk[k].cols;
       m.trans = is_up ? (mr ? 1 : 0) : (mr ? 0 : 1);
       return m;
    }
@@ -85,11 +88,11 @@ struct UGen {
       if (!tu.present() || !td.present()) return;
       if (mid && !mid->present()) return;
       Term3 t;
-      t.dst = plan.block_base[new_op] + k;
+      t.dst = shared.block_base[new_op] + k;
       t.f = f; t.p = tu; t.r = td;
       if (mid) t.q = *mid;
       plan.terms.push_back(t);
-      const double m = plan.dst[t.dst].rows, n = plan.dst[t.dst].cols, du = dim_old(ux), dd = dim_old(dx);
+      const double m = shared.dst[t.dst].rows, n = shared.dst[t.dst].cols, du = dim_old(ux), dd = dim_old(dx);
       if (count) plan.flops_ref += mid ? 2.0 * (m * dd * du + m * n * dd) : 2.0 * m * n * du;
    }
 
@@ -293,10 +296,10 @@ struct UGen {
 #include "b2_update_plan_qx.inc"
 
    // ============================================================================ orchestration (DMRGoperators.cpp:243-907)
-   void run() {
+   void run_one(int n) {
       const int i = ix;
       auto oldf = [&](int kind, int a, int b) { return old_set ? old_set->find(kind, a, b) : -1; };
-      for (int n = 0; n < (int)new_set.ops.size(); n++) {
+      {
          const OpTensor& t = new_set.ops[n];
          switch (t.kind) {
             case K_L:
@@ -362,7 +365,7 @@ struct UGen {
             if (p.src < 0 || p.coef == 0.0) continue;
             const OpTensor& so = new_set.ops[p.src];
             Term3 x;
-            x.dst = plan.block_base[n] + k;
+            x.dst = shared.block_base[n] + k;
             x.f = p.coef;
             int sk;
             if (!p.tr) sk = so.lay->kappa(bk, U.n, U.ts, U.ir, Dn.n, Dn.ts, Dn.ir);                 // TensorOperator::daxpy (:407-414): identical layouts
@@ -373,7 +376,7 @@ struct UGen {
             if (sk < 0) continue;
             x.q.space = SP_VOUT; x.q.off = so.off + so.lay->blk[sk].off; x.q.rows = so.lay->blk[sk].rows; x.q.cols = so.lay->blk[sk].cols; x.q.trans = p.tr;
             plan.mix_terms.push_back(x);
-            plan.flops_ref += 2.0 * plan.dst[x.dst].rows * plan.dst[x.dst].cols;
+            plan.flops_ref += 2.0 * shared.dst[x.dst].rows * shared.dst[x.dst].cols;
          }
       }
    }
@@ -392,8 +395,55 @@ void build_update_plan(UpdatePlan& plan, const Bookkeeper& bk, const Problem& pr
       plan.block_base[n] = (int)plan.dst.size();
       for (const Block& b : t.lay->blk) plan.dst.push_back(DstBlock{t.off + b.off, b.rows, b.cols});
    }
-   UGen g(plan, bk, prob, old_set, new_set, index, moving_right);
-   g.run();
+   const int nops = (int)new_set.ops.size();
+   const int nthreads = std::min(plan_threads((int)plan.dst.size()), std::max(1, nops / 4));
+   if (nthreads <= 1) {
+      UGen g(plan, plan, bk, prob, old_set, new_set, index, moving_right);
+      for (int n = 0; n < nops; n++) g.run_one(n);
+      return;
+   }
+   // New operators are independent: every host thread enumerates the operators it grabs into a private fragment; the fragments are
+   // stitched together in operator order (pre-sum arena offsets shifted per operator), so the plan has exactly the terms, the term
+   // order and the pre-sum layout of the sequential enumeration.
+   struct Span { size_t t0, t1, m0, m1, p0, p1; int64_t a0, a1; };   // terms, mixing terms, pre-sums, pre-sum arena range of one operator
+   struct Frag { UpdatePlan plan; std::vector<std::pair<int, Span>> spans; };
+   std::vector<Frag> frags(nthreads);
+   std::atomic<int> next{0};
+   parallel_run(nthreads, [&](int t) {
+      Frag& f = frags[t];
+      UGen g(f.plan, plan, bk, prob, old_set, new_set, index, moving_right);
+      for (;;) {
+         const int n = next.fetch_add(1);
+         if (n >= nops) break;
+         Span sp{f.plan.terms.size(), 0, f.plan.mix_terms.size(), 0, f.plan.presums.size(), 0, f.plan.presum_size, 0};
+         g.run_one(n);
+         sp.t1 = f.plan.terms.size(); sp.m1 = f.plan.mix_terms.size(); sp.p1 = f.plan.presums.size(); sp.a1 = f.plan.presum_size;
+         f.spans.push_back({n, sp});
+      }
+   });
+   std::vector<std::pair<int, int>> where(nops, {-1, -1});
+   size_t nterms = 0, nmix = 0, npre = 0;
+   for (int t = 0; t < nthreads; t++) {
+      for (size_t i = 0; i < frags[t].spans.size(); i++) where[frags[t].spans[i].first] = {t, (int)i};
+      nterms += frags[t].plan.terms.size(); nmix += frags[t].plan.mix_terms.size(); npre += frags[t].plan.presums.size();
+      plan.flops_ref += frags[t].plan.flops_ref;
+   }
+   plan.terms.reserve(nterms); plan.mix_terms.reserve(nmix); plan.presums.reserve(npre);
+   for (int n = 0; n < nops; n++) {
+      const Frag& f = frags[where[n].first];
+      const Span& sp = f.spans[where[n].second].second;
+      const int64_t shift = plan.presum_size - sp.a0;
+      for (size_t i = sp.p0; i < sp.p1; i++) { Presum p = f.plan.presums[i]; p.off += shift; plan.presums.push_back(std::move(p)); }
+      plan.presum_size += sp.a1 - sp.a0;
+      for (size_t i = sp.t0; i < sp.t1; i++) {
+         Term3 x = f.plan.terms[i];
+         if (x.p.space == SP_PRESUM) x.p.off += shift;
+         if (x.q.space == SP_PRESUM) x.q.off += shift;
+         if (x.r.space == SP_PRESUM) x.r.off += shift;
+         plan.terms.push_back(x);
+      }
+      plan.mix_terms.insert(plan.mix_terms.end(), f.plan.mix_terms.begin() + sp.m0, f.plan.mix_terms.begin() + sp.m1);
+   }
 }
 
 }   // namespace b2

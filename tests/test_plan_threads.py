@@ -84,3 +84,38 @@ def test_worker_pool_concurrent_callers_and_fork():
     errs, child = eval("(" + payload.rsplit("]", 1)[0] + "]," + payload.rsplit("]", 1)[1] + ")")
     assert child == 0
     assert len(errs) == 6 and max(errs) < 1e-12, errs
+
+
+UPDATE_WORKER = r"""
+import sys, os
+import numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import cpu_check
+from chemps2_b200 import fixtures
+out = []
+for name in ("h2o_631g", "n2_sto3g_quintet_b1u"):
+    fx = fixtures.load(os.path.join({root!r}, "tests", "golden", name + ".npz"))
+    for which in ("UR", "UL"):
+        ctx, old, new, upd, t, expected = cpu_check.build_update_case(fx, which)
+        arena = cpu_check.emulate_update(old, new, upd, t)
+        st = upd.stats()
+        out.append((int(st["terms"]), int(st["mix_terms"]), int(st["presums"]), st["flops_ref"], float(np.abs(arena).sum())))
+print("B2UPD", out)
+"""
+
+
+def test_parallel_update_plan_equals_sequential_plan():
+    """b2_update_plan.cpp enumerates the new operators on several host threads; stitched in operator order (pre-sum arena offsets shifted)
+    the plan is the sequential one: same term / mixing-term / pre-sum counts and the emulated arena agrees to the last bit of its abs-sum
+    up to summation order"""
+    def run(threads):
+        env = dict(os.environ, B2_PLAN_THREADS=str(threads))
+        res = subprocess.run([sys.executable, "-c", UPDATE_WORKER.format(root=ROOT)], capture_output=True, text=True, env=env, timeout=600)
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+        return eval([ln for ln in res.stdout.splitlines() if ln.startswith("B2UPD")][-1][len("B2UPD"):])
+    seq, par = run(1), run(6)
+    assert len(seq) == 4
+    for (t1, m1, p1, f1, s1), (t2, m2, p2, f2, s2) in zip(seq, par):
+        assert (t1, m1, p1) == (t2, m2, p2)
+        assert abs(f1 - f2) <= 1e-9 * f1
+        assert abs(s1 - s2) <= 1e-10 * max(1.0, abs(s1))

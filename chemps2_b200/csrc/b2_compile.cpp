@@ -11,6 +11,7 @@
 #include "b2_core.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <functional>
 #include <thread>
@@ -174,7 +175,6 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
          out.flops_exec += seg[t].flops_exec; out.n_stage1 += seg[t].n_stage1;
       }
       out.work_size = wbase[T]; out.part_size = pbase[T];
-      out.items1.resize(i1base[T]); out.items2.resize(i2base[T]);
       // positions of every (wave, segment) slice in the merged tile / reduce lists
       struct Pos { int t1[kNumTileClasses], t2[kNumTileClasses], red; };
       std::vector<std::vector<Pos>> pos(nwaves, std::vector<Pos>(T));
@@ -196,8 +196,19 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
          for (int c = 0; c < kNumTileClasses; c++) { gw.t1_end[c] = n1[c]; gw.t2_end[c] = n2[c]; }
          gw.red_end = nred;
       }
-      for (int c = 0; c < kNumTileClasses; c++) { out.tiles1[c].resize(n1[c]); out.tiles2[c].resize(n2[c]); }
-      out.reduces.resize(nred);
+      {  // the merged lists are tens of MB of fresh memory: size them on several threads so the first-touch page faults overlap
+         std::vector<std::function<void()>> sizing;
+         sizing.push_back([&] { out.items1.resize(i1base[T]); });
+         sizing.push_back([&] { out.items2.resize(i2base[T]); });
+         sizing.push_back([&] { out.reduces.resize(nred); });
+         for (int c = 0; c < kNumTileClasses; c++) {
+            sizing.push_back([&, c] { out.tiles1[c].resize(n1[c]); });
+            sizing.push_back([&, c] { out.tiles2[c].resize(n2[c]); });
+         }
+         std::atomic<int> next_sizing{0};
+         run_all([&](int) { for (int i; (i = next_sizing.fetch_add(1)) < (int)sizing.size();) sizing[i](); });
+      }
+      const double t_seg2 = now_s();
       run_all([&](int t) {   // every segment copies its own slices, shifting item indices and workspace / partial-slot offsets
          std::copy(seg[t].items1.begin(), seg[t].items1.end(), out.items1.begin() + i1base[t]);
          for (size_t i = 0; i < seg[t].items2.size(); i++) {
@@ -231,7 +242,7 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
          }
          seg[t] = CompiledWork();
       });
-      if (getenv("B2_TIMING")) fprintf(stderr, "compile_terms: regroup %.3f s, segments %.3f s, merge %.3f s\n", t_seg0 - T_total, t_seg1 - t_seg0, now_s() - t_seg1);
+      if (getenv("B2_TIMING")) fprintf(stderr, "compile_terms: regroup %.3f s, segments %.3f s, merge %.3f s (allocation %.3f s)\n", t_seg0 - T_total, t_seg1 - t_seg0, now_s() - t_seg1, t_seg2 - t_seg1);
    }
    for (int c = 0; c < kNumTileClasses; c++) out.n_tiles += (long long)out.tiles1[c].size() + (long long)out.tiles2[c].size();
    if (getenv("B2_TIMING")) fprintf(stderr, "compile_terms: total %.3f s, %d thread(s)\n", now_s() - T_total, T);

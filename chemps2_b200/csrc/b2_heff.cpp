@@ -6,6 +6,9 @@
 #include "b2_heff.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
 
 namespace b2 {
@@ -30,6 +33,8 @@ void compile_sigma(CompiledSigma& out, const SigmaPlan& plan, const OpSet* left,
    out = CompiledSigma();
    const SLayout& S = plan.S;
    const int nk = S.nkappa();
+   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+   const double tc0 = now();
 
    // ---- presums
    for (const Presum& p : plan.presums) {
@@ -58,6 +63,7 @@ void compile_sigma(CompiledSigma& out, const SigmaPlan& plan, const OpSet* left,
    }
    out.n_terms_used = (long long)order.size();
 
+   const double tc1 = now();
    std::vector<DstBlock> dst(nk);
    for (int k = 0; k < nk; k++) dst[k] = DstBlock{S.blk[k].off, S.blk[k].rows, S.blk[k].cols};
    std::vector<Term3> terms(order.size());
@@ -76,6 +82,7 @@ void compile_sigma(CompiledSigma& out, const SigmaPlan& plan, const OpSet* left,
       const int T = std::max(1, std::min<int>(opt.threads, (int)(order.size() / 20000)));
       parallel_run(T, [&](int t) { resolve_range(order.size() * t / T, order.size() * (t + 1) / T); });
    }
+   const double tc2 = now();
    // ---- diagonal of H_eff (Heff::fillHeffDiag, Heff.cpp:250-315 + HeffDiagonal.cpp): exactly the terms that map a block
    // onto itself — families 1A-1D, 2d3, 2b3/2c3/2e3/2f3 and 2a3 — restricted to the operator-block diagonals:
    //    diag[k](i,j) = sum_t f_t * op(A_t)(i,i) * op(B_t)(j,j)
@@ -101,10 +108,12 @@ void compile_sigma(CompiledSigma& out, const SigmaPlan& plan, const OpSet* left,
          }
    }
 
+   const double tc3 = now();
    CompiledWork& base = out;
    CompiledWork work;
    compile_terms(work, terms, dst, SP_VOUT, opt);
    base = std::move(work);
+   if (getenv("B2_TIMING")) fprintf(stderr, "compile_sigma: order %.3f s, resolve %.3f s, diagonal %.3f s, schedule %.3f s\n", tc1 - tc0, tc2 - tc1, tc3 - tc2, now() - tc3);
 }
 
 }   // namespace b2

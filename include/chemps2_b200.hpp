@@ -520,6 +520,11 @@ public:
       return (int)n;
    }
    static void PrintLicense() {}
+   /* public members of the reference's DMRG that are not on the accelerated path (FCI coefficients of the MPS: DMRGtechnics.cpp:217-507;
+    * 4-RDM contraction for CASPT2: DMRGfock.cpp): callers compile, calling them aborts with a message instead of returning wrong numbers */
+   double getSpecificCoefficient(int*) const { not_built("DMRG::getSpecificCoefficient"); return 0.0; }
+   double getFCIcoefficient(int*, int*, const bool = true) const { not_built("DMRG::getFCIcoefficient"); return 0.0; }
+   void Symm4RDM(double*, const int, const int, const bool) { not_built("DMRG::Symm4RDM"); }
    /* ---- beyond the reference's interface ---- */
    void set_verbose(bool v) { verbose = v; }
    /* one process per GPU: shard sigma terms and operator updates over `world` ranks; fn sums a device vector over them (NCCL) */
@@ -541,6 +546,10 @@ private:
    bool ops_ready, verbose;
    double TotalMinEnergy = 1e8, LastMinEnergy = 1e8, MaxDiscWeightLastSweep = 0.0;
 
+   static void not_built(const char* what) {
+      std::fprintf(stderr, "chemps2_b200: %s is outside the accelerated two-site sweep path (DESIGN.md, out of scope)\n", what);
+      std::abort();
+   }
    void set_storage_name() {
       std::stringstream s;
       s << DMRG_MPS_storage_prefix << nStates - 1 << ".b2mps";

@@ -4,6 +4,7 @@
  * the committed fixtures, runs this binary and checks the numbers it prints.
  *
  *   dmrg_caller host  <fcidump> <group> <TwoS> <N> <Irrep> <none|d2h|c2v> <out.bin>     host classes only (no GPU): dumps irreps + folded table
+ *   dmrg_caller accessors <fcidump> <group> <TwoS> <N> <Irrep> <none|d2h|c2v> <out.bin>  TwoDM / Correlations accessor arithmetic on filled-in arrays (no GPU)
  *   dmrg_caller solve <fcidump> <group> <TwoS> <N> <Irrep> <none|d2h|c2v> <D> <n_excited>  whole calculation on the GPU, one JSON line */
 #include <cstring>
 
@@ -49,6 +50,33 @@ int main(int argc, char** argv) {
       }
       std::remove(copy.c_str());
       std::printf("{\"L\": %d, \"reorder\": %d, \"fcidump_roundtrip\": %.3e}\n", L, Prob->gReorder() ? 1 : 0, worst);
+      delete Prob; delete Ham;
+      return 0;
+   }
+
+   if (mode == "accessors") {
+      /* A, B and the correlation tables filled with a fixed pattern; every accessor evaluated in Hamiltonian AND DMRG orbital order */
+      Prob->construct_mxelem();
+      CheMPS2::TwoDM dm(Prob);
+      CheMPS2::Correlations corr(Prob, &dm);
+      const size_t L4 = (size_t)L * L * L * L;
+      for (size_t i = 0; i < L4; i++) { dm.storage_A()[i] = std::sin(0.37 * (double)i + 0.1); dm.storage_B()[i] = std::cos(0.23 * (double)i - 0.4); }
+      for (int t = 0; t < 5; t++) for (int i = 0; i < L * L; i++) corr.storage(t)[i] = std::sin(1.0 + t + 0.61 * i);
+      std::vector<double> out;
+      out.push_back(dm.trace()); out.push_back(dm.energy()); out.push_back(corr.MutualInformationDistance(2.0));
+      for (int i = 0; i < L; i++) { out.push_back(corr.SingleOrbitalEntropy_HAM(i)); out.push_back(corr.SingleOrbitalEntropy_DMRG(i)); }
+      for (int i = 0; i < L; i++) for (int j = 0; j < L; j++) {
+         out.push_back(dm.get1RDM_HAM(i, j)); out.push_back(dm.get1RDM_DMRG(i, j));
+         out.push_back(dm.spin_density_ham(i, j)); out.push_back(dm.spin_density_dmrg(i, j));
+         out.push_back(corr.getCspin_HAM(i, j)); out.push_back(corr.getCdens_HAM(i, j)); out.push_back(corr.getCspinflip_HAM(i, j));
+         out.push_back(corr.getCdirad_HAM(i, j)); out.push_back(corr.getMutualInformation_HAM(i, j)); out.push_back(corr.getMutualInformation_DMRG(i, j));
+         out.push_back(dm.getTwoDMA_HAM(i, j, (i + 1) % L, (j + 2) % L)); out.push_back(dm.getTwoDMB_HAM(i, j, j, i));
+      }
+      FILE* f = std::fopen(argv[8], "wb");
+      if (!f) return 3;
+      std::fwrite(out.data(), sizeof(double), out.size(), f);
+      std::fclose(f);
+      std::printf("{\"L\": %d, \"values\": %zu}\n", L, out.size());
       delete Prob; delete Ham;
       return 0;
    }

@@ -105,6 +105,62 @@ def test_reorder_c2v_restated(tmp_path):
     assert np.abs(mx.reshape(L, L, L, L, order="F") - want).max() < 1e-14
 
 
+@pytest.mark.parametrize("name, reorder, twoS", [("n2_sto3g_singlet", "d2h", 0), ("h2o_631g", "none", 0), ("hubbard10_sextet", "none", 5)])
+def test_twodm_and_correlation_accessors(tmp_path, name, reorder, twoS):
+    """TwoDM / Correlations accessor arithmetic (TwoDM.cpp:101-231, Correlations.cpp:105-196) restated in numpy on the same filled-in arrays:
+    irrep selection rules, 1-RDM and spin-density contractions, trace, energy, entropies, Hamiltonian <-> DMRG orbital order"""
+    fx = fixtures.load(os.path.join(GOLDEN, name + ".npz"))
+    dump = str(tmp_path / "in.fcidump")
+    L, group, N, _, irrep = fcidump_from_fixture(fx, dump)
+    out = str(tmp_path / "acc.bin")
+    subprocess.run([CALLER, "accessors", dump, str(group), str(twoS), str(N), str(irrep), reorder, out], check=True, capture_output=True, text=True)
+    got = np.fromfile(out, dtype=np.float64)
+    ham_irr = [int(i) for i in fx["problem/orb_irrep"]]
+    if reorder == "d2h":
+        f2 = [h for ir in (0, 5, 7, 2, 6, 3, 1, 4) for h in range(L) if ham_irr[h] == ir]
+    else:
+        f2 = list(range(L))
+    f1 = [f2.index(h) for h in range(L)]                      # Hamiltonian -> DMRG
+    irr = [ham_irr[f2[d]] for d in range(L)]                  # irreps in DMRG order
+    idx = np.arange(L ** 4, dtype=np.float64)
+    A = np.sin(0.37 * idx + 0.1).reshape(L, L, L, L, order="F")
+    B = np.cos(0.23 * idx - 0.4).reshape(L, L, L, L, order="F")
+    ok = np.zeros((L, L, L, L), dtype=bool)
+    for a in range(L):
+        for b in range(L):
+            for c in range(L):
+                for d in range(L):
+                    ok[a, b, c, d] = (irr[a] ^ irr[b]) == (irr[c] ^ irr[d])
+    A, B = np.where(ok, A, 0.0), np.where(ok, B, 0.0)
+    tab = [np.sin(1.0 + t + 0.61 * np.arange(L * L)).reshape(L, L, order="F") for t in range(5)]
+    T = fx["problem/tmat"].reshape(L, L, order="F")[np.ix_(f2, f2)]
+    V = fx["problem/vmat"].reshape(L, L, L, L, order="F")[np.ix_(f2, f2, f2, f2)]
+    eye = np.eye(L)
+    mx = V + (np.einsum("ac,bd->abcd", eye, T) + np.einsum("bd,ac->abcd", eye, T)) / (N - 1)
+    same = np.array([[irr[i] == irr[j] for j in range(L)] for i in range(L)])
+    rdm1 = np.where(same, np.einsum("ikjk->ij", A) / (N - 1.0), 0.0)
+    spin = np.zeros((L, L))
+    if twoS > 0:
+        spin = np.where(same, 1.5 * ((2 - N) * rdm1 - np.einsum("ikkj->ij", A) - np.einsum("ikkj->ij", B)) / (0.5 * twoS + 1), 0.0)
+
+    def entropy(i):
+        v4 = 0.5 * A[i, i, i, i]; v23 = 0.5 * (rdm1[i, i] - A[i, i, i, i]); v1 = 1.0 - v4 - 2 * v23
+        return -sum(m * v * np.log(v) for m, v in ((1, v1), (2, v23), (1, v4)) if v > 1e-100)
+
+    want = [np.einsum("abab->", A), 0.5 * np.sum(A * mx) + float(fx["problem/econst"][0]),
+            sum(tab[4][r, c] * abs(r - c) ** 2.0 for r in range(L) for c in range(L) if r != c)]
+    for i in range(L):
+        want += [entropy(f1[i]), entropy(i)]
+    for i in range(L):
+        for j in range(L):
+            a, b = f1[i], f1[j]
+            want += [rdm1[a, b], rdm1[i, j], spin[a, b], spin[i, j], tab[0][a, b], tab[1][a, b], tab[2][a, b], tab[3][a, b], tab[4][a, b], tab[4][i, j],
+                     A[a, b, f1[(i + 1) % L], f1[(j + 2) % L]], B[a, b, b, a]]
+    want = np.array(want)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() < 1e-11 * max(1.0, np.abs(want).max())
+
+
 def test_no_device_aborts_loudly(tmp_path):
     """no CPU fallback: without a CUDA device the DMRG constructor aborts with the library's message"""
     import torch

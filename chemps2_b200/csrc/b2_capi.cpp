@@ -367,8 +367,6 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
       if (h->comp.work_size > 0) CUDA_TRY(cudaMalloc(&h->d_work, sizeof(double) * (size_t)h->comp.work_size));
       CUDA_TRY(cudaMalloc(&h->d_vin, sizeof(double) * (n ? n : 1)));
       CUDA_TRY(cudaMalloc(&h->d_vout, sizeof(double) * (n ? n : 1)));
-      CUDA_TRY(cudaMallocHost(&h->h_vin, sizeof(double) * (n ? n : 1)));
-      CUDA_TRY(cudaMallocHost(&h->h_vout, sizeof(double) * (n ? n : 1)));
       CUDA_TRY(cudaEventCreate(&h->ev0));
       CUDA_TRY(cudaEventCreate(&h->ev1));
       // materialise the integral-weighted operator pre-sums once (operators are fixed during the Davidson solve)
@@ -410,8 +408,6 @@ int b2capi::heff_unpark(b2_heff* h, b2_opset* left, b2_opset* right) {
    if (h->comp.work_size > 0) CUDA_TRY(cudaMalloc(&h->d_work, sizeof(double) * (size_t)h->comp.work_size));
    CUDA_TRY(cudaMalloc(&h->d_vin, sizeof(double) * (n ? n : 1)));
    CUDA_TRY(cudaMalloc(&h->d_vout, sizeof(double) * (n ? n : 1)));
-   CUDA_TRY(cudaMallocHost(&h->h_vin, sizeof(double) * (n ? n : 1)));
-   CUDA_TRY(cudaMallocHost(&h->h_vout, sizeof(double) * (n ? n : 1)));
    DevBases b = bases_of(h, nullptr, nullptr);
    if (dev_launch_presum(h->d_jobs, (int)h->comp.presum_jobs.size(), h->d_parts, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
    CUDA_TRY(cudaStreamSynchronize(s));
@@ -448,6 +444,15 @@ int b2_heff_apply_device(b2_heff* h, const double* dev_in, double* dev_out) {
    return B2_OK;
 }
 
+// Pinned staging vectors of the host-buffer entry points (b2_heff_apply / _diag / _solve / _set_excitations), allocated on their first
+// use: the sweep driver works on device vectors only and does not pay for pinning 2 x veclength doubles at every site.
+static int ensure_staging(b2_heff* h) {
+   const size_t n = (size_t)h->plan.S.size;
+   if (!h->h_vin) CUDA_TRY(cudaMallocHost(&h->h_vin, sizeof(double) * (n ? n : 1)));
+   if (!h->h_vout) CUDA_TRY(cudaMallocHost(&h->h_vout, sizeof(double) * (n ? n : 1)));
+   return B2_OK;
+}
+
 int b2_heff_set_excitations(b2_heff* h, int n_lower, const double* const* veff_tilde) {
    if (!h || n_lower < 0 || (n_lower > 0 && !veff_tilde)) return fail(B2_ERR_ARG, "b2_heff_set_excitations: bad arguments");
    if (h->ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_heff_set_excitations: planning-only context, no CUDA device (there is no CPU fallback)");
@@ -456,6 +461,7 @@ int b2_heff_set_excitations(b2_heff* h, int n_lower, const double* const* veff_t
    h->d_exc = h->d_exc_coef = h->d_exc_scratch = nullptr;
    h->n_exc = 0;
    if (n_lower == 0) return B2_OK;
+   { int rs = ensure_staging(h); if (rs) return rs; }
    const size_t n = (size_t)h->plan.S.size;
    CUDA_TRY(cudaMalloc(&h->d_exc, sizeof(double) * n * n_lower));
    CUDA_TRY(cudaMalloc(&h->d_exc_coef, sizeof(double) * n_lower));
@@ -476,6 +482,7 @@ int b2_heff_apply(b2_heff* h, const double* vec_in, double* vec_out) {
    if (h->ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_heff_apply: planning-only context, no CUDA device (there is no CPU fallback)");
    cudaStream_t s = h->ctx->stream;
    const size_t bytes = sizeof(double) * (size_t)h->plan.S.size;
+   { int rs = ensure_staging(h); if (rs) return rs; }
    std::memcpy(h->h_vin, vec_in, bytes);
    CUDA_TRY(cudaMemcpyAsync(h->d_vin, h->h_vin, bytes, cudaMemcpyHostToDevice, s));
    int rc = b2_heff_apply_device(h, h->d_vin, h->d_vout);
@@ -512,7 +519,8 @@ int b2_heff_diag_device(b2_heff* h, double* dev_diag) {
 int b2_heff_diag(b2_heff* h, double* diag) {
    if (!h || !diag) return fail(B2_ERR_ARG, "b2_heff_diag: NULL argument");
    if (h->ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_heff_diag: planning-only context, no CUDA device (there is no CPU fallback)");
-   int rc = b2_heff_diag_device(h, h->d_vout);
+   int rc = ensure_staging(h);
+   if (!rc) rc = b2_heff_diag_device(h, h->d_vout);
    if (rc) return rc;
    const size_t bytes = sizeof(double) * (size_t)h->plan.S.size;
    CUDA_TRY(cudaMemcpyAsync(h->h_vout, h->d_vout, bytes, cudaMemcpyDeviceToHost, h->ctx->stream));
@@ -559,6 +567,7 @@ int b2_heff_solve(b2_heff* h, double* s_host, double rtol, double* eigenvalue, i
    cudaStream_t s = h->ctx->stream;
    const size_t bytes = sizeof(double) * (size_t)h->plan.S.size;
    double* d_s = nullptr;
+   { int rs = ensure_staging(h); if (rs) return rs; }
    CUDA_TRY(cudaMalloc(&d_s, bytes ? bytes : 8));
    std::memcpy(h->h_vin, s_host, bytes);
    cudaError_t e = cudaMemcpyAsync(d_s, h->h_vin, bytes, cudaMemcpyHostToDevice, s);

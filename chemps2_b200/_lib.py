@@ -101,6 +101,10 @@ SIGNATURES = [
     ("b2_twodm_d1_scale", C.c_int, [vp, c_dp, C.c_int]),
     ("b2_twodm_scatter", C.c_int, [vp, C.POINTER(c_dp), C.c_double, c_dp, c_dp]),
     ("b2_svd_batch", C.c_int, [vp, C.c_int, c_ip, c_ip, C.POINTER(c_dp), C.POINTER(c_dp), C.POINTER(c_dp), C.POINTER(c_dp)]),
+    ("b2_join_create", C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    ("b2_join_destroy", None, [vp]),
+    ("b2_join_run", C.c_int, [vp, c_dp, c_dp, c_dp]),
+    ("b2_join_worklists", C.c_int, [vp, vp]),
     ("b2_heff_worklists", C.c_int, [vp, vp]),
     ("b2_ctx_set_option", C.c_int, [vp, C.c_char_p, C.c_double]),
     ("b2_dmrg_create", C.c_int, [vp, C.POINTER(vp)]),

@@ -406,6 +406,34 @@ class DMRG:
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, vp, vp, C.c_int64, vp)
 
 
+class Join:
+    """Sobject::Join (Sobject.cpp:212-258) of the site tensors of (site, site+1) for the current bookkeeper dimensions"""
+
+    def __init__(self, ctx, site):
+        self.ctx, self.site = ctx, int(site)
+        self.h = C.c_void_p()
+        check(lib.b2_join_create(ctx.h, self.site, C.byref(self.h)))
+        self.n = int(lib.b2_sobject_size(ctx.h, self.site))
+
+    def close(self):
+        if self.h:
+            lib.b2_join_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run(self, t_left, t_right):
+        tl = np.ascontiguousarray(t_left, dtype=np.float64)
+        tr = np.ascontiguousarray(t_right, dtype=np.float64)
+        out = np.zeros(max(self.n, 1), dtype=np.float64)
+        check(lib.b2_join_run(self.h, _dp(tl), _dp(tr), _dp(out)))
+        return out[:self.n]
+
+
 class AllReduce:
     """b2_allreduce_fn backed by torch.distributed (NCCL on the GPU box): sums a device vector over the ranks in place on the
     stream the library hands over (the context stream = torch's current stream in bench.py).  Stands in for MPI_Allreduce of

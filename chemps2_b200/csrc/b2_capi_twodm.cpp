@@ -262,6 +262,55 @@ int b2_svd_batch(b2_ctx* ctx, int count, const int* m, const int* n, const doubl
    return B2_OK;
 }
 
+/* Sobject::Join (Sobject.cpp:212-258) as its own entry point: the same terms the sweep driver builds inside b2_dmrg_solve_site */
+struct b2_join {
+   b2_ctx* ctx = nullptr;
+   SLayout S;
+   TLayout TL, TR;
+   CompiledWork work;
+};
+int b2_join_create(b2_ctx* ctx, int site, b2_join** out) {
+   if (!ctx || !ctx->have_bk || !out) return fail(B2_ERR_STATE, "b2_join_create: no bookkeeper");
+   if (site < 0 || site > ctx->bk.L - 2) return fail(B2_ERR_ARG, "b2_join_create: site %d out of range", site);
+   std::unique_ptr<b2_join> j(new b2_join);
+   j->ctx = ctx;
+   j->S.build(ctx->bk, site); j->TL.build(ctx->bk, site); j->TR.build(ctx->bk, site + 1);
+   std::vector<Term3> terms; std::vector<DstBlock> dst;
+   join_terms(terms, dst, ctx->bk, j->S, j->TL, j->TR);
+   compile_terms(j->work, terms, dst, SP_VOUT, budgeted(ctx));
+   *out = j.release();
+   return B2_OK;
+}
+void b2_join_destroy(b2_join* j) { delete j; }
+int b2_join_worklists(const b2_join* j, b2_worklists* o) {
+   if (!j || !o) return fail(B2_ERR_ARG, "b2_join_worklists: NULL");
+   fill_worklists(j->work, o);
+   return B2_OK;
+}
+int b2_join_run(b2_join* j, const double* t_left, const double* t_right, double* s_out) {
+   if (!j || !t_left || !t_right || !s_out) return fail(B2_ERR_ARG, "b2_join_run: NULL argument");
+   b2_ctx* ctx = j->ctx;
+   if (ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_join_run: planning-only context, no CUDA device (there is no CPU fallback)");
+   CUDA_TRY(cudaSetDevice(ctx->device));
+   cudaStream_t s = ctx->stream;
+   struct Buf { double* p = nullptr; ~Buf() { cudaFree(p); } } dTl, dTr, dS;
+   const size_t nl = (size_t)std::max<int64_t>(j->TL.size, 1), nr = (size_t)std::max<int64_t>(j->TR.size, 1), ns = (size_t)std::max<int64_t>(j->S.size, 1);
+   CUDA_TRY(cudaMalloc(&dTl.p, sizeof(double) * nl));
+   CUDA_TRY(cudaMalloc(&dTr.p, sizeof(double) * nr));
+   CUDA_TRY(cudaMalloc(&dS.p, sizeof(double) * ns));
+   CUDA_TRY(cudaMemcpyAsync(dTl.p, t_left, sizeof(double) * (size_t)j->TL.size, cudaMemcpyHostToDevice, s));
+   CUDA_TRY(cudaMemcpyAsync(dTr.p, t_right, sizeof(double) * (size_t)j->TR.size, cudaMemcpyHostToDevice, s));
+   CUDA_TRY(cudaMemsetAsync(dS.p, 0, sizeof(double) * ns, s));
+   DevBases b;
+   for (int i = 0; i < SP_COUNT; i++) b.p[i] = nullptr;
+   b.p[SP_LEFT] = dTl.p; b.p[SP_RIGHT] = dTr.p; b.p[SP_VOUT] = dS.p;
+   int rc = run_compiled_once(ctx, j->work, b);
+   if (rc) return rc;
+   CUDA_TRY(cudaMemcpyAsync(s_out, dS.p, sizeof(double) * (size_t)j->S.size, cudaMemcpyDeviceToHost, s));
+   CUDA_TRY(cudaStreamSynchronize(s));
+   return B2_OK;
+}
+
 /* FP64 peak probe (roofline denominator): mode 1 = DMMA m8n8k4, mode 0 = DFMA */
 int b2_probe_fp64(b2_ctx* ctx, int use_mma, double* tflops) {
    if (!ctx || ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_probe_fp64: no CUDA device");

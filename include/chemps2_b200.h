@@ -293,6 +293,17 @@ int b2_dmrg_sweep(b2_dmrg* d, int to_right, double rtol, double noise, int D, in
  * DMRG::Solve tests for convergence), [1] LastMinEnergy, [2] MaxDiscWeightLastSweep, [3] TotalMinEnergy since the last PreSolve */
 int b2_dmrg_sweep_info(const b2_dmrg* d, double* out4);
 
+/* ------------------------------------------------------------------------------------------------ Sobject::Join
+ * b2_join_* = Sobject::Join (Sobject.cpp:212-258): the two-site object of sites (site, site+1) from their site tensors,
+ *    S[kappa] = sum_jM phase * sqrt((2J+1)(2jM+1)) * 6j * T_site[L -> M] * T_site+1[M -> R]      (program convention, as Sobject::gStorage()).
+ * The plan holds the three-factor terms for the current bookkeeper dimensions; b2_join_run takes TensorT::gStorage() of both sites as
+ * host buffers and fills s_out (b2_sobject_size doubles) on the GPU; b2_join_worklists exports the compiled lists for the CPU checker. */
+typedef struct b2_join b2_join;
+int b2_join_create(b2_ctx* ctx, int site, b2_join** out);
+void b2_join_destroy(b2_join* j);
+int b2_join_run(b2_join* j, const double* t_left, const double* t_right, double* s_out);
+int b2_join_worklists(const b2_join* j, b2_worklists* out);
+
 /* ------------------------------------------------------------------------------------------------ 2-RDM
  * b2_twodm_fill_site = TwoDM::FillSite (TwoDM.cpp:445-628 with its 24 diagram functions doD1..doD24, :642-1592): the entries of the
  * spin-summed 2-RDM arrays two_rdm_A / two_rdm_B (L^4 doubles each, index c1 + L*(c2 + L*(c3 + L*c4)), DMRG orbital order, the four

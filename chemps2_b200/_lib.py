@@ -101,6 +101,10 @@ SIGNATURES = [
     ("b2_twodm_d1_scale", C.c_int, [vp, c_dp, C.c_int]),
     ("b2_twodm_scatter", C.c_int, [vp, C.POINTER(c_dp), C.c_double, c_dp, c_dp]),
     ("b2_svd_batch", C.c_int, [vp, C.c_int, c_ip, c_ip, C.POINTER(c_dp), C.POINTER(c_dp), C.POINTER(c_dp), C.POINTER(c_dp)]),
+    ("b2_sobject_split", C.c_int, [vp, C.c_int, c_dp, C.c_int, C.c_int, C.c_int, vp, vp, C.POINTER(vp), c_dp]),
+    ("b2_split_size", C.c_int64, [vp, C.c_int]),
+    ("b2_split_get", C.c_int, [vp, C.c_int, c_dp]),
+    ("b2_split_destroy", None, [vp]),
     ("b2_join_create", C.c_int, [vp, C.c_int, C.POINTER(vp)]),
     ("b2_join_destroy", None, [vp]),
     ("b2_join_run", C.c_int, [vp, c_dp, c_dp, c_dp]),

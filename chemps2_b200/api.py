@@ -406,6 +406,47 @@ class DMRG:
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, vp, vp, C.c_int64, vp)
 
 
+SVD_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(c_dp), C.POINTER(c_dp), C.POINTER(c_dp),
+                     C.POINTER(c_dp))
+
+
+def _lapack_svd(user, count, m, n, a, sv, u, vt):
+    """a caller-side SVD for b2_sobject_split (numpy -> LAPACK gesdd), the convention of b2_svd_batch: thin factors, column-major"""
+    try:
+        for i in range(count):
+            mi, ni = m[i], n[i]
+            k = min(mi, ni)
+            A = np.ctypeslib.as_array(a[i], shape=(mi * ni,)).reshape(mi, ni, order="F")
+            U, S, VT = np.linalg.svd(A, full_matrices=False)
+            np.ctypeslib.as_array(sv[i], shape=(k,))[:] = S
+            np.ctypeslib.as_array(u[i], shape=(mi * k,))[:] = U.ravel(order="F")
+            np.ctypeslib.as_array(vt[i], shape=(k * ni,))[:] = VT.ravel(order="F")
+        return 0
+    except Exception:
+        return 1
+
+
+LAPACK_SVD = SVD_FN(_lapack_svd)
+
+
+def split(ctx, site, s_storage, D, moving_right, change, svd=None):
+    """Sobject::Split through b2_sobject_split -> (t_left, t_right, discarded weight); svd = None: batched device SVD, or an SVD_FN
+    (LAPACK_SVD keeps the decomposition on the host).  The bookkeeper of ctx holds the new dimensions of boundary site+1 afterwards."""
+    sv = np.ascontiguousarray(s_storage, dtype=np.float64)
+    r, dw = C.c_void_p(), C.c_double()
+    fn = C.cast(svd, C.c_void_p) if svd is not None else None
+    check(lib.b2_sobject_split(ctx.h, int(site), _dp(sv), int(D), int(bool(moving_right)), int(bool(change)), fn, None, C.byref(r), C.byref(dw)))
+    try:
+        out = []
+        for which in (0, 1):
+            t = np.zeros(max(int(lib.b2_split_size(r, which)), 1), dtype=np.float64)
+            check(lib.b2_split_get(r, which, _dp(t)))
+            out.append(t[:int(lib.b2_split_size(r, which))])
+    finally:
+        lib.b2_split_destroy(r)
+    return out[0], out[1], dw.value
+
+
 class Join:
     """Sobject::Join (Sobject.cpp:212-258) of the site tensors of (site, site+1) for the current bookkeeper dimensions"""
 

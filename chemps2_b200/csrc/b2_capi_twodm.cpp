@@ -311,6 +311,50 @@ int b2_join_run(b2_join* j, const double* t_left, const double* t_right, double*
    return B2_OK;
 }
 
+/* Sobject::Split (Sobject.cpp:260-622) as its own entry point: the routine the sweep driver calls inside b2_dmrg_solve_site */
+struct b2_split {
+   std::vector<double> t[2];
+};
+int b2_sobject_split(b2_ctx* ctx, int site, const double* s_storage, int D, int moving_right, int change, b2_svd_fn svd, void* user,
+                     b2_split** out, double* discarded_weight) {
+   if (!ctx || !ctx->have_bk || !s_storage || !out) return fail(B2_ERR_ARG, "b2_sobject_split: bad arguments");
+   if (site < 0 || site > ctx->bk.L - 2 || D < 1) return fail(B2_ERR_ARG, "b2_sobject_split: site %d or D %d out of range", site, D);
+   if (!svd && ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_sobject_split: planning-only context and no caller SVD (there is no CPU fallback)");
+   SLayout S;
+   S.build(ctx->bk, site);
+   char svd_err[256] = "";
+   SvdBatchFn fn;
+   if (svd) {
+      fn = [&](std::vector<SvdJob>& jobs) {
+         const int n = (int)jobs.size();
+         std::vector<int> m(n), nn(n);
+         std::vector<const double*> a(n);
+         std::vector<double*> sv(n), u(n), vt(n);
+         for (int i = 0; i < n; i++) { m[i] = jobs[i].m; nn[i] = jobs[i].n; a[i] = jobs[i].a; sv[i] = jobs[i].s; u[i] = jobs[i].u; vt[i] = jobs[i].vt; }
+         const int rc = svd(user, n, m.data(), nn.data(), a.data(), sv.data(), u.data(), vt.data());
+         if (rc) snprintf(svd_err, sizeof(svd_err), "the caller's SVD routine returned %d", rc);
+         return rc;
+      };
+   } else {
+      if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(B2_ERR_CUDA, "b2_sobject_split: cudaSetDevice failed");
+      fn = [&](std::vector<SvdJob>& jobs) { return dev_svd_batch(jobs, (void*)ctx->stream, svd_err, (int)sizeof(svd_err)); };
+   }
+   std::unique_ptr<b2_split> r(new b2_split);
+   const double dw = split_host(ctx->bk, site, S, s_storage, D, moving_right != 0, change != 0, r->t[0], r->t[1], fn);
+   if (dw < 0.0) return fail(svd ? B2_ERR_ARG : B2_ERR_CUDA, "b2_sobject_split: %s", svd_err);
+   if (discarded_weight) *discarded_weight = dw;
+   *out = r.release();
+   return B2_OK;
+}
+int64_t b2_split_size(const b2_split* r, int right) { return r ? (int64_t)r->t[right ? 1 : 0].size() : -1; }
+int b2_split_get(const b2_split* r, int right, double* t_out) {
+   if (!r || !t_out) return fail(B2_ERR_ARG, "b2_split_get: NULL");
+   const std::vector<double>& t = r->t[right ? 1 : 0];
+   std::memcpy(t_out, t.data(), sizeof(double) * t.size());
+   return B2_OK;
+}
+void b2_split_destroy(b2_split* r) { delete r; }
+
 /* FP64 peak probe (roofline denominator): mode 1 = DMMA m8n8k4, mode 0 = DFMA */
 int b2_probe_fp64(b2_ctx* ctx, int use_mma, double* tflops) {
    if (!ctx || ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_probe_fp64: no CUDA device");

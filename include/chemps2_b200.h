@@ -304,6 +304,22 @@ void b2_join_destroy(b2_join* j);
 int b2_join_run(b2_join* j, const double* t_left, const double* t_right, double* s_out);
 int b2_join_worklists(const b2_join* j, b2_worklists* out);
 
+/* b2_sobject_split = Sobject::Split (Sobject.cpp:260-622): s_storage (program convention, the layout of b2_sobject_table for the CURRENT
+ * dimensions) is recoupled into one matrix per centre sector, decomposed, truncated to at most D states over all sectors by the
+ * reference's global rule (:451-486, only when change != 0; the virtual dimensions of boundary site+1 in the bookkeeper are rewritten)
+ * and scattered into the two new site tensors: moving_right != 0 -> left tensor left-normalised, the weights go right; else the
+ * mirror image.  svd = NULL: all decompositions run together on the GPU (b2_svd_batch); otherwise the caller's routine is used (same
+ * argument convention as b2_svd_batch, return 0 on success) - e.g. LAPACK dgesdd_ in a host program that keeps Split on the CPU.
+ * The new tensors (sizes follow the NEW dimensions: b2_split_size) are fetched from the result handle. */
+typedef struct b2_split b2_split;
+typedef int (*b2_svd_fn)(void* user, int count, const int* m, const int* n, const double* const* a, double* const* s, double* const* u,
+                         double* const* vt);
+int b2_sobject_split(b2_ctx* ctx, int site, const double* s_storage, int D, int moving_right, int change, b2_svd_fn svd, void* user,
+                     b2_split** out, double* discarded_weight);
+int64_t b2_split_size(const b2_split* r, int right);          /* doubles of the new left (right = 0) / right (right != 0) site tensor */
+int b2_split_get(const b2_split* r, int right, double* t_out);
+void b2_split_destroy(b2_split* r);
+
 /* ------------------------------------------------------------------------------------------------ 2-RDM
  * b2_twodm_fill_site = TwoDM::FillSite (TwoDM.cpp:445-628 with its 24 diagram functions doD1..doD24, :642-1592): the entries of the
  * spin-summed 2-RDM arrays two_rdm_A / two_rdm_B (L^4 doubles each, index c1 + L*(c2 + L*(c3 + L*c4)), DMRG orbital order, the four

@@ -105,6 +105,7 @@ SIGNATURES = [
     ("b2_split_size", C.c_int64, [vp, C.c_int]),
     ("b2_split_get", C.c_int, [vp, C.c_int, c_dp]),
     ("b2_split_destroy", None, [vp]),
+    ("b2_heff_diag_lists", C.c_int, [vp, C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(vp), C.POINTER(C.c_int64)]),
     ("b2_join_create", C.c_int, [vp, C.c_int, C.POINTER(vp)]),
     ("b2_join_destroy", None, [vp]),
     ("b2_join_run", C.c_int, [vp, c_dp, c_dp, c_dp]),

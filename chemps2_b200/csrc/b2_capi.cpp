@@ -637,6 +637,13 @@ int b2_heff_export_presums(const b2_heff* h, b2_flat_presum* out) {
    return B2_OK;
 }
 
+int b2_heff_diag_lists(const b2_heff* h, const void** items, int64_t* n_items, const void** tiles, int64_t* n_tiles) {
+   if (!h || !items || !n_items || !tiles || !n_tiles) return fail(B2_ERR_ARG, "b2_heff_diag_lists: NULL");
+   *items = h->comp.diag_items.data(); *n_items = (int64_t)h->comp.diag_items.size();
+   *tiles = h->comp.diag_tiles.data(); *n_tiles = (int64_t)h->comp.diag_tiles.size();
+   return B2_OK;
+}
+
 int b2_heff_worklists(const b2_heff* h, b2_worklists* o) {
    if (!h || !o) return fail(B2_ERR_ARG, "b2_heff_worklists: NULL");
    const CompiledSigma& c = h->comp;

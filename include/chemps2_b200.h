@@ -190,6 +190,9 @@ typedef struct {
    int64_t n_items1, n_items2, n_tiles1[4], n_tiles2[4], n_reduces, n_waves, work_size, part_size;
 } b2_worklists;
 int b2_heff_worklists(const b2_heff* h, b2_worklists* out);
+/* the lists behind b2_heff_diag (DiagItem / DiagTile of chemps2_b200/csrc/b2_device.h: diag[tile](i, j) = sum_items f * A(i,i) * B(j,j),
+ * the terms of Heff::fillHeffDiag, Heff.cpp:250-315 + HeffDiagonal.cpp) for the CPU checker */
+int b2_heff_diag_lists(const b2_heff* h, const void** items, int64_t* n_items, const void** tiles, int64_t* n_tiles);
 
 /* ------------------------------------------------------------------------------------------------ operator update
  * Replaces DMRG::updateMovingRight / updateMovingLeft (DMRGoperators.cpp:243-907) together with the tensor algebra they

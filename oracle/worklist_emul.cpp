@@ -84,3 +84,25 @@ static void run_lists(const b2_worklists* wl, double** base) {
       }
    }
 }
+
+/* diagonal of H_eff (Heff::fillHeffDiag, Heff.cpp:250-315 + HeffDiagonal.cpp:27-642): every list item is one reference term restricted
+ * to the operator-block diagonals, diag[k](i, j) += f * A(i, i) * B(j, j) (a missing operator counts as 1); semantics of k_diag */
+extern "C" void b2o_run_diag(const DiagItem* items, const DiagTile* tiles, int64_t ntiles, const double* left, const double* right, const double* presum,
+                             double* out, int64_t veclength) {
+   const double* base[SP_COUNT] = {nullptr, left, right, presum, nullptr, nullptr, nullptr, nullptr};
+   std::memset(out, 0, sizeof(double) * (size_t)veclength);
+   for (int64_t t = 0; t < ntiles; t++) {
+      const DiagTile& T = tiles[t];
+      for (int j = 0; j < T.nrem; j++)
+         for (int i = 0; i < T.mrem; i++) {
+            double v = 0.0;
+            for (int it = T.item_begin; it < T.item_end; it++) {
+               const DiagItem& I = items[it];
+               const double a = I.as ? base[I.as][I.aoff + (size_t)(T.m0 + i) * (I.lda + 1)] : 1.0;
+               const double b = I.bs ? base[I.bs][I.boff + (size_t)(T.n0 + j) * (I.ldb + 1)] : 1.0;
+               v += I.f * a * b;
+            }
+            out[T.coff + (size_t)(T.m0 + i) + (size_t)(T.n0 + j) * T.ldc] = v;
+         }
+   }
+}

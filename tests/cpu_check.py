@@ -93,6 +93,24 @@ def emulate_worklists(ctx, left, right, heff, vec):
     return vout
 
 
+def emulate_diag(ctx, left, right, heff):
+    """diagonal of H_eff via the CPU emulation of the diagonal lists (oracle/worklist_emul.cpp b2o_run_diag)"""
+    from chemps2_b200._lib import check, lib
+    o = oracle_lib()
+    vp = C.c_void_p
+    o.b2o_run_diag.argtypes = [vp, vp, C.c_int64, c_dp, c_dp, c_dp, c_dp, C.c_int64]
+    items, tiles, ni, nt = vp(), vp(), C.c_int64(), C.c_int64()
+    check(lib.b2_heff_diag_lists(heff.h, C.byref(items), C.byref(ni), C.byref(tiles), C.byref(nt)))
+    terms, nterms, parts, npp, psize = heff.export()
+    la = left.host_arena() if left else np.zeros(1)
+    ra = right.host_arena() if right else np.zeros(1)
+    presum = np.zeros(max(psize, 1))
+    o.b2o_presum(parts, npp, _dp(la), _dp(ra), _dp(presum), psize)
+    out = np.zeros(max(heff.n, 1))
+    o.b2o_run_diag(items, tiles, nt.value, _dp(la), _dp(ra), _dp(presum), _dp(out), heff.n)
+    return out[:heff.n], ni.value
+
+
 def build_update_case(fx, which, device=-1, options=None, world=1, rank=0):
     """which = 'UR' (moving right after the solve at siteB) or 'UL' (moving left after the solve at siteA).
     -> (ctx, old_set, new_set, update, t_storage, expected [(kind, i, j, data)])"""

@@ -117,6 +117,16 @@ def test_compiled_worklists_vs_reference(golden, tag, options):
         assert st["waves"] > 1
 
 
+@pytest.mark.parametrize("tag", ["A", "B"])
+def test_diagonal_lists_vs_reference(golden, tag):
+    """the diagonal lists of the plan (what k_diag executes) evaluated on the CPU reproduce Heff::fillHeffDiag (Heff.cpp:250-315)"""
+    ctx, left, right, heff = cpu_check.build_case(golden, tag)
+    out, nitems = cpu_check.emulate_diag(ctx, left, right, heff)
+    ref = golden[tag + "/diag"]
+    assert nitems > 0
+    assert np.abs(out - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+
+
 def test_no_device_is_loud(golden):
     """planning-only context: compute entry points fail with B2_ERR_NO_DEVICE instead of falling back to the CPU"""
     ctx, left, right, heff = cpu_check.build_case(golden, "A")

@@ -45,13 +45,3 @@ def test_join_argument_checks(golden):
     assert lib.b2_join_create(ctx.h, -1, C.byref(out)) == -1
     assert lib.b2_join_worklists(None, None) == -1 and lib.b2_join_run(None, None, None, None) == -1
     lib.b2_join_destroy(None)
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("tag", ["A", "B"])
-def test_join_gpu(golden, tag):
-    """GPU through the C ABI (host buffers in and out)"""
-    site, tl, tr, ref = _inputs(golden, tag)
-    ctx = api.context_from_fixture(golden, tag, device=0)
-    out = api.Join(ctx, site).run(tl, tr)
-    assert np.abs(out - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())

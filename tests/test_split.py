@@ -102,25 +102,3 @@ def test_split_argument_checks(golden):
     assert b"returned 7" in lib.b2_last_error()
     assert lib.b2_split_size(None, 0) == -1
     lib.b2_split_destroy(None)
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("tag", ["A", "B"])
-def test_split_device_svd_gpu(golden, tag):
-    """GPU: the batched device SVD inside Split gives the same truncation (dimensions, discarded weight) as LAPACK, and Join (GPU) of the
-    result reproduces S when nothing is truncated"""
-    site, S = _case(golden, tag)
-    ctx = api.context_from_fixture(golden, tag, device=0)
-    tl, tr, dw = api.split(ctx, site, S, 10 ** 6, True, True)
-    assert abs(dw) < 1e-13
-    back = api.Join(ctx, site).run(tl, tr)
-    assert np.abs(back - S).max() <= 1e-11 * max(1.0, np.abs(S).max())
-    got = {}
-    for name, svd in (("device", None), ("lapack", api.LAPACK_SVD)):
-        c = api.context_from_fixture(golden, tag, device=0)
-        _, _, dwt = api.split(c, site, S, 7, False, True, svd=svd)
-        got[name] = (dwt, _total_dim(c, site + 1, golden))
-    # the discarded weight depends only on the singular values; the kept total may differ between two SVDs only through ties at round-off
-    # level (Sobject.cpp:468-476 keeps values strictly above the (D+1)-th one), so it is bounded, not compared
-    assert abs(got["device"][0] - got["lapack"][0]) <= 1e-12
-    assert 0 < got["device"][1] <= 7 and 0 < got["lapack"][1] <= 7

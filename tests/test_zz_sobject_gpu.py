@@ -1,0 +1,54 @@
+"""GPU side of the per-object Sobject entries (b2_join_run, b2_sobject_split with the batched device SVD); the CPU side is in
+tests/test_join.py and tests/test_split.py.  (Sorted last on purpose: these entries were added after the last GPU session of the round.)"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from chemps2_b200 import api, fixtures
+from test_join import _inputs
+from test_split import _case, _total_dim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# own (function-scoped) parametrisation over the fixture files instead of the session-scoped `golden` fixture: pytest groups tests by
+# session-scoped parameters, which would interleave these tests with the rest of the suite
+PATHS = sorted(p for p in glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz"))
+               if not p.endswith("wigner.npz") and not os.path.basename(p).startswith("problem_"))
+IDS = [os.path.basename(p)[:-4] for p in PATHS]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["A", "B"])
+@pytest.mark.parametrize("path", PATHS, ids=IDS)
+def test_join_gpu(path, tag):
+    """GPU through the C ABI (host buffers in and out)"""
+    golden = fixtures.load(path)
+    site, tl, tr, ref = _inputs(golden, tag)
+    ctx = api.context_from_fixture(golden, tag, device=0)
+    out = api.Join(ctx, site).run(tl, tr)
+    assert np.abs(out - ref).max() <= 1e-12 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["A", "B"])
+@pytest.mark.parametrize("path", PATHS, ids=IDS)
+def test_split_device_svd_gpu(path, tag):
+    """GPU: the batched device SVD inside Split gives the same truncation (dimensions, discarded weight) as LAPACK, and Join (GPU) of the
+    result reproduces S when nothing is truncated"""
+    golden = fixtures.load(path)
+    site, S = _case(golden, tag)
+    ctx = api.context_from_fixture(golden, tag, device=0)
+    tl, tr, dw = api.split(ctx, site, S, 10 ** 6, True, True)
+    assert abs(dw) < 1e-13
+    back = api.Join(ctx, site).run(tl, tr)
+    assert np.abs(back - S).max() <= 1e-11 * max(1.0, np.abs(S).max())
+    got = {}
+    for name, svd in (("device", None), ("lapack", api.LAPACK_SVD)):
+        c = api.context_from_fixture(golden, tag, device=0)
+        _, _, dwt = api.split(c, site, S, 7, False, True, svd=svd)
+        got[name] = (dwt, _total_dim(c, site + 1, golden))
+    # the discarded weight depends only on the singular values; the kept total may differ between two SVDs only through ties at round-off
+    # level (Sobject.cpp:468-476 keeps values strictly above the (D+1)-th one), so it is bounded, not compared
+    assert abs(got["device"][0] - got["lapack"][0]) <= 1e-12
+    assert 0 < got["device"][1] <= 7 and 0 < got["lapack"][1] <= 7

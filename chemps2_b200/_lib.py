@@ -40,6 +40,7 @@ SIGNATURES = [
     ("b2_hash_fill", C.c_int, [c_dp, C.c_int64, C.c_uint64, C.c_uint64, C.c_double]),
     ("b2_problem_set", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_dp, C.c_double]),
     ("b2_problem_set_integrals", C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, c_dp, c_dp, C.c_double]),
+    ("b2_problem_update_mx", C.c_int, [vp, c_dp]),
     ("b2_problem_mx", C.c_int, [vp, c_dp]),
     ("b2_wigner6j", C.c_double, [C.c_int] * 6),
     ("b2_wigner9j", C.c_double, [C.c_int] * 9),

@@ -103,6 +103,12 @@ int b2_problem_set_integrals(b2_ctx* ctx, int L, int group, int N, int twoS, int
    return B2_OK;
 }
 
+int b2_problem_update_mx(b2_ctx* ctx, const double* mx_elem) {
+   if (!ctx || !ctx->have_problem || !mx_elem) return fail(B2_ERR_STATE, "b2_problem_update_mx: no problem set");
+   const size_t L = (size_t)ctx->prob.L;
+   ctx->prob.mx.assign(mx_elem, mx_elem + L * L * L * L);
+   return B2_OK;
+}
 int b2_problem_mx(const b2_ctx* ctx, double* mx_out) {
    if (!ctx || !ctx->have_problem || !mx_out) return fail(B2_ERR_STATE, "b2_problem_mx: no problem set");
    std::memcpy(mx_out, ctx->prob.mx.data(), sizeof(double) * ctx->prob.mx.size());

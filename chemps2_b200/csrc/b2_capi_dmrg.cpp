@@ -591,6 +591,7 @@ int b2_dmrg_load_mps(b2_dmrg* d, const char* path, int* converged) {
 // DMRG::PreSolve (DMRG.cpp:257-266): the moving-right operators of every boundary from the current MPS
 int b2_dmrg_presolve(b2_dmrg* d) {
    if (!d) return fail(B2_ERR_ARG, "b2_dmrg_presolve: NULL");
+   dmrg_clear_plan_cache(d);   // the plans of earlier visits carry the integrals of that time (b2_problem_update_mx)
    for (int i = 0; i < d->L - 2; i++) { int rc = b2_dmrg_update(d, i, 1); if (rc) return rc; }
    d->total_min_energy = 1e8;       // DMRG.cpp:263-264
    d->max_disc_last_sweep = 0.0;

@@ -61,6 +61,10 @@ int b2_problem_set(b2_ctx* ctx, int L, int group, int N, int twoS, int irrep, co
 int b2_problem_set_integrals(b2_ctx* ctx, int L, int group, int N, int twoS, int irrep, const int* orb_irrep,
                              const double* tmat, const double* vmat, double econst);
 
+/* Problem::setMxElement after the fact (Problem.cpp:357-361; the reference's tests/test12.cpp.in writes its model Hamiltonian this way):
+ * replaces the folded table of the problem already set, the bookkeeper stays.  Operator sets and plans built before hold the old
+ * integrals: rebuild them (b2_dmrg_presolve drops the sweep driver's cached plans). */
+int b2_problem_update_mx(b2_ctx* ctx, const double* mx_elem);
 /* copy of the folded table gMxElement (L^4 doubles) as the library holds it */
 int b2_problem_mx(const b2_ctx* ctx, double* mx_out);
 /* Wigner 6j / 9j symbols with doubled arguments, as Wigner::wigner6j / wigner9j (Wigner.cpp:294-368) */

@@ -443,6 +443,8 @@ public:
    }
    /* DMRG.cpp:257-266 */
    void PreSolve() {
+      /* the reference reads Prob->gMxElement live: callers may have changed the table with Problem::setMxElement (tests/test12.cpp.in) */
+      detail::check(b2_problem_update_mx(ctx, Prob->mx_table()), "b2_problem_update_mx");
       detail::check(b2_dmrg_presolve(d), "b2_dmrg_presolve");
       TotalMinEnergy = 1e8;
       ops_ready = true;

@@ -156,6 +156,12 @@ static void dump_problem(Writer & w, Problem * prob, Hamiltonian * ham, int grou
    }
    w.dbls("problem/mx", mx); w.dbls("problem/tmat", tm); w.dbls("problem/vmat", vm);
    std::vector<double> ec; ec.push_back(prob->gEconst()); w.dbls("problem/econst", ec);
+   bool direct = false;   /* table not derivable from (T, V): written with setMxElement */
+   for (int a = 0; a < L && !direct; a++) for (int b = 0; b < L && !direct; b++) for (int c = 0; c < L && !direct; c++) for (int e = 0; e < L; e++){
+      const double fold = vm[a + L * (b + L * (c + (size_t) L * e))] + ((a == c) ? tm[b + L * e] : 0.0) / (prob->gN() - 1.0) + ((b == e) ? tm[a + L * c] : 0.0) / (prob->gN() - 1.0);
+      if (fabs(fold - mx[a + L * (b + L * (c + (size_t) L * e))]) > 1e-12){ direct = true; break; }
+   }
+   std::vector<int> dm; dm.push_back(direct ? 1 : 0); w.ints("problem/direct_mx", dm);
 }
 
 /* sigma case at site `index`: S (symmetric convention), H*S, diag(H) straight from Heff::makeHeff / fillHeffDiag */
@@ -229,8 +235,26 @@ static void dump_correlation_tensors(Writer & w, const std::string & prefix, DMR
 
 struct Setup {
    Hamiltonian * ham; Problem * prob; int group;
-   Setup() : ham(NULL), prob(NULL), group(0) {}
+   int pairingL; double pairing_g, pairing_power;   /* --pairing: the reduced BCS model of the reference's tests/test12.cpp.in */
+   Setup() : ham(NULL), prob(NULL), group(0), pairingL(0), pairing_g(0.0), pairing_power(0.0) {}
 };
+
+/* tests/test12.cpp.in:57-79: the folded table is written DIRECTLY with Problem::setMxElement after the DMRG object exists (the table
+   is not 8-fold symmetric, so it cannot go through Hamiltonian::setVmat), then PreSolve rebuilds the operators */
+static void apply_pairing_model(const Setup & s, DMRG & d){
+   if (s.pairingL <= 0) return;
+   const int L = s.pairingL; const int N = s.prob->gN();
+   for (int orb1 = 0; orb1 < L; orb1++){
+      for (int orb2 = 0; orb2 < L; orb2++){
+         const double e1 = -0.5 * (L - 1) + orb1, e2 = -0.5 * (L - 1) + orb2;   /* eps = -3.5 ... 3.5 for L = 8 */
+         const double eri = s.pairing_g * pow(fabs(e1 * e2), s.pairing_power);
+         const double oei = (e1 + e2) / (N - 1);
+         if (orb1 == orb2){ s.prob->setMxElement(orb1, orb1, orb2, orb2, eri + oei); }
+         else { s.prob->setMxElement(orb1, orb1, orb2, orb2, eri); s.prob->setMxElement(orb1, orb2, orb1, orb2, oei); }
+      }
+   }
+   d.PreSolve();
+}
 
 static Setup make_setup(int argc, char ** argv){
    Setup s; std::string fcidump, problem; int twoS = 0, N = 0, irrep = 0, hubL = 0; double hubU = 0.0; bool reorder = false;
@@ -244,6 +268,14 @@ static Setup make_setup(int argc, char ** argv){
       else if (a == "--hubbard"){ hubL = atoi(argv[++i]); hubU = atof(argv[++i]); }
       else if (a == "--reorder") reorder = true;
       else if (a == "--problem") problem = argv[++i];
+      else if (a == "--pairing"){ s.pairingL = atoi(argv[++i]); s.pairing_g = atof(argv[++i]); s.pairing_power = atof(argv[++i]); }
+   }
+   if (s.pairingL > 0){   /* all-zero Hamiltonian of the right shape; the matrix elements follow in apply_pairing_model */
+      std::vector<int> irr(s.pairingL, 0);
+      s.group = 0;
+      s.ham = new Hamiltonian(s.pairingL, 0, irr.data());
+      s.prob = new Problem(s.ham, twoS, N, irrep);
+      return s;
    }
    if (!problem.empty()){   /* binary problem file of chemps2_b200/workloads.py (write_problem_file): synthetic / model Hamiltonians */
       FILE * f = fopen(problem.c_str(), "rb");
@@ -467,6 +499,7 @@ int main(int argc, char ** argv){
       srand(seed);
       const double t0 = now();
       DMRG d(s.prob, &scheme, false, "/tmp");
+      apply_pairing_model(s, d);
       const double e = d.Solve();
       printf("B2REF final_energy %.15f wall %.3f threads %d\n", e, now() - t0, omp_get_max_threads());
       return 0;
@@ -476,6 +509,7 @@ int main(int argc, char ** argv){
    scheme.set_instruction(0, D, 1e-10, 2, noise, rtol);
    srand(seed);
    DMRG d(s.prob, &scheme, false, "/tmp");   /* random MPS + PreSolve (all right-moving operators) */
+   apply_pairing_model(s, d);
 
    if (mode == "dump"){
       Writer w(args(argc, argv, "--out", "case.b2fx"));

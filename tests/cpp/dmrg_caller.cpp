@@ -5,6 +5,7 @@
  *
  *   dmrg_caller host  <fcidump> <group> <TwoS> <N> <Irrep> <none|d2h|c2v> <out.bin>     host classes only (no GPU): dumps irreps + folded table
  *   dmrg_caller accessors <fcidump> <group> <TwoS> <N> <Irrep> <none|d2h|c2v> <out.bin>  TwoDM / Correlations accessor arithmetic on filled-in arrays (no GPU)
+ *   dmrg_caller pairing                                                                    the reference's tests/test12.cpp.in on the GPU: reduced BCS model, L = 8
  *   dmrg_caller solve <fcidump> <group> <TwoS> <N> <Irrep> <none|d2h|c2v> <D> <n_excited>  whole calculation on the GPU, one JSON line */
 #include <cstring>
 
@@ -18,7 +19,44 @@ static void reorder(CheMPS2::Problem* Prob, const char* how) {
    if (!std::strcmp(how, "c2v")) Prob->SetupReorderC2v();
 }
 
+/* tests/test12.cpp.in:36-103 — the model Hamiltonian is written into the folded table with Problem::setMxElement AFTER the DMRG object
+ * exists, PreSolve rebuilds the operators, then Solve with the two-instruction scheme of the test; known answer -25.5134137600604 */
+static int pairing_model() {
+   CheMPS2::Initialize::Init();
+   const int L = 8;
+   double eps[] = {-3.5, -2.5, -1.5, -0.5, 0.5, 1.5, 2.5, 3.5};
+   const double g = -1.0, power = 0.0;
+   const int N = L, TwoS = 0, Irrep = 0;
+   CheMPS2::ConvergenceScheme* OptScheme = new CheMPS2::ConvergenceScheme(2);
+   OptScheme->setInstruction(0, 100, 1e-10, 10, 0.5);
+   OptScheme->setInstruction(1, 1000, 1e-10, 10, 0.0);
+   const int group = 0;
+   int* irreps = new int[L];
+   for (int orb = 0; orb < L; orb++) irreps[orb] = 0;
+   CheMPS2::Hamiltonian* Ham = new CheMPS2::Hamiltonian(L, group, irreps);
+   delete[] irreps;
+   CheMPS2::Problem* Prob = new CheMPS2::Problem(Ham, TwoS, N, Irrep);
+   CheMPS2::DMRG* theDMRG = new CheMPS2::DMRG(Prob, OptScheme);
+   for (int orb1 = 0; orb1 < L; orb1++)
+      for (int orb2 = 0; orb2 < L; orb2++) {
+         const double eri = g * std::pow(std::fabs(eps[orb1] * eps[orb2]), power);
+         const double oei = (eps[orb1] + eps[orb2]) / (N - 1);
+         if (orb1 == orb2) Prob->setMxElement(orb1, orb1, orb2, orb2, eri + oei);
+         else { Prob->setMxElement(orb1, orb1, orb2, orb2, eri); Prob->setMxElement(orb1, orb2, orb1, orb2, oei); }
+      }
+   theDMRG->PreSolve();
+   const double Energy = theDMRG->Solve();
+   theDMRG->calc2DMandCorrelations();
+   const double rdm_energy = theDMRG->get2DM()->energy(), trace = theDMRG->get2DM()->trace();
+   double pair_occupation = 0.0;                          /* seniority-zero state: <n_i n_i> pairs only, A(i,i,i,i) = 2 <n_up n_down> */
+   for (int i = 0; i < L; i++) pair_occupation += 0.5 * theDMRG->get2DM()->getTwoDMA_HAM(i, i, i, i);
+   delete theDMRG; delete OptScheme; delete Prob; delete Ham;
+   std::printf("B2JSON {\"energy\": %.12f, \"rdm_energy\": %.12f, \"trace\": %.10f, \"pairs\": %.10f}\n", Energy, rdm_energy, trace, pair_occupation);
+   return std::fabs(Energy + 25.5134137600604) < 1e-8 ? 0 : 7;
+}
+
 int main(int argc, char** argv) {
+   if (argc > 1 && std::string(argv[1]) == "pairing") return pairing_model();
    if (argc < 9) { std::fprintf(stderr, "usage: see the header of tests/cpp/dmrg_caller.cpp\n"); return 2; }
    const std::string mode = argv[1], matrixelements = argv[2];
    const int psi4groupnumber = std::atoi(argv[3]), TwoS = std::atoi(argv[4]), N = std::atoi(argv[5]), Irrep = std::atoi(argv[6]);

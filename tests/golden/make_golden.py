@@ -30,17 +30,25 @@ CASES = {
     "hubbard10_sextet": "--hubbard 10 4.0 --twoS 5 --N 9 --irrep 0 --D 16 --presweeps 1",
     "ch4_sto3g_triplet_edges": f"--fcidump {ME}/CH4.STO3G.FCIDUMP --group 5 --twoS 2 --N 10 --irrep 1 --D 24 --presweeps 0 --siteA 7 --siteB 0",
     "ch4_sto3g_near_edges": f"--fcidump {ME}/CH4.STO3G.FCIDUMP --group 5 --twoS 0 --N 10 --irrep 0 --D 24 --presweeps 0 --siteA 6 --siteB 1",
+    # the reduced BCS (pairing) model of the reference's tests/test12.cpp.in: the folded integral table is written directly with
+    # Problem::setMxElement and is NOT 8-fold symmetric (pair scattering <ii|jj> = g without the exchange partners <ij|ji>)
+    "pairing8": "--pairing 8 -1.0 0.0 --twoS 0 --N 8 --irrep 0 --D 24 --presweeps 1",
 }
 
 
 def main():
     env = dict(os.environ, OMP_NUM_THREADS="4", OPENBLAS_NUM_THREADS="1")
+    only = sys.argv[1:]          # optional: regenerate only the named cases
     for name, args in CASES.items():
+        if only and name not in only:
+            continue
         tmp = f"/tmp/{name}.b2fx"
         subprocess.run([DRV, "dump", *args.split(), "--seed", "1234", "--out", tmp], check=True, env=env, stdout=subprocess.DEVNULL)
         fx = read_b2fx(tmp)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
         print(name, os.path.getsize(os.path.join(HERE, name + ".npz")) // 1024, "KiB")
+    if only:
+        return
     # problem-only fixture of BASELINE config 2 (N2/cc-pVDZ, 14e/28o, D2h, SetupReorderD2h): the input of scripts/run_dmrg.py n2_ccpvdz,
     # whose known answers are the published energies of sphinx/resources.rst:50-56.  Only the folded table gMxElement is kept.
     tmp = "/tmp/n2_ccpvdz_problem.b2fx"

@@ -50,6 +50,8 @@ def test_bookkeeper_fci_dims(golden):
 
 def test_mx_elem_from_integrals(golden):
     """Problem::build == Problem::construct_mxelem (Problem.cpp:363-384): one-body part folded into the two-body table"""
+    if "problem/direct_mx" in golden and int(golden["problem/direct_mx"][0]):
+        pytest.skip("the table of this fixture was written with Problem::setMxElement (tests/test12.cpp.in), not folded from (T, V)")
     L, group, N, twoS, irrep = [int(x) for x in golden["problem/hdr"]]
     ctx = api.Context(-1)
     ctx.set_problem(L, group, N, twoS, irrep, golden["problem/orb_irrep"], tmat=golden["problem/tmat"], vmat=golden["problem/vmat"])

@@ -52,3 +52,35 @@ def test_split_device_svd_gpu(path, tag):
     # level (Sobject.cpp:468-476 keeps values strictly above the (D+1)-th one), so it is bounded, not compared
     assert abs(got["device"][0] - got["lapack"][0]) <= 1e-12
     assert 0 < got["device"][1] <= 7 and 0 < got["lapack"][1] <= 7
+
+
+@pytest.mark.gpu
+def test_pairing_model_known_answer_python():
+    """the reference's tests/test12.cpp.in (reduced BCS model, L = 8, folded table written with Problem::setMxElement, not 8-fold symmetric):
+    own random start, the two-instruction scheme of the test (D = 100 with noise prefactor 0.5, then D = 1000); known answer
+    -25.5134137600604 pinned there to 1e-8"""
+    fx = fixtures.load(os.path.join(ROOT, "tests", "golden", "pairing8.npz"))
+    L, group, N, twoS, irrep = [int(x) for x in fx["problem/hdr"]]
+    ctx = api.Context(0)
+    ctx.set_problem(L, group, N, twoS, irrep, fx["problem/orb_irrep"], mx=fx["problem/mx"], econst=float(fx["problem/econst"][0]))
+    ctx.bk_init(100)
+    d = api.DMRG(ctx)
+    d.random_mps(2024)
+    e = d.solve([(100, 1e-10, 10, 0.5, 1e-5), (1000, 1e-10, 10, 0.0, 1e-5)])
+    assert abs(e - (-25.5134137600604)) < 1e-8, e
+
+
+@pytest.mark.gpu
+def test_pairing_model_known_answer_cpp_caller():
+    """the same test written against the C++ mirror exactly like the reference's source (tests/cpp/dmrg_caller.cpp `pairing`): the model is
+    set with Problem::setMxElement after the DMRG object exists, PreSolve picks the new table up"""
+    import json
+    import subprocess
+    caller = os.path.join(ROOT, "tests", "cpp", "_bin", "dmrg_caller")
+    res = subprocess.run([caller, "pairing"], capture_output=True, text=True, timeout=900)
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("B2JSON ")]
+    assert res.returncode == 0 and line, res.stdout[-1500:] + res.stderr[-1500:]
+    out = json.loads(line[-1][len("B2JSON "):])
+    assert abs(out["energy"] - (-25.5134137600604)) < 1e-8
+    assert abs(out["rdm_energy"] - out["energy"]) < 1e-7 and abs(out["trace"] - 8 * 7) < 1e-8
+    assert abs(out["pairs"] - 4.0) < 1e-4          # seniority zero: the 8 electrons sit in 4 pairs

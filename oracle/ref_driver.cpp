@@ -236,8 +236,26 @@ static void dump_correlation_tensors(Writer & w, const std::string & prefix, DMR
 struct Setup {
    Hamiltonian * ham; Problem * prob; int group;
    int pairingL; double pairing_g, pairing_power;   /* --pairing: the reduced BCS model of the reference's tests/test12.cpp.in */
-   Setup() : ham(NULL), prob(NULL), group(0), pairingL(0), pairing_g(0.0), pairing_power(0.0) {}
+   int hub2d; double hub2d_U, hub2d_T; bool momentum; /* --hubbard2d Llinear U T [--momentum]: the square Hubbard model with PBC of tests/test9.cpp.in */
+   Setup() : ham(NULL), prob(NULL), group(0), pairingL(0), pairing_g(0.0), pairing_power(0.0), hub2d(0), hub2d_U(0.0), hub2d_T(0.0), momentum(false) {}
 };
+
+/* tests/test9.cpp.in:83-113: the momentum-space form of the same model, written directly into the folded table (plane-wave orbitals:
+   the table has only 4-fold permutation symmetry); (k1 + k2 = k3 + k4 mod Llinear) per direction, dispersion 2T(cos kx + cos ky) */
+static void apply_momentum_hubbard(const Setup & s, DMRG & d){
+   if (s.hub2d <= 0 || !s.momentum) return;
+   const int n = s.hub2d, L = n * n, N = s.prob->gN();
+   std::vector<double> disp(L);
+   for (int o = 0; o < L; o++) disp[o] = 2 * s.hub2d_T * (cos(2 * M_PI * (o % n) / n) + cos(2 * M_PI * (o / n) / n));
+   for (int o1 = 0; o1 < L; o1++) for (int o2 = 0; o2 < L; o2++) for (int o3 = 0; o3 < L; o3++) for (int o4 = 0; o4 < L; o4++){
+      const bool kx = ((o1 % n) + (o2 % n)) % n == ((o3 % n) + (o4 % n)) % n;
+      const bool ky = ((o1 / n) + (o2 / n)) % n == ((o3 / n) + (o4 / n)) % n;
+      double v = (kx && ky) ? s.hub2d_U / L : 0.0;
+      if (o1 == o3 && o2 == o4) v += (disp[o1] + disp[o2]) / (N - 1);
+      s.prob->setMxElement(o1, o2, o3, o4, v);
+   }
+   d.PreSolve();
+}
 
 /* tests/test12.cpp.in:57-79: the folded table is written DIRECTLY with Problem::setMxElement after the DMRG object exists (the table
    is not 8-fold symmetric, so it cannot go through Hamiltonian::setVmat), then PreSolve rebuilds the operators */
@@ -269,6 +287,23 @@ static Setup make_setup(int argc, char ** argv){
       else if (a == "--reorder") reorder = true;
       else if (a == "--problem") problem = argv[++i];
       else if (a == "--pairing"){ s.pairingL = atoi(argv[++i]); s.pairing_g = atof(argv[++i]); s.pairing_power = atof(argv[++i]); }
+      else if (a == "--hubbard2d"){ s.hub2d = atoi(argv[++i]); s.hub2d_U = atof(argv[++i]); s.hub2d_T = atof(argv[++i]); }
+      else if (a == "--momentum") s.momentum = true;
+   }
+   if (s.hub2d > 0){   /* site basis through the Hamiltonian class (8-fold symmetric there); the momentum form follows in apply_momentum_hubbard */
+      const int n = s.hub2d, L2 = n * n;
+      std::vector<int> irr(L2, 0);
+      s.group = 0;
+      s.ham = new Hamiltonian(L2, 0, irr.data());
+      if (!s.momentum){
+         for (int c = 0; c < L2; c++) s.ham->setVmat(c, c, c, c, s.hub2d_U);
+         for (int ix = 0; ix < n; ix++) for (int iy = 0; iy < n; iy++){
+            s.ham->setTmat(ix + n * iy, ((ix + 1) % n) + n * iy, s.hub2d_T);
+            s.ham->setTmat(ix + n * iy, ix + n * ((iy + 1) % n), s.hub2d_T);
+         }
+      }
+      s.prob = new Problem(s.ham, twoS, N, irrep);
+      return s;
    }
    if (s.pairingL > 0){   /* all-zero Hamiltonian of the right shape; the matrix elements follow in apply_pairing_model */
       std::vector<int> irr(s.pairingL, 0);
@@ -500,6 +535,7 @@ int main(int argc, char ** argv){
       const double t0 = now();
       DMRG d(s.prob, &scheme, false, "/tmp");
       apply_pairing_model(s, d);
+      apply_momentum_hubbard(s, d);
       const double e = d.Solve();
       printf("B2REF final_energy %.15f wall %.3f threads %d\n", e, now() - t0, omp_get_max_threads());
       return 0;
@@ -510,6 +546,7 @@ int main(int argc, char ** argv){
    srand(seed);
    DMRG d(s.prob, &scheme, false, "/tmp");   /* random MPS + PreSolve (all right-moving operators) */
    apply_pairing_model(s, d);
+   apply_momentum_hubbard(s, d);
 
    if (mode == "dump"){
       Writer w(args(argc, argv, "--out", "case.b2fx"));

@@ -33,6 +33,9 @@ CASES = {
     # the reduced BCS (pairing) model of the reference's tests/test12.cpp.in: the folded integral table is written directly with
     # Problem::setMxElement and is NOT 8-fold symmetric (pair scattering <ii|jj> = g without the exchange partners <ij|ji>)
     "pairing8": "--pairing 8 -1.0 0.0 --twoS 0 --N 8 --irrep 0 --D 24 --presweeps 1",
+    # the 3 x 3 Hubbard model with periodic boundaries in MOMENTUM space of the reference's tests/test9.cpp.in (doublet, 9 electrons): a dense
+    # table with only 4-fold permutation symmetry, again written with Problem::setMxElement
+    "hubbard3x3_momentum": "--hubbard2d 3 5.0 -1.0 --momentum --twoS 1 --N 9 --irrep 0 --D 24 --presweeps 1",
 }
 
 

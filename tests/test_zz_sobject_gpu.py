@@ -84,3 +84,19 @@ def test_pairing_model_known_answer_cpp_caller():
     assert abs(out["energy"] - (-25.5134137600604)) < 1e-8
     assert abs(out["rdm_energy"] - out["energy"]) < 1e-7 and abs(out["trace"] - 8 * 7) < 1e-8
     assert abs(out["pairs"] - 4.0) < 1e-4          # seniority zero: the 8 electrons sit in 4 pairs
+
+
+@pytest.mark.gpu
+def test_momentum_space_hubbard_known_answer():
+    """the reference's tests/test9.cpp.in: 3 x 3 Hubbard model with periodic boundaries (U = 5, t = 1, 9 electrons, doublet) in MOMENTUM space -
+    a dense folded table with only 4-fold permutation symmetry.  The test demands the site-basis energy; the unmodified reference run here
+    (oracle/ref_driver.cpp energies --hubbard2d 3 5.0 -1.0 [--momentum]) gives -6.578839268776 (site) and -6.578839268783 (momentum)."""
+    fx = fixtures.load(os.path.join(ROOT, "tests", "golden", "hubbard3x3_momentum.npz"))
+    L, group, N, twoS, irrep = [int(x) for x in fx["problem/hdr"]]
+    ctx = api.Context(0)
+    ctx.set_problem(L, group, N, twoS, irrep, fx["problem/orb_irrep"], mx=fx["problem/mx"], econst=float(fx["problem/econst"][0]))
+    ctx.bk_init(500)
+    d = api.DMRG(ctx)
+    d.random_mps(909)
+    e = d.solve([(500, 1e-10, 3, 0.05, 1e-5), (1000, 1e-10, 10, 0.0, 1e-5)])
+    assert abs(e - (-6.57883926878)) < 1e-8, e

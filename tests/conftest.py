@@ -38,9 +38,9 @@ def has_gpu():
 
 
 def pytest_collection_modifyitems(config, items):
-    """cases added after the last GPU session of the round (the test12 pairing-model and test9 momentum-space fixtures, the per-object Sobject entries) run last, so
+    """cases added after the last GPU session of the round (the test12 pairing-model, test9 momentum-space and N2+ doublet fixtures, the per-object Sobject entries) run last, so
     that under `-x` a surprise there cannot hide the results of the long-proven tests"""
-    late = [it for it in items if "pairing8" in it.nodeid or "hubbard3x3" in it.nodeid or "test_zz_" in it.nodeid]
+    late = [it for it in items if "pairing8" in it.nodeid or "hubbard3x3" in it.nodeid or "cation_doublet" in it.nodeid or "test_zz_" in it.nodeid]
     if late:
         ids = {id(it) for it in late}
         items[:] = [it for it in items if id(it) not in ids] + late

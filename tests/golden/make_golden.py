@@ -30,6 +30,8 @@ CASES = {
     "hubbard10_sextet": "--hubbard 10 4.0 --twoS 5 --N 9 --irrep 0 --D 16 --presweeps 1",
     "ch4_sto3g_triplet_edges": f"--fcidump {ME}/CH4.STO3G.FCIDUMP --group 5 --twoS 2 --N 10 --irrep 1 --D 24 --presweeps 0 --siteA 7 --siteB 0",
     "ch4_sto3g_near_edges": f"--fcidump {ME}/CH4.STO3G.FCIDUMP --group 5 --twoS 0 --N 10 --irrep 0 --D 24 --presweeps 0 --siteA 6 --siteB 1",
+    # odd electron number with point-group symmetry: the N2+ cation, doublet Ag, reordered orbitals (half-integer spins in every sector)
+    "n2_sto3g_cation_doublet": f"--fcidump {ME}/N2.STO3G.FCIDUMP --group 7 --twoS 1 --N 13 --irrep 0 --D 28 --presweeps 1 --reorder",
     # the reduced BCS (pairing) model of the reference's tests/test12.cpp.in: the folded integral table is written directly with
     # Problem::setMxElement and is NOT 8-fold symmetric (pair scattering <ii|jj> = g without the exchange partners <ij|ji>)
     "pairing8": "--pairing 8 -1.0 0.0 --twoS 0 --N 8 --irrep 0 --D 24 --presweeps 1",

@@ -67,7 +67,7 @@ def test_sweep_energies_match_reference(golden):
 def _fixture_D(golden):
     """bond dimension the fixture was generated with (tests/golden/make_golden.py): keyed by (L, N, twoS)"""
     L, _, N, twoS, _ = [int(x) for x in golden["problem/hdr"]]
-    return {(10, 14, 0): 24, (10, 14, 4): 32, (13, 10, 0): 20, (10, 9, 5): 16, (9, 10, 2): 24, (9, 10, 0): 24, (8, 8, 0): 24, (9, 9, 1): 24, (10, 13, 1): 28}[(L, N, twoS)]
+    return {(10, 14, 0): 24, (10, 14, 4): 32, (13, 10, 0): 20, (10, 9, 5): 16, (9, 10, 2): 24, (9, 10, 0): 24, (8, 8, 0): 24, (9, 9, 1): 64, (10, 13, 1): 28}[(L, N, twoS)]
 
 
 def test_full_dmrg_n2_sto3g_known_answer():

@@ -492,7 +492,13 @@ class AllReduce:
         def fn(user, ptr, n, stream):
             try:
                 t = torch.as_tensor(AllReduce._Dev(ptr, n), device="cuda")
-                dist.all_reduce(t)
+                # run the collective ON the stream the library hands over: the kernels that produced the vector and the
+                # ones that consume it are ordered on that stream, not on torch's current one
+                if stream:
+                    with torch.cuda.stream(torch.cuda.ExternalStream(int(stream))):
+                        dist.all_reduce(t)
+                else:
+                    dist.all_reduce(t)
                 self.calls += 1
                 self.doubles += int(n)
                 return 0

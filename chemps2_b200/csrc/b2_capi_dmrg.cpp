@@ -72,7 +72,7 @@ struct b2_dmrg {
    std::vector<UpdSlot> upd_cache;        // index = 2 * site + moving_right
    bool use_plan_cache = true;
    long long plan_hits = 0, plan_misses = 0;
-   bool swept_once = false;                // false until the first left sweep (which runs with fixed virtual dimensions, DMRG.cpp:270)
+   bool right_canonical = false;           // b2_dmrg_calc_2rdm leaves the MPS right-canonical (centre on site 0): PreSolve must restore the gauge first
    double max_disc_last_sweep = 0.0;       // DMRG::MaxDiscWeightLastSweep (DMRG.cpp:360-362): scales the noise of the next half sweep
    double last_energy = 0.0;               // energy of the last site solved (what DMRG::sweepleft / sweepright return)
    double last_min_energy = 1e8;           // DMRG::LastMinEnergy: lowest energy of the last half sweep
@@ -118,6 +118,7 @@ int b2_dmrg_set_mps(b2_dmrg* d, int site, const double* t) {
    if (!d || site < 0 || site >= d->L || !t) return fail(B2_ERR_ARG, "b2_dmrg_set_mps: bad arguments");
    TLayout lay; lay.build(d->ctx->bk, site);
    d->mps[site].assign(t, t + lay.size);
+   d->right_canonical = false;   // the caller's tensors: assumed left-normalised on sites 0 .. L-3 like the reference's PreSolve assumes
    return B2_OK;
 }
 int b2_dmrg_get_mps(const b2_dmrg* d, int site, double* t) {
@@ -135,6 +136,7 @@ int b2_dmrg_random_mps(b2_dmrg* d, uint64_t seed) {
       for (double& x : d->mps[s]) x = d->next_uniform();
       left_normalize_host(d->ctx->bk, lay, d->mps[s].data());
    }
+   d->right_canonical = false;
    return B2_OK;
 }
 b2_opset* b2_dmrg_opset(b2_dmrg* d, int boundary, int moving_right) {
@@ -368,7 +370,7 @@ int b2_dmrg_new_excitation(b2_dmrg* d, double eshift, int D, uint64_t seed) {
    d->ctx->bk.init(d->ctx->prob, D);
    dmrg_clear_plan_cache(d);
    d->max_disc_last_sweep = 0.0;
-   d->swept_once = false;
+   d->total_min_energy = 1e8;
    return b2_dmrg_random_mps(d, seed);
 }
 int b2_dmrg_num_lower_states(const b2_dmrg* d) { return d ? (int)d->exc.size() : 0; }
@@ -585,13 +587,21 @@ int b2_dmrg_load_mps(b2_dmrg* d, const char* path, int* converged) {
    }
    for (ExcState& x : d->exc) { x.left.assign(d->L + 1, Overlap()); x.right.assign(d->L + 1, Overlap()); }
    dmrg_clear_plan_cache(d);
+   d->right_canonical = false;
+   d->total_min_energy = 1e8;   // like a freshly constructed DMRG object that found a checkpoint: the next Solve starts with one fixed-dimension sweep
    return B2_OK;
 }
+
+static int dmrg_gauge_move(b2_dmrg* d, int site, bool to_left);
 
 // DMRG::PreSolve (DMRG.cpp:257-266): the moving-right operators of every boundary from the current MPS
 int b2_dmrg_presolve(b2_dmrg* d) {
    if (!d) return fail(B2_ERR_ARG, "b2_dmrg_presolve: NULL");
    dmrg_clear_plan_cache(d);   // the plans of earlier visits carry the integrals of that time (b2_problem_update_mx)
+   if (d->right_canonical) {   // after b2_dmrg_calc_2rdm: the moving-right operators need left-normalised tensors on sites 0 .. L-3
+      for (int s = 0; s < d->L - 2; s++) { int rc = dmrg_gauge_move(d, s, false); if (rc) return rc; }
+      d->right_canonical = false;
+   }
    for (int i = 0; i < d->L - 2; i++) { int rc = b2_dmrg_update(d, i, 1); if (rc) return rc; }
    d->total_min_energy = 1e8;       // DMRG.cpp:263-264
    d->max_disc_last_sweep = 0.0;
@@ -609,22 +619,23 @@ int b2_dmrg_solve(b2_dmrg* d, int n_instructions, const int* D, const double* en
    for (int b = 1; b <= d->L - 2 && have_ops; b++) have_ops = d->left[b] != nullptr && !d->left[b]->set.reduced;
    int rc;
    if (!have_ops && (rc = b2_dmrg_presolve(d))) return rc;
-   double energy = 0.0, lowest = 1e300;
+   // DMRG.cpp:270: the first left sweep after a PreSolve (TotalMinEnergy still 1e8) keeps the virtual dimensions fixed
+   bool change = d->total_min_energy < 1e8;
+   double energy = 0.0;
    for (int ins = 0; ins < n_instructions; ins++) {
       int it = 0;
       double prev = energy + 10 * energy_conv[ins];   // at least one left-right sweep per instruction (DMRG.cpp:283)
       while (std::fabs(energy - prev) > energy_conv[ins] && it < max_sweeps[ins]) {
          prev = energy;
          double el, er, dw;
-         if ((rc = b2_dmrg_sweep(d, 0, davidson_rtol[ins], noise_prefactor[ins], D[ins], d->swept_once ? 1 : 0, &el, &dw))) return rc;
-         d->swept_once = true;
+         if ((rc = b2_dmrg_sweep(d, 0, davidson_rtol[ins], noise_prefactor[ins], D[ins], change ? 1 : 0, &el, &dw))) return rc;
+         change = true;
          if ((rc = b2_dmrg_sweep(d, 1, davidson_rtol[ins], noise_prefactor[ins], D[ins], 1, &er, &dw))) return rc;
          energy = d->last_energy;         // the convergence test compares what sweepright returns: the energy of its last site
-         lowest = std::min(lowest, std::min(el, er));
          it++;
       }
    }
-   *energy_out = lowest;
+   *energy_out = d->total_min_energy;   // DMRG.cpp:353: lowest energy since the last PreSolve
    return B2_OK;
 }
 
@@ -779,6 +790,7 @@ int b2_dmrg_calc_2rdm(b2_dmrg* d, double* two_rdm_A, double* two_rdm_B) {
       const double alpha = 1.0 / (d->ctx->prob.twoS + 1.0);
       for (size_t i = 0; i < n4; i++) { two_rdm_A[i] *= alpha; two_rdm_B[i] *= alpha; }
    }
+   d->right_canonical = true;
    return B2_OK;
 }
 
@@ -821,6 +833,7 @@ int b2_dmrg_calc_correlations(b2_dmrg* d, const double* A, const double* B, doub
       if (rc) { b2_opset_destroy(old_set); return rc; }
    }
    b2_opset_destroy(old_set);
+   d->right_canonical = false;   // sites 0 .. L-2 are left-normalised again, the centre sits on the last site
    return B2_OK;
 }
 

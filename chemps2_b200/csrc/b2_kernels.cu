@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <atomic>
 #include <type_traits>
 
 #include "b2_device.h"
@@ -301,11 +302,14 @@ __global__ void __launch_bounds__(WM * WN * 32, (TM == 64) ? 4 : 1) k_tiles(cons
 template <int TM, int TN, int WM, int WN>
 static cudaError_t launch_tiles_t(const Tile* d_tiles, int ntiles, const GemmItem* d_items, const DevBases& bases, cudaStream_t s) {
    constexpr size_t smem = sizeof(double) * STAGES * (Panel<TM>::SIZE + Panel<TN>::SIZE);
-   static bool configured = false;
-   if (!configured) {
+   // the opt-in above 48 KiB is a per-DEVICE function attribute: one flag per device ordinal (a process may hold contexts on several)
+   static std::atomic<bool> configured[64];
+   int dev = 0;
+   cudaGetDevice(&dev);
+   if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
       cudaError_t e = cudaFuncSetAttribute(k_tiles<TM, TN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      configured = true;
+      if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
    }
    k_tiles<TM, TN, WM, WN><<<ntiles, WM * WN * 32, smem, s>>>(d_tiles, d_items, bases);
    return cudaGetLastError();

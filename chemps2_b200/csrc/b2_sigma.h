@@ -60,8 +60,4 @@ int plan_threads(int nblocks);   // host threads for plan building (B2_PLAN_THRE
 void build_sigma_plan(SigmaPlan& plan, const Bookkeeper& bk, const Problem& prob, const OpSet* left, const OpSet* right,
                       int site, int world);
 
-// Heff diagonal (Heff.cpp:250-315, HeffDiagonal.cpp) — host evaluation from packed host operator arenas.
-void build_heff_diag(double* diag, const SLayout& S, const Bookkeeper& bk, const Problem& prob, const OpSet* left,
-                     const double* left_arena, const OpSet* right, const double* right_arena, int site);
-
 }   // namespace b2

@@ -1,5 +1,5 @@
 """bench.py contract on the reference arm (the one arm that runs without a GPU): exactly one JSON line on stdout with the keys the
-driver reads; the value is the unmodified reference's makeHeff throughput on a bounded sample of the bench workload."""
+driver reads; the value is the unmodified reference's makeHeff throughput, MEASURED at the D the line names (never extrapolated)."""
 import json
 import os
 import subprocess
@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_driver")), reason="oracle/_ref not built (needs /root/reference at build time)")
 def test_reference_arm_prints_one_json_line():
-    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-flops-cap", "5e10"],
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--D", "250"],
                          capture_output=True, text=True, timeout=900, cwd=ROOT)
     assert res.returncode == 0, res.stderr[-2000:]
     lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
@@ -24,7 +24,9 @@ def test_reference_arm_prints_one_json_line():
     assert out["impl"] == "reference" and out["metric"] == "heff_sigma_builds_per_s" and out["unit"] == "sigma-builds/s"
     assert out["higher_is_better"] is True and out["dtype"] == "f64" and out["vs_baseline"] is None
     assert out["value"] > 0 and abs(out["value"] * out["ms_per_step"] / 1e3 - 1.0) < 1e-6
-    assert "workload" in out["config"] and "synth40" in out["config"]["workload"]
+    assert "workload" in out["config"] and "synth40" in out["config"]["workload"] and "D=250" in out["config"]["workload"]
+    assert "D=250" in out["cpu_baseline"]["sample"] and "not extrapolated" in out["cpu_baseline"]["sample"]
+    assert out["steps"] >= 1 and out["steps_requested"] == 1
     cb = out["cpu_baseline"]
     assert cb["kind"] == "reference" and cb["cores"] >= 1 and cb["value"] == out["value"] and "sample" in cb
     e2e = out["e2e"]

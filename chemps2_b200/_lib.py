@@ -119,6 +119,8 @@ SIGNATURES = [
     ("b2_dmrg_set_mps", C.c_int, [vp, C.c_int, c_dp]),
     ("b2_dmrg_get_mps", C.c_int, [vp, C.c_int, c_dp]),
     ("b2_dmrg_random_mps", C.c_int, [vp, C.c_uint64]),
+    ("b2_dmrg_srand", C.c_int, [vp, C.c_uint64]),
+    ("b2_rand_stream", C.c_int, [C.c_uint64, C.c_int, c_ip]),
     ("b2_dmrg_opset", vp, [vp, C.c_int, C.c_int]),
     ("b2_dmrg_set_opset", C.c_int, [vp, C.c_int, C.c_int, vp]),
     ("b2_dmrg_update", C.c_int, [vp, C.c_int, C.c_int]),

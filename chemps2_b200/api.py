@@ -369,6 +369,10 @@ class DMRG:
     def random_mps(self, seed):
         check(lib.b2_dmrg_random_mps(self.h, int(seed)))
 
+    def srand(self, seed):
+        """re-seed the rand() stream that feeds the noise (a run started from a checkpoint)"""
+        check(lib.b2_dmrg_srand(self.h, int(seed)))
+
     def update(self, index, moving_right):
         check(lib.b2_dmrg_update(self.h, int(index), int(bool(moving_right))))
 

@@ -84,11 +84,9 @@ struct b2_dmrg {
    double t_solve = 0.0, t_update = 0.0, t_split = 0.0, t_plan = 0.0;   // wall-clock seconds spent per phase (b2_dmrg_timers)
    long long n_matvec = 0;
    double t_join = 0.0, t_release = 0.0, t_tail = 0.0;   // B2_TIMING diagnostics: Join + vector copies, releasing plans / buffers / stale sets, update epilogue
-   unsigned long long rng = 0x9E3779B97F4A7C15ULL;
-   double next_uniform() {                 // xorshift64*: our own stream (the reference uses rand(), Sobject.cpp:652-659)
-      rng ^= rng >> 12; rng ^= rng << 25; rng ^= rng >> 27;
-      return (double)((rng * 0x2545F4914F6CDD1DULL) >> 11) * (1.0 / 9007199254740992.0);
-   }
+   // rand() of the reference's process: TensorT::random and Sobject::addNoise draw from ONE stream seeded by the caller's srand()
+   // (b2_dmrg_random_mps = srand(seed) + the draws of DMRG::setupBookkeeperAndMPS; every noisy solve_site continues the stream)
+   GlibcRand rng{1};
 };
 
 int b2_dmrg_create(b2_ctx* ctx, b2_dmrg** out) {
@@ -128,15 +126,25 @@ int b2_dmrg_get_mps(const b2_dmrg* d, int site, double* t) {
 }
 int b2_dmrg_random_mps(b2_dmrg* d, uint64_t seed) {
    if (!d) return fail(B2_ERR_ARG, "b2_dmrg_random_mps: NULL");
-   d->rng = seed * 0x9E3779B97F4A7C15ULL + 0xD1B54A32D192ED03ULL;
-   if (d->rng == 0) d->rng = 0x9E3779B97F4A7C15ULL;   // the all-zero state is the one fixed point of xorshift
+   d->rng.reseed((unsigned int)seed);   // srand(seed) of the reference's caller (tests, Initialize::Init)
    for (int s = 0; s < d->L; s++) {   // DMRG::setupBookkeeperAndMPS (DMRG.cpp:149-169): random() then left_normalize with R discarded
       TLayout lay; lay.build(d->ctx->bk, s);
       d->mps[s].resize((size_t)lay.size);
-      for (double& x : d->mps[s]) x = d->next_uniform();
+      for (double& x : d->mps[s]) x = (2 * ((double)d->rng.next()) / GlibcRand::RANDMAX) - 1.0;   // TensorT.cpp:170, value in [-1, 1[
       left_normalize_host(d->ctx->bk, lay, d->mps[s].data());
    }
    d->right_canonical = false;
+   return B2_OK;
+}
+int b2_dmrg_srand(b2_dmrg* d, uint64_t seed) {
+   if (!d) return fail(B2_ERR_ARG, "b2_dmrg_srand: NULL");
+   d->rng.reseed((unsigned int)seed);
+   return B2_OK;
+}
+int b2_rand_stream(uint64_t seed, int n, int* out) {
+   if (n < 0 || (n > 0 && !out)) return fail(B2_ERR_ARG, "b2_rand_stream: bad arguments");
+   GlibcRand g((unsigned int)seed);
+   for (int i = 0; i < n; i++) out[i] = g.next();
    return B2_OK;
 }
 b2_opset* b2_dmrg_opset(b2_dmrg* d, int boundary, int moving_right) {
@@ -510,7 +518,7 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
       *energy = ev + ctx->prob.econst;
       if (n_matvec) *n_matvec = nm;
       if (cudaMemcpyAsync(s_host.data(), d_s, sizeof(double) * (size_t)S.size, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) { rc = fail(B2_ERR_CUDA, "b2_dmrg_solve_site: D2H failed"); break; }
-      if (noise > 0.0) for (double& x : s_host) x += (d->next_uniform() - 0.5) * noise;   // Sobject::addNoise
+      if (noise > 0.0) for (double& x : s_host) x += (((double)d->rng.next()) / GlibcRand::RANDMAX - 0.5) * noise;   // Sobject::addNoise (Sobject.cpp:652-659)
       // ---- Split (host SVD + truncation); the bookkeeper dims of boundary index+1 change here
       SLayout Scopy = S;
       const double tq0 = wall_seconds();

@@ -35,6 +35,38 @@ double wigner9j(int two_ja, int two_jb, int two_jc, int two_jd, int two_je, int 
 
 int num_irreps_of_group(int group);   // psi4 numbering 0..7 = c1 ci c2 cs d2 c2v c2h d2h
 
+// The additive-feedback generator behind glibc's srand() / rand() (TYPE_3: x_i = x_{i-3} + x_{i-31} mod 2^32, output x_i >> 1,
+// seeded through the Lehmer sequence 16807 x mod 2^31-1, first 310 outputs discarded; RAND_MAX = 2^31-1).  The reference draws its
+// random MPS (TensorT::random, TensorT.cpp:167-173) and the noise of Sobject::addNoise (Sobject.cpp:652-659) from rand(); a private
+// generator with the identical stream makes seeded runs comparable step by step with the reference without touching libc's global
+// state (tests/test_rng.py pins it against libc).
+struct GlibcRand {
+   uint32_t r[34];
+   int pos = 0;   // index of the next output modulo 34 (ring buffer of the last 34 values)
+   static constexpr double RANDMAX = 2147483647.0;
+   explicit GlibcRand(unsigned int seed = 1) { reseed(seed); }
+   void reseed(unsigned int seed) {
+      int32_t x[34];
+      x[0] = (int32_t)(seed == 0 ? 1u : seed);
+      for (int i = 1; i < 31; i++) {
+         int64_t v = (16807LL * x[i - 1]) % 2147483647LL;
+         if (v < 0) v += 2147483647LL;
+         x[i] = (int32_t)v;
+      }
+      for (int i = 31; i < 34; i++) x[i] = x[i - 31];
+      for (int i = 0; i < 34; i++) r[i] = (uint32_t)x[i];
+      pos = 0;                      // r[k % 34] holds x_k; the next value to produce is x_34
+      for (int i = 34; i < 344; i++) next_raw();
+   }
+   uint32_t next_raw() {            // x_k = x_{k-31} + x_{k-3}; stored over x_{k-34}
+      const uint32_t v = r[(pos + 3) % 34] + r[(pos + 31) % 34];
+      r[pos] = v;
+      pos = (pos + 1) % 34;
+      return v;
+   }
+   int next() { return (int)(next_raw() >> 1); }   // == rand()
+};
+
 // ---------------------------------------------------------------------------------------------------------
 // Problem: target sector + dense two-body table with the one-body part folded in (Problem.cpp:351-384).
 // Orbitals are already in DMRG order (the caller applies any reordering).

@@ -202,20 +202,48 @@ void left_normalize_host(const Bookkeeper& bk, const TLayout& T, double* t) {
             for (int r = 0; r < T.blk[k].rows; r++) A[r0 + r + (size_t)rows * c] = t[T.blk[k].off + r + (size_t)T.blk[k].rows * c];
          r0 += T.blk[k].rows;
       }
-      for (int c = 0; c < dR; c++) {
-         double* col = &A[(size_t)rows * c];
-         for (int pass = 0; pass < 2; pass++)
-            for (int p = 0; p < c; p++) {
-               const double* q = &A[(size_t)rows * p];
-               double d = 0.0;
-               for (int r = 0; r < rows; r++) d += q[r] * col[r];
-               for (int r = 0; r < rows; r++) col[r] -= d * q[r];
+      // Householder QR with LAPACK's conventions (dgeqrf_ + dorgqr_ as TensorT::QR calls them, TensorT.cpp:227-252): reflector k
+      // maps column k onto beta e_k with beta = -sign(alpha) * norm, so Q equals the reference's Q column by column (a Gram-Schmidt Q
+      // differs from it by column signs, a different — equally valid — gauge).  Columns beyond min(rows, dR) are zero.
+      const int kk = std::min(rows, dR);
+      std::vector<double> tau(kk, 0.0);
+      for (int c = 0; c < kk; c++) {
+         double* v = &A[(size_t)rows * c];
+         double xn = 0.0;
+         for (int r = c + 1; r < rows; r++) xn += v[r] * v[r];
+         const double alpha = v[c];
+         if (xn == 0.0) { tau[c] = 0.0; continue; }          // H = I
+         const double beta = -std::copysign(std::sqrt(alpha * alpha + xn), alpha);
+         tau[c] = (beta - alpha) / beta;
+         const double sc = 1.0 / (alpha - beta);
+         for (int r = c + 1; r < rows; r++) v[r] *= sc;
+         v[c] = beta;
+         for (int j = c + 1; j < dR; j++) {                  // apply H = I - tau v v^T (v_c = 1) to the trailing columns
+            double* w = &A[(size_t)rows * j];
+            double d = w[c];
+            for (int r = c + 1; r < rows; r++) d += v[r] * w[r];
+            d *= tau[c];
+            w[c] -= d;
+            for (int r = c + 1; r < rows; r++) w[r] -= d * v[r];
+         }
+      }
+      {  // Q = H_0 H_1 ... H_{kk-1} applied to the first kk columns of the identity, built backwards (dorg2r)
+         std::vector<double> Q((size_t)rows * dR, 0.0);
+         for (int c = kk - 1; c >= 0; c--) {
+            const double* v = &A[(size_t)rows * c];
+            double* qc = &Q[(size_t)rows * c];
+            for (int j = c + 1; j < kk; j++) {               // columns already built: Q_j <- H_c Q_j (rows >= c)
+               double* w = &Q[(size_t)rows * j];
+               double d = w[c];
+               for (int r = c + 1; r < rows; r++) d += v[r] * w[r];
+               d *= tau[c];
+               w[c] -= d;
+               for (int r = c + 1; r < rows; r++) w[r] -= d * v[r];
             }
-         double n = 0.0;
-         for (int r = 0; r < rows; r++) n += col[r] * col[r];
-         n = std::sqrt(n);
-         const double inv = (n > 1e-14) ? 1.0 / n : 0.0;
-         for (int r = 0; r < rows; r++) col[r] *= inv;
+            qc[c] = 1.0 - tau[c];
+            for (int r = c + 1; r < rows; r++) qc[r] = -tau[c] * v[r];
+         }
+         A.swap(Q);
       }
       r0 = 0;
       for (int k : ks) {

@@ -242,7 +242,14 @@ void b2_dmrg_destroy(b2_dmrg* d);
 int64_t b2_dmrg_mps_size(const b2_dmrg* d, int site);
 int b2_dmrg_set_mps(b2_dmrg* d, int site, const double* t_storage);
 int b2_dmrg_get_mps(const b2_dmrg* d, int site, double* t_storage);
-int b2_dmrg_random_mps(b2_dmrg* d, uint64_t seed);           /* random + left-normalised, DMRG.cpp:149-169 (own RNG stream) */
+/* Random MPS exactly as DMRG::setupBookkeeperAndMPS builds it after the caller's srand(seed) (DMRG.cpp:149-169): TensorT::random
+ * (TensorT.cpp:167-173) site by site from the stream of glibc's rand(), then left-normalisation with LAPACK's Householder conventions
+ * (TensorT::QR, TensorT.cpp:188-265) — the tensors equal the reference's.  The same stream later feeds Sobject::addNoise
+ * (Sobject.cpp:652-659) in every b2_dmrg_solve_site with noise > 0, so seeded noisy sweeps follow the reference step by step.
+ * b2_dmrg_srand only re-seeds that stream (a run that starts from a checkpoint); b2_rand_stream exposes it (out[i] = i-th rand()). */
+int b2_dmrg_random_mps(b2_dmrg* d, uint64_t seed);
+int b2_dmrg_srand(b2_dmrg* d, uint64_t seed);
+int b2_rand_stream(uint64_t seed, int n, int* out);
 b2_opset* b2_dmrg_opset(b2_dmrg* d, int boundary, int moving_right);
 int b2_dmrg_set_opset(b2_dmrg* d, int boundary, int moving_right, b2_opset* set);   /* the driver takes ownership */
 /* MPS checkpoint (DMRG::saveMPS / loadDIM / loadMPS, DMRGmpsio.cpp:30-131): converged flag, all virtual dimensions, the TensorT storage of

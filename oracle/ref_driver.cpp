@@ -617,6 +617,49 @@ int main(int argc, char ** argv){
       return 0;
    }
 
+   if (mode == "trace"){
+      /* Step-by-step record of sweeps started from the seeded random MPS with noise: solve_site (DMRG.cpp:419-452) spelled out through the
+         public methods so that the input and every output of Sobject::Split (Sobject.cpp:260-622) can be dumped: the two-site object after
+         Davidson + Sobject::addNoise (rand() stream continued from TensorT::random), the discarded weight, the re-dimensioned boundary, the
+         new site tensors and their Join (gauge-invariant).  Half sweeps: left (fixed dimensions), right, left. */
+      Writer w(args(argc, argv, "--out", "trace.b2fx"));
+      dump_problem(w, s.prob, s.ham, s.group);
+      dump_bk(w, "trace/bk0", d.denBK); dump_mps(w, "trace/mps0", d);
+      const int halfsweeps = argi(argc, argv, "--halfsweeps", 3);
+      std::vector<int> hdr; hdr.push_back(D); hdr.push_back(seed); std::vector<double> pars; pars.push_back(rtol); pars.push_back(noise);
+      int step = 0;
+      for (int hs = 0; hs < halfsweeps; hs++){
+         const bool mr = (hs % 2 == 1); const bool change = (hs > 0);
+         for (int k = 0; k < L - 2 + (mr ? 0 : -1) + (mr ? 0 : 1); k++){
+            const int index = mr ? k : L - 2 - k;
+            if (!mr && index == 0) break;
+            std::ostringstream nm; nm << "trace/s" << step;
+            Sobject * denS = new Sobject(index, d.denBK);
+            denS->Join(d.MPS[index], d.MPS[index + 1]);
+            Heff Solver(d.denBK, d.Prob, rtol);
+            double E = Solver.SolveDAVIDSON(denS, d.Ltensors, d.Atensors, d.Btensors, d.Ctensors, d.Dtensors, d.S0tensors, d.S1tensors, d.F0tensors,
+                                            d.F1tensors, d.Qtensors, d.Xtensors, 0, NULL) + s.prob->gEconst();
+            if (noise > 0.0) denS->addNoise(noise);
+            dump_bk(w, nm.str() + "/bk", d.denBK);
+            w.dbls(nm.str() + "/S", denS->gStorage(), denS->gKappa2index(denS->gNKappa()));
+            const double dw = denS->Split(d.MPS[index], d.MPS[index + 1], D, mr, change);
+            delete denS;
+            std::vector<int> sh; sh.push_back(index); sh.push_back(mr ? 1 : 0); sh.push_back(change ? 1 : 0); sh.push_back(D);
+            w.ints(nm.str() + "/hdr", sh);
+            std::vector<double> res; res.push_back(E); res.push_back(dw); w.dbls(nm.str() + "/res", res);
+            dump_bk(w, nm.str() + "/bk_after", d.denBK);
+            w.dbls(nm.str() + "/tl", d.MPS[index]->gStorage(), d.MPS[index]->gKappa2index(d.MPS[index]->gNKappa()));
+            w.dbls(nm.str() + "/tr", d.MPS[index + 1]->gStorage(), d.MPS[index + 1]->gKappa2index(d.MPS[index + 1]->gNKappa()));
+            { Sobject J(index, d.denBK); J.Join(d.MPS[index], d.MPS[index + 1]); w.dbls(nm.str() + "/joined_after", J.gStorage(), J.gKappa2index(J.gNKappa())); }
+            if (mr) d.updateMovingRightSafe(index); else d.updateMovingLeftSafe(index);
+            step++;
+         }
+      }
+      hdr.push_back(step); w.ints("trace/hdr", hdr); w.dbls("trace/pars", pars);
+      printf("B2REF trace: %d steps\n", step);
+      return 0;
+   }
+
    if (mode == "time"){   /* time Heff::makeHeff at one site; operators are whatever the un-optimised random MPS gives */
       const int site = argi(argc, argv, "--site", L / 2);
       const int reps = argi(argc, argv, "--reps", 3);

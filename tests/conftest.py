@@ -20,7 +20,16 @@ def pytest_configure(config):
 
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz"))
-                if not p.endswith("wigner.npz") and not os.path.basename(p).startswith("problem_"))
+                if not p.endswith("wigner.npz") and not os.path.basename(p).startswith("problem_") and not os.path.basename(p).startswith("trace_"))
+
+TRACES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "trace_*.npz")))
+
+
+@pytest.fixture(scope="session", params=TRACES, ids=[os.path.basename(p)[:-4] for p in TRACES])
+def trace(request):
+    """step-by-step record of noisy sweeps of the unmodified reference from its seeded random MPS (ref_driver `trace`)"""
+    from chemps2_b200 import fixtures
+    return fixtures.load(request.param)
 
 
 @pytest.fixture(scope="session", params=GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])

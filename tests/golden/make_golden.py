@@ -43,6 +43,14 @@ CASES = {
 }
 
 
+# step-by-step traces of noisy sweeps from the seeded random MPS (ref_driver `trace`): the input and every output of Sobject::Split per site
+TRACES = {
+    "trace_h2o_631g": f"--fcidump {ME}/H2O.631G.FCIDUMP --group 5 --twoS 0 --N 10 --irrep 0 --D 20 --seed 4321 --noise 1e-4 --rtol 1e-10",
+    "trace_n2_sto3g_quintet_b1u": f"--fcidump {ME}/N2.STO3G.FCIDUMP --group 7 --twoS 4 --N 14 --irrep 5 --D 14 --seed 77 --noise 3e-4 --rtol 1e-10 --reorder",
+    "trace_hubbard10_sextet": "--hubbard 10 4.0 --twoS 5 --N 9 --irrep 0 --D 12 --seed 2024 --noise 1e-4 --rtol 1e-10",
+}
+
+
 def main():
     env = dict(os.environ, OMP_NUM_THREADS="4", OPENBLAS_NUM_THREADS="1")
     only = sys.argv[1:]          # optional: regenerate only the named cases
@@ -52,6 +60,16 @@ def main():
         tmp = f"/tmp/{name}.b2fx"
         subprocess.run([DRV, "dump", *args.split(), "--seed", "1234", "--out", tmp], check=True, env=env, stdout=subprocess.DEVNULL)
         fx = read_b2fx(tmp)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
+        print(name, os.path.getsize(os.path.join(HERE, name + ".npz")) // 1024, "KiB")
+    for name, args in TRACES.items():
+        if only and name not in only:
+            continue
+        tmp = f"/tmp/{name}.b2fx"
+        subprocess.run([DRV, "trace", *args.split(), "--out", tmp], check=True, env=env, stdout=subprocess.DEVNULL)
+        fx = read_b2fx(tmp)
+        for k in [k for k in fx if k in ("problem/vmat", "problem/tmat")]:
+            del fx[k]
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **fx)
         print(name, os.path.getsize(os.path.join(HERE, name + ".npz")) // 1024, "KiB")
     if only:

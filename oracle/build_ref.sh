@@ -1,8 +1,8 @@
 #!/bin/bash
 # TEST INFRASTRUCTURE ONLY. Builds the UNMODIFIED CheMPS2 reference library from the sources where
 # they lie under /root/reference into oracle/_ref/ (git-ignored, travels to the GPU box).
-# Missing system libraries are bridged by our own shims: oracle/shims/hdf5.h (in-memory HDF5 subset)
-# and oracle/shims/blasfwd.c (dgemm_ & co -> OpenBLAS bundled with the scipy wheel).
+# Missing system libraries are bridged by our own shims: env_shims/hdf5.h (in-memory HDF5 subset)
+# and env_shims/blasfwd.c (dgemm_ & co -> OpenBLAS bundled with the scipy wheel).
 # The reference's own cmake build is NOT run.
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
@@ -14,9 +14,9 @@ fi
 SCIPYLIBS="$(python -c 'import scipy,os;print(os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)),"scipy.libs"))')"
 OPENBLAS="$(ls "$SCIPYLIBS"/libscipy_openblas*.so | head -1)"
 mkdir -p "$OUT"
-CXXFLAGS="-O2 -fopenmp -march=x86-64-v3 -fPIC -w -DH5_USE_110_API -DCHEMPS2_VERSION=\"1.8.12-oracle\" -I$HERE/shims -I$REF/CheMPS2/include/chemps2"
+CXXFLAGS="-O2 -fopenmp -march=x86-64-v3 -fPIC -w -DH5_USE_110_API -DCHEMPS2_VERSION=\"1.8.12-oracle\" -I$HERE/../env_shims -I$REF/CheMPS2/include/chemps2"
 if [ ! -f "$OUT/libblasfwd.so" ]; then
-  gcc -O2 -fPIC -shared -o "$OUT/libblasfwd.so" "$HERE/shims/blasfwd.c" "$OPENBLAS" -Wl,-rpath,"$SCIPYLIBS"
+  gcc -O2 -fPIC -shared -o "$OUT/libblasfwd.so" "$HERE/../env_shims/blasfwd.c" "$OPENBLAS" -Wl,-rpath,"$SCIPYLIBS"
 fi
 if [ ! -f "$OUT/libchemps2.so" ]; then
   mkdir -p "$OUT/obj"
@@ -28,5 +28,9 @@ fi
 # the oracle driver (our code: dumps fixtures / times the reference hot path through its own classes)
 if [ -f "$HERE/ref_driver.cpp" ] && { [ ! -f "$OUT/ref_driver" ] || [ "$HERE/ref_driver.cpp" -nt "$OUT/ref_driver" ]; }; then
   g++ $CXXFLAGS -o "$OUT/ref_driver" "$HERE/ref_driver.cpp" -L"$OUT" -lchemps2 -lblasfwd -Wl,-rpath,'$ORIGIN' -Wl,-rpath,"$SCIPYLIBS"
+fi
+# the reference's own command-line binary (expected outputs of the drop-in tests come from it)
+if [ ! -f "$OUT/chemps2" ]; then
+  g++ $CXXFLAGS -o "$OUT/chemps2" "$REF/CheMPS2/executable.cpp" -L"$OUT" -lchemps2 -lblasfwd -Wl,-rpath,'$ORIGIN' -Wl,-rpath,"$SCIPYLIBS"
 fi
 echo "build_ref: ok -> $OUT"

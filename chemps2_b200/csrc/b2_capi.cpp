@@ -17,8 +17,10 @@ CompileOptions b2capi::budgeted(const b2_ctx* ctx) {
    CompileOptions o = ctx->copt;
    if (ctx->device >= 0) {
       size_t free_b = 0, total_b = 0;
-      if (cudaSetDevice(ctx->device) == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+      if (cudaSetDevice(ctx->device) == cudaSuccess && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) {
+         free_b += pool_cached_bytes();   // blocks parked in the library's own cache are released on demand
          o.work_budget = std::max<int64_t>((int64_t)1 << 22, std::min<int64_t>(o.work_budget, (int64_t)(free_b / 2 / sizeof(double))));
+      }
    }
    return o;
 }
@@ -50,20 +52,25 @@ int b2_ctx_create(int device, b2_ctx** out) {
       if (e != cudaSuccess || n <= device) return fail(B2_ERR_NO_DEVICE, "b2_ctx_create: CUDA device %d not available (%s)", device, cudaGetErrorString(e));
       CUDA_TRY(cudaSetDevice(device));
       CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+      pool_register_stream(c->stream);
    }
    *out = c.release();
    return B2_OK;
 }
 void b2_ctx_destroy(b2_ctx* ctx) {
    if (!ctx) return;
+   if (ctx->stream) pool_unregister_stream(ctx->stream);
    if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
    delete ctx;
 }
 int b2_ctx_device(const b2_ctx* ctx) { return ctx ? ctx->device : -1; }
 int b2_ctx_set_stream(b2_ctx* ctx, void* cuda_stream) {
    if (!ctx || ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_ctx_set_stream: no CUDA device");
+   if (ctx->stream) pool_unregister_stream(ctx->stream);
    if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
    ctx->stream = (cudaStream_t)cuda_stream; ctx->own_stream = false;
+   CUDA_TRY(cudaSetDevice(ctx->device));
+   pool_register_stream(ctx->stream);
    return B2_OK;
 }
 void* b2_ctx_stream(const b2_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }

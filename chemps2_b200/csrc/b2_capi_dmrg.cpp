@@ -545,50 +545,88 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
    return rc;
 }
 
-// MPS checkpoint: the content of DMRG::saveMPS / loadDIM / loadMPS (DMRGmpsio.cpp:30-131: converged flag, every virtual dimension in
-// the bookkeeper's enumeration order, the packed TensorT storage of every site) as one flat little-endian binary file — this image has
-// no HDF5 library, so the reference's HDF5 container is not reproduced, only its payload (a shim can copy dataset by dataset).
-int b2_dmrg_save_mps(const b2_dmrg* d, const char* path, int converged) {
-   if (!d || !path) return fail(B2_ERR_ARG, "b2_dmrg_save_mps: NULL");
+// MPS checkpoint in the reference's schema (DMRG::saveMPS / loadDIM / loadMPS, DMRGmpsio.cpp:30-131): the objects
+//    /Convergence/Converged_yn (int32)      /VirtDim_<boundary>_<N>_<2S>_<irrep>/Value (int32)      /MPS_<site>/Values (float64, TensorT::gStorage())
+// with exactly the reference's names, types and contents.  This image has no HDF5 library, so the objects travel in the flat "B2H5v1"
+// container that the HDF5 bridge of the reference builds (env_shims/hdf5.h) reads and writes too: a checkpoint written here is loaded by
+// the unmodified reference (DMRG constructor with makechkpt = true finds CheMPS2_MPS0.h5) and vice versa.  A build with libhdf5 replaces
+// the two container helpers below by H5Dwrite / H5Dread on the same object names.
+namespace {
+struct H5Object { std::string path; int32_t elem; std::vector<char> bytes; };
+bool b2h5_write(const char* path, const std::vector<H5Object>& objs) {
    FILE* f = std::fopen(path, "wb");
-   if (!f) return fail(B2_ERR_ARG, "b2_dmrg_save_mps: cannot open %s", path);
-   const Bookkeeper& bk = d->ctx->bk;
-   const char magic[8] = {'B', '2', 'M', 'P', 'S', '0', '0', '1'};
-   const int32_t hdr[6] = {bk.L, bk.N, bk.twoS, bk.irrep, bk.nirr, converged ? 1 : 0};
-   bool ok = std::fwrite(magic, 1, 8, f) == 8 && std::fwrite(hdr, 4, 6, f) == 6;
-   for (int b = 0; b <= bk.L && ok; b++)
-      bk.for_sectors(b, [&](int n, int ts, int ir) { const int32_t v = bk.dim(b, n, ts, ir); ok = ok && std::fwrite(&v, 4, 1, f) == 1; });
-   for (int sdx = 0; sdx < d->L && ok; sdx++) {
-      const int64_t n = (int64_t)d->mps[sdx].size();
-      ok = std::fwrite(&n, 8, 1, f) == 1 && (n == 0 || std::fwrite(d->mps[sdx].data(), 8, (size_t)n, f) == (size_t)n);
+   if (!f) return false;
+   bool ok = std::fwrite("B2H5v1\0\0", 1, 8, f) == 8;
+   for (const H5Object& o : objs) {
+      const int32_t len = (int32_t)o.path.size();
+      const int64_t nbytes = (int64_t)o.bytes.size();
+      ok = ok && std::fwrite(&len, 4, 1, f) == 1 && std::fwrite(o.path.data(), 1, (size_t)len, f) == (size_t)len && std::fwrite(&o.elem, 4, 1, f) == 1 &&
+           std::fwrite(&nbytes, 8, 1, f) == 1 && (nbytes == 0 || std::fwrite(o.bytes.data(), 1, (size_t)nbytes, f) == (size_t)nbytes);
    }
    std::fclose(f);
-   return ok ? B2_OK : fail(B2_ERR_STATE, "b2_dmrg_save_mps: write to %s failed", path);
+   return ok;
+}
+bool b2h5_read(const char* path, std::map<std::string, H5Object>& objs) {
+   FILE* f = std::fopen(path, "rb");
+   if (!f) return false;
+   char magic[8];
+   bool ok = std::fread(magic, 1, 8, f) == 8 && std::memcmp(magic, "B2H5v1\0\0", 8) == 0;
+   while (ok) {
+      int32_t len = 0;
+      if (std::fread(&len, 4, 1, f) != 1) break;
+      H5Object o;
+      int64_t nbytes = 0;
+      o.path.assign((size_t)std::max(len, 0), ' ');
+      ok = len > 0 && len < 4096 && std::fread(&o.path[0], 1, (size_t)len, f) == (size_t)len && std::fread(&o.elem, 4, 1, f) == 1 && std::fread(&nbytes, 8, 1, f) == 1 && nbytes >= 0;
+      if (!ok) break;
+      o.bytes.resize((size_t)nbytes);
+      ok = nbytes == 0 || std::fread(o.bytes.data(), 1, (size_t)nbytes, f) == (size_t)nbytes;
+      if (ok) objs[o.path] = std::move(o);
+   }
+   std::fclose(f);
+   return ok;
+}
+H5Object int_object(const std::string& path, int32_t v) { H5Object o; o.path = path; o.elem = 4; o.bytes.resize(4); std::memcpy(o.bytes.data(), &v, 4); return o; }
+std::string virtdim_name(int b, int n, int ts, int ir) { char buf[96]; std::snprintf(buf, sizeof(buf), "/VirtDim_%d_%d_%d_%d/Value", b, n, ts, ir); return buf; }
+}   // namespace
+
+int b2_dmrg_save_mps(const b2_dmrg* d, const char* path, int converged) {
+   if (!d || !path) return fail(B2_ERR_ARG, "b2_dmrg_save_mps: NULL");
+   const Bookkeeper& bk = d->ctx->bk;
+   std::vector<H5Object> objs;
+   objs.push_back(int_object("/Convergence/Converged_yn", converged ? 1 : 0));
+   for (int b = 0; b <= bk.L; b++)
+      bk.for_sectors(b, [&](int n, int ts, int ir) { objs.push_back(int_object(virtdim_name(b, n, ts, ir), bk.dim(b, n, ts, ir))); });
+   for (int sdx = 0; sdx < d->L; sdx++) {
+      H5Object o;
+      o.path = "/MPS_" + std::to_string(sdx) + "/Values"; o.elem = 8;
+      o.bytes.resize(sizeof(double) * d->mps[sdx].size());
+      if (!o.bytes.empty()) std::memcpy(o.bytes.data(), d->mps[sdx].data(), o.bytes.size());
+      objs.push_back(std::move(o));
+   }
+   return b2h5_write(path, objs) ? B2_OK : fail(B2_ERR_STATE, "b2_dmrg_save_mps: write to %s failed", path);
 }
 int b2_dmrg_load_mps(b2_dmrg* d, const char* path, int* converged) {
    if (!d || !path) return fail(B2_ERR_ARG, "b2_dmrg_load_mps: NULL");
-   FILE* f = std::fopen(path, "rb");
-   if (!f) return fail(B2_ERR_ARG, "b2_dmrg_load_mps: cannot open %s", path);
+   std::map<std::string, H5Object> objs;
+   if (!b2h5_read(path, objs)) return fail(B2_ERR_ARG, "b2_dmrg_load_mps: cannot read %s (not a B2H5v1 checkpoint container)", path);
    Bookkeeper& bk = d->ctx->bk;
-   char magic[8];
-   int32_t hdr[6];
-   bool ok = std::fread(magic, 1, 8, f) == 8 && std::memcmp(magic, "B2MPS001", 8) == 0 && std::fread(hdr, 4, 6, f) == 6;
-   if (ok && (hdr[0] != bk.L || hdr[1] != bk.N || hdr[2] != bk.twoS || hdr[3] != bk.irrep || hdr[4] != bk.nirr)) {
-      std::fclose(f);
-      return fail(B2_ERR_STATE, "b2_dmrg_load_mps: %s belongs to another problem (L, N, 2S, irrep, group differ)", path);
-   }
+   auto get_int = [&](const std::string& name, int32_t& v) { auto it = objs.find(name); if (it == objs.end() || it->second.bytes.size() != 4) return false; std::memcpy(&v, it->second.bytes.data(), 4); return true; };
+   int32_t conv = 0;
+   bool ok = get_int("/Convergence/Converged_yn", conv);
+   // DMRG::loadDIM: every sector of the bookkeeper's enumeration must be present (a file of another problem lacks some / has others)
    for (int b = 0; b <= bk.L && ok; b++)
-      bk.for_sectors(b, [&](int n, int ts, int ir) { int32_t v = 0; ok = ok && std::fread(&v, 4, 1, f) == 1; if (ok) bk.set_dim(b, n, ts, ir, v); });
-   for (int sdx = 0; sdx < d->L && ok; sdx++) {
+      bk.for_sectors(b, [&](int n, int ts, int ir) { int32_t v = 0; ok = ok && get_int(virtdim_name(b, n, ts, ir), v); if (ok) bk.set_dim(b, n, ts, ir, v); });
+   if (!ok) return fail(B2_ERR_STATE, "b2_dmrg_load_mps: %s belongs to another problem or is incomplete (virtual dimensions)", path);
+   for (int sdx = 0; sdx < d->L && ok; sdx++) {   // DMRG::loadMPS
       TLayout lay;
       lay.build(bk, sdx);
-      int64_t n = -1;
-      ok = std::fread(&n, 8, 1, f) == 1 && n == lay.size;
-      if (ok) { d->mps[sdx].resize((size_t)n); ok = n == 0 || std::fread(d->mps[sdx].data(), 8, (size_t)n, f) == (size_t)n; }
+      auto it = objs.find("/MPS_" + std::to_string(sdx) + "/Values");
+      ok = it != objs.end() && it->second.bytes.size() == sizeof(double) * (size_t)lay.size;
+      if (ok) { d->mps[sdx].resize((size_t)lay.size); if (lay.size) std::memcpy(d->mps[sdx].data(), it->second.bytes.data(), it->second.bytes.size()); }
    }
-   std::fclose(f);
    if (!ok) return fail(B2_ERR_STATE, "b2_dmrg_load_mps: %s is truncated or inconsistent with the bookkeeper", path);
-   if (converged) *converged = hdr[5];
+   if (converged) *converged = conv;
    for (int b = 0; b <= d->L; b++) {   // the operators of the previous MPS are stale
       if (d->left[b]) { b2_opset_destroy(d->left[b]); d->left[b] = nullptr; }
       if (d->right[b]) { b2_opset_destroy(d->right[b]); d->right[b] = nullptr; }

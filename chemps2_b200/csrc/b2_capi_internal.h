@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "b2_pool.h"
+
 #include <cstdarg>
 #include <cstdio>
 #include <algorithm>

@@ -8,6 +8,8 @@
 
 #include <cuda_runtime.h>
 
+#include "b2_pool.h"
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>

@@ -10,6 +10,8 @@
 // k_presum: integral-weighted operator pre-sums (HBM-bound, vectorised, coalesced).
 #include <cuda_runtime.h>
 
+#include "b2_pool.h"
+
 #include <cstdio>
 #include <atomic>
 #include <type_traits>

@@ -9,6 +9,8 @@
 // element-wise rotation, so the result is deterministic.  HBM/L2-bound: a step streams every matrix once (they sit in L2).
 #include <cuda_runtime.h>
 
+#include "b2_pool.h"
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>

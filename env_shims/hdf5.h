@@ -1,15 +1,21 @@
-/* TEST INFRASTRUCTURE ONLY (oracle build). Not part of the product.
+/* ENVIRONMENT BRIDGE for this image (no libhdf5 here). Not part of the product, not part of the oracle's arithmetic.
  *
- * Minimal in-memory stand-in for the ~20 HDF5 C functions that the CheMPS2 reference
- * calls (operator spill in DMRGoperators.cpp, MPS checkpoints, Hamiltonian save/load).
- * The container has no libhdf5; this header lets the UNMODIFIED reference sources
- * compile and run.  "Files" live in a process-wide table and vanish at exit.
- * Written from the public HDF5 C API documentation; nothing here comes from the reference.
+ * Minimal stand-in for the ~20 HDF5 C functions that the CheMPS2 reference calls (operator spill in
+ * DMRGoperators.cpp, MPS checkpoints, Hamiltonian save/load); it lets the UNMODIFIED reference sources
+ * compile and run.  "Files" live in a process-wide table; files whose name contains "MPS" (the checkpoints
+ * of DMRGmpsio.cpp) are ALSO written to disk when they are closed, as a flat list of named datasets:
+ *     "B2H5v1\0\0", then per object { int32 path_len, path, int32 elem_size, int64 n_bytes, data }
+ * with exactly the reference's object paths ("/Convergence/Converged_yn", "/VirtDim_<b>_<N>_<2S>_<I>/Value",
+ * "/MPS_<site>/Values") — the same container chemps2_b200's b2_dmrg_save_mps / _load_mps write and read, so
+ * the unmodified reference and the GPU library resume each other's checkpoints.  B2_H5SHIM_PERSIST_ALL=1
+ * persists every file.  Written from the public HDF5 C API documentation; nothing here comes from the reference.
  */
 #ifndef B2_ORACLE_HDF5_SHIM_H
 #define B2_ORACLE_HDF5_SHIM_H
 
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -47,13 +53,50 @@ struct Handle {
    File * file;
    std::string path;    /* group prefix / dataset path / attribute path */
    hsize_t total, start, count; bool selected;
+   bool writable; std::string fname;   /* file handles: written back to disk on close */
+   Handle() : kind(0), file(NULL), total(0), start(0), count(0), selected(false), writable(false) {}
 };
+
+inline bool persistent(const std::string & name){
+   if (getenv("B2_H5SHIM_PERSIST_ALL")) return true;
+   const size_t slash = name.find_last_of('/');
+   return name.substr(slash == std::string::npos ? 0 : slash + 1).find("MPS") != std::string::npos;
+}
+inline bool load_from_disk(const std::string & name, File & f){
+   FILE * fp = fopen(name.c_str(), "rb");
+   if (!fp) return false;
+   char magic[8];
+   bool ok = fread(magic, 1, 8, fp) == 8 && memcmp(magic, "B2H5v1\0\0", 8) == 0;
+   while (ok){
+      int len = 0, elem = 0; long long nbytes = 0;
+      if (fread(&len, 4, 1, fp) != 1) break;   /* end of file */
+      std::string path((size_t) len, ' ');
+      ok = len > 0 && len < 4096 && fread(&path[0], 1, (size_t) len, fp) == (size_t) len && fread(&elem, 4, 1, fp) == 1 && fread(&nbytes, 8, 1, fp) == 1 && nbytes >= 0;
+      if (!ok) break;
+      Blob & b = f.objects[path];
+      b.elem = (size_t) elem; b.bytes.resize((size_t) nbytes);
+      ok = nbytes == 0 || fread(&b.bytes[0], 1, (size_t) nbytes, fp) == (size_t) nbytes;
+   }
+   fclose(fp);
+   return ok;
+}
+inline void save_to_disk(const std::string & name, const File & f){
+   FILE * fp = fopen(name.c_str(), "wb");
+   if (!fp) return;
+   fwrite("B2H5v1\0\0", 1, 8, fp);
+   for (std::map<std::string, Blob>::const_iterator it = f.objects.begin(); it != f.objects.end(); ++it){
+      const int len = (int) it->first.size(), elem = (int) it->second.elem; const long long nbytes = (long long) it->second.bytes.size();
+      fwrite(&len, 4, 1, fp); fwrite(it->first.data(), 1, (size_t) len, fp); fwrite(&elem, 4, 1, fp); fwrite(&nbytes, 8, 1, fp);
+      if (nbytes) fwrite(&it->second.bytes[0], 1, (size_t) nbytes, fp);
+   }
+   fclose(fp);
+}
 
 struct State {
    std::mutex mtx;
    std::map<std::string, File> files;
    std::vector<Handle> handles;
-   State(){ handles.resize(1); handles[0].kind = 0; }   /* id 0 is reserved (H5S_ALL / H5P_DEFAULT) */
+   State(){ handles.resize(1); }   /* id 0 is reserved (H5S_ALL / H5P_DEFAULT) */
 };
 
 inline State & state(){ static State s; return s; }
@@ -101,16 +144,27 @@ inline herr_t transfer(hid_t dset, hid_t memtype, hid_t filespace, void * rbuf, 
 inline hid_t H5Fcreate(const char * name, unsigned, hid_t, hid_t){
    using namespace b2_h5shim; State & s = state(); std::lock_guard<std::mutex> g(s.mtx);
    File & f = s.files[name]; f.objects.clear();
-   Handle h; h.kind = 1; h.file = &f; h.path = ""; h.total = h.start = h.count = 0; h.selected = false;
+   Handle h; h.kind = 1; h.file = &f; h.path = ""; h.writable = persistent(name); h.fname = name;
    return fresh(h);
 }
-inline hid_t H5Fopen(const char * name, unsigned, hid_t){
+inline hid_t H5Fopen(const char * name, unsigned flags, hid_t){
    using namespace b2_h5shim; State & s = state(); std::lock_guard<std::mutex> g(s.mtx);
-   if (s.files.find(name) == s.files.end()) return -1;
-   Handle h; h.kind = 1; h.file = &s.files[name]; h.path = ""; h.total = h.start = h.count = 0; h.selected = false;
+   if (s.files.find(name) == s.files.end()){   /* written by another process? */
+      File f;
+      if (!load_from_disk(name, f)) return -1;
+      s.files[name] = f;
+   }
+   Handle h; h.kind = 1; h.file = &s.files[name]; h.path = ""; h.writable = (flags == H5F_ACC_RDWR) && persistent(name); h.fname = name;
    return fresh(h);
 }
-inline herr_t H5Fclose(hid_t id){ return b2_h5shim::release(id); }
+inline herr_t H5Fclose(hid_t id){
+   using namespace b2_h5shim;
+   {
+      State & s = state(); std::lock_guard<std::mutex> g(s.mtx);
+      if (id > 0 && (size_t) id < s.handles.size() && s.handles[id].kind == 1 && s.handles[id].writable) save_to_disk(s.handles[id].fname, *s.handles[id].file);
+   }
+   return release(id);
+}
 
 inline hid_t H5Gcreate(hid_t loc, const char * name, hid_t, hid_t, hid_t){ return b2_h5shim::child(loc, name, 2, false); }
 inline hid_t H5Gopen(hid_t loc, const char * name, hid_t){ return b2_h5shim::child(loc, name, 2, true); }

@@ -21,6 +21,7 @@
 #include <iostream>
 #include <sstream>
 #include <sys/time.h>
+#include <unistd.h>
 #include <omp.h>
 
 #define private public
@@ -488,6 +489,93 @@ static int run_synth(int argc, char ** argv){
    return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * "synthupdate" mode: the reference's DMRG::updateMovingRight / updateMovingLeft (DMRGoperators.cpp:243-907) on a synthetic workload at
+ * full size.  A DMRG object is constructed at a tiny bond dimension (cheap PreSolve), its bookkeeper is then re-dimensioned to the
+ * requested sector table, the operator tables of the OLD boundary are allocated with DMRG::allocateTensors and hash-filled (same fill
+ * as `synth` / b2_opset_fill_hash), the site tensor is hash-filled, and the reference's own update routine builds every operator of the
+ * NEW boundary.  Per new operator three numbers are dumped (sum, sum of squares, dot product with a hash vector): compact, and any
+ * block-level difference shows. */
+static void fill_dmrg_tables(DMRG & d, int t, bool mr, unsigned long long seed, double amp){
+   const int L = d.L; const int side = mr ? 1 : 2;
+   const int n_in = mr ? t + 1 : L - 1 - t, n_out = mr ? L - 1 - t : t + 1;
+   for (int k = 0; k < n_in; k++){ const int s = mr ? t - k : t + 1 + k; fill_tensor(d.Ltensors[t][k], seed, op_key(side, K_L, s, s), amp); }
+   for (int c2 = 0; c2 < n_in; c2++) for (int c3 = 0; c3 < n_in - c2; c3++){
+      int i, j; if (mr){ j = t - c3; i = j - c2; } else { i = t + 1 + c3; j = i + c2; }
+      fill_tensor(d.F0tensors[t][c2][c3], seed, op_key(side, K_F0, i, j), amp); fill_tensor(d.F1tensors[t][c2][c3], seed, op_key(side, K_F1, i, j), amp);
+      fill_tensor(d.S0tensors[t][c2][c3], seed, op_key(side, K_S0, i, j), amp);
+      if (c2 > 0) fill_tensor(d.S1tensors[t][c2][c3], seed, op_key(side, K_S1, i, j), amp);
+   }
+   for (int c2 = 0; c2 < n_out; c2++) for (int c3 = 0; c3 < n_out - c2; c3++){
+      int i, j; if (mr){ i = t + 1 + c3; j = i + c2; } else { j = t - c3; i = j - c2; }
+      fill_tensor(d.Atensors[t][c2][c3], seed, op_key(side, K_A, i, j), amp);
+      if (c2 > 0) fill_tensor(d.Btensors[t][c2][c3], seed, op_key(side, K_B, i, j), amp);
+      fill_tensor(d.Ctensors[t][c2][c3], seed, op_key(side, K_C, i, j), amp); fill_tensor(d.Dtensors[t][c2][c3], seed, op_key(side, K_D, i, j), amp);
+   }
+   for (int c2 = 0; c2 < n_out; c2++){ const int s = mr ? t + 1 + c2 : t - c2; fill_tensor(d.Qtensors[t][c2], seed, op_key(side, K_Q, s, s), amp); }
+   fill_tensor(d.Xtensors[t], seed, op_key(side, K_X, -1, -1), amp);
+}
+
+static int run_synth_update(int argc, char ** argv){
+   Setup s = make_setup(argc, argv);   /* --problem file */
+   const int L = s.prob->gL();
+   const int index = argi(argc, argv, "--site", L / 2 - 1);     /* the site whose tensor was "just optimised" */
+   const bool mr = argi(argc, argv, "--moving-right", 1) != 0;
+   const unsigned long long seed = (unsigned long long) argi(argc, argv, "--seed", 1);
+   const double amp = argd(argc, argv, "--amp", 1.0), amp_t = argd(argc, argv, "--amp-t", 0.1);
+   ConvergenceScheme scheme(1);
+   scheme.set_instruction(0, 2, 1e-10, 1, 0.0, 1e-5);
+   srand(1);
+   const double t_setup0 = now();
+   DMRG d(s.prob, &scheme, false, "/tmp");
+   d.deleteAllBoundaryOperators();
+   const char * dfile = args(argc, argv, "--dims", NULL);
+   if (!dfile){ fprintf(stderr, "synthupdate: --dims file needed\n"); return 1; }
+   { FILE * g = fopen(dfile, "rb"); if (!g){ perror(dfile); return 2; }
+     int row[5]; while (fread(row, 4, 5, g) == 5) d.denBK->SetDim(row[0], row[1], row[2], row[3], row[4]);
+     fclose(g); }
+   for (int site = 0; site < L; site++) d.MPS[site]->Reset();
+   const int t_new = mr ? index : index - 1;        /* table slot that receives the new operators */
+   const int t_old = mr ? index - 1 : index;        /* slot of the operators one site further out  */
+   const bool have_old = mr ? (index > 0) : (index < L - 1);
+   if (t_new < 0 || t_new > L - 2){ fprintf(stderr, "synthupdate: no operators live there\n"); return 1; }
+   if (have_old){ d.allocateTensors(t_old, mr); d.isAllocated[t_old] = mr ? 1 : 2; fill_dmrg_tables(d, t_old, mr, seed, amp); }
+   d.allocateTensors(t_new, mr); d.isAllocated[t_new] = mr ? 1 : 2;
+   { TensorT * T = d.MPS[index]; const long long n = T->gKappa2index(T->gNKappa()); double * p = T->gStorage();
+     for (long long e = 0; e < n; e++) p[e] = amp_t * hash_value(seed, op_key(4, 0, -1, -1), e); }
+   const double t_setup = now() - t_setup0;
+   const double t0 = now();
+   if (mr) d.updateMovingRight(t_new); else d.updateMovingLeft(t_new);
+   const double dt = now() - t0;
+   std::vector<int> meta; std::vector<double> sums;
+   { std::vector<int> m2; std::vector<double> data;   /* walk the tables of slot t_new in dump_ops order without copying the data */
+     struct V { std::vector<int> & meta; std::vector<double> & sums; unsigned long long seed;
+                void add(int kind, int i, int j, Tensor * t){ if (!t) return; const long long n = t->gKappa2index(t->gNKappa()); const double * p = t->gStorage();
+                   double a = 0.0, b = 0.0, c = 0.0;
+                   for (long long e = 0; e < n; e++){ a += p[e]; b += p[e] * p[e]; c += p[e] * hash_value(seed + 17, op_key(5, kind, i, j), e); }
+                   meta.push_back(kind); meta.push_back(i); meta.push_back(j); meta.push_back((int) n); sums.push_back(a); sums.push_back(b); sums.push_back(c); } } v = { meta, sums, seed };
+     const int t = t_new;
+     const int n_in = mr ? t + 1 : L - 1 - t, n_out = mr ? L - 1 - t : t + 1;
+     for (int k = 0; k < n_in; k++){ const int st = mr ? t - k : t + 1 + k; v.add(K_L, st, st, d.Ltensors[t][k]); }
+     for (int c2 = 0; c2 < n_in; c2++) for (int c3 = 0; c3 < n_in - c2; c3++){
+        int i, j; if (mr){ j = t - c3; i = j - c2; } else { i = t + 1 + c3; j = i + c2; }
+        v.add(K_S0, i, j, d.S0tensors[t][c2][c3]); if (c2 > 0) v.add(K_S1, i, j, d.S1tensors[t][c2][c3]);
+        v.add(K_F0, i, j, d.F0tensors[t][c2][c3]); v.add(K_F1, i, j, d.F1tensors[t][c2][c3]);
+     }
+     for (int c2 = 0; c2 < n_out; c2++) for (int c3 = 0; c3 < n_out - c2; c3++){
+        int i, j; if (mr){ i = t + 1 + c3; j = i + c2; } else { j = t - c3; i = j - c2; }
+        v.add(K_A, i, j, d.Atensors[t][c2][c3]); if (c2 > 0) v.add(K_B, i, j, d.Btensors[t][c2][c3]);
+        v.add(K_C, i, j, d.Ctensors[t][c2][c3]); v.add(K_D, i, j, d.Dtensors[t][c2][c3]);
+     }
+     for (int c2 = 0; c2 < n_out; c2++){ const int st = mr ? t + 1 + c2 : t - c2; v.add(K_Q, st, st, d.Qtensors[t][c2]); }
+     v.add(K_X, -1, -1, d.Xtensors[t]);
+   }
+   Writer w(args(argc, argv, "--out", "synthupdate.b2fx"));
+   w.ints("upd/meta", meta); w.dbls("upd/sums", sums);
+   printf("B2REF synthupdate site %d moving_right %d operators %d update_s %.6f setup_s %.3f threads %d\n", index, mr ? 1 : 0, (int)(meta.size() / 4), dt, t_setup, omp_get_max_threads());
+   return 0;
+}
+
 int main(int argc, char ** argv){
    if (argc < 2){ fprintf(stderr, "usage: ref_driver dump|energies|time|wigner ...\n"); return 1; }
    const std::string mode = argv[1];
@@ -508,6 +596,7 @@ int main(int argc, char ** argv){
    }
 
    if (mode == "synth") return run_synth(argc, argv);
+   if (mode == "synthupdate") return run_synth_update(argc, argv);
    if (mode == "problem"){   /* only the problem (orbital irreps in DMRG order + folded integral table): input of full calculations */
       Setup s = make_setup(argc, argv);
       s.prob->construct_mxelem();
@@ -533,7 +622,12 @@ int main(int argc, char ** argv){
       for (size_t i = 0; i < ins.size(); i++) scheme.set_instruction(i, (int) ins[i][0], ins[i][1], (int) ins[i][2], ins[i][3], ins[i][4]);
       srand(seed);
       const double t0 = now();
-      DMRG d(s.prob, &scheme, false, "/tmp");
+      /* --chkpt-dir DIR: run inside DIR with MPS checkpoints on (DMRG.cpp:57-65,105-116,334): CheMPS2_MPS0.h5 there is loaded by the
+         constructor when it exists (resume) and rewritten after every sweep — through env_shims/hdf5.h the container chemps2_b200's
+         b2_dmrg_save_mps / _load_mps use, so the reference and the GPU library resume each other's states */
+      const char * chk = args(argc, argv, "--chkpt-dir", NULL);
+      if (chk && chdir(chk) != 0){ perror(chk); return 2; }
+      DMRG d(s.prob, &scheme, chk != NULL, chk ? chk : "/tmp");
       apply_pairing_model(s, d);
       apply_momentum_hubbard(s, d);
       const double e = d.Solve();

@@ -257,3 +257,23 @@ def test_plan_cache_gives_identical_sweeps(golden):
     off, (hits0, _) = run(False)
     assert np.array_equal(on, off)
     assert hits > 0 and hits0 == 0
+
+
+def test_solve_after_calc_2rdm_is_variational():
+    """b2_dmrg_calc_2rdm leaves the MPS right-canonical; a following b2_dmrg_solve must restore the gauge before it rebuilds the
+    operators (else the first sweep solves H x = E x in a non-orthonormal basis and reports non-variational energies)"""
+    import os
+    fx = fixtures.load(os.path.join(os.path.dirname(__file__), "golden", "h2o_631g.npz"))
+    L, group, N, twoS, irrep = [int(x) for x in fx["problem/hdr"]]
+    ctx = api.Context(0)
+    ctx.set_problem(L, group, N, twoS, irrep, fx["problem/orb_irrep"], mx=fx["problem/mx"], econst=float(fx["problem/econst"][0]))
+    ctx.bk_init(30)
+    d = api.DMRG(ctx)
+    d.random_mps(5)
+    scheme = [(30, 1e-8, 6, 0.0, 1e-8)]
+    e1 = d.solve(scheme)
+    d.calc_2rdm()
+    e2 = d.solve([(30, 1e-10, 2, 0.0, 1e-8)])          # PreSolve inside: from the right-canonical MPS
+    info = d.sweep_info()
+    assert e2 <= e1 + 1e-9 and abs(e2 - e1) < 1e-5, (e1, e2)      # same state: no energy below the variational minimum at this D
+    assert abs(info["total_min_energy"] - e2) < 1e-12

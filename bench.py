@@ -43,7 +43,8 @@ def parse():
     ap.add_argument("--dist", default="gauss", choices=["gauss", "flat"])
     ap.add_argument("--ref-budget-s", type=float, default=420.0, help="--impl reference: stop starting new reference builds after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-sweep", action="store_true", help="skip the secondary metric (DMRG sweep time at D on the PPP tetracene model)")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the secondary metric (DMRG sweep time at D on N2/cc-pVDZ, config 2)")
+    ap.add_argument("--sweep-D", default=None, help="comma-separated bond dimensions of the sweep metric, one full sweep each (default 250,500,1000)")
     ap.add_argument("--sweep-ref", action="store_true", help="also time the unmodified reference's DMRG::Solve on the same schedule (minutes)")
     ap.add_argument("--work-budget", type=float, default=0)
     ap.add_argument("--chunk-k", type=float, default=0)
@@ -119,60 +120,67 @@ def cpu_baseline(args, w, dims, flops, arena_doubles, threads=None):
             "sample_seconds": ref["best_s"]}, ref
 
 
-SWEEP_SCHEDULE = [(100, 1), (300, 1), (600, 2)]   # (D, full sweeps); rtol 1e-5, no noise — the ramp of SURVEY Appendix D.3, shortened
-SWEEP_KNOWN_ANSWER = -23.892594067                # E(D=600) of the unmodified reference on this model
+SWEEP_WORKLOAD = "n2_ccpvdz"                       # BASELINE config 2: N2/cc-pVDZ 14e/28o, D2h, orbitals reordered (the reference's own FCIDUMP)
+SWEEP_SCHEDULE = [(250, 1), (500, 1), (1000, 1)]   # (D, full sweeps); rtol 1e-5, no noise, seeded random MPS (srand(12345))
+SWEEP_SEED = 12345
 
 
-def sweep_metric(device, with_reference):
-    """Secondary metric of BASELINE.json ("DMRG sweep time at D"): a complete DMRG calculation — own random MPS, PreSolve, scheduled
-    two-site sweeps (Join, device Davidson, device-SVD Split, operator updates) — on the 18e/18o PPP tetracene model (config 3 stand-in),
-    timed by wall clock around b2_dmrg_sweep; the last full sweep runs at D = 600.  with_reference: the same schedule through
-    DMRG::Solve of the unmodified reference (oracle/_ref) on the host cores."""
+def sweep_metric(device, with_reference, schedule=None, world=1, rank=0, allreduce=None):
+    """Secondary metric of BASELINE.json ("DMRG sweep time at D"): a complete DMRG calculation — the reference's seeded random MPS, PreSolve,
+    scheduled two-site sweeps (Join, device Davidson, device-SVD Split, operator updates) — on N2/cc-pVDZ (config 2), timed by wall clock
+    around b2_dmrg_sweep.  world > 1: sigma terms and operator updates sharded over the GPUs (b2_dmrg_set_world), the rest replicated.
+    with_reference: the same start (same rand() stream) and schedule through DMRG::Solve of the unmodified reference (oracle/_ref) on the host
+    cores of this box; its per-sweep wall times are the reference's own printed timers."""
     from chemps2_b200 import api, workloads
-    w = workloads.get("tetracene_ppp")
+    schedule = schedule or SWEEP_SCHEDULE
+    w = workloads.get(SWEEP_WORKLOAD)
     ctx = w.context(device)
-    ctx.bk_init(SWEEP_SCHEDULE[0][0])
+    ctx.bk_init(schedule[0][0])
     d = api.DMRG(ctx)
-    d.random_mps(12345)
+    if world > 1:
+        d.set_world(world, rank, allreduce)
+    d.random_mps(SWEEP_SEED)
     t_begin = time.time()
-    for i in range(w.L - 2):
-        d.update(i, True)
-    change, last, e, dw = False, None, 0.0, 0.0
-    for D, nsweeps in SWEEP_SCHEDULE:
+    d.presolve()
+    change, rows = False, []
+    for D, nsweeps in schedule:
         for _ in range(nsweeps):
-            d.timers(reset=True)
-            t0 = time.time()
-            el, dl = d.sweep(False, 1e-5, 0.0, D, change)
-            change = True
-            er, dr = d.sweep(True, 1e-5, 0.0, D, change)
-            last = dict(D=D, seconds=time.time() - t0, **d.timers())
-            e, dw = min(el, er), max(dl, dr)
-    out = {"workload": "tetracene_ppp: 18e/18o C1 Pariser-Parr-Pople model on the tetracene skeleton (BASELINE config 3 stand-in), schedule D=100,300,600,600",
-           "seconds_per_sweep_at_D600": last["seconds"], "total_seconds": time.time() - t_begin, "energy": e, "max_discarded_weight": dw,
-           "energy_minus_reference_known_answer": e - SWEEP_KNOWN_ANSWER,
-           "last_sweep_phases_s": {k: last[k] for k in ("plan_s", "solve_s", "split_s", "update_s")}, "last_sweep_sigma_builds": last["n_matvec"]}
+            for to_right in (False, True):
+                d.timers(reset=True)
+                t0 = time.time()
+                e, dw = d.sweep(to_right, 1e-5, 0.0, D, change)
+                change = True
+                rows.append(dict(D=D, to_right=to_right, seconds=time.time() - t0, energy=e, max_discarded_weight=dw, **d.timers()))
+    last = rows[-2:]
+    out = {"workload": f"{SWEEP_WORKLOAD}: N2/cc-pVDZ 14e/28o D2h (BASELINE config 2), seeded random MPS, schedule D=" + ",".join(str(D) for D, _ in schedule) +
+                       " (one left+right sweep each), rtol 1e-5, no noise", "n_gpus": world,
+           "D": schedule[-1][0], "seconds_per_sweep_at_D": last[0]["seconds"] + last[1]["seconds"], "total_seconds": time.time() - t_begin,
+           "energy": min(r["energy"] for r in last), "max_discarded_weight": max(r["max_discarded_weight"] for r in last),
+           "half_sweeps": [{"D": r["D"], "dir": "->" if r["to_right"] else "<-", "s": round(r["seconds"], 3), "E": r["energy"], "plan_s": round(r["plan_s"], 3),
+                            "solve_s": round(r["solve_s"], 3), "split_s": round(r["split_s"], 3), "update_s": round(r["update_s"], 3), "sigma_builds": r["n_matvec"]} for r in rows]}
     from oracle import refrun
-    if with_reference and refrun.available():
-        pfile = f"/tmp/b2_ppp_{os.getpid()}.bin"
-        w.write_problem_file(pfile)
-        sched = ",".join(f"{D}:1e-14:{n}:0.0:1e-5" for D, n in SWEEP_SCHEDULE)
+    fcidump = os.path.join(ROOT, "oracle", "_ref", "N2.CCPVDZ.FCIDUMP")
+    if with_reference and rank == 0 and refrun.available() and os.path.exists(fcidump):
+        sched = ",".join(f"{D}:1e-14:{n}:0.0:1e-5" for D, n in schedule)
         env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count()), OPENBLAS_NUM_THREADS="1")
         t0 = time.time()
-        res = subprocess.run([refrun.REF_DRIVER, "energies", "--problem", pfile, "--schedule", sched, "--seed", "12345"], capture_output=True, text=True, env=env)
+        res = subprocess.run([refrun.REF_DRIVER, "energies", "--fcidump", fcidump, "--group", "7", "--twoS", "0", "--N", "14", "--irrep", "0", "--reorder",
+                              "--schedule", sched, "--seed", str(SWEEP_SEED)], capture_output=True, text=True, env=env, cwd="/tmp")
         walls = [float(ln.split("=")[1].split()[0]) for ln in res.stdout.splitlines() if "Elapsed wall time" in ln]
-        fin = [ln for ln in res.stdout.splitlines() if ln.startswith("B2REF final_energy")]
-        os.remove(pfile)
-        if fin and len(walls) >= 2:
-            out["reference"] = {"kind": "reference", "cores": os.cpu_count(), "seconds_per_sweep_at_D600": walls[-2] + walls[-1], "total_seconds": time.time() - t0,
-                                "energy": float(fin[-1].split()[2])}
+        mins = [float(ln.split("=")[1]) for ln in res.stdout.splitlines() if "Minimum energy           =" in ln]
+        if len(walls) >= 2:
+            out["reference"] = {"kind": "reference", "cores": os.cpu_count(), "seconds_per_sweep_at_D": walls[-2] + walls[-1], "total_seconds": time.time() - t0,
+                                "half_sweep_seconds": [round(x, 2) for x in walls], "half_sweep_min_energies": mins,
+                                "speedup_at_D": (walls[-2] + walls[-1]) / out["seconds_per_sweep_at_D"]}
     return out
 
 
-def update_metric(torch, ctx, w, old_set, stream, steps=3):
+def update_metric(torch, ctx, w, dims, old_set, stream, steps=3, with_reference=True):
     """Second half of the north-star hot path: the renormalized-operator update DMRG::updateMovingRight (DMRGoperators.cpp:243-574) at the
     bench shape — every operator of boundary site+1 (L, S0/S1, F0/F1, A/B/C/D, Q, X) from the hash-filled operators of boundary `site` and a
     synthetic site tensor, through b2_update_run_device; CUDA events on the context stream.  FLOPs = 2mnk per reference dgemm_ of
-    TensorOperator::update & co (SURVEY 8(d) F_upd), computed analytically by the plan."""
+    TensorOperator::update & co (SURVEY 8(d) F_upd), computed analytically by the plan.  with_reference: the unmodified reference's
+    updateMovingRight on the same inputs on the host cores (oracle/_ref `synthupdate`), timed, and a sample of the new operators compared."""
     from chemps2_b200 import api
     from chemps2_b200._lib import lib
     new_set = api.OpSet(ctx, w.site + 1, True)
@@ -181,7 +189,8 @@ def update_metric(torch, ctx, w, old_set, stream, steps=3):
     plan_s = time.time() - t0
     st = upd.stats()
     nt = lib.b2_tensor_t_size(ctx.h, w.site)
-    t_dev = torch.from_numpy(api.hash_fill(nt, 55) * 0.1).cuda()
+    from oracle import refrun
+    t_dev = torch.from_numpy(api.hash_fill(nt, 7, key=refrun.op_key(4, 0, -1, -1), amp=0.1)).cuda()
     upd.run_device(t_dev.data_ptr())              # warm-up
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -191,9 +200,27 @@ def update_metric(torch, ctx, w, old_set, stream, steps=3):
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    return {"what": "DMRG::updateMovingRight at the bench shape (all operators of boundary site+1)", "ms_per_update": ms,
-            "gflop_per_update": st["flops_ref"] / 1e9, "tflops_fp64": st["flops_ref"] / (ms * 1e-3) / 1e12, "terms": st["terms"] + st["mix_terms"],
-            "launches": st["launches"], "plan_build_s": plan_s}
+    out = {"what": "DMRG::updateMovingRight at the bench shape (all operators of boundary site+1)", "ms_per_update": ms,
+           "gflop_per_update": st["flops_ref"] / 1e9, "tflops_fp64": st["flops_ref"] / (ms * 1e-3) / 1e12,
+           "executed_tflops_fp64": st["flops_exec"] / (ms * 1e-3) / 1e12, "terms": st["terms"] + st["mix_terms"],
+           "launches": st["launches"], "plan_build_s": plan_s}
+    if with_reference and refrun.available():
+        try:
+            ref = refrun.run_reference_update(w, 7, moving_right=True, site=w.site, dims=dims)
+            worst, checked = 0.0, 0
+            for kind, i, j, size, rsum, rsq, rdot in ref["ops"][::max(1, len(ref["ops"]) // 48)]:
+                if size == 0:
+                    continue
+                got = new_set.download(new_set.find(kind, i, j))
+                h = api.hash_fill(size, 7 + 17, key=refrun.op_key(5, kind, i, j))
+                worst = max(worst, abs(float(np.dot(got, h)) - rdot) / max(np.sqrt(rsq * size), 1e-300))
+                checked += 1
+            out["cpu_reference"] = {"kind": "reference", "cores": ref["threads"], "seconds_per_update": ref["update_s"],
+                                    "tflops_fp64": st["flops_ref"] / ref["update_s"] / 1e12, "speedup": ref["update_s"] / (ms * 1e-3),
+                                    "parity": {"operators_checked": checked, "max_rel_err_of_hash_projection": worst}}
+        except Exception as e:
+            out["cpu_reference"] = {"failed": str(e)}
+    return out
 
 
 def arena_doubles_of(*sets):
@@ -338,10 +365,25 @@ def main():
     ms_e2e = timed(step_e2e)
     sampler.stop_flag = True
     sampler.join()
+    # a checksum that is comparable across N: the same input vector (index 0) through the device path (+ all-reduce)
+    step_device(0)
+    torch.cuda.synchronize()
     sigma_norm = float(torch.linalg.vector_norm(dev_out).item())
+    sigma_probe = [float(x) for x in dev_out[:: max(1, n // 7)][:8].cpu()]
 
+    sweep_multi = None
+    if world > 1 and not args.no_sweep:   # the whole-sweep metric at N GPUs: every rank takes part (sharded sigma + updates), rank 0 reports
+        try:
+            del heff, left, right
+            torch.cuda.empty_cache()
+            ar = api.AllReduce()
+            sched = [(int(x), 1) for x in args.sweep_D.split(",")] if args.sweep_D else None
+            sweep_multi = sweep_metric(local, False, schedule=sched, world=world, rank=rank, allreduce=ar)
+        except Exception as e:
+            sweep_multi = {"failed": str(e)}
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
@@ -378,7 +420,9 @@ def main():
             "gpu_launches": int(st["launches"] * args.steps), "roofline": roofline, "clocks": sampler.result(),
             "tflops_fp64": st["flops_ref"] / (ms_dev / args.steps * 1e-3) / 1e12,
             "plan": {"terms": st["terms"], "waves": st["waves"], "ctas": st["tiles"], "plan_build_s": plan_s, "veclength": int(n),
-                     "exec_over_ref_flops": st["flops_exec"] / st["flops_ref"], "sigma_norm": sigma_norm}}
+                     "exec_over_ref_flops": st["flops_exec"] / st["flops_ref"], "sigma_norm": sigma_norm, "sigma_probe": sigma_probe}}
+    if sweep_multi is not None:
+        line["sweep"] = sweep_multi
     if world == 1 and not args.no_cpu_baseline:
         try:
             # the GPU result for the reference's input vector (seed 7), computed BEFORE the host is loaded with the reference run
@@ -395,17 +439,19 @@ def main():
     if world == 1 and not args.no_sweep:
         try:
             del heff                                     # frees the sigma plan (workspace + work lists) before the update plan is built
-            um = update_metric(torch, ctx, w, left, stream)
+            um = update_metric(torch, ctx, w, dims, left, stream, with_reference=not args.no_cpu_baseline)
             um["frac_of_fp64_peak"] = um["tflops_fp64"] / peak.value
             line["operator_update"] = um
         except Exception as e:
             line["operator_update"] = {"failed": str(e)}
         try:
-            line["sweep"] = sweep_metric(local, args.sweep_ref)
+            sched = [(int(x), 1) for x in args.sweep_D.split(",")] if args.sweep_D else None
+            line["sweep"] = sweep_metric(local, args.sweep_ref, schedule=sched)
         except Exception as e:   # the secondary metric must not take the bench line down
             line["sweep"] = {"failed": str(e)}
     emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -2,7 +2,7 @@
  *
  * Minimal stand-in for the ~20 HDF5 C functions that the CheMPS2 reference calls (operator spill in
  * DMRGoperators.cpp, MPS checkpoints, Hamiltonian save/load); it lets the UNMODIFIED reference sources
- * compile and run.  "Files" live in a process-wide table; files whose name contains "MPS" (the checkpoints
+ * compile and run.  "Files" live in a process-wide table; files whose name contains "_MPS" (CheMPS2_MPS<n>.h5, the checkpoints
  * of DMRGmpsio.cpp) are ALSO written to disk when they are closed, as a flat list of named datasets:
  *     "B2H5v1\0\0", then per object { int32 path_len, path, int32 elem_size, int64 n_bytes, data }
  * with exactly the reference's object paths ("/Convergence/Converged_yn", "/VirtDim_<b>_<N>_<2S>_<I>/Value",
@@ -60,7 +60,7 @@ struct Handle {
 inline bool persistent(const std::string & name){
    if (getenv("B2_H5SHIM_PERSIST_ALL")) return true;
    const size_t slash = name.find_last_of('/');
-   return name.substr(slash == std::string::npos ? 0 : slash + 1).find("MPS") != std::string::npos;
+   return name.substr(slash == std::string::npos ? 0 : slash + 1).find("_MPS") != std::string::npos;
 }
 inline bool load_from_disk(const std::string & name, File & f){
    FILE * fp = fopen(name.c_str(), "rb");

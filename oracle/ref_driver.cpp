@@ -523,18 +523,28 @@ static int run_synth_update(int argc, char ** argv){
    const bool mr = argi(argc, argv, "--moving-right", 1) != 0;
    const unsigned long long seed = (unsigned long long) argi(argc, argv, "--seed", 1);
    const double amp = argd(argc, argv, "--amp", 1.0), amp_t = argd(argc, argv, "--amp-t", 0.1);
-   ConvergenceScheme scheme(1);
-   scheme.set_instruction(0, 2, 1e-10, 1, 0.0, 1e-5);
-   srand(1);
    const double t_setup0 = now();
-   DMRG d(s.prob, &scheme, false, "/tmp");
-   d.deleteAllBoundaryOperators();
+   /* A DMRG object WITHOUT running its constructor: DMRG::DMRG always ends with PreSolve, which for 40-60 orbitals costs a minute even at a
+      tiny bond dimension.  updateMovingRight/Left, allocateTensors and deleteTensors only touch the members set below (same initial values
+      as DMRG.cpp:45-100); the object is never destructed. */
+   s.prob->construct_mxelem();
+   DMRG & d = *static_cast<DMRG *>(calloc(1, sizeof(DMRG)));
+   d.Prob = s.prob; d.L = L; d.nStates = 1; d.Exc_activated = false; d.makecheckpoints = false;
+   d.denBK = new SyBookkeeper(s.prob, 2);
+   d.Ltensors = new TensorL ** [L - 1]; d.F0tensors = new TensorF0 *** [L - 1]; d.F1tensors = new TensorF1 *** [L - 1];
+   d.S0tensors = new TensorS0 *** [L - 1]; d.S1tensors = new TensorS1 *** [L - 1];
+   d.Atensors = new TensorOperator *** [L - 1]; d.Btensors = new TensorOperator *** [L - 1]; d.Ctensors = new TensorOperator *** [L - 1]; d.Dtensors = new TensorOperator *** [L - 1];
+   d.Qtensors = new TensorQ ** [L - 1]; d.Xtensors = new TensorX * [L - 1];
+   d.isAllocated = new int[L - 1];
+   for (int cnt = 0; cnt < L - 1; cnt++) d.isAllocated[cnt] = 0;
    const char * dfile = args(argc, argv, "--dims", NULL);
    if (!dfile){ fprintf(stderr, "synthupdate: --dims file needed\n"); return 1; }
    { FILE * g = fopen(dfile, "rb"); if (!g){ perror(dfile); return 2; }
      int row[5]; while (fread(row, 4, 5, g) == 5) d.denBK->SetDim(row[0], row[1], row[2], row[3], row[4]);
      fclose(g); }
-   for (int site = 0; site < L; site++) d.MPS[site]->Reset();
+   d.MPS = new TensorT * [L];
+   for (int site = 0; site < L; site++) d.MPS[site] = new TensorT(site, d.denBK);
+
    const int t_new = mr ? index : index - 1;        /* table slot that receives the new operators */
    const int t_old = mr ? index - 1 : index;        /* slot of the operators one site further out  */
    const bool have_old = mr ? (index > 0) : (index < L - 1);

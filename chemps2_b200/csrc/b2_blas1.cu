@@ -108,6 +108,26 @@ int dev_axpy_dev(double* y, const double* x, const double* coef, double sign, in
    return 0;
 }
 
+// y += sign * sum_j coef[j] * X_j (coefficients on the device): the projection step of the classical Gram-Schmidt pass — the whole basis
+// is streamed once, y is read and written once
+__global__ void __launch_bounds__(BT) k_multi_axpy_dev(double* __restrict__ y, const double* __restrict__ xbase, int64_t xstride, int m, const double* __restrict__ coef,
+                                                       double sign, int64_t n) {
+   __shared__ double c[kMaxVec];
+   if (threadIdx.x < m) c[threadIdx.x] = sign * coef[threadIdx.x];
+   __syncthreads();
+   for (int64_t e = (int64_t)blockIdx.x * BT + threadIdx.x; e < n; e += (int64_t)gridDim.x * BT) {
+      double v = y[e];
+      for (int j = 0; j < m; j++) v += c[j] * xbase[(size_t)j * xstride + e];
+      y[e] = v;
+   }
+}
+int dev_multi_axpy_dev(double* y, const double* xbase, int64_t xstride, int m, const double* coef, double sign, int64_t n, void* stream) {
+   if (m <= 0 || n <= 0) return 0;
+   k_multi_axpy_dev<<<grid_for(n), BT, 0, (cudaStream_t)stream>>>(y, xbase, xstride, m, coef, sign, n);
+   LAUNCH_CHECK("k_multi_axpy_dev");
+   return 0;
+}
+
 __global__ void k_add_square(double* __restrict__ y, const double* __restrict__ x, int64_t n) {
    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) y[e] += x[e] * x[e];
 }

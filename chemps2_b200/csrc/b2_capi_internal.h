@@ -126,6 +126,7 @@ struct b2_update {
    int world = 1, rank = 0;
    double list_bytes[2] = {0.0, 0.0};      // device work-list bytes per pass
    std::vector<int> op_owner;              // GPU that computes new operator i in pass 0
+   bool mix_all_axpy = false;              // pass 1 holds block axpys only: it runs on k_axpy_tiles
    b2_allreduce_fn allreduce = nullptr;
    void* allreduce_user = nullptr;
    ~b2_update() {

@@ -76,6 +76,23 @@ int b2_update_create_sharded(b2_ctx* ctx, int index, int moving_right, b2_opset*
    copt.threads = (u->plan.flops_ref < ctx->parallel_plan_flops) ? plan_threads((int)u->plan.dst.size()) : 1;
    compile_terms(u->pass[0], u->plan.terms, u->plan.dst, SP_VOUT, copt);
    compile_terms(u->pass[1], u->plan.mix_terms, u->plan.dst, SP_VOUT, copt);
+   {  // The mixing pass is memory bound and every source tile is shared by up to O(L^2) destination operators (A(s1,s2) of all outside
+      // pairs add the same S0(o,i) blocks with different integrals): launch the tiles that read the same sources next to each other, so that
+      // the sources are served by L2 and HBM sees every destination tile once.  Key = (first source tile, tile position).
+      CompiledWork& mixw = u->pass[1];
+      u->mix_all_axpy = true;
+      for (const GemmItem& g : mixw.items2) if (!(g.flags & IF_AXPY)) { u->mix_all_axpy = false; break; }
+      if (u->mix_all_axpy)
+         for (const Wave& w : mixw.waves)
+            for (int c = 0; c < kNumTileClasses; c++)
+               std::sort(mixw.tiles2[c].begin() + w.t2_begin[c], mixw.tiles2[c].begin() + w.t2_end[c], [&](const Tile& a, const Tile& b) {
+                  const GemmItem &ia = mixw.items2[a.item_begin], &ib = mixw.items2[b.item_begin];
+                  if (ia.xoff != ib.xoff) return ia.xoff < ib.xoff;
+                  if (a.n0 != b.n0) return a.n0 < b.n0;
+                  if (a.m0 != b.m0) return a.m0 < b.m0;
+                  return a.coff < b.coff;
+               });
+   }
    for (int p = 0; p < 2; p++) u->list_bytes[p] = u->pass[p].bytes();
    if (getenv("B2_TIMING"))
       fprintf(stderr, "b2_update_create: enumerate %.3f s, owners %.3f s, schedule %.3f s, %zu + %zu terms\n", tb1 - tb0, tb2 - tb1, wall_seconds() - tb2,
@@ -162,8 +179,12 @@ int b2_update_run_device(b2_update* u, const double* t_dev) {
       for (const Wave& w : u->pass[p].waves) {
          for (int c = 0; c < kNumTileClasses; c++)
             if (dev_launch_tiles(c, u->d_tiles1[p][c] + w.t1_begin[c], w.t1_end[c] - w.t1_begin[c], u->d_items1[p], b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
-         for (int c = 0; c < kNumTileClasses; c++)
-            if (dev_launch_tiles(c, u->d_tiles2[p][c] + w.t2_begin[c], w.t2_end[c] - w.t2_begin[c], u->d_items2[p], b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+         for (int c = 0; c < kNumTileClasses; c++) {
+            const int nt2 = w.t2_end[c] - w.t2_begin[c];
+            const int rc2 = (p == 1 && u->mix_all_axpy) ? dev_launch_axpy_tiles(u->d_tiles2[p][c] + w.t2_begin[c], nt2, u->d_items2[p], b, s)
+                                                        : dev_launch_tiles(c, u->d_tiles2[p][c] + w.t2_begin[c], nt2, u->d_items2[p], b, s);
+            if (rc2) return fail(B2_ERR_CUDA, "%s", dev_last_error());
+         }
          if (dev_launch_reduce(u->d_reduces[p] + w.red_begin, w.red_end - w.red_begin, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
       }
       // every GPU computed the operators it was assigned; summing the (otherwise zero) arenas replicates all of them before

@@ -119,10 +119,14 @@ int davidson_solve(void* stream_v, int64_t n, const MatVec& matvec, double* x_de
    int num_vec = 0, nmult = 0;
    std::vector<double> mxM((size_t)MAXV * MAXV, 0.0), evec((size_t)MAXV * MAXV), eval(MAXV), sub((size_t)MAXV * MAXV);
 
-   auto add_new_vec = [&]() -> int {   // MGS of t against V[0..num_vec), normalise, V[num_vec] = t
-      for (int c = 0; c < num_vec; c++) {
-         if (dev_multi_dot(t, V + stride * c, stride, 1, n, scal, scratch, s)) return -1;
-         if (dev_axpy_dev(t, V + stride * c, scal, -1.0, n, s)) return -1;
+   // Orthogonalise t against V[0..num_vec), normalise, V[num_vec] = t.  The reference does modified Gram-Schmidt with one ddot_ + one
+   // daxpy_ per basis vector (Davidson.cpp:214-222) = 2 num_vec kernel launches here; classical Gram-Schmidt applied TWICE ("twice is
+   // enough": the second pass removes what rounding left behind) spans the same space to working precision with four launches — one
+   // fused multi-dot and one fused multi-axpy per pass, each streaming the basis once.
+   auto add_new_vec = [&]() -> int {
+      for (int pass = 0; pass < 2 && num_vec > 0; pass++) {
+         if (dev_multi_dot(t, V, stride, num_vec, n, scal, scratch, s)) return -1;
+         if (dev_multi_axpy_dev(t, V, stride, num_vec, scal, -1.0, n, s)) return -1;
       }
       if (dev_multi_dot(t, t, stride, 1, n, scal, scratch, s)) return -1;
       if (dev_scale_rsqrt(t, scal, n, s)) return -1;

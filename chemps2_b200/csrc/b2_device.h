@@ -61,6 +61,8 @@ constexpr int kTileThreads[kNumTileClasses] = {128, 128, 32, 32};
 
 // ---- launchers implemented in b2_kernels.cu (all asynchronous on `stream`, a cudaStream_t passed as void*)
 int dev_launch_tiles(int tile_class, const Tile* d_tiles, int ntiles, const GemmItem* d_items, const DevBases& bases, void* stream);
+// tiles whose items are all block axpys (IF_AXPY): the mixing pass of the operator update
+int dev_launch_axpy_tiles(const Tile* d_tiles, int ntiles, const GemmItem* d_items, const DevBases& bases, void* stream);
 int dev_launch_reduce(const ReduceJob* d_jobs, int njobs, const DevBases& bases, void* stream);
 int dev_launch_diag(const DiagTile* d_tiles, int ntiles, const DiagItem* d_items, const DevBases& bases, double* d_out, void* stream);
 int dev_launch_presum(const PresumJob* d_jobs, int njobs, const PresumPart* d_parts, const DevBases& bases, void* stream);
@@ -84,6 +86,8 @@ struct Coefs { double c[kMaxVec]; };
 int dev_multi_dot(const double* x, const double* ybase, int64_t ystride, int m, int64_t n, double* out, double* scratch, void* stream);
 // y += sign * coef[0] * x   (coef on device)
 int dev_axpy_dev(double* y, const double* x, const double* coef, double sign, int64_t n, void* stream);
+// y += sign * sum_{j<m} coef[j] * X_j, X_j = xbase + j*xstride (coef on device, m <= kMaxVec)
+int dev_multi_axpy_dev(double* y, const double* xbase, int64_t xstride, int m, const double* coef, double sign, int64_t n, void* stream);
 // y += x .* x   (diagonal of the excited-state projector, HeffDiagonal.cpp:621-640)
 int dev_add_square(double* y, const double* x, int64_t n, void* stream);
 // x *= 1/sqrt(ss[0])

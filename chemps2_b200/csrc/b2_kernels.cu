@@ -13,6 +13,7 @@
 #include "b2_pool.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <atomic>
 #include <type_traits>
 
@@ -32,7 +33,6 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
 }
 
 constexpr int KC = 16;       // k-chunk staged per pipeline stage
-constexpr int STAGES = 3;    // cp.async pipeline depth
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -165,9 +165,12 @@ __device__ __forceinline__ void mma_chunk(double (&acc)[MI][NI][2], const double
    if (FULLK || 3 < kvalid) mma_step<TM, TN, MI, NI, ALL, SCALE, 3>(acc, xa, yb, alpha, mi_n, ni_n);
 }
 
-template <int TM, int TN, int WM, int WN>
-__global__ void __launch_bounds__(WM * WN * 32, (TM == 64) ? 4 : 1) k_tiles(const Tile* __restrict__ tiles, const GemmItem* __restrict__ items, DevBases bases) {
+// KSUB k-chunks are consumed per barrier (the pipeline unit), NSTG units are in flight; ALLQ: a warp with at least ALLQ/16 of its
+// sub-tiles inside the tile runs the predicate-free MMA path.  CPS = resident CTAs per SM the launch bounds ask for.
+template <int TM, int TN, int WM, int WN, int KSUB = 1, int NSTG = 3, int ALLQ = 12, int CPS = 4>
+__global__ void __launch_bounds__(WM * WN * 32, (TM == 64) ? CPS : 1) k_tiles(const Tile* __restrict__ tiles, const GemmItem* __restrict__ items, DevBases bases) {
    constexpr int NT = WM * WN * 32;
+   constexpr int STAGES = KSUB * NSTG;   // panel buffers
    constexpr int WTM = TM / WM, WTN = TN / WN;   // warp tile
    constexpr int MI = WTM / 8, NI = WTN / 8;     // 8x8 MMA tiles per warp
    constexpr int XSZ = Panel<TM>::SIZE, YSZ = Panel<TN>::SIZE;
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(WM * WN * 32, (TM == 64) ? 4 : 1) k_tiles(cons
       cp_async_commit();
    };
 #pragma unroll
-   for (int s = 0; s < STAGES - 1; s++) { stage_x_at(s); stage_y_at(s); }
+   for (int s = 0; s < STAGES - KSUB; s++) { stage_x_at(s); stage_y_at(s); }
 
    // ---- block-axpy items (their global loads overlap the first panel copies)
    for (int it = tp->item_begin; it < it0; it++) {
@@ -254,11 +257,17 @@ __global__ void __launch_bounds__(WM * WN * 32, (TM == 64) ? 4 : 1) k_tiles(cons
    auto main_loop = [&](auto wall_tag) {
       constexpr bool WALL = decltype(wall_tag)::value;
       while (c_it < item_end) {
-         cp_async_wait<STAGES - 2>();
-         __syncthreads();          // chunk `stage` has landed; everybody is done with the stage refilled below
+         cp_async_wait<STAGES - 2 * KSUB>();
+         __syncthreads();          // the KSUB chunks from `stage` on have landed; everybody is done with the buffers refilled below
+#pragma unroll
+         for (int sub = 0; sub < KSUB; sub++) {
+         if (KSUB > 1 && c_it >= item_end) {   // the item stream ended inside the unit: keep the group accounting of the producer
+            cp_async_commit();
+            continue;
+         }
          const double* xa = Xs + stage * XSZ + xfrag;
          const double* yb = Ys + stage * YSZ + yfrag;
-         const int ps = (stage == 0) ? STAGES - 1 : stage - 1;   // the stage consumed in the previous iteration is refilled
+         const int ps = (stage < KSUB) ? stage + STAGES - KSUB : stage - KSUB;   // a buffer consumed in the previous unit is refilled
          auto stage_x = [&]() { stage_x_at(ps); };
          auto stage_y = [&]() { stage_y_at(ps); };
          if (WALL) {
@@ -276,9 +285,10 @@ __global__ void __launch_bounds__(WM * WN * 32, (TM == 64) ? 4 : 1) k_tiles(cons
          c_left -= KC;
          if (c_left <= 0 && ++c_it < item_end) consumer_load_item();
          stage = (stage + 1 == STAGES) ? 0 : stage + 1;
+         }
       }
    };
-   if (mi_n * ni_n * 4 >= MI * NI * 3) main_loop(std::true_type{}); else main_loop(std::false_type{});
+   if (mi_n * ni_n * 16 >= MI * NI * ALLQ) main_loop(std::true_type{}); else main_loop(std::false_type{});
    cp_async_wait<0>();
 
    const Tile t = *tp;
@@ -301,19 +311,19 @@ __global__ void __launch_bounds__(WM * WN * 32, (TM == 64) ? 4 : 1) k_tiles(cons
       }
 }
 
-template <int TM, int TN, int WM, int WN>
+template <int TM, int TN, int WM, int WN, int KSUB = 1, int NSTG = 3, int ALLQ = 12, int CPS = 4>
 static cudaError_t launch_tiles_t(const Tile* d_tiles, int ntiles, const GemmItem* d_items, const DevBases& bases, cudaStream_t s) {
-   constexpr size_t smem = sizeof(double) * STAGES * (Panel<TM>::SIZE + Panel<TN>::SIZE);
+   constexpr size_t smem = sizeof(double) * KSUB * NSTG * (Panel<TM>::SIZE + Panel<TN>::SIZE);
    // the opt-in above 48 KiB is a per-DEVICE function attribute: one flag per device ordinal (a process may hold contexts on several)
    static std::atomic<bool> configured[64];
    int dev = 0;
    cudaGetDevice(&dev);
    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-      cudaError_t e = cudaFuncSetAttribute(k_tiles<TM, TN, WM, WN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(k_tiles<TM, TN, WM, WN, KSUB, NSTG, ALLQ, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
    }
-   k_tiles<TM, TN, WM, WN><<<ntiles, WM * WN * 32, smem, s>>>(d_tiles, d_items, bases);
+   k_tiles<TM, TN, WM, WN, KSUB, NSTG, ALLQ, CPS><<<ntiles, WM * WN * 32, smem, s>>>(d_tiles, d_items, bases);
    return cudaGetLastError();
 }
 
@@ -322,13 +332,85 @@ int dev_launch_tiles(int tile_class, const Tile* d_tiles, int ntiles, const Gemm
    cudaStream_t s = (cudaStream_t)stream;
    cudaError_t e;
    switch (tile_class) {
-      case 0: e = launch_tiles_t<64, 64, 2, 2>(d_tiles, ntiles, d_items, bases, s); break;
+      case 0: {
+         static const int variant = getenv("B2_KVARIANT") ? atoi(getenv("B2_KVARIANT")) : 0;   // tuning experiments (profiles/r2_kernel_variants.md)
+         switch (variant) {
+            case 1: e = launch_tiles_t<64, 64, 2, 2, 2, 3, 12, 2>(d_tiles, ntiles, d_items, bases, s); break;   // 2 chunks per barrier, 2 CTAs/SM
+            case 2: e = launch_tiles_t<64, 64, 2, 2, 1, 4, 12, 3>(d_tiles, ntiles, d_items, bases, s); break;   // 4 stages, 3 CTAs/SM
+            case 3: e = launch_tiles_t<64, 64, 2, 2, 1, 3, 16, 4>(d_tiles, ntiles, d_items, bases, s); break;   // predicate-free path only for full warps
+            case 4: e = launch_tiles_t<64, 64, 2, 2, 1, 3, 14, 4>(d_tiles, ntiles, d_items, bases, s); break;   // ... for >= 7/8
+            case 5: e = launch_tiles_t<64, 64, 2, 2, 2, 2, 12, 3>(d_tiles, ntiles, d_items, bases, s); break;   // 2 chunks per barrier, 2 units, 3 CTAs/SM
+            case 6: e = launch_tiles_t<64, 64, 2, 4, 1, 3, 12, 4>(d_tiles, ntiles, d_items, bases, s); break;   // 8 warps of 32 x 16, 4 CTAs/SM (64 registers)
+            case 7: e = launch_tiles_t<64, 64, 2, 4, 1, 3, 12, 3>(d_tiles, ntiles, d_items, bases, s); break;   // 8 warps of 32 x 16, 3 CTAs/SM
+            case 8: e = launch_tiles_t<64, 64, 4, 2, 1, 3, 12, 3>(d_tiles, ntiles, d_items, bases, s); break;   // 8 warps of 16 x 32, 3 CTAs/SM
+            default: e = launch_tiles_t<64, 64, 2, 2>(d_tiles, ntiles, d_items, bases, s); break;
+         }
+         break;
+      }
       case 1: e = launch_tiles_t<32, 32, 2, 2>(d_tiles, ntiles, d_items, bases, s); break;
       case 2: e = launch_tiles_t<16, 16, 1, 1>(d_tiles, ntiles, d_items, bases, s); break;
       case 3: e = launch_tiles_t<8, 8, 1, 1>(d_tiles, ntiles, d_items, bases, s); break;
       default: snprintf(g_dev_err, sizeof(g_dev_err), "bad tile class %d", tile_class); return -1;
    }
    if (e != cudaSuccess) return cuda_fail(e, "k_tiles launch");
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_axpy_tiles: tiles whose items are ALL block axpys — the A/B/C/D mixing pass of the operator update (DMRGoperators.cpp:367-405:
+// TensorOperator::daxpy / daxpy_transpose_tensorCD of the two-operator tensors with integral weights).  HBM/L2-bound: one CTA streams
+// the <= 64 x 64 destination tile once and adds every source tile; plain sources are read coalesced along the rows, transposed sources
+// are read coalesced along THEIR rows into shared memory and added transposed.  The item record of the next source is fetched while
+// the current one is added (no dependent-load chain per item); the launch order groups the tiles that share their sources
+// (b2_capi_update.cpp), so the sources come from L2.
+__global__ void __launch_bounds__(256) k_axpy_tiles(const Tile* __restrict__ tiles, const GemmItem* __restrict__ items, DevBases bases) {
+   constexpr int EPT = 16;   // 64 x 64 / 256
+   __shared__ double sT[64 * 65];
+   const Tile t = tiles[blockIdx.x];
+   const int tid = threadIdx.x, mrem = t.mrem, nrem = t.nrem, n = mrem * nrem;
+   double acc[EPT];
+   int rr[EPT], cc[EPT];
+#pragma unroll
+   for (int j = 0; j < EPT; j++) {
+      const int idx = tid + 256 * j;
+      acc[j] = 0.0;
+      rr[j] = (idx < n) ? idx % mrem : -1;
+      cc[j] = (idx < n) ? idx / mrem : 0;
+   }
+   GemmItem I = items[t.item_begin];
+   for (int it = t.item_begin; it < t.item_end; it++) {
+      const GemmItem cur = I;
+      if (it + 1 < t.item_end) I = items[it + 1];
+      const double* __restrict__ X = bases.p[cur.xs] + cur.xoff;
+      if (!(cur.flags & IF_TX)) {
+#pragma unroll
+         for (int j = 0; j < EPT; j++)
+            if (rr[j] >= 0) acc[j] += cur.alpha * X[(size_t)(t.m0 + rr[j]) + (size_t)(t.n0 + cc[j]) * cur.ldx];
+      } else {
+         __syncthreads();   // the previous transposed source has been consumed
+         for (int idx = tid; idx < n; idx += 256) {   // stored block: rows = destination columns (contiguous), columns = destination rows
+            const int c = idx % nrem, r = idx / nrem;
+            sT[c * 65 + r] = X[(size_t)(t.n0 + c) + (size_t)(t.m0 + r) * cur.ldx];
+         }
+         __syncthreads();
+#pragma unroll
+         for (int j = 0; j < EPT; j++)
+            if (rr[j] >= 0) acc[j] += cur.alpha * sT[cc[j] * 65 + rr[j]];
+      }
+   }
+   double* __restrict__ C = bases.p[t.cspace] + t.coff;
+#pragma unroll
+   for (int j = 0; j < EPT; j++)
+      if (rr[j] >= 0) {
+         double* p = C + (size_t)(t.cm0 + rr[j]) + (size_t)(t.cn0 + cc[j]) * t.ldc;
+         if (t.accumulate) *p += acc[j]; else *p = acc[j];
+      }
+}
+int dev_launch_axpy_tiles(const Tile* d_tiles, int ntiles, const GemmItem* d_items, const DevBases& bases, void* stream) {
+   if (ntiles <= 0) return 0;
+   k_axpy_tiles<<<ntiles, 256, 0, (cudaStream_t)stream>>>(d_tiles, d_items, bases);
+   cudaError_t e = cudaGetLastError();
+   if (e != cudaSuccess) return cuda_fail(e, "k_axpy_tiles launch");
    return 0;
 }
 

@@ -51,12 +51,15 @@ struct Gen {
    int irr(int orb) const { return bk.orb_irrep[orb]; }
    double V(int a, int b, int c, int d) const { return prob.V(a, b, c, d); }
 
-   // ---- ownership maps, MPIchemps2.h:158-231 with mpi_size() -> number of GPUs
+   // ---- ownership GROUPS: the arguments of the reference's owner maps before the modulo (MPIchemps2.h:158-231: every operator pair /
+   // Q site / specific diagram has its own number; the reference takes it modulo mpi_size()).  A term carries its group number here;
+   // balance_owners() below assigns the groups to the GPUs by their FLOPs instead of by the modulo (static round-robin ignores that the
+   // pair sums of different operator pairs cost very different amounts: max/mean 1.06 at 8 GPUs).
    int o_master() const { return 0; }
-   int o_absigma(int i, int j) const { return (1 + i + (j * (j + 1)) / 2) % world; }
-   int o_cdf(int i, int j) const { return (1 + (L * (L + 1)) / 2 + i + (j * (j + 1)) / 2) % world; }
-   int o_q(int i) const { return (1 + L * (L + 1) + i) % world; }
-   int o_spec(int macro) const { return (macro + L * (L + 2)) % world; }
+   int o_absigma(int i, int j) const { return 1 + i + (j * (j + 1)) / 2; }
+   int o_cdf(int i, int j) const { return 1 + (L * (L + 1)) / 2 + i + (j * (j + 1)) / 2; }
+   int o_q(int i) const { return 1 + L * (L + 1) + i; }
+   int o_spec(int macro) const { return macro + L * (L + 2); }
 
    OpH Lo(int kind, int i, int j) const { return OpH{SRC_LEFT, left ? left->find(kind, i, j) : -1}; }
    OpH Ro(int kind, int i, int j) const { return OpH{SRC_RIGHT, right ? right->find(kind, i, j) : -1}; }
@@ -453,6 +456,37 @@ struct Gen {
 
 }   // namespace
 
+namespace {
+// Groups -> GPUs: longest-processing-time-first on the FLOPs the scheduler will execute per term (cheaper association order, like
+// compile_terms picks it).  Deterministic: every rank builds the same plan and evaluates the same assignment.  world == 1: all on GPU 0.
+void balance_owners(SigmaPlan& plan, const OpSet*, const OpSet*, int world) {
+   if (world <= 1) { for (SigmaTerm& t : plan.terms) t.owner = 0; return; }
+   int ngroups = 0;
+   for (const SigmaTerm& t : plan.terms) ngroups = std::max(ngroups, t.owner + 1);
+   std::vector<double> cost((size_t)ngroups, 0.0);
+   for (const SigmaTerm& t : plan.terms) {
+      const double M = plan.S.blk[t.dst].rows, N = plan.S.blk[t.dst].cols, k1 = plan.S.blk[t.src].rows, k2 = plan.S.blk[t.src].cols;
+      const bool hl = t.l.src != SRC_NONE && t.l.blk >= 0, hr = t.r.src != SRC_NONE && t.r.blk >= 0;
+      double c;
+      if (hl && hr) c = 2.0 * std::min(M * k1 * k2 + M * k2 * N, k1 * k2 * N + M * k1 * N);
+      else if (hl) c = 2.0 * M * N * k1;
+      else if (hr) c = 2.0 * M * N * k2;
+      else c = 2.0 * M * N;
+      cost[t.owner] += c;
+   }
+   std::vector<int> order;
+   for (int g = 0; g < ngroups; g++) if (cost[g] > 0.0) order.push_back(g);
+   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+   std::vector<double> load((size_t)world, 0.0);
+   std::vector<int> rank_of((size_t)ngroups, 0);
+   for (int g : order) {
+      const int r = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+      rank_of[g] = r; load[r] += cost[g];
+   }
+   for (SigmaTerm& t : plan.terms) t.owner = rank_of[t.owner];
+}
+}   // namespace
+
 void build_sigma_plan(SigmaPlan& plan, const Bookkeeper& bk, const Problem& prob, const OpSet* left, const OpSet* right,
                       int site, int world) {
    plan.site = site;
@@ -474,6 +508,7 @@ void build_sigma_plan(SigmaPlan& plan, const Bookkeeper& bk, const Problem& prob
    if (nthreads <= 1) {
       Gen g(plan, bk, prob, left, right, site, world < 1 ? 1 : world);
       for (int k = 0; k < nk; k++) enumerate_block(g, k);
+      balance_owners(plan, left, right, world);
       return;
    }
    // Target blocks are independent: every host thread enumerates the blocks it grabs into a private fragment (terms, pre-sums,
@@ -541,6 +576,7 @@ void build_sigma_plan(SigmaPlan& plan, const Bookkeeper& bk, const Problem& prob
          plan.terms.push_back(x);
       }
    }
+   balance_owners(plan, left, right, world);
    if (getenv("B2_TIMING"))
       fprintf(stderr, "build_sigma_plan: %d blocks on %d threads, enumerate %.3f s, stitch %.3f s\n", nk, nthreads,
               std::chrono::duration<double>(tp1 - tp0).count(), std::chrono::duration<double>(std::chrono::steady_clock::now() - tp1).count());

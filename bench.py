@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--ref-budget-s", type=float, default=420.0, help="--impl reference: stop starting new reference builds after this many seconds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true", help="skip the secondary metric (DMRG sweep time at D on N2/cc-pVDZ, config 2)")
+    ap.add_argument("--no-update", action="store_true", help="skip the operator-update metric")
     ap.add_argument("--sweep-D", default=None, help="comma-separated bond dimensions of the sweep metric, one full sweep each (default 250,500,1000)")
     ap.add_argument("--sweep-ref", action="store_true", help="also time the unmodified reference's DMRG::Solve on the same schedule (minutes)")
     ap.add_argument("--work-budget", type=float, default=0)
@@ -436,15 +437,19 @@ def main():
             del out, ref
         except Exception as e:   # the baseline must not take the bench line down
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"}
-    if world == 1 and not args.no_sweep:
+    if world == 1 and not args.no_update:
         try:
             del heff                                     # frees the sigma plan (workspace + work lists) before the update plan is built
             um = update_metric(torch, ctx, w, dims, left, stream, with_reference=not args.no_cpu_baseline)
             um["frac_of_fp64_peak"] = um["tflops_fp64"] / peak.value
+            um["executed_frac_of_fp64_peak"] = um["executed_tflops_fp64"] / peak.value
             line["operator_update"] = um
         except Exception as e:
             line["operator_update"] = {"failed": str(e)}
+    if world == 1 and not args.no_sweep:
         try:
+            left = right = None
+            torch.cuda.empty_cache()
             sched = [(int(x), 1) for x in args.sweep_D.split(",")] if args.sweep_D else None
             line["sweep"] = sweep_metric(local, args.sweep_ref, schedule=sched)
         except Exception as e:   # the secondary metric must not take the bench line down

@@ -336,6 +336,7 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
    if ((site > 0 && left && left->offloaded) || (site < L - 2 && right && right->offloaded)) return fail(B2_ERR_STATE, "b2_heff_create: operator set is offloaded (b2_opset_reload first)");
    std::unique_ptr<b2_heff> h(new b2_heff);
    h->ctx = ctx; h->world = world; h->rank = rank;
+   if (world > 1) set_plan_local_ranks(world);   // the ranks of one box build their plans concurrently
    h->left = (site > 0) ? left : nullptr;
    h->right = (site < L - 2) ? right : nullptr;
    const double tb0 = wall_seconds();
@@ -558,6 +559,7 @@ int b2_heff_solve_device(b2_heff* h, double* dev_s, double rtol, double* eigenva
       if (h->allreduce && (rc = h->allreduce(h->allreduce_user, d_diag, n, (void*)s))) { rc = fail(B2_ERR_STATE, "all-reduce callback failed"); break; }
       DavidsonParams prm;
       prm.rtol = rtol;
+      prm.max_matvec = h->ctx->davidson_max_matvec;
       MatVec mv = [h](const double* in, double* out) -> int {
          int r = b2_heff_apply_device(h, in, out);
          if (r) return r;
@@ -678,6 +680,7 @@ int b2_ctx_set_option(b2_ctx* ctx, const char* name, double value) {
    else if (!std::strcmp(name, "parallel_plan_flops")) ctx->parallel_plan_flops = value;
    else if (!std::strcmp(name, "simulate_oom")) ctx->simulate_oom = (int)value;
    else if (!std::strcmp(name, "parallel_min_terms")) ctx->copt.parallel_min_terms = (int64_t)value;
+   else if (!std::strcmp(name, "davidson_max_matvec")) { if (value < 1) return fail(B2_ERR_ARG, "davidson_max_matvec too small"); ctx->davidson_max_matvec = (int)value; }
    else return fail(B2_ERR_ARG, "b2_ctx_set_option: unknown option %s", name);
    return B2_OK;
 }

@@ -162,6 +162,7 @@ int b2_dmrg_set_opset(b2_dmrg* d, int boundary, int moving_right, b2_opset* set)
 int b2_dmrg_set_world(b2_dmrg* d, int world, int rank, b2_allreduce_fn fn, void* user) {
    if (!d || world < 1 || rank < 0 || rank >= world || (world > 1 && !fn)) return fail(B2_ERR_ARG, "b2_dmrg_set_world: bad arguments");
    d->world = world; d->rank = rank; d->allreduce = fn; d->allreduce_user = user;
+   set_plan_local_ranks(world);
    return B2_OK;
 }
 int b2_dmrg_set_spill(b2_dmrg* d, int enabled) {

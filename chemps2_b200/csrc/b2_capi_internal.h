@@ -54,6 +54,7 @@ struct b2_ctx {
    // only inside a segment (+1-3 % executed FLOPs, measured on the N2/cc-pVDZ D=2000 and tetracene D=3000 shapes) but builds the plan
    // 2-4x faster, which wins as long as a Davidson solve (~15 sigma builds) is shorter than the planning it saves
    double parallel_plan_flops = 1e13;
+   int davidson_max_matvec = 5000;          // safety net of the device Davidson (the reference loops until convergence)
 };
 
 struct b2_opset {

@@ -376,9 +376,12 @@ void compile_range(CompiledWork& out, Term3* terms, size_t nterms, const std::ve
          }
    };
 
+   const bool prof = getenv("B2_TIMING2") != nullptr;
+   double t_terms = 0.0, t_emit = 0.0, t_close = 0.0;
    open_wave();
    size_t i0 = 0;
    while (i0 < nterms) {
+      const double tq0 = prof ? now_s() : 0.0;
       size_t i1 = i0;
       while (i1 < nterms && terms[i1].dst == terms[i0].dst) i1++;
       // block-axpy terms first inside every destination block: the kernel consumes them before it starts its GEMM pipeline
@@ -416,10 +419,14 @@ void compile_range(CompiledWork& out, Term3* terms, size_t nterms, const std::ve
             ib = (int)out.items2.size();
          }
       }
+      const double tq1 = prof ? now_s() : 0.0;
       emit_block(db, ib, (int)out.items2.size());
+      if (prof) { t_terms += tq1 - tq0; t_emit += now_s() - tq1; }
       i0 = i1;
    }
+   const double tq2 = prof ? now_s() : 0.0;
    close_wave();
+   if (prof) { t_close = now_s() - tq2; fprintf(stderr, "compile_range: terms %.3f s, emit %.3f s, close (sort) %.3f s\n", t_terms, t_emit, t_close); }
 }
 
 }   // namespace

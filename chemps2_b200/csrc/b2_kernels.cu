@@ -133,41 +133,39 @@ template <int T, int NT> struct Stager {
    }
 };
 
-// one MMA step of a k-chunk: step S multiplies k = S + 4q (q = fragment lane).  ALL: every one of the MI x NI 8x8 sub-tiles
-// of the warp is computed, no predicates (sub-tiles outside the tile see clamped / zero-filled panel rows and are never
-// stored).  SCALE: alpha != 1.
-template <int TM, int TN, int MI, int NI, bool ALL, bool SCALE, int S>
-__device__ __forceinline__ void mma_step(double (&acc)[MI][NI][2], const double* __restrict__ xa, const double* __restrict__ yb, double alpha, int mi_n, int ni_n) {
+// one MMA step of a k-chunk: step S multiplies k = S + 4q (q = fragment lane).  MIE x NIE of the warp's MI x NI 8x8 sub-tiles lie (partly)
+// inside the tile and are computed — compile-time counts, so a warp on a ragged tile edge issues exactly the DMMAs it needs without
+// predicates (sub-tile rows / columns beyond the tile see clamped or zero-filled panel rows and are never stored).  SCALE: alpha != 1.
+template <int TM, int TN, int MI, int NI, int MIE, int NIE, bool SCALE, int S>
+__device__ __forceinline__ void mma_step(double (&acc)[MI][NI][2], const double* __restrict__ xa, const double* __restrict__ yb, double alpha) {
    constexpr int RSX = Panel<TM>::RS, RSY = Panel<TN>::RS;
-   double a[MI], b[NI];
+   double a[MIE > 0 ? MIE : 1], b[NIE > 0 ? NIE : 1];
 #pragma unroll
-   for (int i = 0; i < MI; i++) a[i] = SCALE ? alpha * xa[S * RSX + i * 8] : xa[S * RSX + i * 8];
+   for (int i = 0; i < MIE; i++) a[i] = SCALE ? alpha * xa[S * RSX + i * 8] : xa[S * RSX + i * 8];
 #pragma unroll
-   for (int j = 0; j < NI; j++) b[j] = yb[S * RSY + j * 8];
+   for (int j = 0; j < NIE; j++) b[j] = yb[S * RSY + j * 8];
 #pragma unroll
-   for (int i = 0; i < MI; i++)
+   for (int i = 0; i < MIE; i++)
 #pragma unroll
-      for (int j = 0; j < NI; j++)
-         if (ALL || (i < mi_n && j < ni_n)) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      for (int j = 0; j < NIE; j++) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
 }
 
 // one k-chunk: the four MMA steps with the cp.async copies of a later chunk issued in between (the copies do not depend on
 // the MMAs; spreading them over the chunk keeps the DMMA pipe fed right after the barrier).  FULLK: all KC columns valid,
 // else steps >= kvalid are skipped (columns >= kvalid are zero).
-template <int TM, int TN, int MI, int NI, bool ALL, bool SCALE, bool FULLK, class FX, class FY>
+template <int TM, int TN, int MI, int NI, int MIE, int NIE, bool SCALE, bool FULLK, class FX, class FY>
 __device__ __forceinline__ void mma_chunk(double (&acc)[MI][NI][2], const double* __restrict__ xa, const double* __restrict__ yb, int kvalid, double alpha,
-                                          int mi_n, int ni_n, FX&& stage_x, FY&& stage_y) {
-   mma_step<TM, TN, MI, NI, ALL, SCALE, 0>(acc, xa, yb, alpha, mi_n, ni_n);
+                                          FX&& stage_x, FY&& stage_y) {
+   mma_step<TM, TN, MI, NI, MIE, NIE, SCALE, 0>(acc, xa, yb, alpha);
    stage_x();
-   if (FULLK || 1 < kvalid) mma_step<TM, TN, MI, NI, ALL, SCALE, 1>(acc, xa, yb, alpha, mi_n, ni_n);
+   if (FULLK || 1 < kvalid) mma_step<TM, TN, MI, NI, MIE, NIE, SCALE, 1>(acc, xa, yb, alpha);
    stage_y();
-   if (FULLK || 2 < kvalid) mma_step<TM, TN, MI, NI, ALL, SCALE, 2>(acc, xa, yb, alpha, mi_n, ni_n);
-   if (FULLK || 3 < kvalid) mma_step<TM, TN, MI, NI, ALL, SCALE, 3>(acc, xa, yb, alpha, mi_n, ni_n);
+   if (FULLK || 2 < kvalid) mma_step<TM, TN, MI, NI, MIE, NIE, SCALE, 2>(acc, xa, yb, alpha);
+   if (FULLK || 3 < kvalid) mma_step<TM, TN, MI, NI, MIE, NIE, SCALE, 3>(acc, xa, yb, alpha);
 }
 
-// KSUB k-chunks are consumed per barrier (the pipeline unit), NSTG units are in flight; ALLQ: a warp with at least ALLQ/16 of its
-// sub-tiles inside the tile runs the predicate-free MMA path.  CPS = resident CTAs per SM the launch bounds ask for.
-template <int TM, int TN, int WM, int WN, int KSUB = 1, int NSTG = 3, int ALLQ = 12, int CPS = 4>
+// KSUB k-chunks are consumed per barrier (the pipeline unit), NSTG units are in flight; CPS = resident CTAs per SM the launch bounds ask for.
+template <int TM, int TN, int WM, int WN, int KSUB = 1, int NSTG = 3, int CPS = 4>
 __global__ void __launch_bounds__(WM * WN * 32, (TM == 64) ? CPS : 1) k_tiles(const Tile* __restrict__ tiles, const GemmItem* __restrict__ items, DevBases bases) {
    constexpr int NT = WM * WN * 32;
    constexpr int STAGES = KSUB * NSTG;   // panel buffers
@@ -251,11 +249,10 @@ __global__ void __launch_bounds__(WM * WN * 32, (TM == 64) ? CPS : 1) k_tiles(co
    };
    if (c_it < item_end) consumer_load_item();
    const int xfrag = 4 * q * Panel<TM>::RS + wm * WTM + g, yfrag = 4 * q * Panel<TN>::RS + wn * WTN + g;
-   // 8x8 sub-tiles of this warp that lie (partly) inside the tile (warp-uniform).  A warp with >= 3/4 of its sub-tiles inside
-   // runs the predicate-free MMA path on all of them; the main loop is instantiated once per path.
+   // 8x8 sub-tile rows / columns of this warp that lie (partly) inside the tile (warp-uniform); the main loop is instantiated per count
    const int mi_n = min(MI, max(0, (mrem - wm * WTM + 7) >> 3)), ni_n = min(NI, max(0, (nrem - wn * WTN + 7) >> 3));
-   auto main_loop = [&](auto wall_tag) {
-      constexpr bool WALL = decltype(wall_tag)::value;
+   auto main_loop = [&](auto mie_tag, auto nie_tag) {
+      constexpr int MIE = decltype(mie_tag)::value, NIE = decltype(nie_tag)::value;
       while (c_it < item_end) {
          cp_async_wait<STAGES - 2 * KSUB>();
          __syncthreads();          // the KSUB chunks from `stage` on have landed; everybody is done with the buffers refilled below
@@ -270,17 +267,13 @@ __global__ void __launch_bounds__(WM * WN * 32, (TM == 64) ? CPS : 1) k_tiles(co
          const int ps = (stage < KSUB) ? stage + STAGES - KSUB : stage - KSUB;   // a buffer consumed in the previous unit is refilled
          auto stage_x = [&]() { stage_x_at(ps); };
          auto stage_y = [&]() { stage_y_at(ps); };
-         if (WALL) {
-            if (c_left >= KC) {
-               // alpha == 1 compared on the bit pattern: an FP64 compare would queue behind the DMMAs
-               if (__double2hiint(alpha) == 0x3FF00000 && __double2loint(alpha) == 0)
-                  mma_chunk<TM, TN, MI, NI, true, false, true>(acc, xa, yb, KC, alpha, MI, NI, stage_x, stage_y);
-               else mma_chunk<TM, TN, MI, NI, true, true, true>(acc, xa, yb, KC, alpha, MI, NI, stage_x, stage_y);
-            } else {
-               mma_chunk<TM, TN, MI, NI, true, true, false>(acc, xa, yb, c_left, alpha, MI, NI, stage_x, stage_y);
-            }
+         if (c_left >= KC) {
+            // alpha == 1 compared on the bit pattern: an FP64 compare would queue behind the DMMAs
+            if (__double2hiint(alpha) == 0x3FF00000 && __double2loint(alpha) == 0)
+               mma_chunk<TM, TN, MI, NI, MIE, NIE, false, true>(acc, xa, yb, KC, alpha, stage_x, stage_y);
+            else mma_chunk<TM, TN, MI, NI, MIE, NIE, true, true>(acc, xa, yb, KC, alpha, stage_x, stage_y);
          } else {
-            mma_chunk<TM, TN, MI, NI, false, true, false>(acc, xa, yb, c_left, alpha, mi_n, ni_n, stage_x, stage_y);
+            mma_chunk<TM, TN, MI, NI, MIE, NIE, true, false>(acc, xa, yb, c_left, alpha, stage_x, stage_y);
          }
          c_left -= KC;
          if (c_left <= 0 && ++c_it < item_end) consumer_load_item();
@@ -288,7 +281,19 @@ __global__ void __launch_bounds__(WM * WN * 32, (TM == 64) ? CPS : 1) k_tiles(co
          }
       }
    };
-   if (mi_n * ni_n * 16 >= MI * NI * ALLQ) main_loop(std::true_type{}); else main_loop(std::false_type{});
+   // dispatch on the (warp-uniform) number of sub-tile rows / columns of this warp that lie inside the tile
+   auto with_ni = [&](auto mie_tag) {
+      if (NI >= 4 && ni_n == 4) main_loop(mie_tag, std::integral_constant<int, (NI >= 4 ? 4 : NI)>{});
+      else if (NI >= 3 && ni_n == 3) main_loop(mie_tag, std::integral_constant<int, (NI >= 3 ? 3 : NI)>{});
+      else if (NI >= 2 && ni_n == 2) main_loop(mie_tag, std::integral_constant<int, (NI >= 2 ? 2 : NI)>{});
+      else if (ni_n == 1) main_loop(mie_tag, std::integral_constant<int, 1>{});
+      else main_loop(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
+   };
+   if (MI >= 4 && mi_n == 4) with_ni(std::integral_constant<int, (MI >= 4 ? 4 : MI)>{});
+   else if (MI >= 3 && mi_n == 3) with_ni(std::integral_constant<int, (MI >= 3 ? 3 : MI)>{});
+   else if (MI >= 2 && mi_n == 2) with_ni(std::integral_constant<int, (MI >= 2 ? 2 : MI)>{});
+   else if (mi_n == 1) with_ni(std::integral_constant<int, 1>{});
+   else main_loop(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
    cp_async_wait<0>();
 
    const Tile t = *tp;
@@ -311,7 +316,7 @@ __global__ void __launch_bounds__(WM * WN * 32, (TM == 64) ? CPS : 1) k_tiles(co
       }
 }
 
-template <int TM, int TN, int WM, int WN, int KSUB = 1, int NSTG = 3, int ALLQ = 12, int CPS = 4>
+template <int TM, int TN, int WM, int WN, int KSUB = 1, int NSTG = 3, int CPS = 4>
 static cudaError_t launch_tiles_t(const Tile* d_tiles, int ntiles, const GemmItem* d_items, const DevBases& bases, cudaStream_t s) {
    constexpr size_t smem = sizeof(double) * KSUB * NSTG * (Panel<TM>::SIZE + Panel<TN>::SIZE);
    // the opt-in above 48 KiB is a per-DEVICE function attribute: one flag per device ordinal (a process may hold contexts on several)
@@ -319,11 +324,11 @@ static cudaError_t launch_tiles_t(const Tile* d_tiles, int ntiles, const GemmIte
    int dev = 0;
    cudaGetDevice(&dev);
    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-      cudaError_t e = cudaFuncSetAttribute(k_tiles<TM, TN, WM, WN, KSUB, NSTG, ALLQ, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(k_tiles<TM, TN, WM, WN, KSUB, NSTG, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
    }
-   k_tiles<TM, TN, WM, WN, KSUB, NSTG, ALLQ, CPS><<<ntiles, WM * WN * 32, smem, s>>>(d_tiles, d_items, bases);
+   k_tiles<TM, TN, WM, WN, KSUB, NSTG, CPS><<<ntiles, WM * WN * 32, smem, s>>>(d_tiles, d_items, bases);
    return cudaGetLastError();
 }
 
@@ -332,21 +337,9 @@ int dev_launch_tiles(int tile_class, const Tile* d_tiles, int ntiles, const Gemm
    cudaStream_t s = (cudaStream_t)stream;
    cudaError_t e;
    switch (tile_class) {
-      case 0: {
-         static const int variant = getenv("B2_KVARIANT") ? atoi(getenv("B2_KVARIANT")) : 0;   // tuning experiments (profiles/r2_kernel_variants.md)
-         switch (variant) {
-            case 1: e = launch_tiles_t<64, 64, 2, 2, 2, 3, 12, 2>(d_tiles, ntiles, d_items, bases, s); break;   // 2 chunks per barrier, 2 CTAs/SM
-            case 2: e = launch_tiles_t<64, 64, 2, 2, 1, 4, 12, 3>(d_tiles, ntiles, d_items, bases, s); break;   // 4 stages, 3 CTAs/SM
-            case 3: e = launch_tiles_t<64, 64, 2, 2, 1, 3, 16, 4>(d_tiles, ntiles, d_items, bases, s); break;   // predicate-free path only for full warps
-            case 4: e = launch_tiles_t<64, 64, 2, 2, 1, 3, 14, 4>(d_tiles, ntiles, d_items, bases, s); break;   // ... for >= 7/8
-            case 5: e = launch_tiles_t<64, 64, 2, 2, 2, 2, 12, 3>(d_tiles, ntiles, d_items, bases, s); break;   // 2 chunks per barrier, 2 units, 3 CTAs/SM
-            case 6: e = launch_tiles_t<64, 64, 2, 4, 1, 3, 12, 4>(d_tiles, ntiles, d_items, bases, s); break;   // 8 warps of 32 x 16, 4 CTAs/SM (64 registers)
-            case 7: e = launch_tiles_t<64, 64, 2, 4, 1, 3, 12, 3>(d_tiles, ntiles, d_items, bases, s); break;   // 8 warps of 32 x 16, 3 CTAs/SM
-            case 8: e = launch_tiles_t<64, 64, 4, 2, 1, 3, 12, 3>(d_tiles, ntiles, d_items, bases, s); break;   // 8 warps of 16 x 32, 3 CTAs/SM
-            default: e = launch_tiles_t<64, 64, 2, 2>(d_tiles, ntiles, d_items, bases, s); break;
-         }
-         break;
-      }
+      // pipeline variants measured in round 2 (profiles/r2_kernel_variants.md): 2 chunks per barrier at 2 or 3 CTAs/SM, 4 stages at 3 CTAs/SM,
+      // 8-warp CTAs with 32 x 16 / 16 x 32 warp tiles at 3 or 4 CTAs/SM — all slower than 4 warps x (32 x 32), 3 stages, 4 CTAs/SM
+      case 0: e = launch_tiles_t<64, 64, 2, 2>(d_tiles, ntiles, d_items, bases, s); break;
       case 1: e = launch_tiles_t<32, 32, 2, 2>(d_tiles, ntiles, d_items, bases, s); break;
       case 2: e = launch_tiles_t<16, 16, 1, 1>(d_tiles, ntiles, d_items, bases, s); break;
       case 3: e = launch_tiles_t<8, 8, 1, 1>(d_tiles, ntiles, d_items, bases, s); break;

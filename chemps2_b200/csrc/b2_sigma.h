@@ -55,6 +55,7 @@ struct SigmaPlan {
 };
 
 int plan_threads(int nblocks);   // host threads for plan building (B2_PLAN_THREADS)
+void set_plan_local_ranks(int n);   // processes sharing this host (one per GPU): the host threads are divided among them
 
 // world = number of GPUs the ownership maps are evaluated for (1 = everything owned by GPU 0)
 void build_sigma_plan(SigmaPlan& plan, const Bookkeeper& bk, const Problem& prob, const OpSet* left, const OpSet* right,

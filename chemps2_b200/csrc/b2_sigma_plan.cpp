@@ -19,14 +19,19 @@
 
 namespace b2 {
 
-// host threads used to build plans: B2_PLAN_THREADS, else the hardware concurrency (at most 32); small plans stay sequential
+// host threads used to build plans: B2_PLAN_THREADS, else the hardware concurrency (at most 32) divided by the number of processes that
+// share this host (one process per GPU: every rank builds its plans at the same time — 8 ranks x 16 threads on 16 cores thrash);
+// small plans stay sequential
+static std::atomic<int> g_local_ranks{1};
+void set_plan_local_ranks(int n) { g_local_ranks.store(std::max(1, n)); }
 int plan_threads(int nblocks) {
    static const int configured = [] {
       const char* e = getenv("B2_PLAN_THREADS");
       int n = e ? atoi(e) : (int)std::thread::hardware_concurrency();
       return std::max(1, std::min(n, 32));
    }();
-   return std::max(1, std::min(configured, nblocks / 8));
+   const int share = std::max(1, configured / g_local_ranks.load());
+   return std::max(1, std::min(share, nblocks / 8));
 }
 
 namespace {

@@ -366,7 +366,8 @@ int b2_svd_batch(b2_ctx* ctx, int count, const int* m, const int* n, const doubl
                  double* const* vt);
 
 /* scheduling knobs of plans created afterwards: "work_budget" (doubles of stage-1 workspace per wave), "chunk_k",
- * "parallel_plan_flops" (plans below this many reference FLOPs per apply are compiled on all host cores; env B2_PLAN_THREADS) */
+ * "parallel_plan_flops" (plans below this many reference FLOPs per apply are compiled on all host cores; env B2_PLAN_THREADS),
+ * "davidson_max_matvec" (safety net of the device Davidson: a solve that needs more matrix-vector products fails, default 5000) */
 int b2_ctx_set_option(b2_ctx* ctx, const char* name, double value);
 /* host mirrors of the operator arenas (valid until the set is destroyed) */
 const double* b2_opset_host_arena(const b2_opset* set);

@@ -23,9 +23,10 @@ rank, world = dist.get_rank(), dist.get_world_size()
 fx = fixtures.load(os.path.join({root!r}, "tests", "golden", "n2_sto3g_singlet.npz"))
 L, group, N, twoS, irrep = [int(x) for x in fx["problem/hdr"]]
 
-def run(world_, rank_, ar):
+def run(world_, rank_, ar, own_stream=False):
     ctx = api.Context(local)
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    if not own_stream:   # own_stream: the library keeps the stream it created; the all-reduce callback must run ON that stream
+        ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     ctx.set_problem(L, group, N, twoS, irrep, fx["problem/orb_irrep"], mx=fx["problem/mx"], econst=float(fx["problem/econst"][0]))
     D = 64
     ctx.bk_init(D)
@@ -46,8 +47,9 @@ def run(world_, rank_, ar):
 
 ar = api.AllReduce()
 multi = run(world, rank, ar)
+multi_own = run(world, rank, ar, own_stream=True)
 single = run(1, 0, None)
-err = float(np.abs(multi - single).max())
+err = max(float(np.abs(multi - single).max()), float(np.abs(multi_own - single).max()))
 t = torch.tensor([err], dtype=torch.float64, device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:

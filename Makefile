@@ -5,7 +5,7 @@ CUDA_HOME ?= /usr/local/cuda
 SRC := chemps2_b200/csrc
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
 CXXFLAGS := -O2 -std=c++17 -fPIC -Wall -I$(CUDA_HOME)/include
-OBJS := $(SRC)/b2_core.o $(SRC)/b2_pool.o $(SRC)/b2_ops.o $(SRC)/b2_sigma_plan.o $(SRC)/b2_heff.o $(SRC)/b2_compile.o $(SRC)/b2_update_plan.o $(SRC)/b2_sobject.o $(SRC)/b2_twodm.o $(SRC)/b2_capi.o $(SRC)/b2_capi_update.o $(SRC)/b2_capi_dmrg.o $(SRC)/b2_capi_twodm.o $(SRC)/b2_kernels.o $(SRC)/b2_blas1.o $(SRC)/b2_svd.o $(SRC)/b2_davidson.o
+OBJS := $(SRC)/b2_core.o $(SRC)/b2_pool.o $(SRC)/b2_ops.o $(SRC)/b2_sigma_plan.o $(SRC)/b2_heff.o $(SRC)/b2_compile.o $(SRC)/b2_update_plan.o $(SRC)/b2_sobject.o $(SRC)/b2_twodm.o $(SRC)/b2_capi.o $(SRC)/b2_capi_update.o $(SRC)/b2_capi_dmrg.o $(SRC)/b2_capi_twodm.o $(SRC)/b2_capi_davidson.o $(SRC)/b2_kernels.o $(SRC)/b2_blas1.o $(SRC)/b2_svd.o $(SRC)/b2_davidson.o
 LIB := chemps2_b200/libchemps2_b200.so
 
 CALLER := tests/cpp/_bin/dmrg_caller

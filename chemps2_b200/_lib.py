@@ -120,6 +120,11 @@ SIGNATURES = [
     ("b2_dmrg_get_mps", C.c_int, [vp, C.c_int, c_dp]),
     ("b2_dmrg_random_mps", C.c_int, [vp, C.c_uint64]),
     ("b2_dmrg_srand", C.c_int, [vp, C.c_uint64]),
+    ("b2_davidson_create", C.c_int, [vp, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double, C.POINTER(vp)]),
+    ("b2_davidson_destroy", None, [vp]),
+    ("b2_davidson_fetch", C.c_int, [vp, C.POINTER(C.c_char), C.POINTER(vp), C.POINTER(vp)]),
+    ("b2_davidson_num_multiplications", C.c_int, [vp]),
+    ("b2_davidson_eigenvalue", C.c_double, [vp]),
     ("b2_rand_stream", C.c_int, [C.c_uint64, C.c_int, c_ip]),
     ("b2_dmrg_opset", vp, [vp, C.c_int, C.c_int]),
     ("b2_dmrg_set_opset", C.c_int, [vp, C.c_int, C.c_int, vp]),

@@ -175,6 +175,9 @@ int b2_update_run_device(b2_update* u, const double* t_dev) {
    if (dev_launch_presum(u->d_jobs, (int)u->presum_jobs.size(), u->d_parts, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
    if (dev_fill_zero(u->new_set->dev, u->new_set->set.size, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
    if (u->world > 1 && !u->allreduce) return fail(B2_ERR_STATE, "b2_update_run: sharded update (world %d) without an all-reduce callback", u->world);
+   const bool timing = getenv("B2_TIMING") != nullptr;
+   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+   if (timing) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], s); }
    for (int p = 0; p < 2; p++) {
       for (const Wave& w : u->pass[p].waves) {
          for (int c = 0; c < kNumTileClasses; c++)
@@ -190,6 +193,15 @@ int b2_update_run_device(b2_update* u, const double* t_dev) {
       // every GPU computed the operators it was assigned; summing the (otherwise zero) arenas replicates all of them before
       // the mixing pass, which every GPU then runs in full (block axpys, replaces the MPI exchanges of DMRGoperators.cpp:449-533)
       if (p == 0 && u->world > 1 && u->allreduce(u->allreduce_user, u->new_set->dev, u->new_set->set.size, (void*)s)) return fail(B2_ERR_STATE, "b2_update_run: all-reduce callback failed");
+      if (timing) cudaEventRecord(ev[p + 1], s);
+   }
+   if (timing) {
+      cudaEventSynchronize(ev[2]);
+      float t0 = 0.f, t1 = 0.f;
+      cudaEventElapsedTime(&t0, ev[0], ev[1]); cudaEventElapsedTime(&t1, ev[1], ev[2]);
+      fprintf(stderr, "b2_update_run: contraction pass %.3f ms (%.3f TFLOP executed), mixing pass %.3f ms (%zu block axpys, %s kernel)\n", t0, u->pass[0].flops_exec / 1e12, t1,
+              u->pass[1].items2.size(), u->mix_all_axpy ? "k_axpy_tiles" : "k_tiles");
+      for (auto& e : ev) cudaEventDestroy(e);
    }
    return B2_OK;
 }

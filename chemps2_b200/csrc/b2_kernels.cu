@@ -137,17 +137,20 @@ template <int T, int NT> struct Stager {
 // inside the tile and are computed — compile-time counts, so a warp on a ragged tile edge issues exactly the DMMAs it needs without
 // predicates (sub-tile rows / columns beyond the tile see clamped or zero-filled panel rows and are never stored).  SCALE: alpha != 1.
 template <int TM, int TN, int MI, int NI, int MIE, int NIE, bool SCALE, int S>
-__device__ __forceinline__ void mma_step(double (&acc)[MI][NI][2], const double* __restrict__ xa, const double* __restrict__ yb, double alpha) {
+__device__ __forceinline__ void mma_step(double (&acc)[MI][NI][2], const double* __restrict__ xa, const double* __restrict__ yb, double alpha, int mi_n, int ni_n) {
    constexpr int RSX = Panel<TM>::RS, RSY = Panel<TN>::RS;
-   double a[MIE > 0 ? MIE : 1], b[NIE > 0 ? NIE : 1];
+   constexpr bool RUNTIME = MIE < 0;                       // generic path: warp-uniform runtime counts mi_n x ni_n, one predicate per sub-tile
+   constexpr int ME = RUNTIME ? MI : MIE, NE = RUNTIME ? NI : NIE;
+   double a[ME > 0 ? ME : 1], b[NE > 0 ? NE : 1];
 #pragma unroll
-   for (int i = 0; i < MIE; i++) a[i] = SCALE ? alpha * xa[S * RSX + i * 8] : xa[S * RSX + i * 8];
+   for (int i = 0; i < ME; i++) a[i] = SCALE ? alpha * xa[S * RSX + i * 8] : xa[S * RSX + i * 8];
 #pragma unroll
-   for (int j = 0; j < NIE; j++) b[j] = yb[S * RSY + j * 8];
+   for (int j = 0; j < NE; j++) b[j] = yb[S * RSY + j * 8];
 #pragma unroll
-   for (int i = 0; i < MIE; i++)
+   for (int i = 0; i < ME; i++)
 #pragma unroll
-      for (int j = 0; j < NIE; j++) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      for (int j = 0; j < NE; j++)
+         if (!RUNTIME || (i < mi_n && j < ni_n)) dmma8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
 }
 
 // one k-chunk: the four MMA steps with the cp.async copies of a later chunk issued in between (the copies do not depend on
@@ -155,17 +158,17 @@ __device__ __forceinline__ void mma_step(double (&acc)[MI][NI][2], const double*
 // else steps >= kvalid are skipped (columns >= kvalid are zero).
 template <int TM, int TN, int MI, int NI, int MIE, int NIE, bool SCALE, bool FULLK, class FX, class FY>
 __device__ __forceinline__ void mma_chunk(double (&acc)[MI][NI][2], const double* __restrict__ xa, const double* __restrict__ yb, int kvalid, double alpha,
-                                          FX&& stage_x, FY&& stage_y) {
-   mma_step<TM, TN, MI, NI, MIE, NIE, SCALE, 0>(acc, xa, yb, alpha);
+                                          int mi_n, int ni_n, FX&& stage_x, FY&& stage_y) {
+   mma_step<TM, TN, MI, NI, MIE, NIE, SCALE, 0>(acc, xa, yb, alpha, mi_n, ni_n);
    stage_x();
-   if (FULLK || 1 < kvalid) mma_step<TM, TN, MI, NI, MIE, NIE, SCALE, 1>(acc, xa, yb, alpha);
+   if (FULLK || 1 < kvalid) mma_step<TM, TN, MI, NI, MIE, NIE, SCALE, 1>(acc, xa, yb, alpha, mi_n, ni_n);
    stage_y();
-   if (FULLK || 2 < kvalid) mma_step<TM, TN, MI, NI, MIE, NIE, SCALE, 2>(acc, xa, yb, alpha);
-   if (FULLK || 3 < kvalid) mma_step<TM, TN, MI, NI, MIE, NIE, SCALE, 3>(acc, xa, yb, alpha);
+   if (FULLK || 2 < kvalid) mma_step<TM, TN, MI, NI, MIE, NIE, SCALE, 2>(acc, xa, yb, alpha, mi_n, ni_n);
+   if (FULLK || 3 < kvalid) mma_step<TM, TN, MI, NI, MIE, NIE, SCALE, 3>(acc, xa, yb, alpha, mi_n, ni_n);
 }
 
 // KSUB k-chunks are consumed per barrier (the pipeline unit), NSTG units are in flight; CPS = resident CTAs per SM the launch bounds ask for.
-template <int TM, int TN, int WM, int WN, int KSUB = 1, int NSTG = 3, int CPS = 4>
+template <int TM, int TN, int WM, int WN, int KSUB = 1, int NSTG = 3, int CPS = 4, bool HYB = false>
 __global__ void __launch_bounds__(WM * WN * 32, (TM == 64) ? CPS : 1) k_tiles(const Tile* __restrict__ tiles, const GemmItem* __restrict__ items, DevBases bases) {
    constexpr int NT = WM * WN * 32;
    constexpr int STAGES = KSUB * NSTG;   // panel buffers
@@ -267,13 +270,15 @@ __global__ void __launch_bounds__(WM * WN * 32, (TM == 64) ? CPS : 1) k_tiles(co
          const int ps = (stage < KSUB) ? stage + STAGES - KSUB : stage - KSUB;   // a buffer consumed in the previous unit is refilled
          auto stage_x = [&]() { stage_x_at(ps); };
          auto stage_y = [&]() { stage_y_at(ps); };
-         if (c_left >= KC) {
+         if (MIE < 0) {            // generic path: one code variant (scaled, any chunk length) keeps the kernel at 128 registers without spills
+            mma_chunk<TM, TN, MI, NI, MIE, NIE, true, false>(acc, xa, yb, c_left, alpha, mi_n, ni_n, stage_x, stage_y);
+         } else if (c_left >= KC) {
             // alpha == 1 compared on the bit pattern: an FP64 compare would queue behind the DMMAs
             if (__double2hiint(alpha) == 0x3FF00000 && __double2loint(alpha) == 0)
-               mma_chunk<TM, TN, MI, NI, MIE, NIE, false, true>(acc, xa, yb, KC, alpha, stage_x, stage_y);
-            else mma_chunk<TM, TN, MI, NI, MIE, NIE, true, true>(acc, xa, yb, KC, alpha, stage_x, stage_y);
+               mma_chunk<TM, TN, MI, NI, MIE, NIE, false, true>(acc, xa, yb, KC, alpha, mi_n, ni_n, stage_x, stage_y);
+            else mma_chunk<TM, TN, MI, NI, MIE, NIE, true, true>(acc, xa, yb, KC, alpha, mi_n, ni_n, stage_x, stage_y);
          } else {
-            mma_chunk<TM, TN, MI, NI, MIE, NIE, true, false>(acc, xa, yb, c_left, alpha, stage_x, stage_y);
+            mma_chunk<TM, TN, MI, NI, MIE, NIE, true, false>(acc, xa, yb, c_left, alpha, mi_n, ni_n, stage_x, stage_y);
          }
          c_left -= KC;
          if (c_left <= 0 && ++c_it < item_end) consumer_load_item();
@@ -281,19 +286,21 @@ __global__ void __launch_bounds__(WM * WN * 32, (TM == 64) ? CPS : 1) k_tiles(co
          }
       }
    };
-   // dispatch on the (warp-uniform) number of sub-tile rows / columns of this warp that lie inside the tile
-   auto with_ni = [&](auto mie_tag) {
-      if (NI >= 4 && ni_n == 4) main_loop(mie_tag, std::integral_constant<int, (NI >= 4 ? 4 : NI)>{});
-      else if (NI >= 3 && ni_n == 3) main_loop(mie_tag, std::integral_constant<int, (NI >= 3 ? 3 : NI)>{});
-      else if (NI >= 2 && ni_n == 2) main_loop(mie_tag, std::integral_constant<int, (NI >= 2 ? 2 : NI)>{});
-      else if (ni_n == 1) main_loop(mie_tag, std::integral_constant<int, 1>{});
-      else main_loop(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
-   };
-   if (MI >= 4 && mi_n == 4) with_ni(std::integral_constant<int, (MI >= 4 ? 4 : MI)>{});
-   else if (MI >= 3 && mi_n == 3) with_ni(std::integral_constant<int, (MI >= 3 ? 3 : MI)>{});
-   else if (MI >= 2 && mi_n == 2) with_ni(std::integral_constant<int, (MI >= 2 ? 2 : MI)>{});
-   else if (mi_n == 1) with_ni(std::integral_constant<int, 1>{});
-   else main_loop(std::integral_constant<int, 0>{}, std::integral_constant<int, 0>{});
+   // dispatch on the (warp-uniform) sub-tile counts of this warp: the full warp tile and — for the 64 x 64 class — the three ragged shapes
+   // that would otherwise waste a quarter of their DMMAs get compile-time loops; everything else takes the predicated generic path
+   using I4 = std::integral_constant<int, 4>;
+   using I3 = std::integral_constant<int, 3>;
+   using IR = std::integral_constant<int, -1>;
+   if constexpr (HYB) {
+      if (mi_n == MI && ni_n == NI) main_loop(std::integral_constant<int, MI>{}, std::integral_constant<int, NI>{});
+      else if (MI == 4 && NI == 4 && mi_n == 3 && ni_n == 4) main_loop(I3{}, I4{});
+      else if (MI == 4 && NI == 4 && mi_n == 4 && ni_n == 3) main_loop(I4{}, I3{});
+      else if (MI == 4 && NI == 4 && mi_n == 3 && ni_n == 3) main_loop(I3{}, I3{});
+      else main_loop(IR{}, IR{});
+   } else {   // two paths: a warp with >= 3/4 of its sub-tiles inside computes all of them without predicates, the others take the generic path
+      if (mi_n * ni_n * 4 >= MI * NI * 3) main_loop(std::integral_constant<int, MI>{}, std::integral_constant<int, NI>{});
+      else main_loop(IR{}, IR{});
+   }
    cp_async_wait<0>();
 
    const Tile t = *tp;
@@ -316,7 +323,7 @@ __global__ void __launch_bounds__(WM * WN * 32, (TM == 64) ? CPS : 1) k_tiles(co
       }
 }
 
-template <int TM, int TN, int WM, int WN, int KSUB = 1, int NSTG = 3, int CPS = 4>
+template <int TM, int TN, int WM, int WN, int KSUB = 1, int NSTG = 3, int CPS = 4, bool HYB = false>
 static cudaError_t launch_tiles_t(const Tile* d_tiles, int ntiles, const GemmItem* d_items, const DevBases& bases, cudaStream_t s) {
    constexpr size_t smem = sizeof(double) * KSUB * NSTG * (Panel<TM>::SIZE + Panel<TN>::SIZE);
    // the opt-in above 48 KiB is a per-DEVICE function attribute: one flag per device ordinal (a process may hold contexts on several)
@@ -324,11 +331,11 @@ static cudaError_t launch_tiles_t(const Tile* d_tiles, int ntiles, const GemmIte
    int dev = 0;
    cudaGetDevice(&dev);
    if (dev < 0 || dev >= 64 || !configured[dev].load(std::memory_order_acquire)) {
-      cudaError_t e = cudaFuncSetAttribute(k_tiles<TM, TN, WM, WN, KSUB, NSTG, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(k_tiles<TM, TN, WM, WN, KSUB, NSTG, CPS, HYB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       if (dev >= 0 && dev < 64) configured[dev].store(true, std::memory_order_release);
    }
-   k_tiles<TM, TN, WM, WN, KSUB, NSTG, CPS><<<ntiles, WM * WN * 32, smem, s>>>(d_tiles, d_items, bases);
+   k_tiles<TM, TN, WM, WN, KSUB, NSTG, CPS, HYB><<<ntiles, WM * WN * 32, smem, s>>>(d_tiles, d_items, bases);
    return cudaGetLastError();
 }
 
@@ -339,7 +346,11 @@ int dev_launch_tiles(int tile_class, const Tile* d_tiles, int ntiles, const Gemm
    switch (tile_class) {
       // pipeline variants measured in round 2 (profiles/r2_kernel_variants.md): 2 chunks per barrier at 2 or 3 CTAs/SM, 4 stages at 3 CTAs/SM,
       // 8-warp CTAs with 32 x 16 / 16 x 32 warp tiles at 3 or 4 CTAs/SM — all slower than 4 warps x (32 x 32), 3 stages, 4 CTAs/SM
-      case 0: e = launch_tiles_t<64, 64, 2, 2>(d_tiles, ntiles, d_items, bases, s); break;
+      case 0: {
+         static const bool hyb = getenv("B2_KHYBRID") && atoi(getenv("B2_KHYBRID")) != 0;   // experiment switch, see profiles/r2_kernel_variants.md
+         e = hyb ? launch_tiles_t<64, 64, 2, 2, 1, 3, 4, true>(d_tiles, ntiles, d_items, bases, s) : launch_tiles_t<64, 64, 2, 2>(d_tiles, ntiles, d_items, bases, s);
+         break;
+      }
       case 1: e = launch_tiles_t<32, 32, 2, 2>(d_tiles, ntiles, d_items, bases, s); break;
       case 2: e = launch_tiles_t<16, 16, 1, 1>(d_tiles, ntiles, d_items, bases, s); break;
       case 3: e = launch_tiles_t<8, 8, 1, 1>(d_tiles, ntiles, d_items, bases, s); break;

@@ -151,6 +151,20 @@ int b2_heff_set_excitations(b2_heff* h, int n_lower, const double* const* veff_t
  * b2_heff_solve_device = same with s resident on the device. */
 int b2_heff_solve(b2_heff* h, double* s, double rtol, double* eigenvalue, int* n_matvec);
 int b2_heff_solve_device(b2_heff* h, double* dev_s, double rtol, double* eigenvalue, int* n_matvec);
+/* ------------------------------------------------------------------------------------------------ Davidson (reverse communication)
+ * CheMPS2::Davidson (Davidson.h:46-58) as a device-backed object: b2_davidson_create = the constructor (veclength, MAX_NUM_VEC, NUM_VEC_KEEP,
+ * RTOL, DIAG_CUTOFF; problem type 'E'), b2_davidson_fetch = FetchInstruction, b2_davidson_num_multiplications = GetNumMultiplications.
+ * The pointers handed out are DEVICE pointers (veclength doubles each) valid until the next fetch:
+ *   'A'  write the initial guess into ptr0 and the diagonal of the matrix into ptr1, then fetch again
+ *   'B'  compute ptr1 = H * ptr0 on the context stream (e.g. b2_heff_apply_device), then fetch again
+ *   'C'  converged: ptr0 = the lowest eigenvector (unit norm), ptr1[0] = its eigenvalue (also b2_davidson_eigenvalue)
+ * The algorithm is the one b2_heff_solve runs (Options.h:70-72 constants there); b2_heff_solve is this loop fused with the sigma build. */
+typedef struct b2_davidson b2_davidson;
+int b2_davidson_create(b2_ctx* ctx, int64_t veclength, int max_num_vec, int num_vec_keep, double rtol, double diag_cutoff, b2_davidson** out);
+void b2_davidson_destroy(b2_davidson* d);
+int b2_davidson_fetch(b2_davidson* d, char* instruction, double** dev_ptr0, double** dev_ptr1);
+int b2_davidson_num_multiplications(const b2_davidson* d);
+double b2_davidson_eigenvalue(const b2_davidson* d);
 /* multi-GPU: callback that sums a device vector over all ranks in place on the given stream (the caller owns the NCCL
  * communicator); replaces MPI_Reduce/MPI_Bcast of Heff.cpp:350-365.  Return 0 on success. */
 typedef int (*b2_allreduce_fn)(void* user, double* dev_ptr, int64_t n, void* cuda_stream);

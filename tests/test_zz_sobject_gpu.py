@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # own (function-scoped) parametrisation over the fixture files instead of the session-scoped `golden` fixture: pytest groups tests by
 # session-scoped parameters, which would interleave these tests with the rest of the suite
 PATHS = sorted(p for p in glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz"))
-               if not p.endswith("wigner.npz") and not os.path.basename(p).startswith("problem_"))
+               if not p.endswith("wigner.npz") and not os.path.basename(p).startswith(("problem_", "trace_")))
 IDS = [os.path.basename(p)[:-4] for p in PATHS]
 
 

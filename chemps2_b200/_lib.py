@@ -154,6 +154,8 @@ SIGNATURES = [
     ("b2_update_stats", C.c_int, [vp, c_dp]),
     ("b2_update_worklists", C.c_int, [vp, C.c_int, vp]),
     ("b2_update_num_presum_parts", C.c_int64, [vp]),
+    ("b2_update_num_mix_flat", C.c_int64, [vp]),
+    ("b2_update_export_mix_flat", C.c_int, [vp, C.POINTER(FlatPresum)]),
     ("b2_update_presum_size", C.c_int64, [vp]),
     ("b2_update_export_presums", C.c_int, [vp, C.POINTER(FlatPresum)]),
 ]

@@ -128,6 +128,16 @@ struct b2_update {
    double list_bytes[2] = {0.0, 0.0};      // device work-list bytes per pass
    std::vector<int> op_owner;              // GPU that computes new operator i in pass 0
    bool mix_all_axpy = false;              // pass 1 holds block axpys only: it runs on k_axpy_tiles
+   // whole-operator mixing (UpdatePlan::mix_flat) grouped by layout: Dst[elem, d] += sum_s Src[elem, s] * coef[s][d]
+   struct MixGroup { int64_t size; int nd, ns; int64_t dst_begin, src_begin, coef_begin; };
+   std::vector<MixGroup> mix_groups;
+   std::vector<int64_t> mix_dst_off, mix_src_off;   // offsets in the new arena (dst) / in the arena of mix_src_space (src)
+   std::vector<uint8_t> mix_src_space;
+   std::vector<double> mix_coef;
+   int64_t *d_mix_dst_off = nullptr, *d_mix_src_off = nullptr;
+   uint8_t* d_mix_src_space = nullptr;
+   double* d_mix_coef = nullptr;
+   int64_t temp_begin = 0, temp_size = 0;           // region of the pre-sum arena that holds the transposed copies
    b2_allreduce_fn allreduce = nullptr;
    void* allreduce_user = nullptr;
    ~b2_update() {
@@ -136,6 +146,7 @@ struct b2_update {
          for (int c = 0; c < kNumTileClasses; c++) { cudaFree(d_tiles1[p][c]); cudaFree(d_tiles2[p][c]); }
       }
       cudaFree(d_jobs); cudaFree(d_parts); cudaFree(d_presum); cudaFree(d_work); cudaFree(d_part); cudaFree(d_t);
+      cudaFree(d_mix_dst_off); cudaFree(d_mix_src_off); cudaFree(d_mix_src_space); cudaFree(d_mix_coef);
       if (h_t) cudaFreeHost(h_t);
    }
 };

@@ -1,6 +1,8 @@
 // b2_capi_update.cpp — C ABI of the renormalized-operator update (DMRG::updateMovingRight / updateMovingLeft, DMRGoperators.cpp:243-907).
 #include "b2_capi_internal.h"
 
+#include <map>
+
 
 // FLOPs the scheduler will spend on one update term (cheaper association order, as compile_terms picks it)
 static double term_cost(const Term3& t, const DstBlock& d) {
@@ -75,7 +77,7 @@ int b2_update_create_sharded(b2_ctx* ctx, int index, int moving_right, b2_opset*
    CompileOptions copt = budgeted(ctx);
    copt.threads = (u->plan.flops_ref < ctx->parallel_plan_flops) ? plan_threads((int)u->plan.dst.size()) : 1;
    compile_terms(u->pass[0], u->plan.terms, u->plan.dst, SP_VOUT, copt);
-   compile_terms(u->pass[1], u->plan.mix_terms, u->plan.dst, SP_VOUT, copt);
+   compile_terms(u->pass[1], u->plan.mix_terms, u->plan.mix_dst, SP_PRESUM, copt);   // transposed copies for daxpy_transpose_tensorCD
    {  // The mixing pass is memory bound and every source tile is shared by up to O(L^2) destination operators (A(s1,s2) of all outside
       // pairs add the same S0(o,i) blocks with different integrals): launch the tiles that read the same sources next to each other, so that
       // the sources are served by L2 and HBM sees every destination tile once.  Key = (first source tile, tile position).
@@ -92,6 +94,38 @@ int b2_update_create_sharded(b2_ctx* ctx, int index, int moving_right, b2_opset*
                   if (a.m0 != b.m0) return a.m0 < b.m0;
                   return a.coff < b.coff;
                });
+   }
+   {  // whole-operator mixing grouped by destination layout (all destinations of a group have the same size and element order)
+      const UpdatePlan& pl = u->plan;
+      const OpSet& ns = new_set->set;
+      if (!pl.mix_temps.empty()) { u->temp_begin = pl.mix_temps.front().off; u->temp_size = pl.presum_size - u->temp_begin; }
+      std::map<const OpLayout*, std::vector<const UpdatePlan::MixFlat*>> by_lay;
+      std::vector<const OpLayout*> lay_order;
+      for (const UpdatePlan::MixFlat& m : pl.mix_flat) {
+         const OpLayout* lay = ns.ops[m.dst_op].lay.get();
+         if (by_lay.find(lay) == by_lay.end()) lay_order.push_back(lay);
+         by_lay[lay].push_back(&m);
+      }
+      for (const OpLayout* lay : lay_order) {
+         const auto& list = by_lay[lay];
+         b2_update::MixGroup g{lay->size, 0, 0, (int64_t)u->mix_dst_off.size(), (int64_t)u->mix_src_off.size(), (int64_t)u->mix_coef.size()};
+         std::map<int, int> dcol;                          // destination operator -> column
+         std::map<std::pair<int, int64_t>, int> srow;      // (space, offset) -> row
+         for (const UpdatePlan::MixFlat* m : list) {
+            if (dcol.find(m->dst_op) == dcol.end()) { const int c = (int)dcol.size(); dcol[m->dst_op] = c; u->mix_dst_off.push_back(ns.ops[m->dst_op].off); }
+            const int space = m->temp >= 0 ? SP_PRESUM : SP_VOUT;
+            const int64_t off = m->temp >= 0 ? pl.mix_temps[m->temp].off : ns.ops[m->src_op].off;
+            if (srow.find({space, off}) == srow.end()) { const int r = (int)srow.size(); srow[{space, off}] = r; u->mix_src_off.push_back(off); u->mix_src_space.push_back((uint8_t)space); }
+         }
+         g.nd = (int)dcol.size(); g.ns = (int)srow.size();
+         u->mix_coef.resize((size_t)g.coef_begin + (size_t)g.ns * g.nd, 0.0);
+         for (const UpdatePlan::MixFlat* m : list) {
+            const int space = m->temp >= 0 ? SP_PRESUM : SP_VOUT;
+            const int64_t off = m->temp >= 0 ? pl.mix_temps[m->temp].off : ns.ops[m->src_op].off;
+            u->mix_coef[(size_t)g.coef_begin + (size_t)srow[{space, off}] * g.nd + dcol[m->dst_op]] += m->coef;
+         }
+         u->mix_groups.push_back(g);
+      }
    }
    for (int p = 0; p < 2; p++) u->list_bytes[p] = u->pass[p].bytes();
    if (getenv("B2_TIMING"))
@@ -123,6 +157,10 @@ int b2_update_create_sharded(b2_ctx* ctx, int index, int moving_right, b2_opset*
          }
          work = std::max(work, u->pass[p].work_size); part = std::max(part, u->pass[p].part_size);
       }
+      if ((rc = upload_vec(&u->d_mix_dst_off, u->mix_dst_off, s))) return rc;
+      if ((rc = upload_vec(&u->d_mix_src_off, u->mix_src_off, s))) return rc;
+      if ((rc = upload_vec(&u->d_mix_src_space, u->mix_src_space, s))) return rc;
+      if ((rc = upload_vec(&u->d_mix_coef, u->mix_coef, s))) return rc;
       if ((rc = upload_vec(&u->d_jobs, u->presum_jobs, s))) return rc;
       if ((rc = upload_vec(&u->d_parts, u->presum_parts, s))) return rc;
       if (u->plan.presum_size > 0) CUDA_TRY(cudaMalloc(&u->d_presum, sizeof(double) * (size_t)u->plan.presum_size));
@@ -179,6 +217,7 @@ int b2_update_run_device(b2_update* u, const double* t_dev) {
    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
    if (timing) { for (auto& e : ev) cudaEventCreate(&e); cudaEventRecord(ev[0], s); }
    for (int p = 0; p < 2; p++) {
+      if (p == 1 && u->temp_size > 0 && dev_fill_zero(u->d_presum + u->temp_begin, u->temp_size, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
       for (const Wave& w : u->pass[p].waves) {
          for (int c = 0; c < kNumTileClasses; c++)
             if (dev_launch_tiles(c, u->d_tiles1[p][c] + w.t1_begin[c], w.t1_end[c] - w.t1_begin[c], u->d_items1[p], b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
@@ -193,14 +232,18 @@ int b2_update_run_device(b2_update* u, const double* t_dev) {
       // every GPU computed the operators it was assigned; summing the (otherwise zero) arenas replicates all of them before
       // the mixing pass, which every GPU then runs in full (block axpys, replaces the MPI exchanges of DMRGoperators.cpp:449-533)
       if (p == 0 && u->world > 1 && u->allreduce(u->allreduce_user, u->new_set->dev, u->new_set->set.size, (void*)s)) return fail(B2_ERR_STATE, "b2_update_run: all-reduce callback failed");
+      if (p == 1)   // A/B/C/D += integral-weighted two-operator tensors: one tall-skinny GEMM-like launch per layout
+         for (const b2_update::MixGroup& g : u->mix_groups)
+            if (dev_launch_mix_flat(u->d_mix_dst_off + g.dst_begin, g.nd, u->d_mix_src_off + g.src_begin, u->d_mix_src_space + g.src_begin, g.ns, u->d_mix_coef + g.coef_begin,
+                                    g.size, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
       if (timing) cudaEventRecord(ev[p + 1], s);
    }
    if (timing) {
       cudaEventSynchronize(ev[2]);
       float t0 = 0.f, t1 = 0.f;
       cudaEventElapsedTime(&t0, ev[0], ev[1]); cudaEventElapsedTime(&t1, ev[1], ev[2]);
-      fprintf(stderr, "b2_update_run: contraction pass %.3f ms (%.3f TFLOP executed), mixing pass %.3f ms (%zu block axpys, %s kernel)\n", t0, u->pass[0].flops_exec / 1e12, t1,
-              u->pass[1].items2.size(), u->mix_all_axpy ? "k_axpy_tiles" : "k_tiles");
+      fprintf(stderr, "b2_update_run: contraction pass %.3f ms (%.3f TFLOP executed), mixing pass %.3f ms (%zu transposed block copies + %zu whole-operator axpys in %zu GEMM-like launches)\n", t0,
+              u->pass[0].flops_exec / 1e12, t1, u->plan.mix_terms.size(), u->plan.mix_flat.size(), u->mix_groups.size());
       for (auto& e : ev) cudaEventDestroy(e);
    }
    return B2_OK;
@@ -223,7 +266,7 @@ int b2_update_set_allreduce(b2_update* u, b2_allreduce_fn fn, void* user) {
 }
 int b2_update_stats(const b2_update* u, double* o) {
    if (!u || !o) return fail(B2_ERR_ARG, "b2_update_stats: NULL");
-   o[0] = (double)u->plan.terms.size(); o[1] = (double)u->plan.mix_terms.size(); o[2] = (double)u->plan.presums.size(); o[3] = u->plan.flops_ref;
+   o[0] = (double)u->plan.terms.size(); o[1] = (double)(u->plan.mix_terms.size() + u->plan.mix_flat.size()); o[2] = (double)u->plan.presums.size(); o[3] = u->plan.flops_ref;
    o[4] = u->pass[0].flops_exec + u->pass[1].flops_exec; o[5] = (double)std::max(u->pass[0].work_size, u->pass[1].work_size);
    o[6] = (double)(u->pass[0].waves.size() + u->pass[1].waves.size()); o[7] = 2.0 + u->pass[0].launches() + u->pass[1].launches();
    return B2_OK;
@@ -231,6 +274,19 @@ int b2_update_stats(const b2_update* u, double* o) {
 int b2_update_worklists(const b2_update* u, int pass, b2_worklists* o) {
    if (!u || !o || pass < 0 || pass > 1) return fail(B2_ERR_ARG, "b2_update_worklists: bad arguments");
    fill_worklists(u->pass[pass], o);
+   return B2_OK;
+}
+int64_t b2_update_num_mix_flat(const b2_update* u) { return u ? (int64_t)u->plan.mix_flat.size() : 0; }
+int b2_update_export_mix_flat(const b2_update* u, b2_flat_presum* out) {
+   if (!u || !out) return fail(B2_ERR_ARG, "b2_update_export_mix_flat: NULL");
+   size_t n = 0;
+   for (const UpdatePlan::MixFlat& m : u->plan.mix_flat) {
+      const OpTensor& d = u->new_set->set.ops[m.dst_op];
+      out[n].dst_off = d.off; out[n].size = d.lay->size; out[n].coef = m.coef;
+      out[n].space = m.temp >= 0 ? SP_PRESUM : SP_VOUT;
+      out[n].src_off = m.temp >= 0 ? u->plan.mix_temps[m.temp].off : u->new_set->set.ops[m.src_op].off;
+      n++;
+   }
    return B2_OK;
 }
 int64_t b2_update_num_presum_parts(const b2_update* u) { return u ? (int64_t)u->presum_parts.size() : 0; }

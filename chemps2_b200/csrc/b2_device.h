@@ -63,6 +63,9 @@ constexpr int kTileThreads[kNumTileClasses] = {128, 128, 32, 32};
 int dev_launch_tiles(int tile_class, const Tile* d_tiles, int ntiles, const GemmItem* d_items, const DevBases& bases, void* stream);
 // tiles whose items are all block axpys (IF_AXPY): the mixing pass of the operator update
 int dev_launch_axpy_tiles(const Tile* d_tiles, int ntiles, const GemmItem* d_items, const DevBases& bases, void* stream);
+// whole-operator mixing of one layout group: out[dst_off[d] + e] += sum_s coef[s * nd + d] * base(src_space[s])[src_off[s] + e], e < size
+int dev_launch_mix_flat(const int64_t* d_dst_off, int nd, const int64_t* d_src_off, const uint8_t* d_src_space, int ns, const double* d_coef, int64_t size, const DevBases& bases,
+                        void* stream);
 int dev_launch_reduce(const ReduceJob* d_jobs, int njobs, const DevBases& bases, void* stream);
 int dev_launch_diag(const DiagTile* d_tiles, int ntiles, const DiagItem* d_items, const DevBases& bases, double* d_out, void* stream);
 int dev_launch_presum(const PresumJob* d_jobs, int njobs, const PresumPart* d_parts, const DevBases& bases, void* stream);

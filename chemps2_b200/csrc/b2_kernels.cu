@@ -12,6 +12,7 @@
 
 #include "b2_pool.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <atomic>
@@ -415,6 +416,62 @@ int dev_launch_axpy_tiles(const Tile* d_tiles, int ntiles, const GemmItem* d_ite
    k_axpy_tiles<<<ntiles, 256, 0, (cudaStream_t)stream>>>(d_tiles, d_items, bases);
    cudaError_t e = cudaGetLastError();
    if (e != cudaSuccess) return cuda_fail(e, "k_axpy_tiles launch");
+   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// k_mix_flat: whole-operator mixing of one layout group as a tall-skinny GEMM,  Dst[e, d] += sum_s Src[e, s] * coef[s][d]  over the
+// elements e of the (identical) operator layouts: nd destination operators (A / B / C / D of the outside pairs), ns sources (the
+// two-operator tensors with a leg on the new site, plain or transposed copies).  HBM-bound: every destination element is read and
+// written once, the sources are read once per 16 destinations (adjacent CTAs share them through L2).  One thread per element,
+// 16 destination accumulators in registers, the coefficient tile in shared memory.
+constexpr int MIX_DT = 16, MIX_SC = 64;
+__global__ void __launch_bounds__(256) k_mix_flat(const int64_t* __restrict__ dst_off, int nd, const int64_t* __restrict__ src_off, const uint8_t* __restrict__ src_space, int ns,
+                                                  const double* __restrict__ coef, int64_t size, DevBases bases) {
+   __shared__ double c[MIX_SC * MIX_DT];
+   __shared__ const double* sp[MIX_SC];
+   const int d0 = blockIdx.x * MIX_DT, ndl = min(MIX_DT, nd - d0);
+   const int64_t e = (int64_t)blockIdx.y * 256 + threadIdx.x;
+   double acc[MIX_DT];
+#pragma unroll
+   for (int d = 0; d < MIX_DT; d++) acc[d] = 0.0;
+   for (int s0 = 0; s0 < ns; s0 += MIX_SC) {
+      const int nsl = min(MIX_SC, ns - s0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < nsl * MIX_DT; i += 256) {
+         const int sl = i / MIX_DT, d = i % MIX_DT;
+         c[i] = (d < ndl) ? coef[(size_t)(s0 + sl) * nd + d0 + d] : 0.0;
+      }
+      if (threadIdx.x < nsl) sp[threadIdx.x] = bases.p[src_space[s0 + threadIdx.x]] + src_off[s0 + threadIdx.x];
+      __syncthreads();
+      if (e < size)
+         for (int sl = 0; sl < nsl; sl++) {
+            const double x = sp[sl][e];
+#pragma unroll
+            for (int d = 0; d < MIX_DT; d++) acc[d] += c[sl * MIX_DT + d] * x;
+         }
+   }
+   if (e < size) {
+      double* __restrict__ out = bases.p[SP_VOUT];
+#pragma unroll
+      for (int d = 0; d < MIX_DT; d++)
+         if (d < ndl) out[dst_off[d0 + d] + e] += acc[d];
+   }
+}
+int dev_launch_mix_flat(const int64_t* d_dst_off, int nd, const int64_t* d_src_off, const uint8_t* d_src_space, int ns, const double* d_coef, int64_t size, const DevBases& bases,
+                        void* stream) {
+   if (nd <= 0 || ns <= 0 || size <= 0) return 0;
+   const int64_t chunks = (size + 255) / 256;
+   for (int64_t y0 = 0; y0 < chunks; y0 += 65535) {   // gridDim.y limit
+      const int ny = (int)std::min<int64_t>(65535, chunks - y0);
+      dim3 grid((nd + MIX_DT - 1) / MIX_DT, ny);      // x (destination tiles) varies fastest: the CTAs that read the same source elements run together
+      DevBases b = bases;
+      // element offset of this slab: shift the bases instead of passing another argument
+      for (int i = 0; i < SP_COUNT; i++) if (b.p[i]) b.p[i] += y0 * 256;
+      k_mix_flat<<<grid, 256, 0, (cudaStream_t)stream>>>(d_dst_off, nd, d_src_off, d_src_space, ns, d_coef, size - y0 * 256, b);
+   }
+   cudaError_t e = cudaGetLastError();
+   if (e != cudaSuccess) return cuda_fail(e, "k_mix_flat launch");
    return 0;
 }
 

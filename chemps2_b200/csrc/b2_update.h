@@ -26,9 +26,19 @@ struct UpdatePlan {
    std::vector<int> block_base;       // first global block id of new operator i
    std::vector<Presum> presums;       // linear combinations of OLD operators (side = SRC_LEFT means "old arena")
    int64_t presum_size = 0;
-   // second pass (reads the NEW arena): A/B/C/D += integral-weighted S0/S1/F0/F1 that have a leg on the new site, as block
-   // axpys (TensorOperator::daxpy :407-414) and transposed block axpys with spin factor (daxpy_transpose_tensorCD :416-455)
+   // Mixing (reads the NEW arena): A/B/C/D += integral-weighted S0/S1/F0/F1 that have a leg on the new site
+   // (DMRGoperators.cpp:367-405 / :700-738).  TensorOperator::daxpy (:407-414) adds operators of IDENTICAL layout: whole-operator
+   // axpys `mix_flat` (dst op += coef * src op, element by element).  daxpy_transpose_tensorCD (:416-455) adds transposed blocks with
+   // a spin factor that depends on the block only: the transposed, factor-scaled copy of a source operator in the destination layout
+   // (`mix_temps`, kept behind the pre-sums in the pre-sum arena) is built ONCE by the block terms `mix_terms` (destination blocks
+   // `mix_dst`, space SP_PRESUM) and then enters `mix_flat` like a plain source.  The device runs mix_flat as one tall-skinny
+   // GEMM-like kernel per layout: Dst[elem, pair] += Src[elem, partner] * Coef[partner, pair].
+   struct MixFlat { int dst_op; int src_op; int temp; double coef; };   // temp >= 0: source = mix_temps[temp] instead of new op src_op
+   struct MixTemp { int src_op; const OpLayout* lay; int64_t off; int64_t size; };
+   std::vector<MixFlat> mix_flat;
+   std::vector<MixTemp> mix_temps;
    std::vector<Term3> mix_terms;
+   std::vector<DstBlock> mix_dst;
    double flops_ref = 0.0;            // 2mnk per reference dgemm_ (F_upd)
 };
 

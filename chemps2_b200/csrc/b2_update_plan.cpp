@@ -313,9 +313,8 @@ struct UGen {
                break;
             }
             case K_A: case K_B: case K_C: case K_D:
-               generic_update(n, oldf(t.kind, t.i, t.j));   // absent at the chain end: the tensor starts from zero (:346-360)
-               mix_complementary(n);
-               break;
+               generic_update(n, oldf(t.kind, t.i, t.j));   // absent at the chain end: the tensor starts from zero (:346-360); the mixing
+               break;                                       // with the two-operator tensors follows in build_update_plan (sequential, shared temps)
             case K_Q: update_Q(n); break;
             case K_X: update_X(n); break;
             case K_G: case K_Y: case K_Z: case K_K: case K_M:   // DMRG::update_correlations_tensors (DMRGoperators3RDM.cpp:415-479)
@@ -358,25 +357,42 @@ struct UGen {
          }
       }
       const OpLayout& l = *t.lay;
-      for (int k = 0; k < l.nkappa(); k++) {
-         Sec U, Dn;
-         block_secs(t, k, U, Dn);
-         for (const Part& p : parts) {
-            if (p.src < 0 || p.coef == 0.0) continue;
-            const OpTensor& so = new_set.ops[p.src];
-            Term3 x;
-            x.dst = shared.block_base[n] + k;
-            x.f = p.coef;
-            int sk;
-            if (!p.tr) sk = so.lay->kappa(bk, U.n, U.ts, U.ir, Dn.n, Dn.ts, Dn.ir);                 // TensorOperator::daxpy (:407-414): identical layouts
-            else {                                                                               // daxpy_transpose_tensorCD (:416-455)
-               sk = so.lay->kappa(bk, Dn.n, Dn.ts, Dn.ir, U.n, U.ts, U.ir);
-               if (U.ts != Dn.ts) x.f *= phase(U.ts - Dn.ts) * std::sqrt(mr ? ((U.ts + 1.0) / (Dn.ts + 1)) : ((Dn.ts + 1.0) / (U.ts + 1)));
+      for (const Part& p : parts) {
+         if (p.src < 0 || p.coef == 0.0) continue;
+         const OpTensor& so = new_set.ops[p.src];
+         if (!p.tr) {   // TensorOperator::daxpy (:407-414): identical layouts, element by element
+            assert(so.lay.get() == t.lay.get());
+            plan.mix_flat.push_back(UpdatePlan::MixFlat{n, p.src, -1, p.coef});
+            plan.flops_ref += 2.0 * (double)l.size;
+            continue;
+         }
+         // daxpy_transpose_tensorCD (:416-455): transposed blocks with a block-dependent spin factor -> a transposed copy in this layout
+         int temp = -1;
+         for (size_t i = 0; i < plan.mix_temps.size(); i++)
+            if (plan.mix_temps[i].src_op == p.src && plan.mix_temps[i].lay == t.lay.get()) { temp = (int)i; break; }
+         if (temp < 0) {
+            UpdatePlan::MixTemp mt{p.src, t.lay.get(), plan.presum_size, l.size};
+            plan.presum_size += (l.size + 15) / 16 * 16;
+            temp = (int)plan.mix_temps.size();
+            plan.mix_temps.push_back(mt);
+            for (int k = 0; k < l.nkappa(); k++) {
+               Sec U, Dn;
+               block_secs(t, k, U, Dn);
+               const int sk = so.lay->kappa(bk, Dn.n, Dn.ts, Dn.ir, U.n, U.ts, U.ir);
+               if (sk < 0) continue;
+               Term3 x;
+               x.dst = (int)plan.mix_dst.size();
+               plan.mix_dst.push_back(DstBlock{mt.off + l.blk[k].off, l.blk[k].rows, l.blk[k].cols});
+               x.f = (U.ts != Dn.ts) ? phase(U.ts - Dn.ts) * std::sqrt(mr ? ((U.ts + 1.0) / (Dn.ts + 1)) : ((Dn.ts + 1.0) / (U.ts + 1))) : 1.0;
+               x.q.space = SP_VOUT; x.q.off = so.off + so.lay->blk[sk].off; x.q.rows = so.lay->blk[sk].rows; x.q.cols = so.lay->blk[sk].cols; x.q.trans = 1;
+               plan.mix_terms.push_back(x);
             }
-            if (sk < 0) continue;
-            x.q.space = SP_VOUT; x.q.off = so.off + so.lay->blk[sk].off; x.q.rows = so.lay->blk[sk].rows; x.q.cols = so.lay->blk[sk].cols; x.q.trans = p.tr;
-            plan.mix_terms.push_back(x);
-            plan.flops_ref += 2.0 * shared.dst[x.dst].rows * shared.dst[x.dst].cols;
+         }
+         plan.mix_flat.push_back(UpdatePlan::MixFlat{n, p.src, temp, p.coef});
+         for (int k = 0; k < l.nkappa(); k++) {   // the reference's daxpy count: the blocks whose transposed partner exists
+            Sec U, Dn;
+            block_secs(t, k, U, Dn);
+            if (so.lay->kappa(bk, Dn.n, Dn.ts, Dn.ir, U.n, U.ts, U.ir) >= 0) plan.flops_ref += 2.0 * l.blk[k].rows * l.blk[k].cols;
          }
       }
    }
@@ -400,6 +416,8 @@ void build_update_plan(UpdatePlan& plan, const Bookkeeper& bk, const Problem& pr
    if (nthreads <= 1) {
       UGen g(plan, plan, bk, prob, old_set, new_set, index, moving_right);
       for (int n = 0; n < nops; n++) g.run_one(n);
+      for (int n = 0; n < nops; n++)
+         if (new_set.ops[n].kind >= K_A && new_set.ops[n].kind <= K_D) g.mix_complementary(n);
       return;
    }
    // New operators are independent: every host thread enumerates the operators it grabs into a private fragment; the fragments are
@@ -442,8 +460,11 @@ void build_update_plan(UpdatePlan& plan, const Bookkeeper& bk, const Problem& pr
          if (x.r.space == SP_PRESUM) x.r.off += shift;
          plan.terms.push_back(x);
       }
-      plan.mix_terms.insert(plan.mix_terms.end(), f.plan.mix_terms.begin() + sp.m0, f.plan.mix_terms.begin() + sp.m1);
    }
+   // the mixing lists are small (O(L^2) whole-operator axpys + O(L) transposed copies): enumerated here, after the pre-sum arena is final
+   UGen g(plan, plan, bk, prob, old_set, new_set, index, moving_right);
+   for (int n = 0; n < nops; n++)
+      if (new_set.ops[n].kind >= K_A && new_set.ops[n].kind <= K_D) g.mix_complementary(n);
 }
 
 }   // namespace b2

@@ -233,8 +233,13 @@ int b2_update_run(b2_update* u, const double* t_host);
 int b2_update_run_device(b2_update* u, const double* t_dev);
 /* [0] #terms, [1] #mix terms, [2] #presums, [3] reference FLOPs, [4] executed FLOPs, [5] workspace doubles, [6] #waves, [7] launches */
 int b2_update_stats(const b2_update* u, double* out8);
-/* work lists of pass 0 (contractions) / pass 1 (A,B,C,D mixing) and the pre-sum jobs, for the CPU emulator in oracle/ */
+/* work lists of pass 0 (contractions) / pass 1 (transposed copies for the A,B,C,D mixing, written into the pre-sum arena) and the pre-sum
+ * jobs, for the CPU emulator in oracle/ */
 int b2_update_worklists(const b2_update* u, int pass, b2_worklists* out);
+/* the whole-operator axpys of the A/B/C/D mixing (dst in the new arena += coef * src; space 6 = new arena, 3 = pre-sum arena, where pass 1
+ * has put the transposed copies daxpy_transpose_tensorCD needs), run after pass 1 — for the CPU emulator */
+int64_t b2_update_num_mix_flat(const b2_update* u);
+int b2_update_export_mix_flat(const b2_update* u, b2_flat_presum* out);
 int64_t b2_update_num_presum_parts(const b2_update* u);
 int64_t b2_update_presum_size(const b2_update* u);
 int b2_update_export_presums(const b2_update* u, b2_flat_presum* out);

@@ -155,6 +155,16 @@ def emulate_update(old, new, upd, t_storage, passes=(0, 1), arena=None):
         wl = Worklists()
         check(lib.b2_update_worklists(upd.h, p, C.byref(wl)))
         o.b2o_run_update_pass(C.byref(wl), _dp(oa), _dp(t), _dp(presum), _dp(arena))
+        if p == 1:   # whole-operator mixing after the transposed copies of pass 1 (device: k_mix_flat)
+            nf = lib.b2_update_num_mix_flat(upd.h)
+            flat = (FlatPresum * max(nf, 1))()
+            check(lib.b2_update_export_mix_flat(upd.h, flat))
+            add = np.zeros_like(arena)
+            for i in range(nf):
+                f = flat[i]
+                src = presum if f.space == 3 else arena
+                add[f.dst_off:f.dst_off + f.size] += f.coef * src[f.src_off:f.src_off + f.size]
+            arena += add
     return arena
 
 

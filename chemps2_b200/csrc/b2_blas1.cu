@@ -66,6 +66,16 @@ template <int M> __device__ __forceinline__ void grid_finish(double (&v)[M], int
    }
 }
 
+// grid-stride loop with four independent iterations in flight per thread: these kernels are pure streaming, and one 8-byte load per
+// thread at a time keeps only ~1.2 MB in flight on the whole chip (measured: 1.0 TB/s on a 62 MB vector); four give the memory system
+// enough outstanding requests to approach the HBM rate
+template <class F> __device__ __forceinline__ void stream4(int64_t n, F&& f) {
+   const int64_t step = (int64_t)gridDim.x * blockDim.x;
+   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+   for (; e + 3 * step < n; e += 4 * step) { f(e); f(e + step); f(e + 2 * step); f(e + 3 * step); }
+   for (; e < n; e += step) f(e);
+}
+
 static inline int grid_for(int64_t n) {
    int64_t b = (n + BT - 1) / BT;
    return (int)(b < 1 ? 1 : (b > kRedBlocks ? kRedBlocks : b));
@@ -80,12 +90,12 @@ __global__ void __launch_bounds__(BT) k_multi_dot(const double* __restrict__ x, 
    double v[MD];
 #pragma unroll
    for (int j = 0; j < MD; j++) v[j] = 0.0;
-   for (int64_t e = (int64_t)blockIdx.x * BT + threadIdx.x; e < n; e += (int64_t)gridDim.x * BT) {
+   stream4(n, [&](int64_t e) {
       const double xe = x[e];
 #pragma unroll
       for (int j = 0; j < MD; j++)
          if (j < m) v[j] += xe * ybase[(size_t)j * ystride + e];
-   }
+   });
    block_sum<MD>(v, sh);
    grid_finish<MD>(v, m, partial, counter, out);
 }
@@ -100,7 +110,7 @@ int dev_multi_dot(const double* x, const double* ybase, int64_t ystride, int m, 
 
 __global__ void k_axpy_dev(double* __restrict__ y, const double* __restrict__ x, const double* __restrict__ coef, double sign, int64_t n) {
    const double a = sign * coef[0];
-   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) y[e] += a * x[e];
+   stream4(n, [&](int64_t e) { y[e] += a * x[e]; });
 }
 int dev_axpy_dev(double* y, const double* x, const double* coef, double sign, int64_t n, void* stream) {
    k_axpy_dev<<<grid_for(n), BT, 0, (cudaStream_t)stream>>>(y, x, coef, sign, n);
@@ -115,11 +125,11 @@ __global__ void __launch_bounds__(BT) k_multi_axpy_dev(double* __restrict__ y, c
    __shared__ double c[kMaxVec];
    if (threadIdx.x < m) c[threadIdx.x] = sign * coef[threadIdx.x];
    __syncthreads();
-   for (int64_t e = (int64_t)blockIdx.x * BT + threadIdx.x; e < n; e += (int64_t)gridDim.x * BT) {
+   stream4(n, [&](int64_t e) {
       double v = y[e];
       for (int j = 0; j < m; j++) v += c[j] * xbase[(size_t)j * xstride + e];
       y[e] = v;
-   }
+   });
 }
 int dev_multi_axpy_dev(double* y, const double* xbase, int64_t xstride, int m, const double* coef, double sign, int64_t n, void* stream) {
    if (m <= 0 || n <= 0) return 0;
@@ -129,7 +139,7 @@ int dev_multi_axpy_dev(double* y, const double* xbase, int64_t xstride, int m, c
 }
 
 __global__ void k_add_square(double* __restrict__ y, const double* __restrict__ x, int64_t n) {
-   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) y[e] += x[e] * x[e];
+   stream4(n, [&](int64_t e) { y[e] += x[e] * x[e]; });
 }
 int dev_add_square(double* y, const double* x, int64_t n, void* stream) {
    if (n <= 0) return 0;
@@ -139,7 +149,7 @@ int dev_add_square(double* y, const double* x, int64_t n, void* stream) {
 
 __global__ void k_scale_rsqrt(double* __restrict__ x, const double* __restrict__ ss, int64_t n) {
    const double a = 1.0 / sqrt(ss[0]);
-   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) x[e] *= a;
+   stream4(n, [&](int64_t e) { x[e] *= a; });
 }
 int dev_scale_rsqrt(double* x, const double* ss, int64_t n, void* stream) {
    k_scale_rsqrt<<<grid_for(n), BT, 0, (cudaStream_t)stream>>>(x, ss, n);
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(BT) k_ritz_residual(double* __restrict__ u, do
                                                       unsigned int* counter) {
    __shared__ double sh[BT / 32];
    double v[1] = {0.0};
-   for (int64_t e = (int64_t)blockIdx.x * BT + threadIdx.x; e < n; e += (int64_t)gridDim.x * BT) {
+   stream4(n, [&](int64_t e) {
       double ue = 0.0, te = 0.0;
       for (int j = 0; j < m; j++) {
          ue += a.c[j] * V[(size_t)j * stride + e];
@@ -161,7 +171,7 @@ __global__ void __launch_bounds__(BT) k_ritz_residual(double* __restrict__ u, do
       te -= theta * ue;
       u[e] = ue; t[e] = te;
       v[0] += te * te;
-   }
+   });
    block_sum<1>(v, sh);
    grid_finish<1>(v, 1, partial, counter, out);
 }
@@ -179,12 +189,12 @@ __global__ void __launch_bounds__(BT) k_precond_dots(double* __restrict__ work, 
                                                      unsigned int* counter) {
    __shared__ double sh[2 * (BT / 32)];
    double v[2] = {0.0, 0.0};
-   for (int64_t e = (int64_t)blockIdx.x * BT + threadIdx.x; e < n; e += (int64_t)gridDim.x * BT) {
+   stream4(n, [&](int64_t e) {
       const double w = u[e] / clamp_diff(diag[e] - theta, cutoff);
       work[e] = w;
       v[0] += w * t[e];
       v[1] += w * u[e];
-   }
+   });
    block_sum<2>(v, sh);
    grid_finish<2>(v, 2, partial, counter, out);
 }
@@ -198,8 +208,7 @@ int dev_precond_dots(double* work, const double* u, const double* t, const doubl
 __global__ void k_precond_apply(double* __restrict__ t, const double* __restrict__ u, const double* __restrict__ diag, const double* __restrict__ dots,
                                 double theta, double cutoff, int64_t n) {
    const double alpha = -dots[0] / dots[1];
-   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
-      t[e] = -(t[e] + alpha * u[e]) / clamp_diff(diag[e] - theta, cutoff);
+   stream4(n, [&](int64_t e) { t[e] = -(t[e] + alpha * u[e]) / clamp_diff(diag[e] - theta, cutoff); });
 }
 int dev_precond_apply(double* t, const double* u, const double* diag, const double* dots, double theta, double cutoff, int64_t n, void* stream) {
    k_precond_apply<<<grid_for(n), BT, 0, (cudaStream_t)stream>>>(t, u, diag, dots, theta, cutoff, n);
@@ -208,11 +217,11 @@ int dev_precond_apply(double* t, const double* u, const double* diag, const doub
 }
 
 __global__ void k_lincomb(double* __restrict__ out, const double* __restrict__ V, int64_t stride, int m, Coefs a, int64_t n) {
-   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+   stream4(n, [&](int64_t e) {
       double s = 0.0;
       for (int j = 0; j < m; j++) s += a.c[j] * V[(size_t)j * stride + e];
       out[e] = s;
-   }
+   });
 }
 int dev_lincomb(double* out, const double* V, int64_t stride, int m, Coefs a, int64_t n, void* stream) {
    k_lincomb<<<grid_for(n), BT, 0, (cudaStream_t)stream>>>(out, V, stride, m, a, n);
@@ -223,11 +232,11 @@ int dev_lincomb(double* out, const double* V, int64_t stride, int m, Coefs a, in
 __global__ void k_scale_blocks(double* __restrict__ x, const int64_t* __restrict__ off, const double* __restrict__ scale) {
    const int64_t b = off[blockIdx.x], e1 = off[blockIdx.x + 1];
    const double a = scale[blockIdx.x];
-   for (int64_t e = b + threadIdx.x; e < e1; e += blockDim.x) x[e] *= a;
+   for (int64_t e = b + (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < e1; e += (int64_t)gridDim.y * blockDim.x) x[e] *= a;
 }
 int dev_scale_blocks(double* x, const int64_t* d_off, const double* d_scale, int nblocks, void* stream) {
    if (nblocks <= 0) return 0;
-   k_scale_blocks<<<nblocks, BT, 0, (cudaStream_t)stream>>>(x, d_off, d_scale);
+   k_scale_blocks<<<dim3(nblocks, 16), BT, 0, (cudaStream_t)stream>>>(x, d_off, d_scale);   // 16 CTAs per block: the large blocks no longer serialise
    LAUNCH_CHECK("k_scale_blocks");
    return 0;
 }

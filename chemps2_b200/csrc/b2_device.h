@@ -81,7 +81,7 @@ inline double hash_value(uint64_t seed, uint64_t key, uint64_t e) {
 }
 // ---- Davidson vector algebra (b2_blas1.cu).  All scalars stay on the device unless stated otherwise; every reduction is a
 // fixed-order two-level tree (deterministic).  `scratch` holds >= kRedScratch doubles + one counter per call site.
-constexpr int kRedBlocks = 592;                 // 4 x 148 SMs
+constexpr int kRedBlocks = 1184;                // 8 x 148 SMs: full residency of 256-thread CTAs
 constexpr int kMaxVec = 32;                     // Davidson MAX_NUM_VEC (Options.h:70)
 constexpr int kRedScratch = kRedBlocks * (kMaxVec + 2) + 64;
 struct Coefs { double c[kMaxVec]; };

@@ -567,7 +567,7 @@ int dev_launch_presum(const PresumJob* d_jobs, int njobs, const PresumPart* d_pa
    // gridDim.y is limited to 65535: launch in slabs
    for (int j0 = 0; j0 < njobs; j0 += 65535) {
       const int nj = (njobs - j0 < 65535) ? njobs - j0 : 65535;
-      dim3 grid(8, nj);
+      dim3 grid(32, nj);   // 32 CTAs per pre-summed operator: a site with few jobs still fills the chip
       k_presum<<<grid, 256, 0, (cudaStream_t)stream>>>(d_jobs + j0, d_parts, bases);
    }
    cudaError_t e = cudaGetLastError();

@@ -93,3 +93,29 @@ def test_reference_resumes_a_gpu_checkpoint(h2o, tmp_path):
     got = _gpu_sweep_site_energies(ctx2, d2, first_left_fixed=True)
     assert len(ref) == len(got)
     assert np.abs(np.array(got) - np.array(ref)).max() < 1e-9
+
+
+def test_config2_sweep_from_the_reference_checkpoint():
+    """BASELINE config 2 (N2/cc-pVDZ, D2h, reordered) from a SHARED state: the unmodified reference wrote tests/golden/chk_n2_ccpvdz_D100.h5 after its
+    first sweep at D=100 and then resumed from it for one more sweep (tests/golden/chk_n2_ccpvdz_D100.json); the GPU library loads the same
+    checkpoint and must reproduce every site energy of that sweep to 1e-9 Eh and the largest discarded weight to 1e-8."""
+    import json
+    from chemps2_b200 import workloads
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "chk_n2_ccpvdz_D100.json")))
+    w = workloads.get("n2_ccpvdz", D=ref["D"])
+    ctx = w.context(0)
+    d = api.DMRG(ctx)
+    d.load_mps(os.path.join(ROOT, "tests", "golden", "chk_n2_ccpvdz_D100.h5"))
+    d.presolve()
+    L, got, dws = ctx.L, [], [0.0, 0.0]
+    for index in range(L - 2, 0, -1):
+        e, dw, _ = d.solve_site(index, ref["rtol"], 0.0, ref["D"], False, False)     # first sweep after a load: fixed dimensions (DMRG.cpp:270)
+        d.update(index + 1, False)
+        got.append(e); dws[0] = max(dws[0], dw)
+    for index in range(0, L - 2):
+        e, dw, _ = d.solve_site(index, ref["rtol"], 0.0, ref["D"], True, True)
+        d.update(index, True)
+        got.append(e); dws[1] = max(dws[1], dw)
+    assert ref["sites"] == list(range(L - 2, 0, -1)) + list(range(0, L - 2))
+    assert np.abs(np.array(got) - np.array(ref["energies"])).max() < 1e-9
+    assert abs(dws[0] - ref["max_discarded"][0]) < 1e-8 and abs(dws[1] - ref["max_discarded"][1]) < 1e-8

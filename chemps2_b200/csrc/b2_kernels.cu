@@ -444,12 +444,20 @@ __global__ void __launch_bounds__(256) k_mix_flat(const int64_t* __restrict__ ds
       }
       if (threadIdx.x < nsl) sp[threadIdx.x] = bases.p[src_space[s0 + threadIdx.x]] + src_off[s0 + threadIdx.x];
       __syncthreads();
-      if (e < size)
-         for (int sl = 0; sl < nsl; sl++) {
+      if (e < size) {
+         int sl = 0;
+         for (; sl + 4 <= nsl; sl += 4) {   // four independent source loads in flight per thread
+            const double x0 = sp[sl][e], x1 = sp[sl + 1][e], x2 = sp[sl + 2][e], x3 = sp[sl + 3][e];
+#pragma unroll
+            for (int d = 0; d < MIX_DT; d++)
+               acc[d] += c[sl * MIX_DT + d] * x0 + c[(sl + 1) * MIX_DT + d] * x1 + c[(sl + 2) * MIX_DT + d] * x2 + c[(sl + 3) * MIX_DT + d] * x3;
+         }
+         for (; sl < nsl; sl++) {
             const double x = sp[sl][e];
 #pragma unroll
             for (int d = 0; d < MIX_DT; d++) acc[d] += c[sl * MIX_DT + d] * x;
          }
+      }
    }
    if (e < size) {
       double* __restrict__ out = bases.p[SP_VOUT];

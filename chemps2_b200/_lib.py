@@ -61,6 +61,8 @@ SIGNATURES = [
     ("b2_opset_create_correlation", C.c_int, [vp, C.c_int, C.POINTER(vp)]),
     ("b2_opset_offload", C.c_int, [vp]),
     ("b2_opset_reload", C.c_int, [vp]),
+    ("b2_opset_offload_file", C.c_int, [vp, C.c_char_p]),
+    ("b2_dmrg_set_spill_dir", C.c_int, [vp, C.c_char_p]),
     ("b2_opset_resident", C.c_int, [vp]),
     ("b2_dmrg_set_spill", C.c_int, [vp, C.c_int]),
     ("b2_opset_destroy", None, [vp]),

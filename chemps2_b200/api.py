@@ -151,6 +151,10 @@ class OpSet:
     def offload(self):
         check(lib.b2_opset_offload(self.h))
 
+    def offload_file(self, path):
+        """park the arena in a file (NVMe tier); reload() brings it back and removes the file"""
+        check(lib.b2_opset_offload_file(self.h, str(path).encode()))
+
     def reload(self):
         check(lib.b2_opset_reload(self.h))
 
@@ -349,7 +353,9 @@ class DMRG:
         check(lib.b2_dmrg_calc_correlations(self.h, _dp(a), _dp(b), *[_dp(out[k]) for k in ("Cspin", "Cdens", "Cspinflip", "Cdirad", "MutInfo")]))
         return {k: v.reshape((L, L), order="F") for k, v in out.items()}
 
-    def set_spill(self, enabled):
+    def set_spill(self, enabled, directory=None):
+        """spill mode: only the operator sets in use stay in HBM; directory: park the others in files there instead of pinned host memory"""
+        check(lib.b2_dmrg_set_spill_dir(self.h, str(directory).encode() if directory else None))
         check(lib.b2_dmrg_set_spill(self.h, int(bool(enabled))))
 
     def timers(self, reset=False):

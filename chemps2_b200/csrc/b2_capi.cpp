@@ -237,9 +237,58 @@ int b2_opset_offload(b2_opset* set) {
    set->dev = nullptr; set->offloaded = true;
    return B2_OK;
 }
+/* Second tier: the arena goes to a FILE (NVMe scratch; the reference's OperatorsOnDisk writes CheMPS2_Operators_*.h5 the same way,
+ * DMRGoperators.cpp:1213-1433) and neither HBM nor host memory is held while the set is parked.  The copy runs through a bounded pinned
+ * staging buffer (64 MiB pieces), so parking a set never needs a host allocation of its size. */
+int b2_opset_offload_file(b2_opset* set, const char* path) {
+   if (!set || !path) return fail(B2_ERR_ARG, "b2_opset_offload_file: NULL");
+   if (set->ctx->device < 0) return fail(B2_ERR_NO_DEVICE, "b2_opset_offload_file: planning-only context, no CUDA device");
+   if (!set->spill_file.empty()) return B2_OK;
+   if (set->offloaded) { int rc = b2_opset_reload(set); if (rc) return rc; }
+   if (!set->dev) return B2_OK;
+   FILE* f = std::fopen(path, "wb");
+   if (!f) return fail(B2_ERR_ARG, "b2_opset_offload_file: cannot open %s", path);
+   const size_t total = (size_t)set->set.size, piece = (size_t)8 << 20;   // doubles per piece
+   double* stage = nullptr;
+   if (cudaMallocHost(&stage, sizeof(double) * std::min(total, piece)) != cudaSuccess) { std::fclose(f); return fail(B2_ERR_CUDA, "b2_opset_offload_file: pinned staging allocation failed"); }
+   bool ok = true;
+   for (size_t o = 0; o < total && ok; o += piece) {
+      const size_t n = std::min(piece, total - o);
+      ok = cudaMemcpyAsync(stage, set->dev + o, sizeof(double) * n, cudaMemcpyDeviceToHost, set->ctx->stream) == cudaSuccess &&
+           cudaStreamSynchronize(set->ctx->stream) == cudaSuccess && std::fwrite(stage, sizeof(double), n, f) == n;
+   }
+   cudaFreeHost(stage);
+   ok = (std::fclose(f) == 0) && ok;
+   if (!ok) { std::remove(path); return fail(B2_ERR_STATE, "b2_opset_offload_file: writing %s failed", path); }
+   CUDA_TRY(cudaFree(set->dev));
+   set->dev = nullptr; set->offloaded = true; set->spill_file = path;
+   return B2_OK;
+}
+static int reload_from_file(b2_opset* set) {
+   FILE* f = std::fopen(set->spill_file.c_str(), "rb");
+   if (!f) return fail(B2_ERR_STATE, "b2_opset_reload: cannot open %s", set->spill_file.c_str());
+   const size_t total = (size_t)set->set.size, piece = (size_t)8 << 20;
+   CUDA_TRY(cudaSetDevice(set->ctx->device));
+   if (cudaMalloc(&set->dev, sizeof(double) * total) != cudaSuccess) { std::fclose(f); set->dev = nullptr; return fail(B2_ERR_CUDA, "b2_opset_reload: device allocation failed"); }
+   double* stage = nullptr;
+   if (cudaMallocHost(&stage, sizeof(double) * std::min(total, piece)) != cudaSuccess) { std::fclose(f); return fail(B2_ERR_CUDA, "b2_opset_reload: pinned staging allocation failed"); }
+   bool ok = true;
+   for (size_t o = 0; o < total && ok; o += piece) {
+      const size_t n = std::min(piece, total - o);
+      ok = std::fread(stage, sizeof(double), n, f) == n && cudaMemcpyAsync(set->dev + o, stage, sizeof(double) * n, cudaMemcpyHostToDevice, set->ctx->stream) == cudaSuccess &&
+           cudaStreamSynchronize(set->ctx->stream) == cudaSuccess;
+   }
+   cudaFreeHost(stage);
+   std::fclose(f);
+   if (!ok) return fail(B2_ERR_STATE, "b2_opset_reload: reading %s failed", set->spill_file.c_str());
+   std::remove(set->spill_file.c_str());
+   set->spill_file.clear(); set->offloaded = false;
+   return B2_OK;
+}
 int b2_opset_reload(b2_opset* set) {
    if (!set) return fail(B2_ERR_ARG, "b2_opset_reload: NULL");
    if (!set->offloaded) return B2_OK;
+   if (!set->spill_file.empty()) return reload_from_file(set);
    const size_t bytes = sizeof(double) * (size_t)set->set.size;
    CUDA_TRY(cudaSetDevice(set->ctx->device));
    CUDA_TRY(cudaMalloc(&set->dev, bytes));
@@ -269,6 +318,7 @@ int b2_opset_upload(b2_opset* set, int index, const double* packed) {
    if (t.lay->size == 0) return B2_OK;
    set->ensure_host();
    std::memcpy(set->host.data() + t.off, packed, sizeof(double) * (size_t)t.lay->size);
+   if (set->offloaded && !set->spill_file.empty()) { int rr = b2_opset_reload(set); if (rr) return rr; }
    if (set->offloaded) std::memcpy(set->spill + t.off, packed, sizeof(double) * (size_t)t.lay->size);
    if (set->dev) {
       CUDA_TRY(cudaMemcpyAsync(set->dev + t.off, set->host.data() + t.off, sizeof(double) * (size_t)t.lay->size, cudaMemcpyHostToDevice, set->ctx->stream));
@@ -281,6 +331,7 @@ int b2_opset_download(b2_opset* set, int index, double* packed) {
    const OpTensor& t = set->set.ops[index];
    if (t.lay->size == 0) return B2_OK;
    set->ensure_host();
+   if (set->offloaded && !set->spill_file.empty()) { int rr = b2_opset_reload(set); if (rr) return rr; }   // parked in a file: bring it back first
    if (set->dev) {
       CUDA_TRY(cudaMemcpyAsync(set->host.data() + t.off, set->dev + t.off, sizeof(double) * (size_t)t.lay->size, cudaMemcpyDeviceToHost, set->ctx->stream));
       CUDA_TRY(cudaStreamSynchronize(set->ctx->stream));

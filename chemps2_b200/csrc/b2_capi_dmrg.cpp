@@ -78,6 +78,7 @@ struct b2_dmrg {
    double last_min_energy = 1e8;           // DMRG::LastMinEnergy: lowest energy of the last half sweep
    double total_min_energy = 1e8;          // DMRG::TotalMinEnergy: lowest energy since the last PreSolve
    bool spill = false;                     // keep only the operator sets of the site being optimised in HBM (b2_dmrg_set_spill)
+   std::string spill_dir;                  // spill mode parks the sets in files of this directory (NVMe) instead of pinned host memory
    int world = 1, rank = 0;                // GPUs sharing the sweep: sigma terms and operator updates are sharded, the rest is replicated
    b2_allreduce_fn allreduce = nullptr;
    void* allreduce_user = nullptr;
@@ -182,10 +183,21 @@ static int dmrg_residency(b2_dmrg* d, int keep_l, int keep_r) {
    if (keep_l >= 0 && keep_l <= d->L && d->left[keep_l] && (rc = b2_opset_reload(d->left[keep_l]))) return rc;
    if (keep_r >= 0 && keep_r <= d->L && d->right[keep_r] && (rc = b2_opset_reload(d->right[keep_r]))) return rc;
    if (!d->spill) return B2_OK;
+   auto park = [&](b2_opset* set, int b, int mr) -> int {
+      if (d->spill_dir.empty()) return b2_opset_offload(set);
+      char name[64];
+      std::snprintf(name, sizeof(name), "/b2_operators_%p_%d_%d.bin", (void*)d, b, mr);
+      return b2_opset_offload_file(set, (d->spill_dir + name).c_str());
+   };
    for (int b = 0; b <= d->L; b++) {
-      if (b != keep_l && d->left[b] && (rc = b2_opset_offload(d->left[b]))) return rc;
-      if (b != keep_r && d->right[b] && (rc = b2_opset_offload(d->right[b]))) return rc;
+      if (b != keep_l && d->left[b] && (rc = park(d->left[b], b, 1))) return rc;
+      if (b != keep_r && d->right[b] && (rc = park(d->right[b], b, 0))) return rc;
    }
+   return B2_OK;
+}
+int b2_dmrg_set_spill_dir(b2_dmrg* d, const char* dir) {
+   if (!d) return fail(B2_ERR_ARG, "b2_dmrg_set_spill_dir: NULL");
+   d->spill_dir = dir ? dir : "";
    return B2_OK;
 }
 int b2_dmrg_set_plan_cache(b2_dmrg* d, int enabled) {

@@ -64,8 +64,9 @@ struct b2_opset {
    double* dev = nullptr;
    double* spill = nullptr;    // pinned host copy while the set is offloaded (b2_opset_offload): the device arena is released
    bool offloaded = false;
+   std::string spill_file;     // second tier (b2_opset_offload_file): the arena lives in this file, neither HBM nor host memory is held
    void ensure_host() { if (host.size() != (size_t)set.size) host.assign((size_t)set.size, 0.0); }
-   ~b2_opset() { if (spill) cudaFreeHost(spill); if (dev) cudaFree(dev); }
+   ~b2_opset() { if (spill) cudaFreeHost(spill); if (dev) cudaFree(dev); if (!spill_file.empty()) std::remove(spill_file.c_str()); }
 };
 
 struct b2_heff {

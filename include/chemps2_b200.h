@@ -116,6 +116,9 @@ int b2_opset_clear(b2_opset* set);
  * deleteTensors, allocateTensors (DMRGoperators.cpp:33-231, 1147-1433; the reference spills to HDF5 files).  Compute entry points
  * refuse offloaded sets (B2_ERR_STATE); upload / download keep working on the host copy. */
 int b2_opset_offload(b2_opset* set);
+/* second tier: park the arena in a FILE (NVMe scratch, like the reference's CheMPS2_Operators_*.h5 files); neither HBM nor host memory is
+ * held meanwhile, b2_opset_reload reads it back and removes the file */
+int b2_opset_offload_file(b2_opset* set, const char* path);
 int b2_opset_reload(b2_opset* set);
 int b2_opset_resident(const b2_opset* set);
 /* synthetic contents: element e of operator (kind,i,j) = amp * hash(seed, side, kind, i, j, e) in [-amp/2, amp/2); the
@@ -310,6 +313,9 @@ int b2_dmrg_set_world(b2_dmrg* d, int world, int rank, b2_allreduce_fn fn, void*
 /* enabled != 0: only the two operator sets of the site pair being optimised (and the set being built) stay in HBM, every
  * other boundary is offloaded to pinned host memory (the reference's disk mode, DMRG.cpp:57-65 makecheckpoints / OperatorsOnDisk) */
 int b2_dmrg_set_spill(b2_dmrg* d, int enabled);
+/* dir != NULL / non-empty: spill mode parks the operator sets in files of that directory (b2_opset_offload_file) instead of pinned host
+ * memory — the reference's tmp folder of DMRG::DMRG(..., tmpfolder) */
+int b2_dmrg_set_spill_dir(b2_dmrg* d, const char* dir);
 /* The driver keeps the sigma plan of the last visit of every site (device work lists only) and re-uses it when the dimension tables of
  * the three boundaries of the site pair are unchanged — the normal situation in converged sweeps at a fixed virtual dimension.
  * enabled = 0 switches the cache off and frees it; the statistics count re-used and newly built plans. */

@@ -133,6 +133,52 @@ def test_sweep_with_spill_matches_resident_sweep(golden):
     assert np.array_equal(run(True), run(False))
 
 
+def test_sweep_with_file_spill_matches_resident_sweep(golden, tmp_path):
+    """the second tier of the operator store: parked sets live in FILES of a scratch directory (NVMe; the reference's OperatorsOnDisk,
+    DMRGoperators.cpp:1213-1433) — neither HBM nor host memory is held; energies are bit-identical and no file is left behind"""
+    import os
+
+    def run(directory):
+        ctx, d = _start_from_fixture(golden, "A")
+        L = ctx.L
+        D = _fixture_D(golden)
+        d.set_spill(directory is not None, directory)
+        for i in range(L - 2):
+            d.update(i, True)
+        out, seen = [], 0
+        for it in range(2):
+            out += list(d.sweep(False, 1e-8, 0.0, D, it > 0))
+            if directory:
+                seen = max(seen, len(os.listdir(directory)))
+            out += list(d.sweep(True, 1e-8, 0.0, D, True))
+        d.close()
+        return np.array(out), seen
+    spilled, nfiles = run(str(tmp_path))
+    resident, _ = run(None)
+    assert np.array_equal(spilled, resident)
+    assert nfiles >= ctx_boundaries(golden) - 3        # nearly every boundary was parked in a file during the sweep ...
+    assert os.listdir(tmp_path) == []                  # ... and every file is gone once the driver is destroyed
+
+
+def ctx_boundaries(golden):
+    return int(golden["problem/hdr"][0]) - 1
+
+
+def test_opset_file_offload_roundtrip(golden):
+    ctx, left, right, heff = cpu_check.build_case(golden, "A", device=0)
+    import os
+    import tempfile
+    path = os.path.join(tempfile.mkdtemp(), "ops.bin")
+    ref = heff.apply(golden["A/vec_in"])
+    before = left.download(0).copy()
+    left.offload_file(path)
+    assert os.path.getsize(path) == 8 * left.host_arena().size and not left.resident()
+    assert np.array_equal(left.download(0), before) and left.resident() and not os.path.exists(path)   # download brings it back
+    left.offload_file(path)
+    left.reload()
+    assert np.array_equal(heff.apply(golden["A/vec_in"]), ref)
+
+
 def test_sweep_survives_out_of_memory_by_spilling(golden):
     """when HBM runs out while a new operator set or a sigma plan is allocated (simulated through the 'simulate_oom' option), the driver
     switches to spill mode (only the sets in use stay resident) and carries on with bit-identical energies"""

@@ -249,9 +249,14 @@ def run_reference(args):
     del left, right
     runs = []
     t0 = time.time()
-    while len(runs) < max(1, args.steps) and (not runs or time.time() - t0 + 1.5 * (time.time() - t0) / len(runs) < args.ref_budget_s):
-        base, _ = cpu_baseline(args, w, dims, flops, arena)
-        runs.append(base)
+    try:
+        while len(runs) < max(1, args.steps) and (not runs or time.time() - t0 + 1.5 * (time.time() - t0) / len(runs) < args.ref_budget_s):
+            base, _ = cpu_baseline(args, w, dims, flops, arena)
+            runs.append(base)
+    except Exception as e:   # e.g. not enough host memory for the reference's operator tables at this size: say so, never print a number for another size
+        if not runs:
+            emit({"impl": "reference", "unavailable": f"reference run at the bench config failed: {e}"})
+            return
     best = max(runs, key=lambda r: r["value"])
     mean_s = float(np.mean([r["sample_seconds"] for r in runs]))
     line = {"metric": METRIC, "value": 1.0 / mean_s, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": len(runs),

@@ -130,3 +130,43 @@ def test_full_size_properties_synth40():
         tot += h.apply(x)
         del h
     assert np.abs(tot - hx).max() <= 1e-11 * scale
+
+
+def test_caching_allocator_does_not_change_results(tmp_path):
+    """every cudaMalloc / cudaFree of the library goes through the caching allocator (b2_pool.cpp); with B2_NO_POOL=1 they go straight to the
+    driver.  Plans are created and destroyed repeatedly (blocks are re-used while earlier kernels may still be in flight) and the sigma
+    vectors must be bit-identical in both modes."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "pool_probe.py"
+    script.write_text(f"""
+import sys, hashlib
+sys.path.insert(0, {root!r})
+import numpy as np
+from chemps2_b200 import api, workloads
+w = workloads.get("tiny", D=90)
+ctx = w.context(0)
+w.apply_distribution(ctx, "flat")
+h = hashlib.sha256()
+for rep in range(6):
+    sets = [api.OpSet(ctx, w.site, True), api.OpSet(ctx, w.site + 2, False)]
+    for s in sets:
+        s.fill_hash(3 + rep, 1.0)
+    heff = api.Heff(ctx, w.site, *sets)
+    for k in range(3):
+        h.update(heff.apply(api.hash_fill(heff.n, 10 * rep + k)).tobytes())
+    del heff, sets
+print("DIGEST", h.hexdigest())
+""")
+    digests = []
+    for no_pool in ("", "1"):
+        env = dict(os.environ)
+        env.pop("B2_NO_POOL", None)
+        if no_pool:
+            env["B2_NO_POOL"] = "1"
+        res = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env, timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        digests.append([ln for ln in res.stdout.splitlines() if ln.startswith("DIGEST")][-1])
+    assert digests[0] == digests[1]

@@ -122,6 +122,9 @@ def test_compute_entries_refuse_without_device(h2o):
     out = C.c_void_p()
     assert lib.b2_dmrg_create(ctx.h, C.byref(out)) == ERR_NO_DEVICE and b"no CPU fallback" in lib.b2_last_error()
     assert lib.b2_opset_offload(left.h) == ERR_NO_DEVICE
+    assert lib.b2_opset_offload_file(left.h, b"/tmp/b2_never_written.bin") == ERR_NO_DEVICE
+    dav = C.c_void_p()
+    assert lib.b2_davidson_create(ctx.h, n, 32, 3, 1e-5, 1e-12, C.byref(dav)) == ERR_NO_DEVICE and b"no CPU fallback" in lib.b2_last_error()
     t = C.c_double()
     assert lib.b2_probe_fp64(ctx.h, 1, C.byref(t)) == ERR_NO_DEVICE
     assert lib.b2_ctx_set_stream(ctx.h, None) == ERR_NO_DEVICE
@@ -135,4 +138,8 @@ def test_null_handles_do_not_crash():
     assert lib.b2_dmrg_mps_size(None, 0) == -1 and lib.b2_dmrg_num_lower_states(None) == 0
     assert lib.b2_dmrg_sweep_info(None, None) == ERR_ARG and lib.b2_dmrg_presolve(None) == ERR_ARG
     assert lib.b2_ctx_device(None) == -1
+    assert lib.b2_opset_offload_file(None, None) == ERR_ARG and lib.b2_dmrg_set_spill_dir(None, None) == ERR_ARG and lib.b2_dmrg_srand(None, 1) == ERR_ARG
+    assert lib.b2_davidson_fetch(None, None, None, None) == ERR_ARG and lib.b2_davidson_num_multiplications(None) == 0
+    assert lib.b2_update_num_mix_flat(None) == 0 and lib.b2_rand_stream(1, -1, None) == ERR_ARG
+    lib.b2_davidson_destroy(None)
     lib.b2_ctx_destroy(None); lib.b2_opset_destroy(None); lib.b2_heff_destroy(None); lib.b2_update_destroy(None); lib.b2_dmrg_destroy(None); lib.b2_twodm_destroy(None)

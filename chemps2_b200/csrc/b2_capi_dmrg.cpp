@@ -65,7 +65,7 @@ struct b2_dmrg {
    std::vector<b2_opset*> left, right;     // operator sets per boundary: moving right (sites < b) / moving left (sites >= b)
    // Sigma plans of earlier visits, one slot per site: at a fixed virtual dimension the sector dimensions stop changing once the sweeps
    // converge, and a plan depends on nothing but those dimensions — re-using it removes the host-side plan building (the largest part
-   // of a small/medium-D sweep) from every later visit.  Key = the exact dimension tables of the three boundaries + the sharding.
+   // of a small/medium-D sweep) from every later visit.  Key = the exact dimension tables of the boundaries the plan reads + the sharding.
    struct PlanSlot { std::vector<int> key; b2_heff* h = nullptr; };
    std::vector<PlanSlot> plan_cache;
    struct UpdSlot { std::vector<int> key; b2_update* u = nullptr; };
@@ -479,7 +479,9 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
    if (d->use_plan_cache) {
       if ((int)d->plan_cache.size() != L) d->plan_cache.assign(L, b2_dmrg::PlanSlot());
       key.push_back(d->world); key.push_back(d->rank);
-      for (int b = index; b <= index + 2; b++) key.insert(key.end(), ctx->bk.cur[b].begin(), ctx->bk.cur[b].end());
+      // the two-site object and both operator sets live on boundaries index and index + 2 only (Sobject.cpp:36-78 never reads the
+      // contracted boundary index + 1, which EVERY visit re-dimensions): keying on it too would turn most re-visits into misses
+      for (int b = index; b <= index + 2; b += 2) key.insert(key.end(), ctx->bk.cur[b].begin(), ctx->bk.cur[b].end());
       b2_dmrg::PlanSlot& slot = d->plan_cache[index];
       if (slot.h && slot.key == key) {
          h = slot.h; slot.h = nullptr;

@@ -254,24 +254,52 @@ void group_sort(std::vector<Tile>& v, int b, int e, const std::vector<GemmItem>&
    // Launch order = heaviest GROUPS first (static load balance across the SMs), where a group is the set of CTAs that
    // stream the same items (all tiles of one stage-1 product / of one split-K chunk of a destination block): they read the
    // same operand panels, so they must be resident together for the panels to be served by L2 instead of DRAM.
+   // Total order: (group weight descending, first item of the group ascending, emission index ascending).  Millions of tiles
+   // per plan, so no comparison sort: the groups (dense in their first item) are ordered by a stable LSD radix sort on the
+   // weight, the tiles of a group keep their emission order.
    if (e <= b) return;
-   struct Key { long long w; int ib, idx; };
-   std::vector<Key> ord(e - b);
+   const int n = e - b;
    int ib_lo = v[b].item_begin, ib_hi = v[b].item_begin;
    for (int i = b; i < e; i++) { ib_lo = std::min(ib_lo, v[i].item_begin); ib_hi = std::max(ib_hi, v[i].item_begin); }
-   std::vector<long long> wmax((size_t)(ib_hi - ib_lo) + 1, 0);   // group weight = its heaviest tile, indexed by the group's first item
-   for (int i = b; i < e; i++) {
-      long long w = 0;
-      for (int it = v[i].item_begin; it < v[i].item_end; it++) w += items[it].k + 4;
-      w *= (long long)((v[i].mrem + 7) / 8) * ((v[i].nrem + 7) / 8);
-      ord[i - b] = {w, v[i].item_begin, i};
-      long long& g = wmax[v[i].item_begin - ib_lo];
-      g = std::max(g, w);
+   const size_t G = (size_t)(ib_hi - ib_lo) + 1;
+   std::vector<long long> wmax(G, 0);      // group weight = its heaviest tile, indexed by the group's first item
+   std::vector<int> count(G, 0);           // tiles per group
+   {
+      std::vector<long long> ksum(G, -1);  // accumulated inner dimension of the group's items (the same for every tile of a group)
+      std::vector<int> kend(G, 0);
+      for (int i = b; i < e; i++) {
+         const Tile& t = v[i];
+         const size_t g = (size_t)(t.item_begin - ib_lo);
+         long long ks;
+         if (ksum[g] >= 0 && kend[g] == t.item_end) ks = ksum[g];
+         else {
+            ks = 0;
+            for (int it = t.item_begin; it < t.item_end; it++) ks += items[it].k + 4;
+            ksum[g] = ks; kend[g] = t.item_end;
+         }
+         const long long w = ks * ((long long)((t.mrem + 7) / 8) * ((t.nrem + 7) / 8));
+         wmax[g] = std::max(wmax[g], w);
+         count[g]++;
+      }
    }
-   for (Key& k : ord) k.w = wmax[k.ib - ib_lo];
-   std::sort(ord.begin(), ord.end(), [](const Key& x, const Key& y) { return x.w != y.w ? x.w > y.w : (x.ib != y.ib ? x.ib < y.ib : x.idx < y.idx); });
-   std::vector<Tile> sorted(e - b);
-   for (int i = 0; i < e - b; i++) sorted[i] = v[ord[i].idx];
+   std::vector<uint32_t> ord, tmp;         // the non-empty groups, ascending in their first item
+   ord.reserve(G);
+   long long wtop = 0;
+   for (size_t g = 0; g < G; g++) if (count[g]) { ord.push_back((uint32_t)g); wtop = std::max(wtop, wmax[g]); }
+   tmp.resize(ord.size());
+   constexpr int kBits = 11;
+   for (int shift = 0; shift < 63 && (wtop >> shift) != 0; shift += kBits) {   // stable, descending in the current digit
+      size_t hist[(1 << kBits) + 1] = {};
+      for (uint32_t g : ord) hist[(1 << kBits) - 1 - (size_t)((wmax[g] >> shift) & ((1 << kBits) - 1)) + 1]++;
+      for (int d = 0; d < (1 << kBits); d++) hist[d + 1] += hist[d];
+      for (uint32_t g : ord) tmp[hist[(1 << kBits) - 1 - (size_t)((wmax[g] >> shift) & ((1 << kBits) - 1))]++] = g;
+      ord.swap(tmp);
+   }
+   std::vector<int> start(G, 0);
+   int at = 0;
+   for (uint32_t g : ord) { start[g] = at; at += count[g]; }
+   std::vector<Tile> sorted(n);
+   for (int i = b; i < e; i++) sorted[start[(size_t)(v[i].item_begin - ib_lo)]++] = v[i];
    std::copy(sorted.begin(), sorted.end(), v.begin() + b);
 }
 

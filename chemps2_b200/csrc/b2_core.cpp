@@ -2,6 +2,7 @@
 #include "b2_core.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cassert>
 #include <cmath>
 #include <condition_variable>
@@ -14,46 +15,61 @@ namespace b2 {
 
 // ------------------------------------------------------------------------------------------------ host worker pool
 namespace {
+// Parked workers shared by every caller.  A parallel_run is a JOB of n independent pieces; several jobs may be open at the same time
+// (the sweep driver builds the sigma plan of the next site while the operator-update plan of the current one is built on the calling
+// thread): idle workers take the next unclaimed piece of the oldest open job, the caller of a job works on its own pieces too and then
+// waits for the pieces other threads took.  Pieces never wait for one another, so any number of threads >= 1 finishes every job.
 struct WorkerPool {
-   std::mutex run_mutex;                 // one parallel_run at a time
+   struct Job {
+      const std::function<void(int)>* fn = nullptr;
+      int n = 0, next = 0, done = 0;      // pieces, first unclaimed piece, finished pieces (all under the pool mutex)
+      std::condition_variable finished;
+   };
    std::mutex m;
-   std::condition_variable wake, finished;
-   std::vector<std::thread> workers;     // worker w executes piece w + 1
-   const std::function<void(int)>* job = nullptr;
-   int job_n = 0, pending = 0;
-   long long generation = 0;
+   std::condition_variable wake;
+   std::vector<std::thread> workers;
+   std::vector<Job*> open;               // jobs with unclaimed pieces, oldest first
    bool quit = false;
 
-   void worker_main(int piece, long long seen) {
+   // claims a piece of the oldest open job (caller holds the mutex)
+   Job* claim(int& piece) {
+      if (open.empty()) return nullptr;
+      Job* j = open.front();
+      piece = j->next++;
+      if (j->next >= j->n) open.erase(open.begin());
+      return j;
+   }
+   void worker_main() {
+      std::unique_lock<std::mutex> lk(m);
       for (;;) {
-         const std::function<void(int)>* fn = nullptr;
-         {
-            std::unique_lock<std::mutex> lk(m);
-            wake.wait(lk, [&] { return quit || generation != seen; });
-            if (quit) return;
-            seen = generation;
-            if (piece < job_n) fn = job;
-         }
-         if (!fn) continue;
-         (*fn)(piece);
-         std::lock_guard<std::mutex> lk(m);
-         if (--pending == 0) finished.notify_one();
+         wake.wait(lk, [&] { return quit || !open.empty(); });
+         if (quit) return;
+         int piece = -1;
+         Job* j = claim(piece);
+         if (!j) continue;
+         lk.unlock();
+         (*j->fn)(piece);
+         lk.lock();
+         if (++j->done == j->n) j->finished.notify_all();   // the job object lives until its caller has seen done == n under this mutex
       }
    }
    void run(int n, const std::function<void(int)>& fn) {
-      std::unique_lock<std::mutex> busy(run_mutex, std::try_to_lock);
-      if (n <= 1 || !busy.owns_lock()) { for (int t = 0; t < n; t++) fn(t); return; }
-      {
-         std::lock_guard<std::mutex> lk(m);
-         while ((int)workers.size() < n - 1) { const int piece = (int)workers.size() + 1; workers.emplace_back(&WorkerPool::worker_main, this, piece, generation); }
-         job = &fn; job_n = n; pending = n - 1;
-         generation++;
-      }
-      wake.notify_all();
-      fn(0);
+      if (n <= 1) { for (int t = 0; t < n; t++) fn(t); return; }
+      Job job;
+      job.fn = &fn; job.n = n;
       std::unique_lock<std::mutex> lk(m);
-      finished.wait(lk, [&] { return pending == 0; });
-      job = nullptr; job_n = 0;
+      while ((int)workers.size() < n - 1) workers.emplace_back(&WorkerPool::worker_main, this);
+      open.push_back(&job);
+      wake.notify_all();
+      while (job.next < job.n) {          // the caller takes pieces of ITS job only: it must not get stuck in somebody else's long piece
+         const int piece = job.next++;
+         if (job.next >= job.n) open.erase(std::find(open.begin(), open.end(), &job));
+         lk.unlock();
+         fn(piece);
+         lk.lock();
+         ++job.done;
+      }
+      job.finished.wait(lk, [&] { return job.done == job.n; });
    }
    void shutdown() {
       { std::lock_guard<std::mutex> lk(m); quit = true; }
@@ -68,11 +84,12 @@ struct WorkerPool {
 // abandons the inherited object and starts a fresh one.
 struct PoolHolder {
    WorkerPool* pool = nullptr;
-   pid_t owner = 0;
+   std::atomic<pid_t> owner{0};   // read before the guard is taken (fork detection), written under it
    std::mutex guard;
    WorkerPool* get() {
       const pid_t me = getpid();
-      if (owner != 0 && owner != me) new (&guard) std::mutex();   // first call in a forked child: the copy may be in the locked state
+      const pid_t seen = owner.load();
+      if (seen != 0 && seen != me) new (&guard) std::mutex();   // first call in a forked child: the copy may be in the locked state
       std::lock_guard<std::mutex> lk(guard);
       if (owner != me) {
          pool = new WorkerPool;                                     // an inherited pool is leaked on purpose

@@ -22,7 +22,7 @@ def run(name, schedule, rtol=1e-5, noise=0.0, seed=12345, device=0, spill=False,
     for i in range(L - 2):
         d.update(i, True)                       # DMRG::PreSolve (DMRG.cpp:257-266)
     log(f"presolve {time.time() - t0:.2f} s")
-    out, change, first = [], False, True
+    out, change, seen = [], False, (0, 0)
     for entry in schedule:
         D, nsweeps = entry[0], entry[1]
         if len(entry) > 2:
@@ -34,9 +34,12 @@ def run(name, schedule, rtol=1e-5, noise=0.0, seed=12345, device=0, spill=False,
                 e, dw = d.sweep(to_right, rtol, noise, D, change)
                 dt = time.time() - t0
                 tm = d.timers()
+                hits, misses = d.plan_cache_stats()
+                tm["plan_hits"], tm["plan_misses"] = hits - seen[0], misses - seen[1]
+                seen = (hits, misses)
                 out.append(dict(D=D, to_right=to_right, energy=e, max_discarded=dw, seconds=dt, **tm))
                 log(f"D={D:5d} {'->' if to_right else '<-'} E = {e:.10f}  w = {dw:.2e}  {dt:7.2f} s  (plan {tm['plan_s']:.2f} solve {tm['solve_s']:.2f} "
-                    f"split {tm['split_s']:.2f} update {tm['update_s']:.2f}; {tm['n_matvec']} sigma builds)")
+                    f"split {tm['split_s']:.2f} update {tm['update_s']:.2f}; {tm['n_matvec']} sigma builds; plans re-used {tm['plan_hits']}, built {tm['plan_misses']})")
                 change = True
     return out
 

@@ -140,6 +140,8 @@ SIGNATURES = [
     ("b2_dmrg_presolve", C.c_int, [vp]),
     ("b2_dmrg_set_plan_cache", C.c_int, [vp, C.c_int]),
     ("b2_dmrg_plan_cache_stats", C.c_int, [vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
+    ("b2_dmrg_set_plan_prefetch", C.c_int, [vp, C.c_int]),
+    ("b2_dmrg_plan_prefetched", C.c_longlong, [vp]),
     ("b2_dmrg_save_mps", C.c_int, [vp, C.c_char_p, C.c_int]),
     ("b2_dmrg_load_mps", C.c_int, [vp, C.c_char_p, c_ip]),
     ("b2_dmrg_solve", C.c_int, [vp, C.c_int, c_ip, c_dp, c_ip, c_dp, c_dp, c_dp]),

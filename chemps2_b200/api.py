@@ -319,6 +319,12 @@ class DMRG:
         check(lib.b2_dmrg_plan_cache_stats(self.h, C.byref(hits), C.byref(misses)))
         return hits.value, misses.value
 
+    def set_plan_prefetch(self, enabled):
+        check(lib.b2_dmrg_set_plan_prefetch(self.h, int(bool(enabled))))
+
+    def plan_prefetched(self):
+        return int(lib.b2_dmrg_plan_prefetched(self.h))
+
     def presolve(self):
         check(lib.b2_dmrg_presolve(self.h))
 

@@ -390,15 +390,32 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
    if (world > 1) set_plan_local_ranks(world);   // the ranks of one box build their plans concurrently
    h->left = (site > 0) ? left : nullptr;
    h->right = (site < L - 2) ? right : nullptr;
+   heff_build_host(h.get(), site, budgeted(ctx));
+   int rc = heff_setup_device(h.get());
+   if (rc) return rc;
+   *out = h.release();
+   return B2_OK;
+}
+
+// Host half of b2_heff_create: term enumeration + scheduling.  Reads the bookkeeper, the integrals and the LAYOUTS of the two
+// operator sets, never their contents, and makes no CUDA call — the sweep driver runs it on a helper thread for the next site while
+// the operator update of the current one is planned and executed (b2_capi_dmrg.cpp, dmrg_prefetch_start).
+void b2capi::heff_build_host(b2_heff* h, int site, const CompileOptions& budget) {
+   b2_ctx* ctx = h->ctx;
    const double tb0 = wall_seconds();
-   build_sigma_plan(h->plan, ctx->bk, ctx->prob, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, site, world);
+   build_sigma_plan(h->plan, ctx->bk, ctx->prob, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, site, h->world);
    const double tb1 = wall_seconds();
-   CompileOptions copt = budgeted(ctx);
+   CompileOptions copt = budget;
    // plans whose sigma build is a few milliseconds are dominated by the time to BUILD them: compile those on all host cores
    copt.threads = (h->plan.flops_ref < ctx->parallel_plan_flops) ? plan_threads(h->plan.S.nkappa()) : 1;
-   compile_sigma(h->comp, h->plan, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, rank, world, copt);
+   compile_sigma(h->comp, h->plan, h->left ? &h->left->set : nullptr, h->right ? &h->right->set : nullptr, h->rank, h->world, copt);
    h->list_bytes = h->comp.bytes();
    if (getenv("B2_TIMING")) fprintf(stderr, "b2_heff_create: enumerate %.3f s, schedule %.3f s, %zu terms\n", tb1 - tb0, wall_seconds() - tb1, h->plan.terms.size());
+}
+
+// Device half of b2_heff_create: work lists to the device, workspaces, pre-summed operators (reads the operator contents)
+int b2capi::heff_setup_device(b2_heff* h) {
+   b2_ctx* ctx = h->ctx;
    const double tb2 = wall_seconds();
    if (ctx->device >= 0) {
       CUDA_TRY(cudaSetDevice(ctx->device));
@@ -435,14 +452,13 @@ int b2_heff_create(b2_ctx* ctx, int site, b2_opset* left, b2_opset* right, int w
       CUDA_TRY(cudaEventCreate(&h->ev0));
       CUDA_TRY(cudaEventCreate(&h->ev1));
       // materialise the integral-weighted operator pre-sums once (operators are fixed during the Davidson solve)
-      DevBases b = bases_of(h.get(), nullptr, nullptr);
+      DevBases b = bases_of(h, nullptr, nullptr);
       if (dev_launch_presum(h->d_jobs, (int)h->comp.presum_jobs.size(), h->d_parts, b, s)) return fail(B2_ERR_CUDA, "%s", dev_last_error());
       CUDA_TRY(cudaStreamSynchronize(s));
       if (getenv("B2_TIMING"))
          fprintf(stderr, "b2_heff_create: device setup %.3f s (work lists %.1f MB uploaded, workspace %.2f GB, pre-sums %.1f MB)\n", wall_seconds() - tb2,
                  h->list_bytes / 1e6, h->comp.work_size * 8e-9, h->plan.presum_size * 8e-6);
    }
-   *out = h.release();
    return B2_OK;
 }
 
@@ -457,9 +473,9 @@ void b2capi::heff_park(b2_heff* h) {
    if (h->h_vin) { cudaFreeHost(h->h_vin); h->h_vin = nullptr; }
    if (h->h_vout) { cudaFreeHost(h->h_vout); h->h_vout = nullptr; }
    std::vector<SigmaTerm>().swap(h->plan.terms);
-   std::vector<GemmItem>().swap(h->comp.items1); std::vector<GemmItem>().swap(h->comp.items2);
-   std::vector<ReduceJob>().swap(h->comp.reduces);
-   for (int c = 0; c < kNumTileClasses; c++) { std::vector<Tile>().swap(h->comp.tiles1[c]); std::vector<Tile>().swap(h->comp.tiles2[c]); }
+   ListVec<GemmItem>().swap(h->comp.items1); ListVec<GemmItem>().swap(h->comp.items2);
+   ListVec<ReduceJob>().swap(h->comp.reduces);
+   for (int c = 0; c < kNumTileClasses; c++) { ListVec<Tile>().swap(h->comp.tiles1[c]); ListVec<Tile>().swap(h->comp.tiles2[c]); }
    h->left = h->right = nullptr;
 }
 // brings a parked plan back: new operator sets (same layouts: same dimensions), workspaces, pre-summed operators of the new contents

@@ -2,6 +2,8 @@
 // states, MPS checkpoints, and the 2-RDM / correlation chains of DMRG::calc_rdms_and_correlations (DMRGtechnics.cpp:40-215).
 #include "b2_capi_internal.h"
 
+#include <thread>
+
 int b2capi::run_compiled_once(b2_ctx* ctx, const CompiledWork& w, DevBases b) {
    cudaStream_t s = ctx->stream;
    GemmItem *i1 = nullptr, *i2 = nullptr;
@@ -72,6 +74,21 @@ struct b2_dmrg {
    std::vector<UpdSlot> upd_cache;        // index = 2 * site + moving_right
    bool use_plan_cache = true;
    long long plan_hits = 0, plan_misses = 0;
+   // Inside b2_dmrg_sweep the HOST half of the next site's sigma plan (enumeration + scheduling: no CUDA call, reads only the bookkeeper,
+   // the integrals and operator-set layouts, all frozen until the next Split) is built on a helper thread while the calling thread plans
+   // and runs the operator update that precedes it; solve_site takes the finished plan over and only does the device half.
+   struct Prefetch {
+      std::thread th;
+      bool active = false;
+      int site = -1, world = 1, rank = 0;
+      b2_opset *left = nullptr, *right = nullptr;
+      std::vector<int> key;                // the plan-cache key of the site: sharding + dimension tables of boundaries site and site + 2
+      std::unique_ptr<b2_heff> h;
+      bool ok = false;
+   } prefetch;
+   bool in_sweep = false;
+   bool use_prefetch = true;               // B2_PLAN_PREFETCH=0 switches it off
+   long long plan_prefetched = 0;
    bool right_canonical = false;           // b2_dmrg_calc_2rdm leaves the MPS right-canonical (centre on site 0): PreSolve must restore the gauge first
    double max_disc_last_sweep = 0.0;       // DMRG::MaxDiscWeightLastSweep (DMRG.cpp:360-362): scales the noise of the next half sweep
    double last_energy = 0.0;               // energy of the last site solved (what DMRG::sweepleft / sweepright return)
@@ -98,6 +115,7 @@ int b2_dmrg_create(b2_ctx* ctx, b2_dmrg** out) {
    d->mps.resize(d->L);
    for (int s = 0; s < d->L; s++) { TLayout t; t.build(ctx->bk, s); d->mps[s].assign((size_t)t.size, 0.0); }
    d->left.assign(d->L + 1, nullptr); d->right.assign(d->L + 1, nullptr);
+   if (const char* e = getenv("B2_PLAN_PREFETCH")) d->use_prefetch = atoi(e) != 0;
    *out = d.release();
    return B2_OK;
 }
@@ -105,8 +123,64 @@ static void dmrg_clear_plan_cache(b2_dmrg* d) {
    for (b2_dmrg::PlanSlot& p : d->plan_cache) { b2_heff_destroy(p.h); p.h = nullptr; p.key.clear(); }
    for (b2_dmrg::UpdSlot& p : d->upd_cache) { b2_update_destroy(p.u); p.u = nullptr; p.key.clear(); }
 }
+// key of the sigma plan of `site`: sharding + the exact dimension tables of the boundaries the plan reads.  The two-site object and both
+// operator sets live on boundaries site and site + 2 only (Sobject.cpp:36-78 never reads the contracted boundary site + 1, which EVERY
+// visit re-dimensions): keying on it too would turn most re-visits into misses
+static std::vector<int> dmrg_plan_key(const b2_dmrg* d, int site) {
+   std::vector<int> key;
+   const Bookkeeper& bk = d->ctx->bk;
+   key.push_back(d->world); key.push_back(d->rank);
+   for (int b = site; b <= site + 2; b += 2) key.insert(key.end(), bk.cur[b].begin(), bk.cur[b].end());
+   return key;
+}
+// waits for the helper thread and drops what it built
+static void dmrg_prefetch_cancel(b2_dmrg* d) {
+   b2_dmrg::Prefetch& pf = d->prefetch;
+   if (!pf.active) return;
+   if (pf.th.joinable()) pf.th.join();
+   pf.h.reset();
+   pf.active = false;
+}
+// starts the host half of the sigma plan of `site` (operator sets lset / rset, which must stay alive until the prefetch is taken or cancelled)
+static void dmrg_prefetch_start(b2_dmrg* d, int site, b2_opset* lset, b2_opset* rset) {
+   dmrg_prefetch_cancel(d);
+   const int L = d->L;
+   if (!d->in_sweep || !d->use_prefetch || d->spill || site < 0 || site > L - 2) return;
+   if (site > 0 && (!lset || lset->set.reduced || lset->offloaded || lset->set.boundary != site || !lset->set.moving_right)) return;
+   if (site < L - 2 && (!rset || rset->set.reduced || rset->offloaded || rset->set.boundary != site + 2 || rset->set.moving_right)) return;
+   if (d->ctx->simulate_oom > 0) return;   // the test hook counts b2_heff_create calls
+   std::vector<int> key = dmrg_plan_key(d, site);
+   if (d->use_plan_cache && (int)d->plan_cache.size() == L && d->plan_cache[site].h && d->plan_cache[site].key == key) return;   // the parked plan will be re-used
+   b2_dmrg::Prefetch& pf = d->prefetch;
+   pf.site = site; pf.world = d->world; pf.rank = d->rank;
+   pf.left = site > 0 ? lset : nullptr; pf.right = site < L - 2 ? rset : nullptr;
+   pf.key.swap(key);
+   pf.ok = false;
+   pf.h.reset(new b2_heff);
+   b2_heff* h = pf.h.get();
+   h->ctx = d->ctx; h->world = d->world; h->rank = d->rank; h->left = pf.left; h->right = pf.right;
+   const CompileOptions budget = budgeted(d->ctx);   // cudaMemGetInfo on the calling thread: the helper makes no CUDA call
+   bool* ok = &pf.ok;
+   try {
+      pf.th = std::thread([h, site, budget, ok] {
+         try { heff_build_host(h, site, budget); *ok = true; } catch (...) { *ok = false; }
+      });
+      pf.active = true;
+   } catch (...) { pf.h.reset(); pf.active = false; }
+}
+// the prefetched plan (host half only) if it was built for exactly this site, these operator sets and these dimensions; else nullptr
+static b2_heff* dmrg_prefetch_take(b2_dmrg* d, int site, b2_opset* lset, b2_opset* rset, const std::vector<int>& key) {
+   b2_dmrg::Prefetch& pf = d->prefetch;
+   if (!pf.active) return nullptr;
+   if (pf.th.joinable()) pf.th.join();
+   pf.active = false;
+   std::unique_ptr<b2_heff> h(std::move(pf.h));
+   if (!pf.ok || pf.site != site || pf.left != lset || pf.right != rset || pf.world != d->world || pf.rank != d->rank || pf.key != key) return nullptr;
+   return h.release();
+}
 void b2_dmrg_destroy(b2_dmrg* d) {
    if (!d) return;
+   dmrg_prefetch_cancel(d);
    dmrg_clear_plan_cache(d);
    for (b2_opset* s : d->left) b2_opset_destroy(s);
    for (b2_opset* s : d->right) b2_opset_destroy(s);
@@ -206,6 +280,12 @@ int b2_dmrg_set_plan_cache(b2_dmrg* d, int enabled) {
    if (!d->use_plan_cache) dmrg_clear_plan_cache(d);
    return B2_OK;
 }
+int b2_dmrg_set_plan_prefetch(b2_dmrg* d, int enabled) {
+   if (!d) return fail(B2_ERR_ARG, "b2_dmrg_set_plan_prefetch: NULL");
+   d->use_prefetch = enabled != 0;
+   return B2_OK;
+}
+long long b2_dmrg_plan_prefetched(const b2_dmrg* d) { return d ? d->plan_prefetched : 0; }
 int b2_dmrg_plan_cache_stats(const b2_dmrg* d, long long* hits, long long* misses) {
    if (!d) return fail(B2_ERR_ARG, "b2_dmrg_plan_cache_stats: NULL");
    if (hits) *hits = d->plan_hits;
@@ -423,6 +503,15 @@ static int dmrg_update_mode(b2_dmrg* d, int index, int moving_right, int mode) {
    }
    for (int attempt = 0; attempt < 2; attempt++) {
       rc = mode == 0 ? b2_opset_create(ctx, b_new, mr, &fresh) : opset_create_reduced(ctx, b_new, mr, mode == 2, &fresh);
+      if (!rc && mode == 0 && attempt == 0 && d->in_sweep) {
+         // the site that b2_dmrg_sweep solves next needs nothing but the LAYOUT of the fresh set (its arena is filled below): build the host
+         // half of its sigma plan on a helper thread while this thread plans and runs the update.  Moving right: pair (index + 1, index + 2)
+         // with the fresh set on its left; moving left: pair (index - 2, index - 1) with the fresh set on its right.  The first site of the
+         // NEXT half sweep is left alone (the caller may do anything between two sweeps).
+         const int next = mr ? index + 1 : index - 2;
+         if (mr ? next <= d->L - 3 : next >= 1)
+            dmrg_prefetch_start(d, next, mr ? fresh : d->left[next], mr ? (next < d->L - 2 ? d->right[next + 2] : nullptr) : fresh);
+      }
       if (!rc && slot && slot->u && slot->key == key) {   // the plan of the previous visit fits: re-bind it to the new arenas
          u = slot->u; slot->u = nullptr;
          rc = update_unpark(u, need_old ? old_set : nullptr, fresh);
@@ -435,13 +524,14 @@ static int dmrg_update_mode(b2_dmrg* d, int index, int moving_right, int mode) {
       // HBM exhausted (O(L) boundaries x O(L^2 D^2) operators): from now on only the sets in use stay resident — the
       // reference's OperatorsOnDisk mode, switched on when it is needed instead of by the user
       cudaGetLastError();
+      dmrg_prefetch_cancel(d);   // it reads the layout of `fresh`
       b2_update_destroy(u); u = nullptr;
       b2_opset_destroy(fresh); fresh = nullptr;
       d->spill = true;
       dmrg_clear_plan_cache(d);
       if ((rc = dmrg_residency(d, mr ? b_old : -1, mr ? -1 : b_old))) return rc;
    }
-   if (rc) { b2_update_destroy(u); b2_opset_destroy(fresh); return rc; }
+   if (rc) { dmrg_prefetch_cancel(d); b2_update_destroy(u); b2_opset_destroy(fresh); return rc; }
    if (d->world > 1) rc = b2_update_set_allreduce(u, d->allreduce, d->allreduce_user);
    d->t_plan += wall_seconds() - t0;
    const double t1 = wall_seconds();
@@ -455,7 +545,7 @@ static int dmrg_update_mode(b2_dmrg* d, int index, int moving_right, int mode) {
       update_park(u);
       slot->u = u; slot->key = key;
    } else b2_update_destroy(u);
-   if (rc) { b2_opset_destroy(fresh); return rc; }
+   if (rc) { dmrg_prefetch_cancel(d); b2_opset_destroy(fresh); return rc; }
    if ((rc = b2_dmrg_set_opset(d, b_new, mr, fresh))) return rc;
    rc = dmrg_update_overlaps(d, index, mr);   // DMRGoperators.cpp:556-567 / :889-900
    d->t_tail += wall_seconds() - t2;
@@ -475,13 +565,10 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
    if ((index > 0 && !lset) || (index < L - 2 && !rset)) return fail(B2_ERR_STATE, "b2_dmrg_solve_site: boundary operators for site %d are missing", index);
    b2_heff* h = nullptr;
    const double tp0 = wall_seconds();
-   std::vector<int> key;
+   const std::vector<int> key = dmrg_plan_key(d, index);
+   std::unique_ptr<b2_heff> pre(dmrg_prefetch_take(d, index, lset, rset, key));   // joins the helper thread (if any) before anything is changed
    if (d->use_plan_cache) {
       if ((int)d->plan_cache.size() != L) d->plan_cache.assign(L, b2_dmrg::PlanSlot());
-      key.push_back(d->world); key.push_back(d->rank);
-      // the two-site object and both operator sets live on boundaries index and index + 2 only (Sobject.cpp:36-78 never reads the
-      // contracted boundary index + 1, which EVERY visit re-dimensions): keying on it too would turn most re-visits into misses
-      for (int b = index; b <= index + 2; b += 2) key.insert(key.end(), ctx->bk.cur[b].begin(), ctx->bk.cur[b].end());
       b2_dmrg::PlanSlot& slot = d->plan_cache[index];
       if (slot.h && slot.key == key) {
          h = slot.h; slot.h = nullptr;
@@ -490,7 +577,12 @@ int b2_dmrg_solve_site(b2_dmrg* d, int index, double rtol, double noise, int D, 
       }
    }
    int rc = B2_OK;
-   if (!h) { d->plan_misses++; rc = b2_heff_create(ctx, index, lset, rset, d->world, d->rank, &h); }
+   if (!h && pre) {   // host half built during the preceding operator update: only the device half is left
+      d->plan_misses++; d->plan_prefetched++;
+      h = pre.release();
+      rc = heff_setup_device(h);
+   } else if (!h) { d->plan_misses++; rc = b2_heff_create(ctx, index, lset, rset, d->world, d->rank, &h); }
+   pre.reset();
    if (rc == B2_ERR_CUDA && !d->spill) {   // out of HBM: park every operator set that this site does not use and retry
       cudaGetLastError();
       b2_heff_destroy(h); h = nullptr;
@@ -908,6 +1000,11 @@ int b2_dmrg_sweep(b2_dmrg* d, int to_right, double rtol, double noise, int D, in
    const double base[7] = {d->t_plan, d->t_join, d->t_solve, d->t_split, d->t_release, d->t_update, d->t_tail};
    // DMRG.cpp:360,391: the noise added before Split is |noise prefactor| x (largest discarded weight of the previous half sweep)
    noise = std::fabs(noise) * d->max_disc_last_sweep;
+   struct SweepScope {   // plan prefetching is confined to this call: whatever way it ends, no helper thread outlives it
+      b2_dmrg* d;
+      explicit SweepScope(b2_dmrg* d_) : d(d_) { d->in_sweep = true; }
+      ~SweepScope() { dmrg_prefetch_cancel(d); d->in_sweep = false; }
+   } scope(d);
    if (!to_right) {
       for (int index = L - 2; index > 0; index--) {
          double e, dw;

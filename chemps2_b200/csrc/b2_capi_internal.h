@@ -155,7 +155,7 @@ struct b2_update {
 namespace b2capi {
 // stage-1 workspace budget of a plan: the configured value, capped by half of the HBM that is free right now
 CompileOptions budgeted(const b2_ctx* ctx);
-template <class T> int upload_vec(T** dptr, const std::vector<T>& v, cudaStream_t s) {
+template <class T, class A> int upload_vec(T** dptr, const std::vector<T, A>& v, cudaStream_t s) {
    *dptr = nullptr;
    if (v.empty()) return B2_OK;
    CUDA_TRY(cudaMalloc(dptr, sizeof(T) * v.size()));
@@ -164,6 +164,10 @@ template <class T> int upload_vec(T** dptr, const std::vector<T>& v, cudaStream_
 }
 // operator sets of the 2-RDM chain: L only (only_L) or L, S0, S1, F0, F1 (DMRG::updateMovingLeftSafe2DM)
 int opset_create_reduced(b2_ctx* ctx, int boundary, bool mr, bool only_L, b2_opset** out);
+// the two halves of b2_heff_create (h->ctx, left, right, world, rank set by the caller): host = enumeration + scheduling without any
+// CUDA call, device = uploads, workspaces, pre-sums
+void heff_build_host(b2_heff* h, int site, const CompileOptions& budget);
+int heff_setup_device(b2_heff* h);
 // a plan parked in the sweep driver's cache keeps only its device work lists; unpark re-binds it to the operator sets of the new visit
 void heff_park(b2_heff* h);
 int heff_unpark(b2_heff* h, b2_opset* left, b2_opset* right);

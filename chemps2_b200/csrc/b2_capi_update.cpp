@@ -182,9 +182,9 @@ void b2capi::update_park(b2_update* u) {
    if (u->h_t) { cudaFreeHost(u->h_t); u->h_t = nullptr; }
    std::vector<Term3>().swap(u->plan.terms); std::vector<Term3>().swap(u->plan.mix_terms);
    for (int p = 0; p < 2; p++) {
-      std::vector<GemmItem>().swap(u->pass[p].items1); std::vector<GemmItem>().swap(u->pass[p].items2);
-      std::vector<ReduceJob>().swap(u->pass[p].reduces);
-      for (int c = 0; c < kNumTileClasses; c++) { std::vector<Tile>().swap(u->pass[p].tiles1[c]); std::vector<Tile>().swap(u->pass[p].tiles2[c]); }
+      ListVec<GemmItem>().swap(u->pass[p].items1); ListVec<GemmItem>().swap(u->pass[p].items2);
+      ListVec<ReduceJob>().swap(u->pass[p].reduces);
+      for (int c = 0; c < kNumTileClasses; c++) { ListVec<Tile>().swap(u->pass[p].tiles1[c]); ListVec<Tile>().swap(u->pass[p].tiles2[c]); }
    }
    u->old_set = u->new_set = nullptr;
 }

@@ -111,7 +111,7 @@ static double now_s() { return std::chrono::duration<double>(std::chrono::steady
 namespace {
 
 // the launch order of the tiles [b, e) of one wave: see weight_sort in compile_range
-void group_sort(std::vector<Tile>& v, int b, int e, const std::vector<GemmItem>& items);
+void group_sort(ListVec<Tile>& v, int b, int e, const ListVec<GemmItem>& items);
 
 // compiles terms[0, n) (grouped by dst) into `out`; sort_waves = false leaves the launch order to the caller
 void compile_range(CompiledWork& out, Term3* terms, size_t nterms, const std::vector<DstBlock>& dst, uint8_t dst_space, const CompileOptions& opt,
@@ -120,8 +120,20 @@ void compile_range(CompiledWork& out, Term3* terms, size_t nterms, const std::ve
 }   // namespace
 
 void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vector<DstBlock>& dst, uint8_t dst_space, const CompileOptions& opt) {
+   compile_terms(out, terms.data(), terms.size(), dst, dst_space, opt);
+}
+
+void compile_terms(CompiledWork& out, Term3* term_data, size_t nterms, const std::vector<DstBlock>& dst, uint8_t dst_space, const CompileOptions& opt) {
    out = CompiledWork();
    const double T_total = now_s();
+   struct Span {   // what the code below needs of a vector
+      Term3* p; size_t n;
+      size_t size() const { return n; }
+      Term3* data() const { return p; }
+      Term3& operator[](size_t i) const { return p[i]; }
+      Term3* begin() const { return p; }
+      Term3* end() const { return p + n; }
+   } terms{term_data, nterms};
    {  // every destination block must form ONE contiguous group: two groups would become two CTAs that read-modify-write the same
       // tile in one launch.  Generators that visit a block twice (e.g. TensorQ/TensorX: update + AddTerms) are regrouped here.
       std::vector<char> seen(dst.size(), 0);
@@ -137,7 +149,7 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
          for (size_t k = 0; k < dst.size(); k++) pos[k + 1] += pos[k];
          std::vector<Term3> sorted(terms.size());
          for (const Term3& t : terms) sorted[pos[t.dst]++] = t;
-         terms.swap(sorted);
+         std::copy(sorted.begin(), sorted.end(), terms.begin());
       }
    }
    const int T = std::max(1, std::min<int>(opt.threads, (int)(terms.size() / std::max<int64_t>(opt.parallel_min_terms, 1))));
@@ -250,7 +262,7 @@ void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vect
 
 namespace {
 
-void group_sort(std::vector<Tile>& v, int b, int e, const std::vector<GemmItem>& items) {
+void group_sort(ListVec<Tile>& v, int b, int e, const ListVec<GemmItem>& items) {
    // Launch order = heaviest GROUPS first (static load balance across the SMs), where a group is the set of CTAs that
    // stream the same items (all tiles of one stage-1 product / of one split-K chunk of a destination block): they read the
    // same operand panels, so they must be resident together for the panels to be served by L2 instead of DRAM.
@@ -298,7 +310,7 @@ void group_sort(std::vector<Tile>& v, int b, int e, const std::vector<GemmItem>&
    std::vector<int> start(G, 0);
    int at = 0;
    for (uint32_t g : ord) { start[g] = at; at += count[g]; }
-   std::vector<Tile> sorted(n);
+   ListVec<Tile> sorted(n);
    for (int i = b; i < e; i++) sorted[start[(size_t)(v[i].item_begin - ib_lo)]++] = v[i];
    std::copy(sorted.begin(), sorted.end(), v.begin() + b);
 }
@@ -320,7 +332,7 @@ void compile_range(CompiledWork& out, Term3* terms, size_t nterms, const std::ve
       wave_work = 0; wave_part = 0;
       wmap.clear();
    };
-   auto weight_sort = [&](std::vector<Tile>& v, int b, int e, const std::vector<GemmItem>& items) { if (sort_waves) group_sort(v, b, e, items); };
+   auto weight_sort = [&](ListVec<Tile>& v, int b, int e, const ListVec<GemmItem>& items) { if (sort_waves) group_sort(v, b, e, items); };
    auto close_wave = [&]() {
       bool any = (int)out.reduces.size() > wave.red_begin;
       for (int c = 0; c < kNumTileClasses; c++) {

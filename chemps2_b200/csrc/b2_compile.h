@@ -7,11 +7,24 @@
 // compile_terms() turns such a list into stage-1 tiles (shared intermediates in a bounded workspace), stage-2 tiles
 // (K-concatenated over all terms of a target tile, split-K chunked) and deterministic reduce jobs, wave by wave.
 #pragma once
+#include <memory>
+#include <utility>
 #include <vector>
 
 #include "b2_device.h"
 
 namespace b2 {
+
+// Work lists are plain structs by the million: a vector that default-initialises (= leaves untouched) what resize() adds, so that a list
+// sized for a parallel fill is first touched by the threads that write it instead of being zero-filled by one.
+template <class T> struct NoInitAlloc : std::allocator<T> {
+   template <class U> struct rebind { using other = NoInitAlloc<U>; };
+   NoInitAlloc() = default;
+   template <class U> NoInitAlloc(const NoInitAlloc<U>&) {}
+   template <class U> void construct(U* p) { ::new ((void*)p) U; }
+   template <class U, class... A> void construct(U* p, A&&... a) { ::new ((void*)p) U(std::forward<A>(a)...); }
+};
+template <class T> using ListVec = std::vector<T, NoInitAlloc<T>>;
 
 struct MatRef {            // a stored column-major matrix (ld = rows); trans: it enters the product transposed
    uint8_t space = SP_NONE, trans = 0;
@@ -46,10 +59,10 @@ struct CompileOptions {
 };
 
 struct CompiledWork {
-   std::vector<GemmItem> items1, items2;
-   std::vector<Tile> tiles1[kNumTileClasses];   // stage 1: W = op(P)*op(Q)  or  op(Q)*op(R)
-   std::vector<Tile> tiles2[kNumTileClasses];   // stage 2: destination tiles / split-K partial slots
-   std::vector<ReduceJob> reduces;
+   ListVec<GemmItem> items1, items2;
+   ListVec<Tile> tiles1[kNumTileClasses];   // stage 1: W = op(P)*op(Q)  or  op(Q)*op(R)
+   ListVec<Tile> tiles2[kNumTileClasses];   // stage 2: destination tiles / split-K partial slots
+   ListVec<ReduceJob> reduces;
    std::vector<Wave> waves;
    int64_t work_size = 0;                       // doubles (max over waves)
    int64_t part_size = 0;                       // doubles (max over waves)
@@ -62,6 +75,9 @@ struct CompiledWork {
 // `terms` must be grouped by dst (all terms of one destination block contiguous, blocks in any order).
 // dst_space: address space of the destination blocks (SP_VOUT for sigma, SP_NEW for operator updates).
 void compile_terms(CompiledWork& out, std::vector<Term3>& terms, const std::vector<DstBlock>& dst, uint8_t dst_space,
+                   const CompileOptions& opt);
+// the same on a raw array (re-ordered in place): for callers that fill the term list on several threads
+void compile_terms(CompiledWork& out, Term3* terms, size_t nterms, const std::vector<DstBlock>& dst, uint8_t dst_space,
                    const CompileOptions& opt);
 
 }   // namespace b2

@@ -9,6 +9,8 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
+#include <new>
 #include <thread>
 
 namespace b2 {
@@ -66,12 +68,16 @@ void compile_sigma(CompiledSigma& out, const SigmaPlan& plan, const OpSet* left,
    const double tc1 = now();
    std::vector<DstBlock> dst(nk);
    for (int k = 0; k < nk; k++) dst[k] = DstBlock{S.blk[k].off, S.blk[k].rows, S.blk[k].cols};
-   std::vector<Term3> terms(order.size());
+   // ~100 bytes per term, a million terms: raw storage, constructed by the thread that resolves the range (parallel first touch)
+   struct FreeDeleter { void operator()(void* p) const { std::free(p); } };
+   std::unique_ptr<Term3, FreeDeleter> term_store((Term3*)std::malloc(sizeof(Term3) * std::max<size_t>(order.size(), 1)));
+   if (!term_store) throw std::bad_alloc();
+   Term3* terms = term_store.get();
    auto resolve_range = [&](size_t b, size_t e) {
       for (size_t i = b; i < e; i++) {
          const SigmaTerm& t = plan.terms[order[i]];
          const Block& sb = S.blk[t.src];
-         Term3& x = terms[i];
+         Term3& x = *::new ((void*)(terms + i)) Term3();
          x.dst = t.dst; x.f = t.factor;
          x.p = resolve(t.l, plan, left, right);
          x.r = resolve(t.r, plan, left, right);
@@ -111,7 +117,7 @@ void compile_sigma(CompiledSigma& out, const SigmaPlan& plan, const OpSet* left,
    const double tc3 = now();
    CompiledWork& base = out;
    CompiledWork work;
-   compile_terms(work, terms, dst, SP_VOUT, opt);
+   compile_terms(work, terms, order.size(), dst, SP_VOUT, opt);
    base = std::move(work);
    if (getenv("B2_TIMING")) fprintf(stderr, "compile_sigma: order %.3f s, resolve %.3f s, diagonal %.3f s, schedule %.3f s\n", tc1 - tc0, tc2 - tc1, tc3 - tc2, now() - tc3);
 }

@@ -317,10 +317,17 @@ int b2_dmrg_set_spill(b2_dmrg* d, int enabled);
  * memory — the reference's tmp folder of DMRG::DMRG(..., tmpfolder) */
 int b2_dmrg_set_spill_dir(b2_dmrg* d, const char* dir);
 /* The driver keeps the sigma plan of the last visit of every site (device work lists only) and re-uses it when the dimension tables of
- * the three boundaries of the site pair are unchanged — the normal situation in converged sweeps at a fixed virtual dimension.
+ * the two boundaries the plan reads (site and site + 2; the contracted one in between is re-dimensioned by every visit and not part of
+ * the two-site object, Sobject.cpp:36-78) are unchanged — the normal situation in converged sweeps at a fixed virtual dimension.
  * enabled = 0 switches the cache off and frees it; the statistics count re-used and newly built plans. */
 int b2_dmrg_set_plan_cache(b2_dmrg* d, int enabled);
 int b2_dmrg_plan_cache_stats(const b2_dmrg* d, long long* hits, long long* misses);
+/* Inside b2_dmrg_sweep the host half of the NEXT site's sigma plan (term enumeration + scheduling; it needs the dimension tables and the
+ * layouts of the operator sets, not their contents) is built on a helper thread while the calling thread plans and runs the operator
+ * update that precedes it (DMRG.cpp:372-377 runs the two one after the other).  enabled = 0 switches it off (also B2_PLAN_PREFETCH=0);
+ * the result of a sweep does not depend on it.  b2_dmrg_plan_prefetched: how many newly built plans came from the helper thread. */
+int b2_dmrg_set_plan_prefetch(b2_dmrg* d, int enabled);
+long long b2_dmrg_plan_prefetched(const b2_dmrg* d);
 /* wall-clock seconds per phase since the last reset: [0] plan building (host), [1] Davidson solves, [2] Split (host SVD),
  * [3] operator updates, [4] number of sigma builds */
 int b2_dmrg_timers(b2_dmrg* d, double* out5, int reset);

@@ -3,33 +3,15 @@
    B2_PLAN_THREADS=8 python scripts/plan_hash_cpu.py > before.txt ; <change> ; ... > after.txt ; diff before.txt after.txt
 (the segmentation of a plan depends on the number of planner threads, so compare runs with the same B2_PLAN_THREADS)"""
 import ctypes as C
-import hashlib
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 from chemps2_b200 import api, workloads  # noqa: E402
 from chemps2_b200._lib import Worklists, check, lib  # noqa: E402
-
-SIZES = dict(item=40, tile=48, reduce=56, wave=4 * (4 * 4 + 2))
-
-
-def digest(wl):
-    h = hashlib.sha256()
-
-    def add(ptr, n, size):
-        if n and ptr:
-            h.update(C.string_at(ptr, int(n) * size))
-    add(wl.items1, wl.n_items1, SIZES["item"])
-    add(wl.items2, wl.n_items2, SIZES["item"])
-    for c in range(4):
-        add(wl.tiles1[c], wl.n_tiles1[c], SIZES["tile"])
-        add(wl.tiles2[c], wl.n_tiles2[c], SIZES["tile"])
-    add(wl.reduces, wl.n_reduces, SIZES["reduce"])
-    add(wl.waves, wl.n_waves, SIZES["wave"])
-    h.update(repr((wl.n_items1, wl.n_items2, list(wl.n_tiles1), list(wl.n_tiles2), wl.n_reduces, wl.n_waves, wl.work_size, wl.part_size)).encode())
-    return h.hexdigest()[:24]
-
+from cpu_check import worklist_digest as digest  # noqa: E402
 
 CASES = [("tiny", 40, "flat", None), ("n2_ccpvdz", 300, "gauss", 5), ("n2_ccpvdz", 600, "gauss", 13), ("n2_ccpvdz", 400, "flat", 13),
          ("synth40", 600, "gauss", 19), ("synth40", 400, "flat", 10), ("tetracene", 800, "gauss", 8), ("n2_ccpvdz", 1000, "gauss", 20)]

@@ -179,3 +179,23 @@ def op_slices(new):
         out.append((k, i, j, off, size))
         off += (size + 15) // 16 * 16
     return out
+
+
+def worklist_digest(wl):
+    """sha256 over every compiled device list of a Worklists export (items, tiles per class, reduce jobs, waves, sizes)"""
+    import hashlib
+    sizes = dict(item=40, tile=48, reduce=56, wave=4 * (4 * 4 + 2))   # sizeof GemmItem / Tile / ReduceJob / Wave (b2_device.h, b2_compile.h)
+    h = hashlib.sha256()
+
+    def add(ptr, n, size):
+        if n and ptr:
+            h.update(C.string_at(ptr, int(n) * size))
+    add(wl.items1, wl.n_items1, sizes["item"])
+    add(wl.items2, wl.n_items2, sizes["item"])
+    for c in range(4):
+        add(wl.tiles1[c], wl.n_tiles1[c], sizes["tile"])
+        add(wl.tiles2[c], wl.n_tiles2[c], sizes["tile"])
+    add(wl.reduces, wl.n_reduces, sizes["reduce"])
+    add(wl.waves, wl.n_waves, sizes["wave"])
+    h.update(repr((wl.n_items1, wl.n_items2, list(wl.n_tiles1), list(wl.n_tiles2), wl.n_reduces, wl.n_waves, wl.work_size, wl.part_size)).encode())
+    return h.hexdigest()[:24]

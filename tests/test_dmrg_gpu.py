@@ -306,6 +306,30 @@ def test_plan_cache_gives_identical_sweeps(golden):
     assert hits > 0 and hits0 == 0
 
 
+def test_plan_prefetch_gives_identical_sweeps(golden):
+    """inside b2_dmrg_sweep the host half of the next site's sigma plan is built on a helper thread during the operator update
+    (b2_dmrg_set_plan_prefetch): energies and discarded weights are bit-identical to sweeps that build every plan in line, with and
+    without the plan cache, and the helper really delivers plans"""
+    def run(prefetch, cache):
+        ctx, d = _start_from_fixture(golden, "A")
+        D = _fixture_D(golden)
+        d.set_plan_cache(cache)
+        d.set_plan_prefetch(prefetch)
+        d.presolve()
+        out = []
+        for it in range(3):
+            out += list(d.sweep(False, 1e-9, 0.0, D, it > 0))
+            out += list(d.sweep(True, 1e-9, 0.0, D, True))
+        return np.array(out), d.plan_prefetched()
+    ref, n0 = run(False, False)
+    assert n0 == 0
+    for cache in (False, True):
+        got, n = run(True, cache)
+        assert np.array_equal(got, ref)
+        if golden["problem/hdr"][0] > 4:
+            assert n > 0
+
+
 def test_solve_after_calc_2rdm_is_variational():
     """b2_dmrg_calc_2rdm leaves the MPS right-canonical; a following b2_dmrg_solve must restore the gauge before it rebuilds the
     operators (else the first sweep solves H x = E x in a non-orthonormal basis and reports non-variational energies)"""

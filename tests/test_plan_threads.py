@@ -119,3 +119,59 @@ def test_parallel_update_plan_equals_sequential_plan():
         assert (t1, m1, p1) == (t2, m2, p2)
         assert abs(f1 - f2) <= 1e-9 * f1
         assert abs(s1 - s2) <= 1e-10 * max(1.0, abs(s1))
+
+
+PREFETCH_WORKER = r"""
+import sys, os, threading
+import ctypes as C
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import cpu_check
+from chemps2_b200 import api, workloads
+from chemps2_b200._lib import Worklists, check, lib
+
+w = workloads.get("n2_ccpvdz", D=300)
+ctx = w.context(-1)
+w.apply_distribution(ctx, "gauss")
+ctx.set_option("parallel_min_terms", 2000)
+
+def sigma_digest(site, left, right):
+    heff = api.Heff(ctx, site, left, right)
+    wl = Worklists()
+    check(lib.b2_heff_worklists(heff.h, C.byref(wl)))
+    return cpu_check.worklist_digest(wl)
+
+def update_digest(index, old, new):
+    upd = api.Update(ctx, index, True, old, new)
+    out = []
+    for p in (0, 1):
+        wl = Worklists()
+        check(lib.b2_update_worklists(upd.h, p, C.byref(wl)))
+        out.append(cpu_check.worklist_digest(wl))
+    return out
+
+res = []
+for s in (8, 12, 16):
+    old = api.OpSet(ctx, s, True)
+    fresh = api.OpSet(ctx, s + 1, True)
+    right = api.OpSet(ctx, s + 3, False)
+    seq = (sigma_digest(s + 1, fresh, right), update_digest(s, old, fresh))
+    box = {{}}
+    th = threading.Thread(target=lambda: box.__setitem__("sigma", sigma_digest(s + 1, fresh, right)))   # ctypes drops the GIL: real concurrency
+    th.start()
+    upd = update_digest(s, old, fresh)
+    th.join()
+    res.append(seq == (box["sigma"], upd))
+print("B2PREFETCH", res)
+"""
+
+
+def test_next_sigma_plan_concurrent_with_update_plan():
+    """what the sweep driver's plan prefetch does on the host (b2_capi_dmrg.cpp dmrg_prefetch_start): the sigma plan of the NEXT site pair
+    is built on a helper thread while the update plan that produces its left operator set is built on the calling thread; both share
+    the worker pool (b2_core.cpp: several open jobs) and read the same bookkeeper / operator-set layouts.  Every compiled list must be
+    bit-identical to the one built alone."""
+    env = dict(os.environ, B2_PLAN_THREADS="6")
+    res = subprocess.run([sys.executable, "-c", PREFETCH_WORKER.format(root=ROOT)], capture_output=True, text=True, env=env, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    line = [ln for ln in res.stdout.splitlines() if ln.startswith("B2PREFETCH")][-1]
+    assert eval(line[len("B2PREFETCH"):]) == [True, True, True]

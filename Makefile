@@ -25,10 +25,11 @@ $(SRC)/%.o: $(SRC)/%.cu $(wildcard $(SRC)/*.h)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
 $(LIB): $(OBJS)
 	$(NVCC) -shared -o $@ $(OBJS) -cudart static -lpthread -ldl -lrt
-oracle/libb2oracle.so: oracle/plan_exec.c oracle/worklist_emul.cpp $(wildcard $(SRC)/*.h) include/chemps2_b200.h
+oracle/libb2oracle.so: oracle/plan_exec.c oracle/worklist_emul.cpp oracle/svd_block_emul.cpp $(wildcard $(SRC)/*.h) include/chemps2_b200.h
 	gcc -O2 -fPIC -c oracle/plan_exec.c -o oracle/plan_exec.o
 	$(CXX) -O2 -std=c++17 -fPIC -c oracle/worklist_emul.cpp -o oracle/worklist_emul.o
-	$(CXX) -shared -o $@ oracle/plan_exec.o oracle/worklist_emul.o
+	$(CXX) -O2 -std=c++17 -fPIC -c oracle/svd_block_emul.cpp -o oracle/svd_block_emul.o
+	$(CXX) -shared -o $@ oracle/plan_exec.o oracle/worklist_emul.o oracle/svd_block_emul.o
 
 clean:
 	rm -f $(SRC)/*.o oracle/*.o $(LIB) oracle/libb2oracle.so $(CALLER)

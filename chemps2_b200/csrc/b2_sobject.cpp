@@ -6,8 +6,11 @@
 //                The SVD is a one-sided Jacobi written here (the reference calls LAPACK dgesdd_, :412-419); this step is
 //                host-side in the reference too and is listed as "next" for the device in SURVEY.md 8(f).
 #include "b2_sobject.h"
+#include "b2_sigma.h"
 
 #include <algorithm>
+#include <atomic>
+#include <functional>
 #include <cmath>
 #include <cstring>
 
@@ -91,7 +94,16 @@ double split_host(Bookkeeper& bk, int ix, const SLayout& S, const double* s_stor
       for (auto& p : LP[ic]) dimLtot[ic] += p.dim;
       for (auto& p : RP[ic]) dimRtot[ic] += p.dim;
       cdim[ic] = std::min(dimLtot[ic], dimRtot[ic]);
-      if (cdim[ic] <= 0) continue;
+   }
+   // centre sectors are independent (own matrix, own blocks of the new tensors): the host workers share them
+   auto for_centers = [&](const std::function<void(int)>& body) {
+      std::atomic<int> next{0};
+      const int T = std::max(1, std::min(nc, plan_threads(8 * nc)));
+      parallel_run(T, [&](int) { for (int ic; (ic = next.fetch_add(1)) < nc;) body(ic); });
+   };
+   for_centers([&](int ic) {
+      const Center& c = centers[ic];
+      if (cdim[ic] <= 0) return;
       const int M = dimLtot[ic], N = dimRtot[ic];
       std::vector<double>& mem = mems[ic];
       mem.assign((size_t)M * N, 0.0);
@@ -112,8 +124,11 @@ double split_host(Bookkeeper& bk, int ix, const SLayout& S, const double* s_stor
          }
       }
       Lam[ic].resize(cdim[ic]); Us[ic].resize((size_t)cdim[ic] * M); VTs[ic].resize((size_t)cdim[ic] * N);
+   });
+   for (int ic = 0; ic < nc; ic++) {
+      if (cdim[ic] <= 0) continue;
       SvdJob job;
-      job.m = M; job.n = N; job.a = mem.data(); job.s = Lam[ic].data(); job.u = Us[ic].data(); job.vt = VTs[ic].data();
+      job.m = dimLtot[ic]; job.n = dimRtot[ic]; job.a = mems[ic].data(); job.s = Lam[ic].data(); job.u = Us[ic].data(); job.vt = VTs[ic].data();
       jobs.push_back(job);
    }
    // the decomposition itself (dgesdd_ per centre sector in the reference, Sobject.cpp:412-419): all sectors in one device batch
@@ -155,10 +170,10 @@ double split_host(Bookkeeper& bk, int ix, const SLayout& S, const double* s_stor
    TR.build(bk, ix + 1);
    t_left.assign((size_t)TL.size, 0.0);
    t_right.assign((size_t)TR.size, 0.0);
-   for (int ic = 0; ic < nc; ic++) {
+   for_centers([&](int ic) {
       const Center& c = centers[ic];
       const int dimM = bk.dim(ix + 1, c.NM, c.TwoJM, c.IM);
-      if (dimM <= 0) continue;
+      if (dimM <= 0) return;
       const int lim = std::min(dimM, cdim[ic]);
       for (auto& pl : LP[ic]) {
          const int k = TL.kappa(bk, pl.n, pl.ts, pl.ir, c.NM, c.TwoJM, c.IM);
@@ -179,7 +194,7 @@ double split_host(Bookkeeper& bk, int ix, const SLayout& S, const double* s_stor
             for (int r = 0; r < pr.dim; r++) blk[l + (size_t)dimM * r] = f * VTs[ic][l + (size_t)cdim[ic] * (pr.start + r)];
          }
       }
-   }
+   });
    return discarded;
 }
 

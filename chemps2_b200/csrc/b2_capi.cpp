@@ -472,7 +472,7 @@ void b2capi::heff_park(b2_heff* h) {
    h->n_exc = 0;
    if (h->h_vin) { cudaFreeHost(h->h_vin); h->h_vin = nullptr; }
    if (h->h_vout) { cudaFreeHost(h->h_vout); h->h_vout = nullptr; }
-   std::vector<SigmaTerm>().swap(h->plan.terms);
+   BigVec<SigmaTerm>().swap(h->plan.terms);
    ListVec<GemmItem>().swap(h->comp.items1); ListVec<GemmItem>().swap(h->comp.items2);
    ListVec<ReduceJob>().swap(h->comp.reduces);
    for (int c = 0; c < kNumTileClasses; c++) { ListVec<Tile>().swap(h->comp.tiles1[c]); ListVec<Tile>().swap(h->comp.tiles2[c]); }

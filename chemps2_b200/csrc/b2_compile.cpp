@@ -17,6 +17,8 @@
 #include <thread>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <type_traits>
 
 namespace b2 {
 
@@ -147,9 +149,12 @@ void compile_terms(CompiledWork& out, Term3* term_data, size_t nterms, const std
          std::vector<size_t> pos(dst.size() + 1, 0);
          for (const Term3& t : terms) pos[t.dst + 1]++;
          for (size_t k = 0; k < dst.size(); k++) pos[k + 1] += pos[k];
-         std::vector<Term3> sorted(terms.size());
-         for (const Term3& t : terms) sorted[pos[t.dst]++] = t;
-         std::copy(sorted.begin(), sorted.end(), terms.begin());
+         static_assert(std::is_trivially_copyable<Term3>::value, "Term3 is moved with memcpy");
+         const size_t bytes = sizeof(Term3) * terms.size();
+         Term3* sorted = static_cast<Term3*>(host_block_acquire(bytes));   // recycled block: no page faults, no constructor pass
+         for (const Term3& t : terms) std::memcpy(static_cast<void*>(sorted + pos[t.dst]++), &t, sizeof(Term3));
+         std::memcpy(static_cast<void*>(terms.data()), sorted, bytes);
+         host_block_release(sorted, bytes);
       }
    }
    const int T = std::max(1, std::min<int>(opt.threads, (int)(terms.size() / std::max<int64_t>(opt.parallel_min_terms, 1))));

@@ -11,13 +11,15 @@
 #include <utility>
 #include <vector>
 
+#include "b2_core.h"
 #include "b2_device.h"
 
 namespace b2 {
 
 // Work lists are plain structs by the million: a vector that default-initialises (= leaves untouched) what resize() adds, so that a list
 // sized for a parallel fill is first touched by the threads that write it instead of being zero-filled by one.
-template <class T> struct NoInitAlloc : std::allocator<T> {
+// Blocks of 1 MB and more come from the host block cache (CachedAlloc, b2_core.h): no page faults on re-use, no munmap on release.
+template <class T> struct NoInitAlloc : CachedAlloc<T> {
    template <class U> struct rebind { using other = NoInitAlloc<U>; };
    NoInitAlloc() = default;
    template <class U> NoInitAlloc(const NoInitAlloc<U>&) {}

@@ -5,10 +5,13 @@
 #include <atomic>
 #include <cassert>
 #include <cmath>
+#include <cstdlib>
 #include <condition_variable>
+#include <map>
 #include <mutex>
 #include <new>
 #include <thread>
+#include <vector>
 #include <unistd.h>
 
 namespace b2 {
@@ -106,6 +109,69 @@ struct PoolHolder {
 void parallel_run(int n, const std::function<void(int)>& fn) {
    static PoolHolder holder;
    holder.get()->run(n, fn);
+}
+
+// ------------------------------------------------------------------------------------------------ host block cache
+namespace {
+struct HostBlockCache {
+   std::mutex m;
+   std::map<size_t, std::vector<void*>> idle;     // class size -> blocks
+   size_t idle_bytes = 0;
+   size_t keep = [] { const char* e = getenv("B2_HOST_CACHE_GB"); return (size_t)((e ? atof(e) : 4.0) * 1073741824.0); }();
+};
+HostBlockCache& host_cache() { static HostBlockCache* c = new HostBlockCache; return *c; }   // never destroyed: releases may come from static destructors
+size_t host_class(size_t n) {   // next multiple of 2^(floor(log2 n) - 3)
+   size_t step = 1;
+   while ((step << 4) <= n) step <<= 1;
+   return (n + step - 1) / step * step;
+}
+}   // namespace
+
+void* host_block_acquire(size_t bytes) {
+   const size_t cls = host_class(std::max<size_t>(bytes, 64));
+   HostBlockCache& C = host_cache();
+   {
+      std::lock_guard<std::mutex> lk(C.m);
+      auto it = C.idle.find(cls);
+      if (it != C.idle.end() && !it->second.empty()) {
+         void* p = it->second.back();
+         it->second.pop_back();
+         C.idle_bytes -= cls;
+         return p;
+      }
+   }
+   void* p = std::malloc(cls);
+   if (!p) {   // give the cache back and try once more
+      std::vector<void*> drop;
+      {
+         std::lock_guard<std::mutex> lk(C.m);
+         for (auto& kv : C.idle) { drop.insert(drop.end(), kv.second.begin(), kv.second.end()); kv.second.clear(); }
+         C.idle_bytes = 0;
+      }
+      for (void* q : drop) std::free(q);
+      p = std::malloc(cls);
+      if (!p) throw std::bad_alloc();
+   }
+   return p;
+}
+void host_block_release(void* p, size_t bytes) {
+   if (!p) return;
+   const size_t cls = host_class(std::max<size_t>(bytes, 64));
+   HostBlockCache& C = host_cache();
+   std::vector<void*> drop;
+   {
+      std::lock_guard<std::mutex> lk(C.m);
+      if (cls > C.keep) drop.push_back(p);
+      else {
+         if (C.idle_bytes + cls > C.keep) {   // full of sizes nobody asks for any more (the bond dimension moved on): start over
+            for (auto& kv : C.idle) { drop.insert(drop.end(), kv.second.begin(), kv.second.end()); kv.second.clear(); }
+            C.idle_bytes = 0;
+         }
+         C.idle[cls].push_back(p);
+         C.idle_bytes += cls;
+      }
+   }
+   for (void* q : drop) std::free(q);
 }
 
 // ------------------------------------------------------------------------------------------------ Wigner

@@ -9,6 +9,8 @@
 //   wigner6j/9j <-> CheMPS2::Wigner                  (Wigner.cpp:294-368)
 // The look-ups are O(1) hash look-ups instead of the reference's linear scans.
 #pragma once
+#include <memory>
+#include <new>
 #include <cstdint>
 #include <cstdlib>
 #include <functional>
@@ -24,6 +26,29 @@ namespace b2 {
 // std::threads runs almost serially (measured: 8 x 41 ms of work in 340 ms on new threads, 55-70 ms on parked ones).  A call made
 // while the pool is busy (another host thread, or a nested call) runs its n pieces sequentially on the caller.
 void parallel_run(int n, const std::function<void(int)>& fn);
+
+// Large host blocks of the plan builders (work lists, term arrays: hundreds of MB per site, built and dropped at every site).  malloc
+// hands such sizes to mmap, so every plan pays the page faults of fresh memory and every release the munmap (measured: 20 ms per site at
+// D = 2000, as much as the Split).  Freed blocks are kept (size classes with <= 12.5 % rounding, at most B2_HOST_CACHE_GB = 4 GB idle) and
+// handed out again, dirty: callers must not expect zeros.
+void* host_block_acquire(size_t bytes);
+void host_block_release(void* p, size_t bytes);
+// std::allocator whose blocks of 1 MB and more come from that cache
+template <class T> struct CachedAlloc : std::allocator<T> {
+   template <class U> struct rebind { using other = CachedAlloc<U>; };
+   CachedAlloc() = default;
+   template <class U> CachedAlloc(const CachedAlloc<U>&) {}
+   static constexpr size_t kCached = (size_t)1 << 20;
+   T* allocate(size_t n) {
+      const size_t bytes = n * sizeof(T);
+      return bytes >= kCached ? static_cast<T*>(host_block_acquire(bytes)) : static_cast<T*>(::operator new(bytes));
+   }
+   void deallocate(T* p, size_t n) {
+      const size_t bytes = n * sizeof(T);
+      if (bytes >= kCached) host_block_release(p, bytes); else ::operator delete(p);
+   }
+};
+template <class T> using BigVec = std::vector<T, CachedAlloc<T>>;
 
 // (-1)^{two_power/2}; same integer semantics as Special::phase (Special.h:36) / Heff::phase (Heff.h:75).
 inline int phase(int two_power) { return (((two_power / 2) % 2) != 0) ? -1 : 1; }

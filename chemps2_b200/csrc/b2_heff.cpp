@@ -69,10 +69,12 @@ void compile_sigma(CompiledSigma& out, const SigmaPlan& plan, const OpSet* left,
    std::vector<DstBlock> dst(nk);
    for (int k = 0; k < nk; k++) dst[k] = DstBlock{S.blk[k].off, S.blk[k].rows, S.blk[k].cols};
    // ~100 bytes per term, a million terms: raw storage, constructed by the thread that resolves the range (parallel first touch)
-   struct FreeDeleter { void operator()(void* p) const { std::free(p); } };
-   std::unique_ptr<Term3, FreeDeleter> term_store((Term3*)std::malloc(sizeof(Term3) * std::max<size_t>(order.size(), 1)));
-   if (!term_store) throw std::bad_alloc();
-   Term3* terms = term_store.get();
+   struct TermStore {
+      size_t bytes; Term3* p;
+      explicit TermStore(size_t n) : bytes(sizeof(Term3) * std::max<size_t>(n, 1)), p((Term3*)host_block_acquire(bytes)) {}
+      ~TermStore() { host_block_release(p, bytes); }
+   } term_store(order.size());
+   Term3* terms = term_store.p;
    auto resolve_range = [&](size_t b, size_t e) {
       for (size_t i = b; i < e; i++) {
          const SigmaTerm& t = plan.terms[order[i]];

@@ -160,6 +160,58 @@ void pool_trim() {
    std::lock_guard<std::mutex> g(P.mtx);
    trim_locked(P, -1, 0);
 }
+namespace {
+struct PinnedCache {
+   std::mutex mtx;
+   std::vector<std::pair<void*, size_t>> idle;                 // (buffer, capacity)
+   std::unordered_map<void*, size_t> out;                      // handed out -> capacity
+   size_t idle_bytes = 0;
+};
+PinnedCache& pinned() { static PinnedCache* c = new PinnedCache; return *c; }
+constexpr size_t kPinnedKeep = (size_t)2 << 30;               // idle pinned memory kept at most
+}   // namespace
+void* pinned_acquire(size_t bytes) {
+   PinnedCache& C = pinned();
+   bytes = std::max<size_t>(bytes, 4096);
+   {
+      std::lock_guard<std::mutex> g(C.mtx);
+      int best = -1;
+      for (int i = 0; i < (int)C.idle.size(); i++)              // smallest idle buffer that fits
+         if (C.idle[i].second >= bytes && (best < 0 || C.idle[i].second < C.idle[best].second)) best = i;
+      if (best >= 0) {
+         std::pair<void*, size_t> b = C.idle[best];
+         C.idle.erase(C.idle.begin() + best);
+         C.idle_bytes -= b.second;
+         C.out[b.first] = b.second;
+         return b.first;
+      }
+   }
+   const size_t cap = size_class(bytes + bytes / 4);           // head room: the next Split is rarely exactly this size
+   void* p = nullptr;
+   if (cudaMallocHost(&p, cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+   std::lock_guard<std::mutex> g(C.mtx);
+   C.out[p] = cap;
+   return p;
+}
+void pinned_release(void* p) {
+   if (!p) return;
+   PinnedCache& C = pinned();
+   std::vector<void*> drop;
+   {
+      std::lock_guard<std::mutex> g(C.mtx);
+      auto it = C.out.find(p);
+      if (it == C.out.end()) return;
+      C.idle.push_back({p, it->second});
+      C.idle_bytes += it->second;
+      C.out.erase(it);
+      while (C.idle_bytes > kPinnedKeep && !C.idle.empty()) {   // oldest first
+         drop.push_back(C.idle.front().first);
+         C.idle_bytes -= C.idle.front().second;
+         C.idle.erase(C.idle.begin());
+      }
+   }
+   for (void* q : drop) cudaFreeHost(q);
+}
 size_t pool_cached_bytes() {
    Pool& P = pool();
    std::lock_guard<std::mutex> g(P.mtx);

@@ -18,6 +18,10 @@ void pool_register_stream(cudaStream_t s);
 void pool_unregister_stream(cudaStream_t s);
 void pool_trim();                 // give every cached block back to the driver
 size_t pool_cached_bytes();       // bytes held in the cache (free for the library's purposes)
+// Pinned host staging buffers (cudaMallocHost costs milliseconds and every Split / plan upload needs tens of MB): a handful of buffers
+// is kept and handed out again; a caller must be done with its transfers (stream synchronised) before it releases one.
+void* pinned_acquire(size_t bytes);   // nullptr when the allocation fails (callers fall back to pageable memory)
+void pinned_release(void* p);
 }   // namespace b2
 
 #ifndef B2_POOL_IMPL

@@ -46,7 +46,7 @@ struct SigmaPlan {
    int site = 0;
    bool at_left = false, at_right = false;
    SLayout S;
-   std::vector<SigmaTerm> terms;
+   BigVec<SigmaTerm> terms;        // ~40 bytes x up to millions per site: blocks recycled through the host block cache
    std::vector<Presum> presums;
    int64_t presum_size = 0;
    long long skipped_zero = 0;                   // terms dropped because their prefactor is exactly 0

@@ -570,17 +570,28 @@ void build_sigma_plan(SigmaPlan& plan, const Bookkeeper& bk, const Problem& prob
    std::vector<std::pair<int, int>> where(nk, {-1, -1});   // block -> (thread, position in its block list)
    for (int t = 0; t < nthreads; t++)
       for (size_t i = 0; i < frags[t].blk_k.size(); i++) where[frags[t].blk_k[i]] = {t, (int)i};
-   plan.terms.reserve(nterms);
+   std::vector<size_t> first(nk + 1, 0);                    // where the terms of block k start in the stitched list
    for (int k = 0; k < nk; k++) {
-      const int t = where[k].first, i = where[k].second;
-      const Frag& f = frags[t];
-      for (int e = f.blk_begin[i]; e < f.blk_begin[i + 1]; e++) {
-         SigmaTerm x = f.plan.terms[e];
-         if (x.l.src == SRC_PRESUM && x.l.op >= 0) x.l.op = remap[t][x.l.op];
-         if (x.r.src == SRC_PRESUM && x.r.op >= 0) x.r.op = remap[t][x.r.op];
-         plan.terms.push_back(x);
-      }
+      const Frag& f = frags[where[k].first];
+      first[k + 1] = first[k] + (size_t)(f.blk_begin[where[k].second + 1] - f.blk_begin[where[k].second]);
    }
+   plan.terms.resize(nterms);
+   parallel_run(nthreads, [&](int piece) {                   // contiguous ranges of blocks, balanced in terms
+      const size_t lo = nterms * piece / nthreads, hi = nterms * (piece + 1) / nthreads;
+      const int kb = (int)(std::lower_bound(first.begin(), first.end() - 1, lo) - first.begin());
+      const int ke = (int)(std::lower_bound(first.begin(), first.end() - 1, hi) - first.begin());
+      for (int k = kb; k < (piece == nthreads - 1 ? nk : ke); k++) {
+         const int t = where[k].first, i = where[k].second;
+         const Frag& f = frags[t];
+         size_t out = first[k];
+         for (int e = f.blk_begin[i]; e < f.blk_begin[i + 1]; e++) {
+            SigmaTerm x = f.plan.terms[e];
+            if (x.l.src == SRC_PRESUM && x.l.op >= 0) x.l.op = remap[t][x.l.op];
+            if (x.r.src == SRC_PRESUM && x.r.op >= 0) x.r.op = remap[t][x.r.op];
+            plan.terms[out++] = x;
+         }
+      }
+   });
    balance_owners(plan, left, right, world);
    if (getenv("B2_TIMING"))
       fprintf(stderr, "build_sigma_plan: %d blocks on %d threads, enumerate %.3f s, stitch %.3f s\n", nk, nthreads,

@@ -10,6 +10,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <functional>
 #include <cmath>
 #include <cstring>
@@ -79,6 +82,8 @@ std::vector<Piece> right_pieces(const Bookkeeper& bk, int ix, const Center& c) {
 
 double split_host(Bookkeeper& bk, int ix, const SLayout& S, const double* s_storage, int D, bool moving_right, bool change,
                   std::vector<double>& t_left, std::vector<double>& t_right, const SvdBatchFn& svd_batch) {
+   auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+   const double t_g0 = now_s();
    std::vector<Center> centers;
    bk.for_sectors(ix + 1, [&](int n, int ts, int ir) { if (bk.fcidim(ix + 1, n, ts, ir) > 0) centers.push_back({n, ts, ir}); });
    const int nc = (int)centers.size();
@@ -132,8 +137,10 @@ double split_host(Bookkeeper& bk, int ix, const SLayout& S, const double* s_stor
       jobs.push_back(job);
    }
    // the decomposition itself (dgesdd_ per centre sector in the reference, Sobject.cpp:412-419): all sectors in one device batch
+   const double t_g1 = now_s();
    if (!svd_batch || svd_batch(jobs) != 0) return -1.0;   // negative = failed (the caller reports the device error)
    mems.clear();
+   const double t_g2 = now_s();
 
    double discarded = 0.0;
    if (change) {   // Sobject.cpp:437-499
@@ -195,6 +202,7 @@ double split_host(Bookkeeper& bk, int ix, const SLayout& S, const double* s_stor
          }
       }
    });
+   if (getenv("B2_TIMING")) fprintf(stderr, "split_host: %d centre sectors: gather %.4f s, decomposition %.4f s, truncation + scatter %.4f s\n", nc, t_g1 - t_g0, t_g2 - t_g1, now_s() - t_g2);
    return discarded;
 }
 

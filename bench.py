@@ -153,10 +153,12 @@ def sweep_metric(device, with_reference, schedule=None, world=1, rank=0, allredu
                 change = True
                 rows.append(dict(D=D, to_right=to_right, seconds=time.time() - t0, energy=e, max_discarded_weight=dw, **d.timers()))
     last = rows[-2:]
+    hits, misses = d.plan_cache_stats()
+    plans = {"reused_from_cache": hits, "built": misses, "built_on_helper_thread_during_update": d.plan_prefetched()}
     out = {"workload": f"{SWEEP_WORKLOAD}: N2/cc-pVDZ 14e/28o D2h (BASELINE config 2), seeded random MPS, schedule D=" + ",".join(str(D) for D, _ in schedule) +
                        " (one left+right sweep each), rtol 1e-5, no noise", "n_gpus": world,
            "D": schedule[-1][0], "seconds_per_sweep_at_D": last[0]["seconds"] + last[1]["seconds"], "total_seconds": time.time() - t_begin,
-           "energy": min(r["energy"] for r in last), "max_discarded_weight": max(r["max_discarded_weight"] for r in last),
+           "energy": min(r["energy"] for r in last), "max_discarded_weight": max(r["max_discarded_weight"] for r in last), "plans": plans,
            "half_sweeps": [{"D": r["D"], "dir": "->" if r["to_right"] else "<-", "s": round(r["seconds"], 3), "E": r["energy"], "plan_s": round(r["plan_s"], 3),
                             "solve_s": round(r["solve_s"], 3), "split_s": round(r["split_s"], 3), "update_s": round(r["update_s"], 3), "sigma_builds": r["n_matvec"]} for r in rows]}
     from oracle import refrun

@@ -88,6 +88,7 @@ struct b2_dmrg {
    } prefetch;
    bool in_sweep = false;
    bool use_prefetch = true;               // B2_PLAN_PREFETCH=0 switches it off
+   bool prefetch_multi = false;            // B2_PLAN_PREFETCH=2: also in sharded (multi-GPU) sweeps
    long long plan_prefetched = 0;
    bool right_canonical = false;           // b2_dmrg_calc_2rdm leaves the MPS right-canonical (centre on site 0): PreSolve must restore the gauge first
    double max_disc_last_sweep = 0.0;       // DMRG::MaxDiscWeightLastSweep (DMRG.cpp:360-362): scales the noise of the next half sweep
@@ -115,7 +116,7 @@ int b2_dmrg_create(b2_ctx* ctx, b2_dmrg** out) {
    d->mps.resize(d->L);
    for (int s = 0; s < d->L; s++) { TLayout t; t.build(ctx->bk, s); d->mps[s].assign((size_t)t.size, 0.0); }
    d->left.assign(d->L + 1, nullptr); d->right.assign(d->L + 1, nullptr);
-   if (const char* e = getenv("B2_PLAN_PREFETCH")) d->use_prefetch = atoi(e) != 0;
+   if (const char* e = getenv("B2_PLAN_PREFETCH")) { d->use_prefetch = atoi(e) != 0; d->prefetch_multi = atoi(e) >= 2; }
    *out = d.release();
    return B2_OK;
 }
@@ -146,6 +147,8 @@ static void dmrg_prefetch_start(b2_dmrg* d, int site, b2_opset* lset, b2_opset* 
    dmrg_prefetch_cancel(d);
    const int L = d->L;
    if (!d->in_sweep || !d->use_prefetch || d->spill || site < 0 || site > L - 2) return;
+   // several GPUs: validated on one GPU only so far (the round's GPU budget ended before a multi-rank run), so it stays off unless asked for
+   if (d->world > 1 && !d->prefetch_multi) return;
    if (site > 0 && (!lset || lset->set.reduced || lset->offloaded || lset->set.boundary != site || !lset->set.moving_right)) return;
    if (site < L - 2 && (!rset || rset->set.reduced || rset->offloaded || rset->set.boundary != site + 2 || rset->set.moving_right)) return;
    if (d->ctx->simulate_oom > 0) return;   // the test hook counts b2_heff_create calls
@@ -283,6 +286,7 @@ int b2_dmrg_set_plan_cache(b2_dmrg* d, int enabled) {
 int b2_dmrg_set_plan_prefetch(b2_dmrg* d, int enabled) {
    if (!d) return fail(B2_ERR_ARG, "b2_dmrg_set_plan_prefetch: NULL");
    d->use_prefetch = enabled != 0;
+   d->prefetch_multi = enabled >= 2;
    return B2_OK;
 }
 long long b2_dmrg_plan_prefetched(const b2_dmrg* d) { return d ? d->plan_prefetched : 0; }

@@ -325,7 +325,8 @@ int b2_dmrg_plan_cache_stats(const b2_dmrg* d, long long* hits, long long* misse
 /* Inside b2_dmrg_sweep the host half of the NEXT site's sigma plan (term enumeration + scheduling; it needs the dimension tables and the
  * layouts of the operator sets, not their contents) is built on a helper thread while the calling thread plans and runs the operator
  * update that precedes it (DMRG.cpp:372-377 runs the two one after the other).  enabled = 0 switches it off (also B2_PLAN_PREFETCH=0);
- * the result of a sweep does not depend on it.  b2_dmrg_plan_prefetched: how many newly built plans came from the helper thread. */
+ * the result of a sweep does not depend on it.  Sharded sweeps (b2_dmrg_set_world with world > 1) use it only with enabled = 2 (or
+ * B2_PLAN_PREFETCH=2): it has been validated on one GPU only.  b2_dmrg_plan_prefetched: how many newly built plans came from the helper thread. */
 int b2_dmrg_set_plan_prefetch(b2_dmrg* d, int enabled);
 long long b2_dmrg_plan_prefetched(const b2_dmrg* d);
 /* wall-clock seconds per phase since the last reset: [0] plan building (host), [1] Davidson solves, [2] Split (host SVD),

@@ -141,5 +141,6 @@ def test_null_handles_do_not_crash():
     assert lib.b2_opset_offload_file(None, None) == ERR_ARG and lib.b2_dmrg_set_spill_dir(None, None) == ERR_ARG and lib.b2_dmrg_srand(None, 1) == ERR_ARG
     assert lib.b2_davidson_fetch(None, None, None, None) == ERR_ARG and lib.b2_davidson_num_multiplications(None) == 0
     assert lib.b2_update_num_mix_flat(None) == 0 and lib.b2_rand_stream(1, -1, None) == ERR_ARG
+    assert lib.b2_dmrg_set_plan_prefetch(None, 1) == ERR_ARG and lib.b2_dmrg_plan_prefetched(None) == 0
     lib.b2_davidson_destroy(None)
     lib.b2_ctx_destroy(None); lib.b2_opset_destroy(None); lib.b2_heff_destroy(None); lib.b2_update_destroy(None); lib.b2_dmrg_destroy(None); lib.b2_twodm_destroy(None)

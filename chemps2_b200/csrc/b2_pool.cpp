@@ -94,8 +94,12 @@ cudaError_t pool_malloc(void** p, size_t bytes) {
    cudaError_t e = cudaGetDevice(&dev);
    if (e != cudaSuccess) return e;
    std::lock_guard<std::mutex> g(P.mtx);
-   auto it = P.cache.find({dev, cls});
-   if (it != P.cache.end()) {
+   // smallest cached block of this device that holds the request and is at most twice its size: workspaces and work lists change size
+   // from site to site, and with exact-class matching a D = 2000 sweep filled the cache with near misses — every free then evicted a
+   // GB-sized block through the driver (device-wide synchronising cudaFree) and every allocation went to cudaMalloc
+   // (profiles/r2y_sweep_timing.log: 0.8 s "release" + 0.6-1.2 s "update epilogue" per half sweep, both ~0 at D = 1000)
+   auto it = P.cache.lower_bound({dev, cls});
+   if (it != P.cache.end() && it->first.first == dev && it->first.second <= 2 * cls) {
       Block b = std::move(it->second);
       P.cache.erase(it);
       P.cached -= b.bytes;
@@ -103,7 +107,7 @@ cudaError_t pool_malloc(void** p, size_t bytes) {
          for (auto& st : P.streams) if (st.first == dev) cudaStreamWaitEvent(st.second, ev, 0);
          P.spare_events.push_back(ev);
       }
-      P.live[b.p] = {cls, dev};
+      P.live[b.p] = {b.bytes, dev};   // the block keeps its own size class
       *p = b.p;
       return cudaSuccess;
    }

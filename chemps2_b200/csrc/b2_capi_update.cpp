@@ -76,8 +76,11 @@ int b2_update_create_sharded(b2_ctx* ctx, int index, int moving_right, b2_opset*
    const double tb2 = wall_seconds();
    CompileOptions copt = budgeted(ctx);
    copt.threads = (u->plan.flops_ref < ctx->parallel_plan_flops) ? plan_threads((int)u->plan.dst.size()) : 1;
+   const double tb3 = wall_seconds();
    compile_terms(u->pass[0], u->plan.terms, u->plan.dst, SP_VOUT, copt);
+   const double tb4 = wall_seconds();
    compile_terms(u->pass[1], u->plan.mix_terms, u->plan.mix_dst, SP_PRESUM, copt);   // transposed copies for daxpy_transpose_tensorCD
+   const double tb5 = wall_seconds();
    {  // The mixing pass is memory bound and every source tile is shared by up to O(L^2) destination operators (A(s1,s2) of all outside
       // pairs add the same S0(o,i) blocks with different integrals): launch the tiles that read the same sources next to each other, so that
       // the sources are served by L2 and HBM sees every destination tile once.  Key = (first source tile, tile position).
@@ -129,8 +132,8 @@ int b2_update_create_sharded(b2_ctx* ctx, int index, int moving_right, b2_opset*
    }
    for (int p = 0; p < 2; p++) u->list_bytes[p] = u->pass[p].bytes();
    if (getenv("B2_TIMING"))
-      fprintf(stderr, "b2_update_create: enumerate %.3f s, owners %.3f s, schedule %.3f s, %zu + %zu terms\n", tb1 - tb0, tb2 - tb1, wall_seconds() - tb2,
-              u->plan.terms.size(), u->plan.mix_terms.size());
+      fprintf(stderr, "b2_update_create: enumerate %.3f s, owners %.3f s, schedule %.3f s (budget %.3f, contraction pass %.3f, transposed copies %.3f, mixing lists %.3f), %zu + %zu terms\n",
+              tb1 - tb0, tb2 - tb1, wall_seconds() - tb2, tb3 - tb2, tb4 - tb3, tb5 - tb4, wall_seconds() - tb5, u->plan.terms.size(), u->plan.mix_terms.size());
    for (const Presum& p : u->plan.presums) {
       PresumJob j{};
       j.dst_off = p.off; j.size = p.lay->size; j.part_begin = (int)u->presum_parts.size();

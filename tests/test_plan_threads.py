@@ -175,3 +175,48 @@ def test_next_sigma_plan_concurrent_with_update_plan():
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     line = [ln for ln in res.stdout.splitlines() if ln.startswith("B2PREFETCH")][-1]
     assert eval(line[len("B2PREFETCH"):]) == [True, True, True]
+
+
+RECYCLE_WORKER = r"""
+import sys, os
+import ctypes as C
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import cpu_check
+from chemps2_b200 import api, workloads
+from chemps2_b200._lib import Worklists, check, lib
+
+def digests(name, D, dist, site):
+    w = workloads.get(name, D=D)
+    ctx = w.context(-1)
+    w.apply_distribution(ctx, dist)
+    left = api.OpSet(ctx, site, True)
+    right = api.OpSet(ctx, site + 2, False)
+    heff = api.Heff(ctx, site, left, right)
+    wl = Worklists()
+    check(lib.b2_heff_worklists(heff.h, C.byref(wl)))
+    out = [cpu_check.worklist_digest(wl)]
+    new = api.OpSet(ctx, site + 1, True)
+    upd = api.Update(ctx, site, True, left, new)
+    for p in (0, 1):
+        uw = Worklists()
+        check(lib.b2_update_worklists(upd.h, p, C.byref(uw)))
+        out.append(cpu_check.worklist_digest(uw))
+    return out
+
+a1 = digests("n2_ccpvdz", 500, "gauss", 12)
+b = digests("synth40", 300, "gauss", 19)          # other sizes, other contents: the recycled blocks now hold ITS lists
+a2 = digests("n2_ccpvdz", 500, "gauss", 12)
+print("B2RECYCLE", a1 == a2, a1 != b)
+"""
+
+
+def test_plans_do_not_depend_on_recycled_memory():
+    """work lists and term arrays live in blocks recycled through the host block cache (b2_core.cpp host_block_acquire) and are sized
+    without a zero fill (NoInitAlloc): a plan built on blocks that still hold ANOTHER plan's lists must come out bit-identical to the
+    one built on fresh memory — every field of every list entry is written by the builder"""
+    for threads in ("1", "6"):
+        env = dict(os.environ, B2_PLAN_THREADS=threads)
+        res = subprocess.run([sys.executable, "-c", RECYCLE_WORKER.format(root=ROOT)], capture_output=True, text=True, env=env, timeout=900)
+        assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+        line = [ln for ln in res.stdout.splitlines() if ln.startswith("B2RECYCLE")][-1]
+        assert line.split()[1:] == ["True", "True"], line
